@@ -1,0 +1,127 @@
+// On-device synthetic count generator for the large benchmark configurations.
+// Generative model of the reference package (pkg/R/data_generation.R:393-463):
+//   Lambda = U V^T, Xnzi ~ Poisson(Lambda), D_ij ~ Bernoulli(prob1_j) (prob1 = probability of NOT dropping out), X = Xnzi * D
+// written straight into CSR (two passes: count, fill).  Philox counter-based streams keyed by the GLOBAL entry index,
+// so the matrix does not depend on the launch configuration or on how cells are sharded over GPUs.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include <cub/cub.cuh>
+#include <curand_kernel.h>
+
+#include "../../include/pcmf_b200.h"
+
+namespace {
+
+struct GenArgs {
+    int64_t n, row_offset;
+    int32_t p;
+    int K;
+    const double *U;   // n x K row-major
+    const double *V;   // p x K row-major
+    const double *prob1;   // p or null
+    unsigned long long seed;
+};
+
+__device__ __forceinline__ int draw_entry(const GenArgs &a, int64_t i, int j) {
+    curandStatePhilox4_32_10_t st;
+    curand_init(a.seed, (unsigned long long)((a.row_offset + i) * (int64_t)a.p + j), 0ull, &st);
+    if (a.prob1) {
+        const float u = curand_uniform(&st);           // (0, 1]
+        if (!(u <= (float)a.prob1[j])) return 0;       // dropped out
+    }
+    double lam = 0.0;
+    const double *u = a.U + i * a.K, *v = a.V + (int64_t)j * a.K;
+    for (int k = 0; k < a.K; ++k) lam = fma(u[k], v[k], lam);
+    return (int)curand_poisson(&st, lam);
+}
+
+// one warp per cell; pass 0 counts, pass 1 writes (ordered by gene inside the cell)
+template <bool FILL>
+__global__ void k_generate(GenArgs a, int64_t *rowcount, const int64_t *rowptr, int32_t *colidx, float *val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < a.n; i += nw) {
+        int64_t base = FILL ? rowptr[i] : 0;
+        int64_t cnt = 0;
+        for (int j0 = 0; j0 < a.p; j0 += 32) {
+            const int j = j0 + lane;
+            const int x = j < a.p ? draw_entry(a, i, j) : 0;
+            const unsigned m = __ballot_sync(0xffffffffu, x != 0);
+            if (FILL && x != 0) {
+                const int64_t pos = base + __popc(m & ((1u << lane) - 1u));
+                colidx[pos] = j;
+                val[pos] = (float)x;
+            }
+            base += __popc(m);
+            cnt += __popc(m);
+        }
+        if (!FILL && lane == 0) rowcount[i] = cnt;
+    }
+}
+
+__global__ void k_transpose_in(int64_t rows, int K, const double *src_colmajor, double *dst_rowmajor) {
+    const int64_t total = rows * K;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % K);
+        const int64_t r = o / K;
+        dst_rowmajor[o] = src_colmajor[r + (int64_t)k * rows];
+    }
+}
+
+#define GK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            if (errbuf && errlen) snprintf(errbuf, errlen, "CUDA error %s at %s:%d", cudaGetErrorName(e_), __FILE__, __LINE__); \
+            return PCMF_ECUDA;                                                                               \
+        }                                                                                                    \
+    } while (0)
+
+}  // namespace
+
+extern "C" int pcmf_generate_counts_device(int device, int64_t n_local, int32_t p, int32_t K_true, const double *U, const double *V,
+                                           const double *prob1, uint64_t seed, int64_t row_offset, int64_t **rowptr_dev,
+                                           int32_t **colidx_dev, float **val_dev, int64_t *nnz_out, char *errbuf, size_t errlen) {
+    if (!U || !V || !rowptr_dev || !colidx_dev || !val_dev || !nnz_out || n_local <= 0 || p <= 0 || K_true <= 0) {
+        if (errbuf && errlen) snprintf(errbuf, errlen, "bad argument to pcmf_generate_counts_device");
+        return PCMF_EINVAL;
+    }
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        if (errbuf && errlen) snprintf(errbuf, errlen, "no CUDA device available");
+        return PCMF_ECUDA;
+    }
+    GK(cudaSetDevice(device));
+    double *dU = nullptr, *dV = nullptr, *dUr = nullptr, *dVr = nullptr, *dP = nullptr;
+    int64_t *rc = nullptr, *rp = nullptr;
+    const size_t nK = (size_t)n_local * K_true, pK = (size_t)p * K_true;
+    GK(cudaMalloc(&dU, nK * 8)); GK(cudaMalloc(&dUr, nK * 8)); GK(cudaMalloc(&dV, pK * 8)); GK(cudaMalloc(&dVr, pK * 8));
+    GK(cudaMemcpy(dU, U, nK * 8, cudaMemcpyHostToDevice)); GK(cudaMemcpy(dV, V, pK * 8, cudaMemcpyHostToDevice));
+    k_transpose_in<<<1024, 256>>>(n_local, K_true, dU, dUr);
+    k_transpose_in<<<256, 256>>>(p, K_true, dV, dVr);
+    if (prob1) { GK(cudaMalloc(&dP, (size_t)p * 8)); GK(cudaMemcpy(dP, prob1, (size_t)p * 8, cudaMemcpyHostToDevice)); }
+    GK(cudaMalloc(&rc, (size_t)(n_local + 1) * 8)); GK(cudaMalloc(&rp, (size_t)(n_local + 1) * 8));
+    GK(cudaMemset(rc, 0, (size_t)(n_local + 1) * 8));
+    GenArgs a{n_local, row_offset, p, K_true, dUr, dVr, dP, (unsigned long long)seed};
+    const int block = 256;
+    const int grid = (int)std::min<int64_t>((n_local * 32 + block - 1) / block, 148 * 64);
+    k_generate<false><<<grid, block>>>(a, rc, nullptr, nullptr, nullptr);
+    size_t tmp_bytes = 0;
+    GK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, rc, rp, n_local + 1));
+    void *tmp = nullptr;
+    GK(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    GK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rc, rp, n_local + 1));
+    int64_t nnz = 0;
+    GK(cudaMemcpy(&nnz, rp + n_local, 8, cudaMemcpyDeviceToHost));
+    int32_t *ci = nullptr; float *vv = nullptr;
+    GK(cudaMalloc(&ci, (size_t)std::max<int64_t>(nnz, 1) * 4)); GK(cudaMalloc(&vv, (size_t)std::max<int64_t>(nnz, 1) * 4));
+    k_generate<true><<<grid, block>>>(a, nullptr, rp, ci, vv);
+    GK(cudaDeviceSynchronize());
+    GK(cudaGetLastError());
+    cudaFree(tmp); cudaFree(rc); cudaFree(dU); cudaFree(dV); cudaFree(dUr); cudaFree(dVr); if (dP) cudaFree(dP);
+    *rowptr_dev = rp; *colidx_dev = ci; *val_dev = vv; *nnz_out = nnz;
+    return PCMF_OK;
+}

@@ -1,0 +1,939 @@
+// sm_100a kernels of the pCMF variational-EM core.  FP64 throughout (the reference is MatrixXd).
+//
+// Data layout in HBM:
+//   * factor-side state is ROW-major with a padded leading dimension KP (K rounded up to a supported width,
+//     multiple of 4 -> every K-vector is 32-byte aligned and read with 16-byte vector loads);
+//     padded entries are kept at values that make them inert (eu = ev = 0, ...).
+//   * X lives twice: CSR (cells ordered) for the U-side pass and CSC (genes ordered) for the V-side passes,
+//     int32 indices + FP32 (or FP64) values, plus two 1-bit/entry occupancy bitmaps for the dense ZI passes.
+//   * hyper-parameters alpha*/beta* have identical rows in every reachable state and are
+//     stored as K-vectors.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "specfun.cuh"
+
+namespace pcmf {
+
+// indices into the per-iteration scalar block (device doubles)
+enum Scal : int {
+    S_GAPU_D = 0, S_GAPU_O, S_ENTU, S_GAPV_D, S_GAPV_O, S_ENTV,
+    S_BERNS_PRIOR, S_BERNS_SELF, S_BERND_PRIOR, S_BERND_SELF, S_SUM_PUVT, S_DATA, S_LGX,
+    S_GAMMAU, S_GAMMAV, S_SUMUVT_CLOSED, S_ABS_GAP, S_NORM_GAP, S_ELBO_NODATA,
+    S_COUNT = 32
+};
+// guard block: min/max of ElogU / ElogV stored as ordered long long
+enum Guard : int { G_MINU = 0, G_MAXU, G_MINV, G_MAXV, G_COUNT };
+
+struct GuardView {
+    const long long *g;   // G_COUNT ordered ints
+};
+__device__ __forceinline__ bool need_exact(const long long *g) {
+    // gap_factor_model.cpp:483 (shift when max_k s_k >= 100) and internal.h:121-127 (floor below -100): the hoisted
+    // exp(ElogU)*exp(ElogV) form is only valid while neither guard can fire for any (i,j,k) of this rank.
+    const double mnU = dbl_from_ordered(g[G_MINU]), mxU = dbl_from_ordered(g[G_MAXU]);
+    const double mnV = dbl_from_ordered(g[G_MINV]), mxV = dbl_from_ordered(g[G_MAXV]);
+    return !(mxU + mxV < 99.0) || !(mnU + mnV > -99.0);
+}
+
+template <int KP>
+__device__ __forceinline__ void load_vec(const double *__restrict__ p, double (&r)[KP]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < KP / 2; ++i) {
+        const double2 t = __ldg(q + i);
+        r[2 * i] = t.x;
+        r[2 * i + 1] = t.y;
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh /* >= 32 doubles */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    return v;   // valid in warp 0
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// U-side epilogue shared by the E-step row kernel and the init kernel: given the new shape/rate of element (i,k)
+// produce the sufficient statistics (gap_factor_model.cpp:408-411, probability.h:76-108) and the per-lane partial
+// sums of everything that is reduced over cells.
+// ------------------------------------------------------------------------------------------------------------
+struct UAcc {
+    double cs_eu = 0, cs_elog = 0, gap_d = 0, gap_o = 0, ent = 0;
+    double mn = 1e300, mx = -1e300;
+};
+__device__ __forceinline__ void u_element(double a1n, double a2n, double a1o, double a2o, double *EU, double *ElogU,
+                                          double *eu, UAcc &acc) {
+    const double d1 = a1n - a1o, d2 = a2n - a2o;
+    acc.gap_d += d1 * d1 + d2 * d2;            // gap_factor_model.cpp:258-259
+    acc.gap_o += a1o * a1o + a2o * a2o;        // gap_factor_model.cpp:256-257
+    const double psi = digamma_pos(a1n);
+    const double el = psi - log(a2n);
+    const double e = a1n / a2n;
+    *EU = e;
+    *ElogU = el;
+    *eu = exp(el);
+    acc.cs_eu += e;
+    acc.cs_elog += el;
+    acc.ent += gamma_entropy1(a1n, a2n, psi);  // probability.h:157-160
+    acc.mn = fmin(acc.mn, el);
+    acc.mx = fmax(acc.mx, el);
+}
+
+struct RowArgs {
+    int64_t n;
+    int K;
+    const int64_t *rowptr;
+    const int32_t *colidx;
+    const void *val;
+    // V side (old stats)
+    const double *ev;      // p x KP: S o exp(ElogV)                      (fast path)
+    const double *evw;     // p x KP: ev o wS                              (fast path)
+    const double *ElogV;   // p x KP                                       (exact path)
+    const double *Sd;      // p x KP mask as double                        (exact path)
+    const double *wS;      // p x KP: prob_S o colw (or colw, or 1)        (exact path)
+    // U side, updated in place
+    double *a1, *a2, *EU_new, *ElogU, *eu;
+    const double *alpha1, *alpha2;   // K-vectors
+    const double *rate_vec;          // KP: colsum(EV o prob_S) (non-ZI)   gap...cpp:531 / sparse...cpp:400
+    const double *PV;                // n x KP: prob_D * (EV o prob_S) (ZI) zi...cpp:336 / zi_sparse...cpp:363
+    int first_iter;                  // old iterate is Ones (gap_factor_model.cpp:72-75; never copied before iter 0)
+    const long long *guard_cur;      // guards of the stats being read
+    long long *guard_next;           // min/max of the new ElogU
+    double *cs_eu, *cs_elog;         // KP each (atomic)
+    double *usc;                     // 3 doubles (atomic): gap_d, gap_o, entropy of the local cells (all-reduced later)
+};
+
+// E-step, cell side + fused U-side M-step.  One warp per cell; lanes stride over the cell's non-zeros.
+// Reference: update_variational_multinomial_param (gap...cpp:458-499, zi...:289-330, sparse...:327-368,
+// zi_sparse...:316-357) restricted to the entries with X != 0 (the others contribute 0), then
+// update_variational_gamma_param, factor U part (gap...cpp:530-532 and variants) + U_stats.
+template <int KP, typename VT>
+__global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t warp0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
+    const VT *__restrict__ val = static_cast<const VT *>(a.val);
+    const bool exact = need_exact(a.guard_cur);
+    UAcc acc[(KP + 31) / 32];
+
+    for (int64_t i = warp0; i < a.n; i += nwarps) {
+        double u[KP], r[KP];
+        load_vec<KP>((exact ? a.ElogU : a.eu) + i * KP, u);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) r[k] = 0.0;
+        const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const int j = __ldg(a.colidx + e);
+            const double x = (double)__ldg(val + e);
+            if (!exact) {
+                double v[KP];
+                load_vec<KP>(a.ev + (int64_t)j * KP, v);
+                double T = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) T = fma(u[k], v[k], T);
+                const double q = x / (T > 0.0 ? T : 1.0);
+                if (a.evw != a.ev) load_vec<KP>(a.evw + (int64_t)j * KP, v);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) r[k] = fma(q, v[k], r[k]);
+            } else {
+                double s[KP], t[KP];
+                load_vec<KP>(a.ElogV + (int64_t)j * KP, s);
+                double m = -1e300;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    s[k] += u[k];
+                    if (k < a.K) m = fmax(m, s[k]);
+                }
+                if (m < 100.0) m = 0.0;
+                load_vec<KP>(a.Sd + (int64_t)j * KP, t);
+                double T = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    s[k] = (k < a.K) ? custom_exp(s[k] - m) * t[k] : 0.0;
+                    T += s[k];
+                }
+                const double q = x / (T > 0.0 ? T : 1.0);
+                load_vec<KP>(a.wS + (int64_t)j * KP, t);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) r[k] = fma(q * s[k], t[k], r[k]);
+            }
+        }
+        // reduce over lanes; lane (k & 31) keeps component k
+        double mine[(KP + 31) / 32], um[(KP + 31) / 32];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const double t = warp_sum(r[k]);
+            if ((k & 31) == lane) { mine[k >> 5] = t; um[k >> 5] = u[k]; }
+        }
+#pragma unroll
+        for (int c = 0; c < (KP + 31) / 32; ++c) {
+            const int k = c * 32 + lane;
+            if (k < a.K) {
+                const int64_t o = i * KP + k;
+                const double ez = exact ? mine[c] : um[c] * mine[c];
+                const double a1o = a.first_iter ? 1.0 : a.a1[o], a2o = a.first_iter ? 1.0 : a.a2[o];
+                const double a1n = a.alpha1[k] + ez;
+                const double a2n = a.alpha2[k] + (a.PV ? a.PV[o] : a.rate_vec[k]);
+                a.a1[o] = a1n;
+                a.a2[o] = a2n;
+                u_element(a1n, a2n, a1o, a2o, a.EU_new + o, a.ElogU + o, a.eu + o, acc[c]);
+            }
+        }
+    }
+    // flush per-lane partials
+    __shared__ double sh[32];
+    double gd = 0, go = 0, en = 0, mn = 1e300, mx = -1e300;
+#pragma unroll
+    for (int c = 0; c < (KP + 31) / 32; ++c) {
+        const int k = c * 32 + lane;
+        if (k < a.K) {
+            atomicAdd(a.cs_eu + k, acc[c].cs_eu);
+            atomicAdd(a.cs_elog + k, acc[c].cs_elog);
+        }
+        gd += acc[c].gap_d; go += acc[c].gap_o; en += acc[c].ent;
+        mn = fmin(mn, acc[c].mn); mx = fmax(mx, acc[c].mx);
+    }
+    gd = block_sum(gd, sh); go = block_sum(go, sh); en = block_sum(en, sh);
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (threadIdx.x == 0) {
+        atomicAdd(a.usc + 0, gd);
+        atomicAdd(a.usc + 1, go);
+        atomicAdd(a.usc + 2, en);
+    }
+    if (lane == 0 && mn <= mx) {
+        atomicMin(a.guard_next + G_MINU, dbl_ordered(mn));
+        atomicMax(a.guard_next + G_MAXU, dbl_ordered(mx));
+    }
+}
+
+// init: statistics of given (a1, a2) without an E-step (gap_factor_model.cpp:119, 140, 170: U_stats()).
+struct UInitArgs {
+    int64_t n; int K, KP;
+    const double *a1, *a2;
+    double *EU, *ElogU, *eu;
+    long long *guard_next;
+    double *cs_eu, *cs_elog, *usc;
+};
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_stats_u(UInitArgs a) {
+    __shared__ double sh[32];
+    __shared__ double scs[2][64];
+    if (threadIdx.x < 64) { scs[0][threadIdx.x] = 0; scs[1][threadIdx.x] = 0; }
+    __syncthreads();
+    UAcc acc;
+    const int64_t total = a.n * a.KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % a.KP);
+        if (k < a.K) {
+            UAcc one;
+            u_element(a.a1[o], a.a2[o], 1.0, 1.0, a.EU + o, a.ElogU + o, a.eu + o, one);
+            atomicAdd(&scs[0][k], one.cs_eu);
+            atomicAdd(&scs[1][k], one.cs_elog);
+            acc.ent += one.ent;
+            acc.mn = fmin(acc.mn, one.mn); acc.mx = fmax(acc.mx, one.mx);
+        } else {
+            a.EU[o] = 0; a.ElogU[o] = 0; a.eu[o] = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < a.K) {
+        atomicAdd(a.cs_eu + threadIdx.x, scs[0][threadIdx.x]);
+        atomicAdd(a.cs_elog + threadIdx.x, scs[1][threadIdx.x]);
+    }
+    const double en = block_sum(acc.ent, sh);
+    const double mn = warp_min(acc.mn), mx = warp_max(acc.mx);
+    if (threadIdx.x == 0) atomicAdd(a.usc + 2, en);
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+        atomicMin(a.guard_next + G_MINU, dbl_ordered(mn));
+        atomicMax(a.guard_next + G_MAXU, dbl_ordered(mx));
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+
+// ------------------------------------------------------------------------------------------------------------
+// Gene-side non-zero pass over CSC: one block per gene.  B1(j,k) = sum_i q_ij e_ijk, B2(j,k) = sum_i q_ij e_ijk
+// ElogU(i,k), xlogT(j) = sum_i x_ij log T_ij, with e_ijk = S_jk cexp(ElogU_ik + ElogV_jk - m), T = sum_k e, q = x / T'.
+// Used three ways:
+//   E-step gene side (old stats): EZ_i = wS o B1 (gap...cpp:491 and variants); B2 / xlogT feed the ELBO data term of
+//     the previous iterate (gap...cpp:308-312, sparse...cpp:194-212);
+//   sparse-probability pass (new stats, old mask): sparse...cpp:444-460, zi_sparse...cpp:433-449;
+//   final ELBO data term.
+// ------------------------------------------------------------------------------------------------------------
+struct ColArgs {
+    int32_t p; int K;
+    const int64_t *colptr;
+    const int32_t *rowidx;
+    const void *val;
+    const double *eu, *ElogU;         // n x KP
+    const double *ev, *ElogV, *Sd;    // p x KP
+    const long long *guard;
+    double *B1, *B2;                  // p x KP (plain stores: the block owns the gene)
+    double *xlogT;                    // p
+};
+template <int KP, typename VT, bool WITH_B2, bool WITH_LOGT>
+__global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
+    __shared__ double sh[4][KP];
+    __shared__ double sh2[4][KP];
+    __shared__ double shl[4];
+    const VT *__restrict__ val = static_cast<const VT *>(a.val);
+    const bool exact = need_exact(a.guard);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int j = blockIdx.x; j < a.p; j += gridDim.x) {
+        double v[KP], b1[KP], b2[WITH_B2 ? KP : 1], msk[KP];
+        load_vec<KP>((exact ? a.ElogV : a.ev) + (int64_t)j * KP, v);
+        if (exact) load_vec<KP>(a.Sd + (int64_t)j * KP, msk);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) { b1[k] = 0.0; if (WITH_B2) b2[k] = 0.0; }
+        double lt = 0.0;
+        const int64_t e0 = a.colptr[j], e1 = a.colptr[j + 1];
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int64_t i = __ldg(a.rowidx + e);
+            const double x = (double)__ldg(val + e);
+            double u[KP];
+            if (!exact) {
+                load_vec<KP>(a.eu + i * KP, u);
+                double T = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) T = fma(u[k], v[k], T);
+                const double q = x / (T > 0.0 ? T : 1.0);
+                if (WITH_LOGT) lt += x * log(T);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) b1[k] = fma(q, u[k], b1[k]);
+                if (WITH_B2) {
+                    double el[KP];
+                    load_vec<KP>(a.ElogU + i * KP, el);
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) b2[k] = fma(q * u[k], el[k], b2[k]);
+                }
+            } else {
+                double el[KP];
+                load_vec<KP>(a.ElogU + i * KP, el);
+                double m = -1e300;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    u[k] = el[k] + v[k];
+                    if (k < a.K) m = fmax(m, u[k]);
+                }
+                if (m < 100.0) m = 0.0;
+                double T = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    u[k] = (k < a.K) ? custom_exp(u[k] - m) * msk[k] : 0.0;
+                    T += u[k];
+                }
+                const double q = x / (T > 0.0 ? T : 1.0);
+                if (WITH_LOGT) lt += x * log(T);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    b1[k] = fma(q, u[k], b1[k]);
+                    if (WITH_B2) b2[k] = fma(q * u[k], el[k], b2[k]);
+                }
+            }
+        }
+        // block reduction: warp shuffles then 4 partial rows in shared memory
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const double t = warp_sum(b1[k]);
+            if (lane == 0) sh[w][k] = t;
+            if (WITH_B2) {
+                const double t2 = warp_sum(b2[k]);
+                if (lane == 0) sh2[w][k] = t2;
+            }
+        }
+        if (WITH_LOGT) { lt = warp_sum(lt); if (lane == 0) shl[w] = lt; }
+        __syncthreads();
+        if (threadIdx.x < KP) {
+            const int k = threadIdx.x;
+            double t = sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k];
+            // fast path accumulated sum_i q eu_ik; e_ijk = eu_ik ev_jk
+            if (!exact) t *= __ldg(a.ev + (int64_t)j * KP + k);
+            a.B1[(int64_t)j * KP + k] = t;
+            if (WITH_B2) {
+                double t2 = sh2[0][k] + sh2[1][k] + sh2[2][k] + sh2[3][k];
+                if (!exact) t2 *= __ldg(a.ev + (int64_t)j * KP + k);
+                a.B2[(int64_t)j * KP + k] = t2;
+            }
+        }
+        if (WITH_LOGT && threadIdx.x == 0) a.xlogT[j] = shl[0] + shl[1] + shl[2] + shl[3];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// V-side M-step, one thread per (gene, factor): update_variational_gamma_param, factor V part
+// (gap...cpp:535-537, zi...:340-342, sparse...:404-420, zi_sparse...:367-385) + V_stats, the V half of
+// gap_between_iterates, the V entropy, and -- before the old statistics are overwritten -- the ELBO data term
+// of the previous iterate (sparse...cpp:206-210).
+// ------------------------------------------------------------------------------------------------------------
+struct VArgs {
+    int32_t p; int K, KP;
+    int sparse, zi, first_iter, want_data, stats_only;
+    const double *B1, *B2, *xlogT;        // from the E-step gene pass (all-reduced)
+    const double *tmpMat;                 // p x KP: prob_D^T EU_new (ZI, all-reduced)
+    const double *cs_eu;                  // KP: colsum(EU_new) (all-reduced)
+    const double *beta1, *beta2;          // K-vectors
+    double *b1, *b2, *EV, *ElogV;
+    const double *prob_S, *Sd, *colw;     // old sparse state / nnz weight of the gene
+    double *ev, *evw, *EVS, *wS;          // refreshed here for the non-sparse models; ev (old mask) for the sparse pass
+    long long *guard_next;
+    double *cs_ev, *cs_elogv, *cs_evs;    // KP each
+    double *scal;
+};
+#ifdef PCMF_COMMON_KERNELS
+__global__ void __launch_bounds__(256) k_mstep_genes(VArgs a) {
+    __shared__ double sh[32];
+    __shared__ double scs[3][64];
+    if (threadIdx.x < 64) { scs[0][threadIdx.x] = 0; scs[1][threadIdx.x] = 0; scs[2][threadIdx.x] = 0; }
+    __syncthreads();
+    double gd = 0, go = 0, en = 0, data = 0, mn = 1e300, mx = -1e300;
+    const int64_t total = (int64_t)a.p * a.KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % a.KP);
+        const int j = (int)(o / a.KP);
+        if (k >= a.K) {
+            a.EV[o] = 0; a.ElogV[o] = 0; a.ev[o] = 0; a.evw[o] = 0; a.EVS[o] = 0; a.wS[o] = 0;
+            continue;
+        }
+        const double ps = a.sparse ? a.prob_S[o] : 1.0;
+        const double cw = a.zi ? a.colw[j] : 1.0;
+        double b1n, b2n, b1o, b2o;
+        if (!a.stats_only) {
+            if (a.want_data) {
+                // ELBO data term of the state the E-step just read (old ElogV / prob_S / colw)
+                if (a.sparse) data += ps * cw * (a.B2[o] + a.ElogV[o] * a.B1[o]);
+                else if (k == 0) data += cw * a.xlogT[j];
+            }
+            b1o = a.first_iter ? 1.0 : a.b1[o];
+            b2o = a.first_iter ? 1.0 : a.b2[o];
+            b1n = a.beta1[k] + ps * cw * a.B1[o];
+            b2n = a.beta2[k] + ps * (a.zi ? a.tmpMat[o] : a.cs_eu[k]);
+            a.b1[o] = b1n;
+            a.b2[o] = b2n;
+            const double d1 = b1n - b1o, d2 = b2n - b2o;
+            gd += d1 * d1 + d2 * d2;
+            go += b1o * b1o + b2o * b2o;
+        } else {
+            b1n = a.b1[o];
+            b2n = a.b2[o];
+        }
+        const double psi = digamma_pos(b1n);
+        const double el = psi - log(b2n);
+        const double EVn = b1n / b2n;
+        a.EV[o] = EVn;
+        a.ElogV[o] = el;
+        en += gamma_entropy1(b1n, b2n, psi);
+        mn = fmin(mn, el); mx = fmax(mx, el);
+        atomicAdd(&scs[0][k], EVn);
+        atomicAdd(&scs[1][k], el);
+        // multinomial weights for the passes that follow.  Sparse models: old mask for the sparse-probability pass
+        // (sparse...cpp:448-451); everything is refreshed again by k_sparse_genes once the new mask exists.
+        const double sd = a.sparse ? a.Sd[o] : 1.0;
+        const double evn = sd * exp(el);
+        a.ev[o] = evn;
+        a.wS[o] = ps * cw;
+        a.evw[o] = evn * ps * cw;
+        a.EVS[o] = EVn * ps;
+        atomicAdd(&scs[2][k], EVn * ps);
+    }
+    __syncthreads();
+    if (threadIdx.x < a.K) {
+        atomicAdd(a.cs_ev + threadIdx.x, scs[0][threadIdx.x]);
+        atomicAdd(a.cs_elogv + threadIdx.x, scs[1][threadIdx.x]);
+        atomicAdd(a.cs_evs + threadIdx.x, scs[2][threadIdx.x]);
+    }
+    gd = block_sum(gd, sh); go = block_sum(go, sh); en = block_sum(en, sh); data = block_sum(data, sh);
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (threadIdx.x == 0) {
+        if (!a.stats_only) { atomicAdd(a.scal + S_GAPV_D, gd); atomicAdd(a.scal + S_GAPV_O, go); }
+        atomicAdd(a.scal + S_ENTV, en);
+        if (a.want_data) atomicAdd(a.scal + S_DATA, data);
+    }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+        atomicMin(a.guard_next + G_MINV, dbl_ordered(mn));
+        atomicMax(a.guard_next + G_MAXV, dbl_ordered(mx));
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+
+// ELBO data term only (final loss / on-demand ELBO): same expression as in k_mstep_genes, nothing is updated.
+struct DataArgs {
+    int32_t p; int K, KP; int sparse, zi;
+    const double *B1, *B2, *xlogT, *ElogV, *prob_S, *colw;
+    double *scal;
+};
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_data_term(DataArgs a) {
+    __shared__ double sh[32];
+    double data = 0;
+    const int64_t total = (int64_t)a.p * a.KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % a.KP);
+        const int j = (int)(o / a.KP);
+        if (k >= a.K) continue;
+        const double cw = a.zi ? a.colw[j] : 1.0;
+        if (a.sparse) data += a.prob_S[o] * cw * (a.B2[o] + a.ElogV[o] * a.B1[o]);
+        else if (k == 0) data += cw * a.xlogT[j];
+    }
+    data = block_sum(data, sh);
+    if (threadIdx.x == 0) atomicAdd(a.scal + S_DATA, data);
+}
+#endif  // PCMF_COMMON_KERNELS
+
+// ------------------------------------------------------------------------------------------------------------
+// Spike-and-slab update, one thread per gene: update_variational_sparse_param (sparse...cpp:424-471,
+// zi_sparse...:413-460) from the all-reduced gene-pass sums, S = prob_S >= sel_bound, then
+// update_prior_sparse_param (sparse...cpp:474-476), the Bernoulli ELBO terms (sparse...cpp:172-173) and the refreshed
+// multinomial weights for the next E-step.
+// ------------------------------------------------------------------------------------------------------------
+struct SparseArgs {
+    int32_t p; int K, KP; int zi, update;
+    double sel_bound;
+    const double *B1, *B2;        // sparse pass (new stats, old mask), all-reduced
+    const double *tmpMat;         // ZI: prob_D^T EU_new
+    const double *cs_eu;          // non-ZI: colsum(EU_new)
+    const double *EV, *ElogV, *colw;
+    double *prob_S, *Sd, *prior_S;
+    int32_t *S;
+    double *ev, *evw, *EVS, *wS;
+    double *cs_evs;
+    double *scal;
+};
+#ifdef PCMF_COMMON_KERNELS
+__global__ void __launch_bounds__(128) k_sparse_genes(SparseArgs a) {
+    __shared__ double sh[32];
+    __shared__ double scs[64];
+    if (threadIdx.x < 64) scs[threadIdx.x] = 0;
+    __syncthreads();
+    double bp = 0, bs = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.p; j += gridDim.x * blockDim.x) {
+        const double pr = a.prior_S[j];
+        const double cw = a.zi ? a.colw[j] : 1.0;
+        const double lg = logit_clamped(pr);
+        double rs = 0;
+        for (int k = 0; k < a.K; ++k) {
+            const int64_t o = (int64_t)j * a.KP + k;
+            double ps;
+            if (a.update) {
+                if (pr == 1.0) ps = 1.0;
+                else if (pr == 0.0) ps = 0.0;
+                else {
+                    const double t = -a.EV[o] * (a.zi ? a.tmpMat[o] : a.cs_eu[k]) + cw * (a.B2[o] + a.ElogV[o] * a.B1[o]);
+                    ps = expit_clamped(lg + t);
+                }
+                a.prob_S[o] = ps;
+            } else {
+                ps = a.prob_S[o];
+            }
+            const int s = ps >= a.sel_bound;
+            a.S[o] = s;
+            a.Sd[o] = (double)s;
+            const double evn = (double)s * exp(a.ElogV[o]);
+            a.ev[o] = evn;
+            a.wS[o] = ps * cw;
+            a.evw[o] = evn * ps * cw;
+            const double evs = a.EV[o] * ps;
+            a.EVS[o] = evs;
+            atomicAdd(&scs[k], evs);
+            rs += ps;
+        }
+        const double prn = rs / a.K;
+        a.prior_S[j] = prn;
+        // likelihood::bernoulli_loglike_vec(prob_S, prior_S) with the intended gene index + bernoulli_loglike(prob_S, prob_S)
+        const bool gate = prn > 0.0 && prn < 1.0;
+        const double l1 = gate ? log(prn) : 0.0, l0 = gate ? log(1.0 - prn) : 0.0;
+        for (int k = 0; k < a.K; ++k) {
+            const double ps = a.prob_S[(int64_t)j * a.KP + k];
+            if (gate) bp += ps * l1 + (1.0 - ps) * l0;
+            if (ps > 0.0 && ps < 1.0) bs += ps * log(ps) + (1.0 - ps) * log(1.0 - ps);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < a.K) atomicAdd(a.cs_evs + threadIdx.x, scs[threadIdx.x]);
+    bp = block_sum(bp, sh); bs = block_sum(bs, sh);
+    if (threadIdx.x == 0) { atomicAdd(a.scal + S_BERNS_PRIOR, bp); atomicAdd(a.scal + S_BERNS_SELF, bs); }
+}
+#endif  // PCMF_COMMON_KERNELS
+
+// ------------------------------------------------------------------------------------------------------------
+// Zero-inflation, dense passes.  prob_D is never stored: P_ij = 1 where X_ij != 0 (bitmap), otherwise
+// expit(logit(prior_D_j) - EU_i . EVS_j) from the triple saved when update_variational_zi_param ran
+// (zi...cpp:346-367, zi_sparse...:389-410); whole-gene shortcuts for prior_D in {0,1} are per-gene flags.
+// ------------------------------------------------------------------------------------------------------------
+// per-gene preparation right before pass A: c_j = logit(prior_D_j), flag, nnz weight colw_j and the lgamma term
+struct ZiPrepArgs {
+    int32_t p; int init;
+    const double *prior_D, *Lg;
+    double *cz, *colw; int32_t *flag;
+    double *scal;
+};
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_zi_prepare(ZiPrepArgs a) {
+    __shared__ double sh[32];
+    double lgx = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.p; j += gridDim.x * blockDim.x) {
+        int f = 0; double c, w = 1.0;
+        if (a.init) { c = -1e300; }                    // init_zi_param: prob_D = (X > 0)  (zi...cpp:98-105)
+        else {
+            const double pr = a.prior_D[j];
+            if (pr == 1.0) f = 1; else if (pr == 0.0) { f = 2; w = 0.0; }
+            c = logit_clamped(pr);
+        }
+        a.cz[j] = c; a.flag[j] = f; a.colw[j] = w;
+        lgx += w * a.Lg[j];                            // sum_ij prob_D_ij lgamma(X_ij + 1)  (zi...cpp:207-212)
+    }
+    lgx = block_sum(lgx, sh);
+    if (threadIdx.x == 0) atomicAdd(a.scal + S_LGX, lgx);
+}
+#endif  // PCMF_COMMON_KERNELS
+
+struct ZiAArgs {
+    int64_t n; int32_t p; int K;
+    const double *EU;            // n x KP (new)
+    const double *EVS;           // p x KP (new)
+    const double *cz; const int32_t *flag;
+    const uint32_t *bitT;        // [ceil(p/32)][n]: bit c of word (jb, i) <-> X(i, 32 jb + c) != 0
+    double *PV;                  // n x KP out: prob_D * EVS  (next iteration's a2, zi...cpp:336)
+    double *colsumP;             // p (atomic): colsum(prob_D) -> prior_D (zi...cpp:370-372)
+    double *zsc;                 // 2 doubles (atomic): sum prob_D o UVt, sum P log P + (1-P) log(1-P)   (all-reduced later)
+};
+// Pass A: one thread per cell, genes streamed through shared memory in tiles of TJ.
+template <int KP, int TJ>
+__global__ void __launch_bounds__(128) k_zi_pass_cells(ZiAArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_evs = reinterpret_cast<double *>(smem_raw);          // TJ x KP
+    double *s_c = s_evs + TJ * KP;                                 // TJ
+    double *s_cs = s_c + TJ;                                       // 4 x TJ per-warp gene sums
+    double *s_P = s_cs + 4 * TJ;                                   // 4 x 32 x 33 transposition buffer
+    int *s_f = reinterpret_cast<int *>(s_P + 4 * 32 * 33);         // TJ
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    double u[KP], pv[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { u[k] = 0.0; pv[k] = 0.0; }
+    if (live) load_vec<KP>(a.EU + i * KP, u);
+    double sum_pl = 0, ent = 0;
+    for (int j0 = 0; j0 < a.p; j0 += TJ) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < TJ * KP; t += blockDim.x) {
+            const int jj = j0 + t / KP;
+            s_evs[t] = jj < a.p ? a.EVS[(int64_t)j0 * KP + t] : 0.0;
+        }
+        for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
+            const int jj = j0 + t;
+            s_c[t] = jj < a.p ? a.cz[jj] : 0.0;
+            s_f[t] = jj < a.p ? a.flag[jj] : 3;
+        }
+        for (int t = threadIdx.x; t < 4 * TJ; t += blockDim.x) s_cs[t] = 0.0;
+        __syncthreads();
+        for (int jb = 0; jb < TJ; jb += 32) {
+            if (j0 + jb >= a.p) break;
+            const uint32_t bits = live ? a.bitT[(int64_t)((j0 + jb) >> 5) * a.n + i] : 0u;
+#pragma unroll 2
+            for (int c = 0; c < 32; ++c) {
+                const double *ev = s_evs + (jb + c) * KP;
+                double lam = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(ev + k);
+                    lam = fma(u[k], t.x, lam);
+                    lam = fma(u[k + 1], t.y, lam);
+                }
+                const int f = live ? s_f[jb + c] : 3;
+                const double z = s_c[jb + c] - lam;
+                double pj;
+                if (f == 0) {
+                    if ((bits >> c) & 1u) pj = 1.0;
+                    else {
+                        pj = expit_clamped(z);
+                        // -bernoulli_loglike(prob_D, prob_D): sum over 0<P<1 of P log P + (1-P) log(1-P)
+                        //   = (1-P) * (-z) - log(1 + exp(-z))   with P = 1/(1+exp(-z))
+                        if (pj > 0.0 && pj < 1.0) ent += (1.0 - pj) * (-z) - log1p(exp(-z));
+                    }
+                } else pj = (f == 1) ? 1.0 : 0.0;
+                sum_pl = fma(pj, lam, sum_pl);                     // sum prob_D o UVt  (zi...cpp:182)
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(ev + k);
+                    pv[k] = fma(pj, t.x, pv[k]);
+                    pv[k + 1] = fma(pj, t.y, pv[k + 1]);
+                }
+                s_P[(w * 32 + c) * 33 + lane] = pj;
+            }
+            __syncwarp();
+            double cs = 0.0;   // lane l sums gene (jb + l) over the warp's 32 cells
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) cs += s_P[(w * 32 + lane) * 33 + r];
+            __syncwarp();
+            s_cs[w * TJ + jb + lane] += cs;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
+            if (j0 + t < a.p) atomicAdd(a.colsumP + j0 + t, s_cs[t] + s_cs[TJ + t] + s_cs[2 * TJ + t] + s_cs[3 * TJ + t]);
+        }
+    }
+    if (live) {
+        double2 *o = reinterpret_cast<double2 *>(a.PV + i * KP);
+#pragma unroll
+        for (int k = 0; k < KP; k += 2) o[k / 2] = make_double2(pv[k], pv[k + 1]);
+    }
+    sum_pl = block_sum(sum_pl, sh); ent = block_sum(ent, sh);
+    if (threadIdx.x == 0) { atomicAdd(a.zsc + 0, sum_pl); atomicAdd(a.zsc + 1, ent); }
+}
+
+struct ZiBArgs {
+    int64_t n; int32_t p; int K;
+    int64_t rows_per_chunk;
+    const double *EUz;           // n x KP: EU when prob_D was defined
+    const double *EUn;           // n x KP: EU_new
+    const double *EVSz;          // p x KP
+    const double *cz; const int32_t *flag;
+    const uint32_t *bitB;        // [ceil(n/32)][p]: bit r of word (ib, j) <-> X(32 ib + r, j) != 0
+    double *tmpMat;              // p x KP (atomic): prob_D^T EU_new (zi...cpp:341, zi_sparse...:369)
+};
+// Pass B: one thread per gene, cells streamed through shared memory in tiles of TI (multiple of 32).
+template <int KP, int TI>
+__global__ void __launch_bounds__(128) k_zi_pass_genes(ZiBArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_uz = reinterpret_cast<double *>(smem_raw);   // TI x KP
+    double *s_un = s_uz + TI * KP;                         // TI x KP
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = j < a.p;
+    double v[KP], acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { v[k] = 0.0; acc[k] = 0.0; }
+    double c = 0.0; int f = 3;
+    if (live) { load_vec<KP>(a.EVSz + (int64_t)j * KP, v); c = a.cz[j]; f = a.flag[j]; }
+    const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_chunk;
+    const int64_t r1 = min(a.n, r0 + a.rows_per_chunk);
+    for (int64_t i0 = r0; i0 < r1; i0 += TI) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < TI * KP; t += blockDim.x) {
+            const int64_t ii = i0 + t / KP;
+            const bool ok = ii < r1;
+            s_uz[t] = ok ? a.EUz[i0 * KP + t] : 0.0;
+            s_un[t] = ok ? a.EUn[i0 * KP + t] : 0.0;
+        }
+        __syncthreads();
+        for (int ib = 0; ib < TI; ib += 32) {
+            if (i0 + ib >= r1) break;
+            const uint32_t bits = live ? a.bitB[(int64_t)((i0 + ib) >> 5) * a.p + j] : 0u;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                const double *uz = s_uz + (ib + r) * KP;
+                const double *un = s_un + (ib + r) * KP;
+                double lam = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(uz + k);
+                    lam = fma(v[k], t.x, lam);
+                    lam = fma(v[k + 1], t.y, lam);
+                }
+                double pj;
+                if (f == 0) pj = ((bits >> r) & 1u) ? 1.0 : expit_clamped(c - lam);
+                else pj = (f == 1) ? 1.0 : 0.0;
+                if (i0 + ib + r >= r1) pj = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(un + k);
+                    acc[k] = fma(pj, t.x, acc[k]);
+                    acc[k + 1] = fma(pj, t.y, acc[k + 1]);
+                }
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < a.K) atomicAdd(a.tmpMat + (int64_t)j * KP + k, acc[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Hyper-parameter update + iteration scalars, one block:
+//   update_prior_gamma_param (gap...cpp:541-548) with internal::digammaInv(., 6); update_prior_zi_param
+//   (zi...cpp:370-372); closed-form Gamma ELBO terms (likelihood.h:108-113 summed over identical rows);
+//   gap_between_iterates (gap...cpp:255-262).
+// ------------------------------------------------------------------------------------------------------------
+struct HyperArgs {
+    int64_t n_global; int32_t p; int K; int zi, sparse;
+    double *alpha1, *alpha2, *beta1, *beta2;   // K
+    const double *cs_eu, *cs_elog, *cs_ev, *cs_elogv, *cs_evs;
+    const double *colsumP; double *prior_D;
+    const double *usc;     // gap_d, gap_o, entropy of U (all-reduced)
+    const double *zsc;     // sum prob_D o UVt, Bernoulli self term (all-reduced; ZI only)
+    double lgx_const;      // sum_ij lgamma(X_ij + 1) for the non-ZI models
+    double *scal;
+};
+#ifdef PCMF_COMMON_KERNELS
+__global__ void __launch_bounds__(256) k_hyper(HyperArgs a) {
+    __shared__ double sh[32];
+    double gU = 0, gV = 0, closed = 0, bd = 0;
+    if (threadIdx.x < a.K) {
+        const int k = threadIdx.x;
+        const double n = (double)a.n_global, p = (double)a.p;
+        const double al1 = digamma_inv(log(a.alpha2[k]) + a.cs_elog[k] / n, 6);
+        const double al2 = al1 / (a.cs_eu[k] / n);
+        a.alpha1[k] = al1; a.alpha2[k] = al2;
+        const double be1 = digamma_inv(log(a.beta2[k]) + a.cs_elogv[k] / p, 6);
+        const double be2 = be1 / (a.cs_ev[k] / p);
+        a.beta1[k] = be1; a.beta2[k] = be2;
+        gU = n * (al1 * log(al2) - lgamma(al1)) + (al1 - 1.0) * a.cs_elog[k] - al2 * a.cs_eu[k];
+        gV = p * (be1 * log(be2) - lgamma(be1)) + (be1 - 1.0) * a.cs_elogv[k] - be2 * a.cs_ev[k];
+        closed = a.cs_eu[k] * a.cs_evs[k];     // sum_ij UVt = sum_k colsum(EU)_k colsum(EVS)_k  (gap...cpp:298)
+    }
+    if (a.zi) {
+        const double n = (double)a.n_global;
+        for (int j = threadIdx.x; j < a.p; j += blockDim.x) {
+            const double c = a.colsumP[j];
+            const double pr = c / n;
+            a.prior_D[j] = pr;
+            // bernoulli_loglike_vec(prob_D, prior_D), intended semantics
+            if (pr > 0.0 && pr < 1.0) bd += c * log(pr) + (n - c) * log(1.0 - pr);
+        }
+    }
+    gU = block_sum(gU, sh); gV = block_sum(gV, sh); closed = block_sum(closed, sh); bd = block_sum(bd, sh);
+    if (threadIdx.x == 0) {
+        double *s = a.scal;
+        s[S_GAMMAU] = gU; s[S_GAMMAV] = gV; s[S_SUMUVT_CLOSED] = closed; s[S_BERND_PRIOR] = bd;
+        s[S_GAPU_D] = a.usc[0]; s[S_GAPU_O] = a.usc[1]; s[S_ENTU] = a.usc[2];
+        if (a.zi) { s[S_SUM_PUVT] = a.zsc[0]; s[S_BERND_SELF] = a.zsc[1]; }
+        else s[S_LGX] = a.lgx_const;
+        const double diff = sqrt(s[S_GAPU_D] + s[S_GAPV_D]);
+        const double nrm = sqrt(s[S_GAPU_O] + s[S_GAPV_O]);
+        s[S_ABS_GAP] = diff;
+        s[S_NORM_GAP] = diff / nrm;
+        double e = gU + s[S_ENTU] + gV + s[S_ENTV];
+        if (a.sparse) e += s[S_BERNS_PRIOR] - s[S_BERNS_SELF];
+        if (a.zi) e += bd - s[S_BERND_SELF] - s[S_SUM_PUVT];
+        else e -= closed;
+        e -= s[S_LGX];
+        s[S_ELBO_NODATA] = e;
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+
+// ------------------------------------------------------------------------------------------------------------
+// one-off preprocessing kernels
+// ------------------------------------------------------------------------------------------------------------
+// occupancy bitmaps for the dense ZI passes, from CSR
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_build_bitmaps(int64_t n, int32_t p, const int64_t *rowptr, const int32_t *colidx, uint32_t *bitT,
+                                uint32_t *bitB) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nw) {
+        for (int64_t e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) {
+            const int j = colidx[e];
+            atomicOr(bitT + (int64_t)(j >> 5) * n + i, 1u << (j & 31));
+            atomicOr(bitB + (i >> 5) * (int64_t)p + j, 1u << (i & 31));
+        }
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+// per-gene constants: sum_i lgamma(X_ij + 1) (ELBO, gap...cpp:319-323), nnz count and sum of the gene (init, freq_D)
+template <typename VT>
+__global__ void k_gene_constants(int32_t p, const int64_t *colptr, const void *val_, double *Lg, double *colsumX,
+                                 double *colnnz) {
+    const VT *val = static_cast<const VT *>(val_);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < p; j += nw) {
+        double lg = 0, sx = 0, cn = 0;
+        for (int64_t e = colptr[j] + lane; e < colptr[j + 1]; e += 32) {
+            const double x = (double)val[e];
+            lg += lgamma(x + 1.0); sx += x; cn += (x != 0.0) ? 1.0 : 0.0;
+        }
+        lg = warp_sum(lg); sx = warp_sum(sx); cn = warp_sum(cn);
+        if (lane == 0) { Lg[j] = lg; colsumX[j] = sx; colnnz[j] = cn; }
+    }
+}
+template <typename VT>
+__global__ void k_row_sums(int64_t n, const int64_t *rowptr, const void *val_, double *rowsumX) {
+    const VT *val = static_cast<const VT *>(val_);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nw) {
+        double s = 0;
+        for (int64_t e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) s += (double)val[e];
+        s = warp_sum(s);
+        if (lane == 0) rowsumX[i] = s;
+    }
+}
+
+// column-major (R / Eigen) <-> padded row-major
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_colmajor_to_rowpad(int64_t rows, int K, int KP, const double *src, double *dst, double padval) {
+    const int64_t total = rows * KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % KP);
+        const int64_t r = o / KP;
+        dst[o] = k < K ? src[r + (int64_t)k * rows] : padval;
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_rowpad_to_colmajor(int64_t rows, int K, int KP, const double *src, double *dst) {
+    const int64_t total = rows * K;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = o % rows;
+        const int k = (int)(o / rows);
+        dst[o] = src[r * KP + k];
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_rowpad_to_colmajor_i32(int64_t rows, int K, int KP, const int32_t *src, int32_t *dst) {
+    const int64_t total = rows * K;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = o % rows;
+        const int k = (int)(o / rows);
+        dst[o] = src[r * KP + k];
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_fill(double *p, int64_t n, double v) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) p[o] = v;
+}
+#endif  // PCMF_COMMON_KERNELS
+// dense prob_D output (n x p column-major) for the return object: ZI_param$prob_D (zi...cpp:251)
+struct ProbDArgs {
+    int64_t n; int32_t p; int K, KP;
+    const double *EUz, *EVSz, *cz; const int32_t *flag; const uint32_t *bitT;
+    double *out;
+};
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_prob_d_dense(ProbDArgs a) {
+    const int64_t total = a.n * (int64_t)a.p;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = o % a.n;
+        const int j = (int)(o / a.n);
+        const int f = a.flag[j];
+        double pj;
+        if (f == 1) pj = 1.0;
+        else if (f == 2) pj = 0.0;
+        else if ((a.bitT[(int64_t)(j >> 5) * a.n + i] >> (j & 31)) & 1u) pj = 1.0;
+        else {
+            double lam = 0.0;
+            for (int k = 0; k < a.K; ++k) lam = fma(a.EUz[i * a.KP + k], a.EVSz[(int64_t)j * a.KP + k], lam);
+            pj = expit_clamped(a.cz[j] - lam);
+        }
+        a.out[o] = pj;
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+
+}  // namespace pcmf

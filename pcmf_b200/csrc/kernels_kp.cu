@@ -1,0 +1,63 @@
+// One instantiation set of the K-templated kernels; compiled once per padded width with -DPCMF_KP=<n>.
+#include "launch.cuh"
+
+#ifndef PCMF_KP
+#error "compile with -DPCMF_KP=<padded K>"
+#endif
+
+namespace pcmf {
+namespace {
+
+constexpr int KP = PCMF_KP;
+constexpr int ZI_TJ = 128;                       // genes per shared-memory tile in the cell-threaded ZI pass
+constexpr int ZI_TI = (KP <= 32) ? 64 : 32;      // cells per shared-memory tile in the gene-threaded ZI pass
+
+void launch_estep_rows(bool f32, const RowArgs &a, int grid, int block, cudaStream_t st) {
+    if (f32) k_estep_rows<KP, float><<<grid, block, 0, st>>>(a);
+    else k_estep_rows<KP, double><<<grid, block, 0, st>>>(a);
+}
+
+template <typename VT>
+void launch_gene_t(int mode, const ColArgs &a, int grid, cudaStream_t st) {
+    switch (mode) {
+        case GENE_B1: k_gene_pass<KP, VT, false, false><<<grid, 128, 0, st>>>(a); break;
+        case GENE_B1_LOGT: k_gene_pass<KP, VT, false, true><<<grid, 128, 0, st>>>(a); break;
+        default: k_gene_pass<KP, VT, true, false><<<grid, 128, 0, st>>>(a); break;
+    }
+}
+void launch_gene_pass(bool f32, int mode, const ColArgs &a, int grid, cudaStream_t st) {
+    if (f32) launch_gene_t<float>(mode, a, grid, st);
+    else launch_gene_t<double>(mode, a, grid, st);
+}
+
+void launch_zi_cells(const ZiAArgs &a, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (ZI_TJ * KP + ZI_TJ + 4 * ZI_TJ + 4 * 32 * 33) + sizeof(int) * ZI_TJ;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_pass_cells<KP, ZI_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    const int64_t grid = (a.n + 127) / 128;
+    k_zi_pass_cells<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
+}
+
+void launch_zi_genes(const ZiBArgs &a, int chunks, cudaStream_t st) {
+    const size_t smem = sizeof(double) * 2 * ZI_TI * KP;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_pass_genes<KP, ZI_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    dim3 grid((a.p + 127) / 128, chunks);
+    k_zi_pass_genes<KP, ZI_TI><<<grid, 128, smem, st>>>(a);
+}
+
+const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes};
+
+}  // namespace
+
+#define PCMF_CAT_(a, b) a##b
+#define PCMF_CAT(a, b) PCMF_CAT_(a, b)
+const Launchers *PCMF_CAT(get_launchers_, PCMF_KP)() { return &table; }
+
+}  // namespace pcmf

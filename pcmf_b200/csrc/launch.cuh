@@ -1,0 +1,44 @@
+// Per-KP kernel launch tables.  Every padded factor width KP is compiled in its own translation unit
+// (kernels_kp.cu with -DPCMF_KP=<n>) so the build parallelises; the solver picks a table at run time.
+#pragma once
+#include "kernels.cuh"
+
+namespace pcmf {
+
+enum GeneMode : int { GENE_B1 = 0, GENE_B1_LOGT = 1, GENE_B1_B2 = 2 };
+
+struct Launchers {
+    int KP;
+    void (*estep_rows)(bool f32, const RowArgs &, int grid, int block, cudaStream_t);
+    void (*gene_pass)(bool f32, int mode, const ColArgs &, int grid, cudaStream_t);
+    void (*zi_cells)(const ZiAArgs &, cudaStream_t);
+    void (*zi_genes)(const ZiBArgs &, int chunks, cudaStream_t);
+};
+
+const Launchers *get_launchers_4();
+const Launchers *get_launchers_8();
+const Launchers *get_launchers_12();
+const Launchers *get_launchers_16();
+const Launchers *get_launchers_20();
+const Launchers *get_launchers_32();
+const Launchers *get_launchers_64();
+
+inline int padded_K(int K) {
+    const int w[] = {4, 8, 12, 16, 20, 32, 64};
+    for (int x : w) if (K <= x) return x;
+    return -1;
+}
+inline const Launchers *get_launchers(int KP) {
+    switch (KP) {
+        case 4: return get_launchers_4();
+        case 8: return get_launchers_8();
+        case 12: return get_launchers_12();
+        case 16: return get_launchers_16();
+        case 20: return get_launchers_20();
+        case 32: return get_launchers_32();
+        case 64: return get_launchers_64();
+    }
+    return nullptr;
+}
+
+}  // namespace pcmf

@@ -1,0 +1,882 @@
+// libpcmf_b200: host-side engine + C ABI (include/pcmf_b200.h).
+//
+// Mirrors, on the host, the reference's wrapper (wrapper_gap_factor.h:164-393, wrapper_sparse_gap_factor.h:176-435:
+// argument checks, init dispatch, optimize, order, output) and iteration driver (algorithm.h:158-210, :412-450);
+// everything per-iteration runs in the sm_100a kernels of kernels.cuh.  There is no CPU compute path.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "../../include/pcmf_b200.h"
+#define PCMF_COMMON_KERNELS 1
+#include "launch.cuh"
+
+using namespace pcmf;
+
+namespace {
+
+struct Err : std::runtime_error {
+    int code;
+    Err(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+[[noreturn]] void fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Err(code, buf);
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) fail(PCMF_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                                    cudaGetErrorString(e_));                                             \
+    } while (0)
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+T *dmalloc(size_t count) {
+    T *p = nullptr;
+    CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    return p;
+}
+
+enum Phase : int { PH_GENE_E = 0, PH_ROWS, PH_ZI_B, PH_AR1, PH_MSTEP_V, PH_GENE_S, PH_SPARSE, PH_ZI_A, PH_HYPER, PH_COUNT };
+const char *kPhaseNames[PH_COUNT] = {"estep_genes", "estep_cells_mstep_u", "zi_pass_genes", "allreduce", "mstep_v",
+                                     "sparse_gene_pass", "sparse_update", "zi_pass_cells", "hyper_scalars"};
+
+}  // namespace
+
+struct pcmf_solver {
+    pcmf_options opt{};
+    int K = 0, KP = 0, p = 0;
+    int64_t n = 0, n_global = 0, row_offset = 0, nnz = 0;
+    bool zi = false, sparse = false, f32 = true;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    const Launchers *L = nullptr;
+    int sms = 148;
+
+    // X
+    const int64_t *rowptr = nullptr; const int32_t *colidx = nullptr; const void *val_csr = nullptr;
+    bool own_csr = false;
+    int64_t *colptr = nullptr; int32_t *rowidx = nullptr; void *val_csc = nullptr;
+    uint32_t *bitT = nullptr, *bitB = nullptr;
+    double *Lg = nullptr, *colsumX = nullptr, *colnnz = nullptr, *rowsumX = nullptr;
+    double lgx_const = 0;
+
+    // U side (n x KP)
+    double *a1 = nullptr, *a2 = nullptr, *EU[2] = {nullptr, nullptr}, *ElogU = nullptr, *eu = nullptr, *PV = nullptr;
+    int cur = 0;   // EU[cur] is the current E[U]
+    // V side (p x KP)
+    double *b1 = nullptr, *b2 = nullptr, *EV = nullptr, *ElogV = nullptr, *ev = nullptr, *evw = nullptr, *EVS = nullptr,
+           *wS = nullptr, *prob_S = nullptr, *Sd = nullptr;
+    int32_t *S = nullptr, *flag = nullptr;
+    double *prior_S = nullptr, *prior_D = nullptr, *cz = nullptr, *colw = nullptr;
+    double *hyp = nullptr;   // alpha1, alpha2, beta1, beta2, colsum(EV o prob_S) kept for the next a2 update: 5 x 64
+    double *csv = nullptr;   // cs_ev, cs_elogv, cs_evs: 3 x 64
+    // reduction buffers
+    double *ar1 = nullptr; size_t ar1_B1 = 0, ar1_tmp = 0, ar1_cseu = 0, ar1_cselog = 0, ar1_usc = 0, ar1_core = 0, ar1_B2 = 0,
+                                  ar1_xlogT = 0, ar1_total = 0;
+    double *ar2 = nullptr; size_t ar2_B1 = 0, ar2_B2 = 0, ar2_xlogT = 0, ar2_total = 0;
+    double *ar3 = nullptr; size_t ar3_csP = 0, ar3_zsc = 0, ar3_total = 0;
+    double *scal = nullptr;
+    long long *guard[2] = {nullptr, nullptr};
+    int gcur = 0;
+    double *h_scal = nullptr;   // pinned
+
+    // iteration state (algorithm.h:50-64)
+    int iter = 0;
+    bool first_iter = true, converged = false;
+    int nb_iter_stab = 0;
+    double last_nodata = 0;        // ELBO without its data term, state after the last update
+    bool have_pending = false;     // the ELBO of iteration (iter-1) still waits for its data term
+    std::vector<double> elbo_hist; // per iteration (monitor)
+    std::vector<int> factor_order;
+
+    // instrumentation
+    int64_t launches = 0;
+    double ph_ms[PH_COUNT] = {0};
+    int64_t ph_launch[PH_COUNT] = {0};
+    cudaEvent_t ev_a[PH_COUNT] = {nullptr}, ev_b[PH_COUNT] = {nullptr};
+    bool ph_used[PH_COUNT] = {false};
+
+    ~pcmf_solver();
+    void setup_problem(const pcmf_problem &pr);
+    void build_csc();
+    void alloc_state();
+    void init_state(const pcmf_init *in);
+    void run_init_stats();
+    void allreduce(double *ptr, size_t count);
+    void step(bool want_data);
+    double data_term_now();
+    void begin(Phase ph) { CK(cudaEventRecord(ev_a[ph], stream)); }
+    void end(Phase ph, int nl) { CK(cudaEventRecord(ev_b[ph], stream)); ph_used[ph] = true; ph_launch[ph] += nl; launches += nl; }
+    void collect_phase_times() {
+        for (int i = 0; i < PH_COUNT; ++i)
+            if (ph_used[i]) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev_a[i], ev_b[i])); ph_ms[i] += ms; ph_used[i] = false; }
+    }
+    void upload_colmajor(const double *host, int64_t rows, double *dst, double padval);
+    void download_colmajor(const double *src, int64_t rows, double *host);
+    void read_scal() {
+        CK(cudaMemcpyAsync(h_scal, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    int grid_for(int64_t work, int block) const {
+        int64_t g = (work + block - 1) / block;
+        return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sms * 16));
+    }
+};
+
+pcmf_solver::~pcmf_solver() {
+    cudaSetDevice(device);
+    if (own_csr) { cudaFree((void *)rowptr); cudaFree((void *)colidx); cudaFree((void *)val_csr); }
+    void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
+                    b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
+                    ar3, scal, guard[0], guard[1]};
+    for (void *q : ptrs) if (q) cudaFree(q);
+    if (h_scal) cudaFreeHost(h_scal);
+    for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+void pcmf_solver::allreduce(double *ptr, size_t count) {
+    if (opt.world <= 1 || count == 0) return;
+    if (!opt.allreduce) fail(PCMF_ECOMM, "world > 1 but no allreduce callback was supplied");
+    const int rc = opt.allreduce(opt.allreduce_ctx, ptr, count, (void *)stream);
+    if (rc != 0) fail(PCMF_ECOMM, "allreduce callback failed with code %d", rc);
+}
+
+// ---- preprocessing kernels local to this TU ------------------------------------------------------------------
+namespace {
+__global__ void k_expand_rows(int64_t n, const int64_t *rowptr, int32_t *rowids, int64_t *perm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nw)
+        for (int64_t e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) { rowids[e] = (int32_t)i; perm[e] = e; }
+}
+template <typename VT>
+__global__ void k_gather_csc(int64_t nnz, const int64_t *perm, const int32_t *rowids, const VT *val, int32_t *rowidx, VT *val_csc) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = perm[t];
+        rowidx[t] = rowids[e];
+        val_csc[t] = val[e];
+    }
+}
+__global__ void k_colptr_from_sorted(int64_t nnz, int32_t p, const int32_t *keys, int64_t *colptr) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= p; j += gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nnz;   // first position with key >= j
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] < j) lo = mid + 1; else hi = mid; }
+        colptr[j] = lo;
+    }
+}
+__global__ void k_init_guard(long long *g) {
+    if (threadIdx.x == 0) {
+        g[G_MINU] = dbl_ordered(1e300); g[G_MAXU] = dbl_ordered(-1e300);
+        g[G_MINV] = dbl_ordered(1e300); g[G_MAXV] = dbl_ordered(-1e300);
+    }
+}
+__global__ void k_copy_guard_v(long long *dst, const long long *src) {
+    if (threadIdx.x == 0) { dst[G_MINV] = src[G_MINV]; dst[G_MAXV] = src[G_MAXV]; }
+}
+__global__ void k_refresh_weights(int32_t p, int K, int KP, int sparse, const double *prob_S, const double *colw, const double *ev,
+                                  double *wS, double *evw) {
+    const int64_t total = (int64_t)p * KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % KP); const int j = (int)(o / KP);
+        if (k >= K) continue;
+        const double w = (sparse ? prob_S[o] : 1.0) * colw[j];
+        wS[o] = w; evw[o] = ev[o] * w;
+    }
+}
+__global__ void k_vec_scale(double *dst, const double *src, int64_t n, double s) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) dst[o] = src[o] * s;
+}
+}  // namespace
+
+void pcmf_solver::setup_problem(const pcmf_problem &pr) {
+    n = pr.n_local; n_global = pr.n_global > 0 ? pr.n_global : pr.n_local; row_offset = pr.row_offset; p = pr.p;
+    if (n <= 0 || p <= 0) fail(PCMF_EINVAL, "empty count matrix");
+    const int nrep = (pr.dense_f64 != nullptr) + (pr.dense_i32 != nullptr) + (pr.csr_rowptr != nullptr);
+    if (nrep != 1) fail(PCMF_EINVAL, "exactly one of dense_f64, dense_i32, csr_* must be given");
+    if (pr.csr_rowptr) {
+        if (!pr.csr_colidx || (!pr.csr_val_f32 && !pr.csr_val_f64)) fail(PCMF_EINVAL, "incomplete CSR input");
+        f32 = pr.csr_val_f32 != nullptr;
+        if (pr.csr_on_device) {
+            rowptr = pr.csr_rowptr; colidx = pr.csr_colidx;
+            val_csr = f32 ? (const void *)pr.csr_val_f32 : (const void *)pr.csr_val_f64;
+            CK(cudaMemcpy(&nnz, rowptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost));
+            own_csr = false;
+        } else {
+            nnz = pr.csr_rowptr[n];
+            int64_t *rp = dmalloc<int64_t>(n + 1); int32_t *ci = dmalloc<int32_t>(nnz);
+            void *vv = f32 ? (void *)dmalloc<float>(nnz) : (void *)dmalloc<double>(nnz);
+            CK(cudaMemcpyAsync(rp, pr.csr_rowptr, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(ci, pr.csr_colidx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(vv, f32 ? (const void *)pr.csr_val_f32 : (const void *)pr.csr_val_f64,
+                               (f32 ? sizeof(float) : sizeof(double)) * nnz, cudaMemcpyHostToDevice, stream));
+            rowptr = rp; colidx = ci; val_csr = vv; own_csr = true;
+        }
+    } else {
+        // dense R matrix (wrapper_gap_factor.h:204-211) -> CSR on the host, two column-major sweeps
+        std::vector<int64_t> rp(n + 1, 0);
+        bool fits32 = true;
+        auto at = [&](int64_t i, int64_t j) -> double {
+            return pr.dense_f64 ? pr.dense_f64[i + j * n] : (double)pr.dense_i32[i + j * n];
+        };
+        for (int64_t j = 0; j < p; ++j)
+            for (int64_t i = 0; i < n; ++i) {
+                const double x = at(i, j);
+                if (x != 0.0) { rp[i + 1]++; if ((double)(float)x != x) fits32 = false; }
+            }
+        for (int64_t i = 0; i < n; ++i) rp[i + 1] += rp[i];
+        nnz = rp[n];
+        f32 = fits32;
+        std::vector<int32_t> ci(nnz);
+        std::vector<float> vf(f32 ? nnz : 0);
+        std::vector<double> vd(f32 ? 0 : nnz);
+        std::vector<int64_t> pos(rp.begin(), rp.end() - 1);
+        for (int64_t j = 0; j < p; ++j)
+            for (int64_t i = 0; i < n; ++i) {
+                const double x = at(i, j);
+                if (x != 0.0) { const int64_t e = pos[i]++; ci[e] = (int32_t)j; if (f32) vf[e] = (float)x; else vd[e] = x; }
+            }
+        int64_t *drp = dmalloc<int64_t>(n + 1); int32_t *dci = dmalloc<int32_t>(nnz);
+        void *dv = f32 ? (void *)dmalloc<float>(nnz) : (void *)dmalloc<double>(nnz);
+        CK(cudaMemcpy(drp, rp.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dci, ci.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dv, f32 ? (const void *)vf.data() : (const void *)vd.data(), (f32 ? 4 : 8) * (size_t)nnz, cudaMemcpyHostToDevice));
+        rowptr = drp; colidx = dci; val_csr = dv; own_csr = true;
+    }
+    build_csc();
+}
+
+void pcmf_solver::build_csc() {
+    // CSR -> CSC by a stable radix sort on the gene index (rows stay ascending inside a gene -> deterministic sums)
+    int32_t *rowids = dmalloc<int32_t>(nnz);
+    int64_t *perm_in = dmalloc<int64_t>(nnz), *perm_out = dmalloc<int64_t>(nnz);
+    int32_t *keys_out = dmalloc<int32_t>(nnz);
+    k_expand_rows<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, rowids, perm_in);
+    int end_bit = 1; while ((1ll << end_bit) < (int64_t)p) ++end_bit;
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, colidx, keys_out, perm_in, perm_out, nnz, 0, end_bit, stream));
+    void *tmp = nullptr;
+    CK(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 1)));
+    CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, colidx, keys_out, perm_in, perm_out, nnz, 0, end_bit, stream));
+    colptr = dmalloc<int64_t>(p + 1);
+    rowidx = dmalloc<int32_t>(nnz);
+    k_colptr_from_sorted<<<grid_for(p + 1, 256), 256, 0, stream>>>(nnz, p, keys_out, colptr);
+    if (f32) {
+        val_csc = dmalloc<float>(nnz);
+        k_gather_csc<float><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, (const float *)val_csr, rowidx, (float *)val_csc);
+    } else {
+        val_csc = dmalloc<double>(nnz);
+        k_gather_csc<double><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, (const double *)val_csr, rowidx, (double *)val_csc);
+    }
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    cudaFree(tmp); cudaFree(rowids); cudaFree(perm_in); cudaFree(perm_out); cudaFree(keys_out);
+
+    Lg = dmalloc<double>(p); colsumX = dmalloc<double>(p); colnnz = dmalloc<double>(p); rowsumX = dmalloc<double>(n);
+    if (f32) {
+        k_gene_constants<float><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz);
+        k_row_sums<float><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
+    } else {
+        k_gene_constants<double><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz);
+        k_row_sums<double><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
+    }
+    if (zi) {
+        const size_t wT = (size_t)((p + 31) / 32) * n, wB = (size_t)((n + 31) / 32) * p;
+        bitT = dmalloc<uint32_t>(wT); bitB = dmalloc<uint32_t>(wB);
+        CK(cudaMemsetAsync(bitT, 0, wT * 4, stream)); CK(cudaMemsetAsync(bitB, 0, wB * 4, stream));
+        k_build_bitmaps<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, p, rowptr, colidx, bitT, bitB);
+    }
+    // gene constants are sums over cells -> all-reduce across the row shards
+    allreduce(Lg, p); allreduce(colsumX, p); allreduce(colnnz, p);
+    std::vector<double> h(p);
+    CK(cudaMemcpyAsync(h.data(), Lg, sizeof(double) * p, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    lgx_const = 0; for (double x : h) lgx_const += x;
+    CK(cudaGetLastError());
+}
+
+void pcmf_solver::alloc_state() {
+    const size_t nK = (size_t)n * KP, pK = (size_t)p * KP;
+    a1 = dmalloc<double>(nK); a2 = dmalloc<double>(nK); EU[0] = dmalloc<double>(nK); ElogU = dmalloc<double>(nK); eu = dmalloc<double>(nK);
+    if (zi) { EU[1] = dmalloc<double>(nK); PV = dmalloc<double>(nK); CK(cudaMemsetAsync(EU[1], 0, nK * 8, stream)); }
+    b1 = dmalloc<double>(pK); b2 = dmalloc<double>(pK); EV = dmalloc<double>(pK); ElogV = dmalloc<double>(pK);
+    ev = dmalloc<double>(pK); evw = dmalloc<double>(pK); EVS = dmalloc<double>(pK); wS = dmalloc<double>(pK);
+    prob_S = dmalloc<double>(pK); Sd = dmalloc<double>(pK); S = dmalloc<int32_t>(pK); flag = dmalloc<int32_t>(p);
+    prior_S = dmalloc<double>(p); prior_D = dmalloc<double>(p); cz = dmalloc<double>(p); colw = dmalloc<double>(p);
+    hyp = dmalloc<double>(5 * 64); csv = dmalloc<double>(3 * 64);
+    CK(cudaMemsetAsync(S, 0, pK * 4, stream)); CK(cudaMemsetAsync(flag, 0, p * 4, stream));
+    k_fill<<<grid_for(pK, 256), 256, 0, stream>>>(prob_S, pK, 1.0);
+    k_fill<<<grid_for(pK, 256), 256, 0, stream>>>(Sd, pK, 1.0);
+    k_fill<<<grid_for(p, 256), 256, 0, stream>>>(colw, p, 1.0);
+    k_fill<<<grid_for(p, 256), 256, 0, stream>>>(prior_S, p, 1.0);
+    k_fill<<<grid_for(p, 256), 256, 0, stream>>>(prior_D, p, 1.0);
+    // reduction buffers: [B1 | tmpMat | cs_eu | cs_elog | usc(4)] is the per-iteration core, [B2 | xlogT] only when the
+    // ELBO data term is wanted
+    ar1_B1 = 0; ar1_tmp = ar1_B1 + pK; ar1_cseu = ar1_tmp + (zi ? pK : 0); ar1_cselog = ar1_cseu + 64; ar1_usc = ar1_cselog + 64;
+    ar1_core = ar1_usc + 4; ar1_B2 = ar1_core; ar1_xlogT = ar1_B2 + pK; ar1_total = ar1_xlogT + p;
+    ar1 = dmalloc<double>(ar1_total); CK(cudaMemsetAsync(ar1, 0, ar1_total * 8, stream));
+    ar2_B1 = 0; ar2_B2 = pK; ar2_xlogT = 2 * pK; ar2_total = 2 * pK + p;
+    ar2 = dmalloc<double>(ar2_total); CK(cudaMemsetAsync(ar2, 0, ar2_total * 8, stream));
+    ar3_csP = 0; ar3_zsc = p; ar3_total = p + 2;
+    ar3 = dmalloc<double>(ar3_total); CK(cudaMemsetAsync(ar3, 0, ar3_total * 8, stream));
+    scal = dmalloc<double>(S_COUNT); CK(cudaMemsetAsync(scal, 0, S_COUNT * 8, stream));
+    guard[0] = dmalloc<long long>(G_COUNT); guard[1] = dmalloc<long long>(G_COUNT);
+    k_init_guard<<<1, 32, 0, stream>>>(guard[0]); k_init_guard<<<1, 32, 0, stream>>>(guard[1]);
+    CK(cudaMallocHost(&h_scal, sizeof(double) * S_COUNT));
+    for (int i = 0; i < PH_COUNT; ++i) { CK(cudaEventCreate(&ev_a[i])); CK(cudaEventCreate(&ev_b[i])); }
+    factor_order.resize(K);
+    for (int k = 0; k < K; ++k) factor_order[k] = k;
+}
+
+void pcmf_solver::upload_colmajor(const double *host, int64_t rows, double *dst, double padval) {
+    double *tmp = dmalloc<double>((size_t)rows * K);
+    CK(cudaMemcpyAsync(tmp, host, sizeof(double) * rows * K, cudaMemcpyHostToDevice, stream));
+    k_colmajor_to_rowpad<<<grid_for(rows * KP, 256), 256, 0, stream>>>(rows, K, KP, tmp, dst, padval);
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(tmp);
+}
+void pcmf_solver::download_colmajor(const double *src, int64_t rows, double *host) {
+    double *tmp = dmalloc<double>((size_t)rows * K);
+    k_rowpad_to_colmajor<<<grid_for(rows * K, 256), 256, 0, stream>>>(rows, K, KP, src, tmp);
+    CK(cudaMemcpyAsync(host, tmp, sizeof(double) * rows * K, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(tmp);
+}
+
+void pcmf_solver::init_state(const pcmf_init *in) {
+    const pcmf_init none{};
+    if (!in) in = &none;
+    // ---- argument consistency, with the reference's messages (wrapper_gap_factor.h:215-258)
+    if ((in->U != nullptr) != (in->V != nullptr))
+        fail(PCMF_EINVAL, "You should supply initial values for both U and V or for neither of them");
+    const int nab = (in->a1 != nullptr) + (in->a2 != nullptr) + (in->b1 != nullptr) + (in->b2 != nullptr);
+    if (nab != 0 && nab != 4) fail(PCMF_EINVAL, "You should supply initial values for all a1, a2, b1, b2 or for none of them");
+    const int nhy = (in->alpha1 != nullptr) + (in->alpha2 != nullptr) + (in->beta1 != nullptr) + (in->beta2 != nullptr);
+    if (nhy != 0 && nhy != 4)
+        fail(PCMF_EINVAL, "You should supply initial values for all alpha1, alpha2, beta1, beta2 or for none of them");
+
+    // hyper-parameters: Ones (gap_factor_model.cpp:56-59) unless given
+    std::vector<double> h(4 * 64, 1.0);
+    if (nhy == 4) {
+        for (int k = 0; k < K; ++k) { h[k] = in->alpha1[k]; h[64 + k] = in->alpha2[k]; h[128 + k] = in->beta1[k]; h[192 + k] = in->beta2[k]; }
+    }
+    CK(cudaMemcpyAsync(hyp, h.data(), sizeof(double) * 4 * 64, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+
+    // sparse parameters first (wrapper_sparse_gap_factor.h:390-394)
+    std::mt19937 rng(opt.has_seed ? opt.seed : (uint32_t)std::chrono::system_clock::now().time_since_epoch().count());
+    auto unif = [](std::mt19937 &g) { return ((double)g() + 0.5) / 4294967296.0; };
+    int64_t draws_before_U = 0;
+    if (sparse) {
+        if (in->prob_S && in->prior_S) {
+            upload_colmajor(in->prob_S, p, prob_S, 0.0);
+            CK(cudaMemcpy(prior_S, in->prior_S, sizeof(double) * p, cudaMemcpyHostToDevice));
+        } else {
+            // init_sparse_param(sel_bound, rng): uniform prob_S (sparse_gap_factor_model.cpp:71-88)
+            std::vector<double> ps((size_t)p * K), pr(p);
+            for (int j = 0; j < p; ++j) {
+                double s = 0;
+                for (int k = 0; k < K; ++k) { const double u = unif(rng); ps[j + (size_t)k * p] = u; s += u; }
+                pr[j] = s / K;
+            }
+            draws_before_U = (int64_t)p * K;
+            upload_colmajor(ps.data(), p, prob_S, 0.0);
+            CK(cudaMemcpy(prior_S, pr.data(), sizeof(double) * p, cudaMemcpyHostToDevice));
+        }
+    }
+    // variational parameters (wrapper_gap_factor.h:352-375)
+    if (in->U) {
+        upload_colmajor(in->U, n, a1, 1.0); upload_colmajor(in->V, p, b1, 1.0);
+        k_fill<<<grid_for(n * KP, 256), 256, 0, stream>>>(a2, n * KP, 1.0);
+        k_fill<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(b2, (int64_t)p * KP, 1.0);
+    } else if (nab == 4) {
+        upload_colmajor(in->a1, n, a1, 1.0); upload_colmajor(in->a2, n, a2, 1.0);
+        upload_colmajor(in->b1, p, b1, 1.0); upload_colmajor(in->b2, p, b2, 1.0);
+    } else {
+        // random_init_model_param (gap_factor_model.cpp:147-174): a1(i,.) ~ Gamma(1, rate sqrt(K / rowmean_i)),
+        // b1(j,.) ~ Gamma(1, rate sqrt(K / colmean_j)); one MT19937 stream, cells first (in global order) then genes.
+        std::vector<double> rs(n), cs(p);
+        CK(cudaMemcpy(rs.data(), rowsumX, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cs.data(), colsumX, sizeof(double) * p, cudaMemcpyDeviceToHost));
+        std::vector<double> A((size_t)n * K), B((size_t)p * K);
+        std::mt19937 gu = rng; gu.discard((unsigned long long)row_offset * K);
+        for (int64_t i = 0; i < n; ++i) {
+            const double rate = std::sqrt((double)K / (rs[i] / p));
+            for (int k = 0; k < K; ++k) A[i + (size_t)k * n] = -std::log(unif(gu)) / rate;
+        }
+        std::mt19937 gv = rng; gv.discard((unsigned long long)n_global * K);
+        for (int j = 0; j < p; ++j) {
+            const double rate = std::sqrt((double)K / (cs[j] / (double)n_global));
+            for (int k = 0; k < K; ++k) B[j + (size_t)k * p] = -std::log(unif(gv)) / rate;
+        }
+        (void)draws_before_U;
+        upload_colmajor(A.data(), n, a1, 1.0); upload_colmajor(B.data(), p, b1, 1.0);
+        k_fill<<<grid_for(n * KP, 256), 256, 0, stream>>>(a2, n * KP, 1.0);
+        k_fill<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(b2, (int64_t)p * KP, 1.0);
+    }
+    run_init_stats();
+}
+
+// U_stats, V_stats, update_poisson_param, update_hyper_param after any initialisation (gap_factor_model.cpp:119-122)
+void pcmf_solver::run_init_stats() {
+    const size_t pK = (size_t)p * KP;
+    double *alpha1 = hyp, *alpha2 = hyp + 64, *beta1 = hyp + 128, *beta2 = hyp + 192;
+    CK(cudaMemsetAsync(scal, 0, S_COUNT * 8, stream));
+    CK(cudaMemsetAsync(csv, 0, 3 * 64 * 8, stream));
+    CK(cudaMemsetAsync(ar1 + ar1_cseu, 0, (64 + 64 + 4) * 8, stream));
+    CK(cudaMemsetAsync(ar3, 0, ar3_total * 8, stream));
+    k_init_guard<<<1, 32, 0, stream>>>(guard[gcur]);
+    UInitArgs ua{n, K, KP, a1, a2, EU[cur], ElogU, eu, guard[gcur], ar1 + ar1_cseu, ar1 + ar1_cselog, ar1 + ar1_usc};
+    k_stats_u<<<grid_for(n * KP, 256), 256, 0, stream>>>(ua);
+    VArgs va{};
+    va.p = p; va.K = K; va.KP = KP; va.sparse = sparse; va.zi = zi; va.first_iter = 1; va.want_data = 0; va.stats_only = 1;
+    va.beta1 = beta1; va.beta2 = beta2; va.b1 = b1; va.b2 = b2; va.EV = EV; va.ElogV = ElogV; va.prob_S = prob_S; va.Sd = Sd;
+    va.colw = colw; va.ev = ev; va.evw = evw; va.EVS = EVS; va.wS = wS; va.guard_next = guard[gcur];
+    va.cs_ev = csv; va.cs_elogv = csv + 64; va.cs_evs = csv + 128; va.scal = scal;
+    k_mstep_genes<<<grid_for(pK, 256), 256, 0, stream>>>(va);
+    if (sparse) {
+        CK(cudaMemsetAsync(csv + 128, 0, 64 * 8, stream));
+        SparseArgs sa{};
+        sa.p = p; sa.K = K; sa.KP = KP; sa.zi = zi; sa.update = 0; sa.sel_bound = opt.sel_bound; sa.EV = EV; sa.ElogV = ElogV;
+        sa.colw = colw; sa.prob_S = prob_S; sa.Sd = Sd; sa.prior_S = prior_S; sa.S = S; sa.ev = ev; sa.evw = evw; sa.EVS = EVS;
+        sa.wS = wS; sa.cs_evs = csv + 128; sa.scal = scal;
+        k_sparse_genes<<<grid_for(p, 128), 128, 0, stream>>>(sa);
+    }
+    launches += 2 + (sparse ? 1 : 0);
+    if (zi) {
+        // init_zi_param (zi_gap_factor_model.cpp:98-105): prob_D = (X > 0); realised as pass A with c_j = -inf
+        ZiPrepArgs zp{p, 1, prior_D, Lg, cz, colw, flag, scal};
+        k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
+        ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc};
+        L->zi_cells(za, stream);
+        launches += 2;
+    }
+    allreduce(ar1 + ar1_cseu, 64 + 64 + 4);
+    if (zi) allreduce(ar3, ar3_total);
+    HyperArgs ha{n_global, p, K, zi, sparse, alpha1, alpha2, beta1, beta2, ar1 + ar1_cseu, ar1 + ar1_cselog, csv, csv + 64, csv + 128,
+                 ar3 + ar3_csP, prior_D, ar1 + ar1_usc, ar3 + ar3_zsc, lgx_const, scal};
+    k_hyper<<<1, 256, 0, stream>>>(ha);
+    k_vec_scale<<<1, 64, 0, stream>>>(hyp + 256, csv + 128, 64, 1.0);
+    launches += 2;
+    read_scal();
+    CK(cudaGetLastError());
+    last_nodata = h_scal[S_ELBO_NODATA];
+    first_iter = true; have_pending = false;
+}
+
+// One VEM iteration: model.update_param() (model.cpp:243-246) + the quantities check_convergence needs.
+void pcmf_solver::step(bool want_data) {
+    const size_t pK = (size_t)p * KP;
+    double *alpha1 = hyp, *alpha2 = hyp + 64, *beta1 = hyp + 128, *beta2 = hyp + 192;
+    long long *gc = guard[gcur], *gn = guard[1 - gcur];
+    const int nxt = zi ? 1 - cur : cur;
+    CK(cudaMemsetAsync(scal, 0, S_COUNT * 8, stream));
+    CK(cudaMemsetAsync(csv, 0, 3 * 64 * 8, stream));
+    CK(cudaMemsetAsync(ar1 + ar1_tmp, 0, (ar1_core - ar1_tmp) * 8, stream));   // tmpMat, cs_eu, cs_elog, usc
+    if (zi) CK(cudaMemsetAsync(ar3, 0, ar3_total * 8, stream));
+    k_init_guard<<<1, 32, 0, stream>>>(gn);
+
+    // 1. E-step, gene side (old statistics): B1 [+ B2 | xlogT for the ELBO data term of the previous iterate]
+    begin(PH_GENE_E);
+    {
+        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT};
+        const int mode = !want_data ? GENE_B1 : (sparse ? GENE_B1_B2 : GENE_B1_LOGT);
+        L->gene_pass(f32, mode, ca, std::min<int>(p, sms * 32), stream);
+    }
+    end(PH_GENE_E, 1);
+    // 2. E-step, cell side + U-side M-step (in place)
+    begin(PH_ROWS);
+    {
+        RowArgs ra{};
+        ra.n = n; ra.K = K; ra.rowptr = rowptr; ra.colidx = colidx; ra.val = val_csr; ra.ev = ev; ra.evw = evw; ra.ElogV = ElogV;
+        ra.Sd = Sd; ra.wS = wS; ra.a1 = a1; ra.a2 = a2; ra.EU_new = EU[nxt]; ra.ElogU = ElogU; ra.eu = eu; ra.alpha1 = alpha1;
+        ra.alpha2 = alpha2; ra.rate_vec = csv + 128; ra.PV = zi ? PV : nullptr; ra.first_iter = first_iter; ra.guard_cur = gc;
+        ra.guard_next = gn; ra.cs_eu = ar1 + ar1_cseu; ra.cs_elog = ar1 + ar1_cselog; ra.usc = ar1 + ar1_usc;
+        // colsum(EV o prob_S) of the OLD state: csv+128 is re-accumulated during this iteration, hyp+256 keeps the copy
+        ra.rate_vec = hyp + 256;
+        const int block = 256;
+        const int64_t warps = std::min<int64_t>(n, (int64_t)sms * 8 * 8);
+        L->estep_rows(f32, ra, (int)((warps + 7) / 8), block, stream);
+    }
+    end(PH_ROWS, 1);
+    // 3. ZI: prob_D^T EU_new with prob_D recomputed from the triple saved when it was defined
+    if (zi) {
+        begin(PH_ZI_B);
+        ZiBArgs zb{};
+        zb.n = n; zb.p = p; zb.K = K; zb.EUz = EU[cur]; zb.EUn = EU[nxt]; zb.EVSz = EVS; zb.cz = cz; zb.flag = flag; zb.bitB = bitB;
+        zb.tmpMat = ar1 + ar1_tmp;
+        const int gx = (p + 127) / 128;
+        int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, (int64_t)(sms * 4 + gx - 1) / gx));
+        int64_t rpc = (n + chunks - 1) / chunks; rpc = (rpc + 63) / 64 * 64;
+        chunks = (int)((n + rpc - 1) / rpc);
+        zb.rows_per_chunk = rpc;
+        L->zi_genes(zb, chunks, stream);
+        end(PH_ZI_B, 1);
+    }
+    // 4. all-reduce of the gene-side sums + U partials over the row shards
+    begin(PH_AR1);
+    allreduce(ar1, want_data ? ar1_total : ar1_core);
+    end(PH_AR1, 0);
+    // 5. V-side M-step
+    begin(PH_MSTEP_V);
+    {
+        VArgs va{};
+        va.p = p; va.K = K; va.KP = KP; va.sparse = sparse; va.zi = zi; va.first_iter = first_iter; va.want_data = want_data;
+        va.stats_only = 0; va.B1 = ar1 + ar1_B1; va.B2 = ar1 + ar1_B2; va.xlogT = ar1 + ar1_xlogT; va.tmpMat = ar1 + ar1_tmp;
+        va.cs_eu = ar1 + ar1_cseu; va.beta1 = beta1; va.beta2 = beta2; va.b1 = b1; va.b2 = b2; va.EV = EV; va.ElogV = ElogV;
+        va.prob_S = prob_S; va.Sd = Sd; va.colw = colw; va.ev = ev; va.evw = evw; va.EVS = EVS; va.wS = wS; va.guard_next = gn;
+        va.cs_ev = csv; va.cs_elogv = csv + 64; va.cs_evs = csv + 128; va.scal = scal;
+        k_mstep_genes<<<grid_for(pK, 256), 256, 0, stream>>>(va);
+    }
+    end(PH_MSTEP_V, 1);
+    // 6. spike-and-slab probabilities: second non-zero pass with the new statistics and the old mask
+    if (sparse) {
+        begin(PH_GENE_S);
+        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, gn, ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
+        L->gene_pass(f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
+        allreduce(ar2, 2 * pK);
+        end(PH_GENE_S, 1);
+        begin(PH_SPARSE);
+        CK(cudaMemsetAsync(csv + 128, 0, 64 * 8, stream));
+        SparseArgs sa{};
+        sa.p = p; sa.K = K; sa.KP = KP; sa.zi = zi; sa.update = 1; sa.sel_bound = opt.sel_bound; sa.B1 = ar2 + ar2_B1; sa.B2 = ar2 + ar2_B2;
+        sa.tmpMat = ar1 + ar1_tmp; sa.cs_eu = ar1 + ar1_cseu; sa.EV = EV; sa.ElogV = ElogV; sa.colw = colw; sa.prob_S = prob_S; sa.Sd = Sd;
+        sa.prior_S = prior_S; sa.S = S; sa.ev = ev; sa.evw = evw; sa.EVS = EVS; sa.wS = wS; sa.cs_evs = csv + 128; sa.scal = scal;
+        k_sparse_genes<<<grid_for(p, 128), 128, 0, stream>>>(sa);
+        end(PH_SPARSE, 1);
+    }
+    // 7. ZI probabilities: define the new prob_D (cz/flag/colw), its row products, column sums and ELBO terms
+    if (zi) {
+        begin(PH_ZI_A);
+        ZiPrepArgs zp{p, 0, prior_D, Lg, cz, colw, flag, scal};
+        k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
+        k_refresh_weights<<<grid_for(pK, 256), 256, 0, stream>>>(p, K, KP, sparse, prob_S, colw, ev, wS, evw);
+        ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc};
+        L->zi_cells(za, stream);
+        allreduce(ar3, ar3_total);
+        end(PH_ZI_A, 3);
+    }
+    // 8. hyper-parameters + scalars
+    begin(PH_HYPER);
+    k_vec_scale<<<1, 64, 0, stream>>>(hyp + 256, csv + 128, 64, 1.0);   // keep colsum(EV o prob_S) for the next a2 update
+    HyperArgs ha{n_global, p, K, zi, sparse, alpha1, alpha2, beta1, beta2, ar1 + ar1_cseu, ar1 + ar1_cselog, csv, csv + 64, csv + 128,
+                 ar3 + ar3_csP, prior_D, ar1 + ar1_usc, ar3 + ar3_zsc, lgx_const, scal};
+    k_hyper<<<1, 256, 0, stream>>>(ha);
+    end(PH_HYPER, 2);
+    read_scal();
+    collect_phase_times();
+    cur = nxt; gcur = 1 - gcur; first_iter = false;
+}
+
+// ELBO data term of the current state (gap...cpp:301-313, sparse...cpp:194-212): one gene pass, nothing updated.
+double pcmf_solver::data_term_now() {
+    const size_t pK = (size_t)p * KP;
+    ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, guard[gcur], ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
+    L->gene_pass(f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
+    allreduce(ar2, ar2_total);
+    CK(cudaMemsetAsync(scal + S_DATA, 0, 8, stream));
+    DataArgs da{p, K, KP, sparse, zi, ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT, ElogV, prob_S, colw, scal};
+    k_data_term<<<grid_for(pK, 256), 256, 0, stream>>>(da);
+    launches += 2;
+    read_scal();
+    return h_scal[S_DATA];
+}
+
+// ================================================================================================================
+// C ABI
+// ================================================================================================================
+namespace {
+int guarded(char *errbuf, size_t errlen, const std::function<void()> &fn) {
+    try {
+        fn();
+        return PCMF_OK;
+    } catch (const Err &e) {
+        if (errbuf && errlen) snprintf(errbuf, errlen, "%s", e.what());
+        return e.code;
+    } catch (const std::exception &e) {
+        if (errbuf && errlen) snprintf(errbuf, errlen, "%s", e.what());
+        return PCMF_EINVAL;
+    }
+}
+
+void check_options(const pcmf_problem *prob, const pcmf_options *opt) {
+    if (!prob || !opt) fail(PCMF_EINVAL, "null problem/options");
+    const int64_t nglob = prob->n_global > 0 ? prob->n_global : prob->n_local;
+    // wrapper_gap_factor.h:210-213
+    if (opt->K > std::min<int64_t>(nglob, prob->p))
+        fail(PCMF_EINVAL, "Input paramter K should be lower than min(n,p) where n and p are the number of rows and columns in input matrix X");
+    if (opt->K < 1) fail(PCMF_EINVAL, "K must be >= 1");
+    if (padded_K(opt->K) < 0) fail(PCMF_EUNSUPPORTED, "K = %d exceeds the largest compiled factor width (64)", opt->K);
+    // wrapper_sparse_gap_factor.h:236
+    if (opt->sparsity && (opt->sel_bound < 0 || opt->sel_bound > 1))
+        fail(PCMF_EINVAL, "Input parameter sel_bound should be a real value between 0 and 1");
+    // algorithm.h:427
+    if (opt->conv_mode < 0 || opt->conv_mode > 2) fail(PCMF_EINVAL, "`conv_mode` parameter should take value in {0,1,2}");
+    if (opt->conv_mode == 2)
+        fail(PCMF_EUNSUPPORTED, "conv_mode = 2 (RV coefficient, O(n^2)) is out of scope; pCMF() always uses conv_mode = 1");
+}
+}  // namespace
+
+extern "C" {
+
+const char *pcmf_version(void) { return "pcmf_b200 0.1.0 (sm_100a, fp64)"; }
+
+int pcmf_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+
+int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_init *init, pcmf_solver **out, char *errbuf,
+                size_t errlen) {
+    pcmf_solver *s = nullptr;
+    int rc = guarded(errbuf, errlen, [&] {
+        if (!out) fail(PCMF_EINVAL, "null output handle");
+        check_options(prob, opt);
+        int cnt = 0;
+        if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0)
+            fail(PCMF_ECUDA, "no CUDA device available: libpcmf_b200 has no CPU fallback");
+        s = new pcmf_solver();
+        s->opt = *opt;
+        if (s->opt.world < 1) s->opt.world = 1;
+        if (s->opt.progress_every <= 0) s->opt.progress_every = 10;
+        s->device = opt->device;
+        CK(cudaSetDevice(s->device));
+        cudaDeviceProp dp;
+        CK(cudaGetDeviceProperties(&dp, s->device));
+        s->sms = dp.multiProcessorCount;
+        if (opt->stream) { s->stream = (cudaStream_t)opt->stream; s->own_stream = false; }
+        else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+        s->K = opt->K; s->KP = padded_K(opt->K); s->zi = opt->zero_inflation != 0; s->sparse = opt->sparsity != 0;
+        s->L = get_launchers(s->KP);
+        if (!s->L) fail(PCMF_EUNSUPPORTED, "no kernels compiled for padded K = %d", s->KP);
+        s->setup_problem(*prob);
+        s->alloc_state();
+        s->init_state(init);
+    });
+    if (rc != PCMF_OK) { delete s; s = nullptr; }
+    if (out) *out = s;
+    return rc;
+}
+
+void pcmf_destroy(pcmf_solver *s) { delete s; }
+
+int pcmf_iterate(pcmf_solver *s, int niter, double *conv_crit_out, char *errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        if (!s) fail(PCMF_EINVAL, "null solver");
+        CK(cudaSetDevice(s->device));
+        for (int it = 0; it < niter; ++it) {
+            s->step(false);
+            const double crit = s->opt.conv_mode == 0 ? s->h_scal[S_ABS_GAP] : s->h_scal[S_NORM_GAP];
+            if (conv_crit_out) conv_crit_out[it] = crit;
+            s->last_nodata = s->h_scal[S_ELBO_NODATA];
+            s->iter++;
+        }
+    });
+}
+
+int pcmf_optimize(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        if (!s || !res) fail(PCMF_EINVAL, "null solver/result");
+        CK(cudaSetDevice(s->device));
+        const pcmf_options &o = s->opt;
+        const double t0 = now_s();
+        s->converged = false;
+        // algorithm.h:158-210
+        int pending = -1;   // iteration whose ELBO still lacks its data term
+        while (s->iter < o.iter_max && !s->converged) {
+            if (o.progress && (s->iter % o.progress_every == 0)) {
+                const double c = s->iter > 0 && res->conv_crit ? res->conv_crit[s->iter - 1] : NAN;
+                if (o.progress(o.progress_ctx, s->iter, c) != 0) fail(PCMF_EINTERRUPT, "interrupted at iteration %d", s->iter);
+            }
+            const bool want = o.monitor && pending >= 0;
+            s->step(want);
+            const int it = s->iter;
+            if (want && res->optim_criterion) res->optim_criterion[pending] = s->last_nodata + s->h_scal[S_DATA];
+            s->last_nodata = s->h_scal[S_ELBO_NODATA];
+            pending = it;
+            const double ag = s->h_scal[S_ABS_GAP], ng = s->h_scal[S_NORM_GAP];
+            const double crit = o.conv_mode == 0 ? ag : ng;   // algorithm.h:417-423
+            if (res->conv_crit) res->conv_crit[it] = crit;
+            if (res->abs_gap) res->abs_gap[it] = ag;
+            if (res->norm_gap) res->norm_gap[it] = ng;
+            if (std::fabs(crit) < o.epsilon) s->nb_iter_stab++; else s->nb_iter_stab = 0;         // algorithm.h:440-444
+            if (s->nb_iter_stab > o.additional_iter && it > o.iter_min) s->converged = true;     // algorithm.h:447
+            s->iter++;
+        }
+        // optim_criterion() after the loop (algorithm.h:209)
+        const double data = s->data_term_now();
+        res->loss = s->last_nodata + data;
+        if (o.monitor && pending >= 0 && res->optim_criterion) res->optim_criterion[pending] = res->loss;
+        res->nb_iter = s->iter;
+        res->converged = s->converged ? 1 : 0;
+        res->seconds_iter = now_s() - t0;
+    });
+}
+
+int pcmf_elbo(pcmf_solver *s, double *elbo_out, double *terms, char *errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        if (!s) fail(PCMF_EINVAL, "null solver");
+        CK(cudaSetDevice(s->device));
+        // the no-data part was produced by the last k_hyper launch; h_scal still mirrors it unless data_term_now overwrote S_DATA only
+        const double data = s->data_term_now();
+        const double *h = s->h_scal;
+        if (elbo_out) *elbo_out = s->last_nodata + data;
+        if (terms) {
+            terms[0] = h[S_GAMMAU]; terms[1] = h[S_ENTU]; terms[2] = h[S_GAMMAV]; terms[3] = h[S_ENTV];
+            terms[4] = h[S_BERNS_PRIOR]; terms[5] = h[S_BERNS_SELF]; terms[6] = h[S_BERND_PRIOR]; terms[7] = h[S_BERND_SELF];
+            terms[8] = s->zi ? h[S_SUM_PUVT] : h[S_SUMUVT_CLOSED]; terms[9] = data; terms[10] = h[S_LGX];
+        }
+    });
+}
+
+int pcmf_set_variational(pcmf_solver *s, const double *a1, const double *a2, const double *b1, const double *b2, char *errbuf,
+                         size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        if (!s || !a1 || !a2 || !b1 || !b2) fail(PCMF_EINVAL, "null argument");
+        CK(cudaSetDevice(s->device));
+        s->upload_colmajor(a1, s->n, s->a1, 1.0); s->upload_colmajor(a2, s->n, s->a2, 1.0);
+        s->upload_colmajor(b1, s->p, s->b1, 1.0); s->upload_colmajor(b2, s->p, s->b2, 1.0);
+        s->run_init_stats();
+    });
+}
+
+int pcmf_order_factor(pcmf_solver *s, char *errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        if (!s) fail(PCMF_EINVAL, "null solver");
+        fail(PCMF_EUNSUPPORTED, "order_factor is not implemented yet (SURVEY 8f rank 2)");
+    });
+}
+
+int pcmf_monitors(pcmf_solver *s, double *loglikelihood, double *deviance, double *exp_deviance, char *errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        if (!s) fail(PCMF_EINVAL, "null solver");
+        (void)loglikelihood; (void)deviance; (void)exp_deviance;
+        fail(PCMF_EUNSUPPORTED, "monitors are not implemented yet (SURVEY 8f rank 1)");
+    });
+}
+
+int pcmf_get_output(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        if (!s || !res) fail(PCMF_EINVAL, "null solver/result");
+        CK(cudaSetDevice(s->device));
+        const int K = s->K; const int64_t n = s->n; const int p = s->p;
+        if (res->EU) s->download_colmajor(s->EU[s->cur], n, res->EU);
+        if (res->ElogU) s->download_colmajor(s->ElogU, n, res->ElogU);
+        if (res->a1) s->download_colmajor(s->a1, n, res->a1);
+        if (res->a2) s->download_colmajor(s->a2, n, res->a2);
+        if (res->EV) s->download_colmajor(s->EV, p, res->EV);
+        if (res->ElogV) s->download_colmajor(s->ElogV, p, res->ElogV);
+        if (res->b1) s->download_colmajor(s->b1, p, res->b1);
+        if (res->b2) s->download_colmajor(s->b2, p, res->b2);
+        std::vector<double> h(4 * 64);
+        CK(cudaMemcpy(h.data(), s->hyp, sizeof(double) * 4 * 64, cudaMemcpyDeviceToHost));
+        auto rep = [&](double *dst, int64_t rows, const double *vec) {   // hyper_params are returned replicated (gap...cpp:379-382)
+            if (!dst) return;
+            for (int k = 0; k < K; ++k) for (int64_t r = 0; r < rows; ++r) dst[r + (size_t)k * rows] = vec[k];
+        };
+        rep(res->alpha1, n, h.data()); rep(res->alpha2, n, h.data() + 64); rep(res->beta1, p, h.data() + 128); rep(res->beta2, p, h.data() + 192);
+        if (s->sparse) {
+            if (res->prob_S) s->download_colmajor(s->prob_S, p, res->prob_S);
+            if (res->prior_prob_S) CK(cudaMemcpy(res->prior_prob_S, s->prior_S, sizeof(double) * p, cudaMemcpyDeviceToHost));
+            if (res->S) {
+                int32_t *tmp = dmalloc<int32_t>((size_t)p * K);
+                k_rowpad_to_colmajor_i32<<<s->grid_for((int64_t)p * K, 256), 256, 0, s->stream>>>(p, K, s->KP, s->S, tmp);
+                CK(cudaMemcpyAsync(res->S, tmp, sizeof(int32_t) * p * K, cudaMemcpyDeviceToHost, s->stream));
+                CK(cudaStreamSynchronize(s->stream));
+                cudaFree(tmp);
+            }
+        }
+        if (s->zi) {
+            if (res->prior_prob_D) CK(cudaMemcpy(res->prior_prob_D, s->prior_D, sizeof(double) * p, cudaMemcpyDeviceToHost));
+            if (res->freq_D) {
+                double *tmp = dmalloc<double>(p);
+                k_vec_scale<<<s->grid_for(p, 256), 256, 0, s->stream>>>(tmp, s->colnnz, p, 1.0 / (double)s->n_global);
+                CK(cudaMemcpyAsync(res->freq_D, tmp, sizeof(double) * p, cudaMemcpyDeviceToHost, s->stream));
+                CK(cudaStreamSynchronize(s->stream));
+                cudaFree(tmp);
+            }
+            if (res->prob_D) {
+                // prob_D is defined by the triple saved at the last ZI update: EU[cur] (the EU of that update), EVS, cz/flag
+                double *tmp = dmalloc<double>((size_t)n * p);
+                ProbDArgs pa{n, p, K, s->KP, s->EU[s->cur], s->EVS, s->cz, s->flag, s->bitT, tmp};
+                k_prob_d_dense<<<s->grid_for(n * (int64_t)p, 256), 256, 0, s->stream>>>(pa);
+                CK(cudaMemcpyAsync(res->prob_D, tmp, sizeof(double) * n * p, cudaMemcpyDeviceToHost, s->stream));
+                CK(cudaStreamSynchronize(s->stream));
+                cudaFree(tmp);
+            }
+        }
+        if (res->factor_order) for (int k = 0; k < K; ++k) res->factor_order[k] = s->factor_order[k];
+        res->nb_iter = s->iter;
+        res->converged = s->converged ? 1 : 0;
+        CK(cudaGetLastError());
+    });
+}
+
+int pcmf_phase_times(pcmf_solver *s, const char **names, double *ms, int64_t *launches, int cap) {
+    if (!s) return 0;
+    int c = 0;
+    for (int i = 0; i < PH_COUNT && c < cap; ++i) {
+        if (names) names[c] = kPhaseNames[i];
+        if (ms) ms[c] = s->ph_ms[i];
+        if (launches) launches[c] = s->ph_launch[i];
+        ++c;
+    }
+    return c;
+}
+
+int64_t pcmf_launch_count(pcmf_solver *s) { return s ? s->launches : 0; }
+
+int pcmf_fit(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_init *init, pcmf_result *res, char *errbuf, size_t errlen) {
+    if (!res) { if (errbuf && errlen) snprintf(errbuf, errlen, "null result"); return PCMF_EINVAL; }
+    const double t0 = now_s();
+    pcmf_solver *s = nullptr;
+    int rc = pcmf_create(prob, opt, init, &s, errbuf, errlen);
+    if (rc != PCMF_OK) return rc;
+    res->seconds_setup = now_s() - t0;
+    if (opt->ninit > 1) {
+        pcmf_destroy(s);
+        if (errbuf && errlen) snprintf(errbuf, errlen, "ninit > 1 (multi-init) is not implemented yet (SURVEY 8f rank 4)");
+        return PCMF_EUNSUPPORTED;
+    }
+    rc = pcmf_optimize(s, res, errbuf, errlen);
+    if (rc == PCMF_OK) {
+        res->exp_dev = NAN;
+        rc = pcmf_get_output(s, res, errbuf, errlen);
+    }
+    pcmf_destroy(s);
+    res->seconds_total = now_s() - t0;
+    return rc;
+}
+
+int pcmf_device_free(int device, void *ptr) {
+    if (cudaSetDevice(device) != cudaSuccess) return PCMF_ECUDA;
+    return cudaFree(ptr) == cudaSuccess ? PCMF_OK : PCMF_ECUDA;
+}
+int pcmf_device_to_host(int device, void *dst_host, const void *src_dev, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return PCMF_ECUDA;
+    return cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? PCMF_OK : PCMF_ECUDA;
+}
+
+}  // extern "C"
