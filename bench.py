@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- VEM iterations/sec of the pCMF hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W           (N>1 under torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W     (the CPU path of the reference, see below)
+
+A "step" is one VEM iteration of the zero-inflated + sparse-V model: E-step, M-step, spike-and-slab update, ZI update,
+hyper-parameter update, normalised-gap check and ELBO, on the configuration BASELINE.json quotes the
+metric on: 1M cells x 20k genes, ~5% non-zeros, K=20, synthetic counts from the package's own generative model
+(pkg/R/data_generation.R), generated on the GPU.  For N>1 the cells are sharded over the ranks (fixed total problem:
+strong scaling) and the p x K gene-side statistics are all-reduced over NCCL every iteration.
+
+The reference arm: the reference's own implementation cannot be built here (needs R + Rcpp + RcppEigen + BH, none of
+which exist in the image, no network), so `--impl reference` times the CPU oracle -- the dense, OpenMP, loop-for-loop
+restatement of the reference's C++ (oracle/pcmf_oracle.c) -- on all host cores on a bounded row sample of the same
+workload and extrapolates linearly in n (the reference's cost is linear in n at fixed p, K).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: n, p, K_true, K, prob1, target density, zi, sparse
+    "c4": dict(n=1_000_000, p=20_000, K_true=20, K=20, prob1=0.4, density=0.05, zi=True, sparse=True,
+               label="C4: 1M cells x 20k genes, ~5% nnz, ZI + sparse-V, K=20"),
+    "c3": dict(n=50_000, p=5_000, K_true=20, K=20, prob1=0.5, density=0.30, zi=True, sparse=True,
+               label="C3: 50k x 5k, ~30% nnz, ZI + sparse-V, K=20"),
+    "c2": dict(n=10_000, p=2_000, K_true=10, K=10, prob1=None, density=None, zi=False, sparse=False,
+               label="C2: 10k x 2k dense Gamma-Poisson, K=10"),
+    "tiny": dict(n=20_000, p=2_000, K_true=20, K=20, prob1=0.4, density=0.05, zi=True, sparse=True,
+                 label="tiny: 20k x 2k, ~5% nnz, ZI + sparse-V, K=20 (smoke only)"),
+}
+
+
+def factor_matrices(cfg, seed):
+    """U (n x K_true, 3 cell groups), V (p x K_true, 2 gene groups, 60% noise genes): SURVEY 8d / README.md:119-137.
+    U is rescaled by a constant calibrated on a row sample so that the realised density hits the target."""
+    from pcmf_b200 import datagen
+    rng = np.random.Generator(np.random.Philox(seed))
+    n, p, Kt = cfg["n"], cfg["p"], cfg["K_true"]
+    U = datagen.generate_factor_matrix(n, Kt, ngroup=3, average_signal=60.0, group_separation=0.8,
+                                       distribution="exponential", shuffle_feature=True, rng=rng)["factor_matrix"]
+    V = datagen.generate_factor_matrix(p, Kt, ngroup=2, average_signal=60.0, group_separation=0.8,
+                                       distribution="exponential", shuffle_feature=True, prop_noise_feature=0.6,
+                                       rng=rng)["factor_matrix"]
+    if cfg["density"] is not None:
+        keep = cfg["prob1"] if cfg["prob1"] is not None else 1.0
+        lam = U[:: max(1, n // 512)][:512] @ V.T
+        lo, hi = 1e-8, 1.0
+        for _ in range(60):   # density(c) = keep * mean(1 - exp(-c * lambda)) is increasing in c
+            mid = np.sqrt(lo * hi)
+            if keep * (1 - np.exp(-mid * lam)).mean() > cfg["density"]:
+                hi = mid
+            else:
+                lo = mid
+        U = U * np.sqrt(lo * hi)
+    return U, V
+
+
+def shard_rows(n, rank, world):
+    """contiguous, equal-count row ranges (the synthetic cells are exchangeable, so equal rows ~ equal nnz)"""
+    base, rem = divmod(n, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None):
+    """The oracle (dense OpenMP restatement of the reference) on the first `max_rows` cells of the same workload."""
+    from oracle import pyoracle as po
+    from pcmf_b200 import datagen
+    n, p, K = cfg["n"], cfg["p"], cfg["K"]
+    ns = min(max_rows, n)
+    rng = np.random.Generator(np.random.Philox(seed + 77))
+    lam = U[:ns] @ V.T
+    X = rng.poisson(lam).astype(np.float64)
+    if cfg["prob1"] is not None:
+        X *= rng.uniform(size=X.shape) < cfg["prob1"]
+    X[X.sum(1) == 0, 0] = 1
+    X[0, X.sum(0) == 0] = 1
+    if threads:
+        po.lib().orc_set_num_threads(int(threads))
+    cores = po.lib().orc_num_threads()
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=seed + 1000)
+    m = po.Model(X, K, cfg["zi"], cfg["sparse"])
+    if cfg["sparse"]:
+        prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+        m.init_sparse_param(0.5, prob_S, prior_S)
+    if cfg["zi"]:
+        m.init_zi_param()
+    m.init_variational_param(a1, a2, b1, b2)
+    times = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        m.update_param()
+        m.elbo()
+        m.gap_between_iterates()
+        m.prepare_next_iterate()
+        times.append(time.perf_counter() - t0)
+    t_iter = float(np.mean(times))
+    full = (1.0 / t_iter) * (ns / n)
+    return {"value": full, "unit": "iter/s", "cores": int(cores), "kind": "port",
+            "sample": "oracle (dense OpenMP restatement of the reference C++) on %d of %d cells, same p=%d K=%d, %d timed "
+                      "iterations of update_param+elbo+gap, %.3f s/iter on the sample; extrapolated linearly in n (x %d/%d)"
+                      % (ns, n, p, K, iters, t_iter, ns, n),
+            "sample_seconds_per_iter": t_iter}
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    U, V = factor_matrices(cfg, args.seed)
+    iters = max(1, min(args.steps, 3))
+    cb = cpu_baseline(cfg, U, V, args.seed, args.cpu_rows, iters)
+    line = {"impl": "reference", "metric": "VEM iterations/sec", "value": cb["value"], "unit": "iter/s", "n_gpus": args.gpus,
+            "steps": iters, "warmup": 0, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["label"], "model": "zi_sparse_gap" if cfg["zi"] and cfg["sparse"] else "gap"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference binary unbuildable here (needs R/Rcpp/RcppEigen/BH); this is the oracle port on the host cores"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--cpu-rows", type=int, default=1500)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import torch
+    import torch.distributed as dist
+    import pcmf_b200
+    from pcmf_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the pcmf_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = api._Comm()
+    args.warmup = max(args.warmup, 3)
+    n, p, K = cfg["n"], cfg["p"], cfg["K"]
+    r0, r1 = shard_rows(n, rank, world)
+    nl = r1 - r0
+
+    # ---- synthetic input, generated on the device straight into CSR (package's generative model)
+    t_gen = time.perf_counter()
+    U, V = factor_matrices(cfg, args.seed)
+    csr = pcmf_b200.generate_counts_device(nl, p, cfg["K_true"], U[r0:r1], V, prob1=cfg["prob1"], seed=args.seed,
+                                           device=local, row_offset=r0)
+    t_gen = time.perf_counter() - t_gen
+    nnz_local = csr.nnz
+    nnz_t = torch.tensor([float(nnz_local)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz = int(nnz_t.item())
+    # prior_S heuristic of the R wrapper (pCMF.R:228-229) from per-gene sums
+    prob_S = prior_S = None
+    if cfg["sparse"]:
+        s1, s2, cn = api.csr_column_stats(csr)
+        st = torch.tensor(np.stack([s1, s2, cn]), device="cuda")
+        if world > 1:
+            dist.all_reduce(st)
+        s1, s2, cn = st.cpu().numpy()
+        prob_S, prior_S = api.prior_S_from_stats(s1, s2, cn, n, K)
+
+    stream = torch.cuda.current_stream()
+    solver = pcmf_b200.Solver(csr, K, cfg["zi"], cfg["sparse"], seed=args.seed + 1000, prob_S=prob_S, prior_S=prior_S,
+                              device=local, stream=stream.cuda_stream, comm=comm, n_global=n, row_offset=r0,
+                              iter_max=10 ** 6)
+    # ---- warm-up, then exactly `steps` timed iterations (ELBO evaluated every iteration, as monitor=TRUE does)
+    solver.iterate(args.warmup, with_elbo=True)
+    ph0, l0 = solver.phase_times(), solver.launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    crit, elbo = solver.iterate(args.steps, with_elbo=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clk = clocks.stop() if rank == 0 else None
+    ph1, l1 = solver.phase_times(), solver.launch_count()
+    launches = l1 - l0
+    value = args.steps / (ms * 1e-3)
+
+    # ---- roofline of the E-step kernels, from the per-phase CUDA-event times taken inside the timed region
+    hbm_peak, peak_src = measured_peaks()
+    per = {k: ((ph1[k][0] - ph0[k][0]) / max(1, args.steps), (ph1[k][1] - ph0[k][1]) // max(1, args.steps)) for k in ph1}
+    w = 8
+    zi, sparse = cfg["zi"], cfg["sparse"]
+    # algorithmic bytes per launch, this rank
+    b_cells = 8 * nnz_local + 8 * (nl + 1) + w * K * nl * (1 + 2 + 5 + (1 if zi else 0)) + w * K * p * (2 if (zi or sparse) else 1)
+    b_genes = 8 * nnz_local + 8 * (p + 1) + w * K * nl * (2 if sparse else 1) + w * K * p * (1 + (2 if sparse else 1))
+    kernels = []
+    for name, byts in (("estep_cells_mstep_u", b_cells), ("estep_genes", b_genes)):
+        t = per[name][0]
+        kernels.append({"kernel": name, "ms": t, "share": t * args.steps / ms if ms else None, "bound": "hbm",
+                        "algorithmic_bytes": byts, "achieved": byts / (t * 1e-3) / 1e9 if t > 0 else None,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": (byts / (t * 1e-3) / 1e9 / hbm_peak) if t > 0 else None})
+    fp64_peak = api.measure_fp64_tflops(local)
+    if zi:
+        # dense ZI passes: 2 contractions of length K per entry (4K flop) + expit; FP64-pipe bound
+        for name in ("zi_pass_cells", "zi_pass_genes"):
+            t = per[name][0]
+            fl = 4.0 * K * nl * p
+            kernels.append({"kernel": name, "ms": t, "share": t * args.steps / ms, "bound": "fp64", "algorithmic_flops": fl,
+                            "achieved": fl / (t * 1e-3) / 1e12 if t > 0 else None, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": (fl / (t * 1e-3) / 1e12 / fp64_peak) if t > 0 else None})
+    dom = max(kernels[:2], key=lambda k: k["ms"])
+    roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": None, "kernel": dom["kernel"], "peak_source": peak_src, "ms_per_launch": dom["ms"]}
+    phases = {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in per.items()}
+    solver.close()
+
+    # ---- end-to-end leg: the reference-facing call (run_zi_sparse_gap_factor -> pcmf C ABI) with HOST buffers:
+    # H2D of the CSR matrix, preprocessing, `steps` iterations with the ELBO, D2H of the factors, all inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        rp, ci, vv = csr.to_host()
+        csr.free()
+        hrp = torch.from_numpy(rp).pin_memory()
+        hci = torch.from_numpy(ci).pin_memory()
+        hvv = torch.from_numpy(vv).pin_memory()
+        del rp, ci, vv
+        Xh = (hrp.numpy(), hci.numpy(), hvv.numpy(), p)
+        fn = {(False, False): pcmf_b200.run_gap_factor, (True, False): pcmf_b200.run_zi_gap_factor,
+              (False, True): pcmf_b200.run_sparse_gap_factor, (True, True): pcmf_b200.run_zi_sparse_gap_factor}[(zi, sparse)]
+        kw = dict(verbose=False, monitor=True, iter_max=args.steps, iter_min=args.steps, epsilon=0.0, reorder_factor=False,
+                  seed=args.seed + 1000, device=local, comm=comm, n_global=n, row_offset=r0, return_prob_D=False)
+        if sparse:
+            kw.update(prob_S=prob_S, prior_S=prior_S)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res = fn(Xh, K, **kw)
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+        h2d = hrp.numel() * 8 + hci.numel() * 4 + hvv.numel() * 4 + (p * K + p) * 8 * (1 if sparse else 0)
+        d2h = 8 * (6 * nl * K + 6 * p * K) + (8 * (p * K + p) + 4 * p * K if sparse else 0) + (16 * p if zi else 0)
+        e2e = {"value": args.steps / t_e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds_total": t_e2e, "nb_iter": res["convergence"]["nb_iter"],
+               "note": "whole run_* call from pinned host CSR: H2D + CSC/bitmap preprocessing + init + %d iterations with ELBO "
+                       "+ D2H of the return object; copies and preprocessing are amortised over the %d steps" % (args.steps, args.steps)}
+    else:
+        csr.free()
+
+    cb = None
+    if rank == 0 and not args.no_cpu:
+        cb = cpu_baseline(cfg, U, V, args.seed, args.cpu_rows, 2)
+
+    if rank == 0:
+        line = {"metric": "VEM iterations/sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": cfg["label"], "n": n, "p": p, "K": K, "nnz": nnz, "density": nnz / (n * p),
+                           "model": ("zi_" if zi else "") + ("sparse_" if sparse else "") + "gap",
+                           "parallelism": "cells sharded over %d GPU(s), all-reduce of p x K gene statistics" % world,
+                           "l2": "inputs larger than L2 (CSR+CSC %.1f GB per rank); no explicit flush" % (16e-9 * nnz_local),
+                           "generator_seconds": t_gen},
+                "roofline": roofline, "kernels": kernels, "phases": phases, "cpu_baseline": cb, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clk, "fp64_peak_tflops_measured": fp64_peak,
+                "elbo_last": float(elbo[-1]), "conv_crit_last": float(crit[-1])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

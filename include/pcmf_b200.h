@@ -144,9 +144,11 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
 /* algorithm<model>::optimize (algorithm.h:158-210): runs until iter_max / convergence, continuing from the current
  * iteration counter.  Writes the per-iteration vectors and scalars of `res` (other fields untouched). */
 int pcmf_optimize(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen);
-/* exactly `niter` x { update_param; check_convergence; prepare_next_iterate } without the stopping rule
- * (teacher-forced parity tests and fixed-length timing).  conv_crit_out: niter doubles or NULL. */
-int pcmf_iterate(pcmf_solver *s, int niter, double *conv_crit_out, char *errbuf, size_t errlen);
+/* exactly `niter` x { update_param; [monitor]; check_convergence; prepare_next_iterate } without the stopping rule
+ * (teacher-forced parity tests and fixed-length timing).  conv_crit_out: niter doubles or NULL.
+ * elbo_out: niter doubles or NULL; when given, the ELBO is evaluated after every iteration like
+ * algorithm::monitor() does when monitor=TRUE (algorithm.h:391-397). */
+int pcmf_iterate(pcmf_solver *s, int niter, double *conv_crit_out, double *elbo_out, char *errbuf, size_t errlen);
 /* ELBO of the current state (model::optim_criterion, gap_factor_model.cpp:287-326 and variants);
  * terms (nullable): 11 doubles in the order gammaU, entU, gammaV, entV, bernS_prior, bernS_self, bernD_prior,
  * bernD_self, sumUVt, data, lgammaX */
@@ -176,6 +178,15 @@ int pcmf_generate_counts_device(int device, int64_t n_local, int32_t p, int32_t 
                                 const double *V, const double *prob1, uint64_t seed, int64_t row_offset,
                                 int64_t **rowptr_dev, int32_t **colidx_dev, float **val_dev, int64_t *nnz_out,
                                 char *errbuf, size_t errlen);
+/* Per-gene sums over the LOCAL cells of a CSR matrix (host or device resident): sum_i x, sum_i x^2, #non-zeros.
+ * Host outputs of length p.  This is what the R wrapper's prior_S heuristic needs (pCMF.R:228-229:
+ * 1 - exp(-sd_j / mean(X[X != 0]))) when X never exists as a dense matrix. */
+int pcmf_csr_column_stats(int device, int64_t n_local, int32_t p, const int64_t *rowptr, const int32_t *colidx,
+                          const float *val_f32, int32_t on_device, double *colsum, double *colsumsq, double *colnnz,
+                          char *errbuf, size_t errlen);
+/* Measured FP64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA microbenchmark, ~50 ms): the
+ * roofline denominator of the dense zero-inflation passes, which are FP64-pipe bound, not HBM bound. */
+int pcmf_measure_fp64_tflops(int device, double *tflops_out);
 int pcmf_device_free(int device, void *ptr);
 /* copy device CSR arrays to host buffers (bench e2e leg) */
 int pcmf_device_to_host(int device, void *dst_host, const void *src_dev, size_t bytes);

@@ -71,7 +71,7 @@ def lib():
     L.pcmf_fit.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(Init), C.POINTER(Result)] + err
     L.pcmf_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(Init), C.POINTER(C.c_void_p)] + err
     L.pcmf_optimize.argtypes = [C.c_void_p, C.POINTER(Result)] + err
-    L.pcmf_iterate.argtypes = [C.c_void_p, C.c_int, dp] + err
+    L.pcmf_iterate.argtypes = [C.c_void_p, C.c_int, dp, dp] + err
     L.pcmf_elbo.argtypes = [C.c_void_p, dp, dp] + err
     L.pcmf_order_factor.argtypes = [C.c_void_p] + err
     L.pcmf_monitors.argtypes = [C.c_void_p, dp, dp, dp] + err
@@ -85,11 +85,14 @@ def lib():
     L.pcmf_generate_counts_device.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, dp, dp, dp, C.c_uint64, C.c_int64,
                                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                               lp] + err
+    L.pcmf_csr_column_stats.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, dp, dp, dp] + err
+    L.pcmf_measure_fp64_tflops.argtypes = [C.c_int, dp]
     L.pcmf_device_free.argtypes = [C.c_int, C.c_void_p]
     L.pcmf_device_to_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
     for name in ("pcmf_fit", "pcmf_create", "pcmf_optimize", "pcmf_iterate", "pcmf_elbo", "pcmf_order_factor",
                  "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational", "pcmf_phase_times",
-                 "pcmf_generate_counts_device", "pcmf_device_free", "pcmf_device_to_host"):
+                 "pcmf_generate_counts_device", "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats",
+                 "pcmf_measure_fp64_tflops"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -104,4 +107,4 @@ def check(rc, errbuf):
 HEADER_SYMBOLS = ["pcmf_version", "pcmf_device_count", "pcmf_fit", "pcmf_create", "pcmf_optimize", "pcmf_iterate",
                   "pcmf_elbo", "pcmf_order_factor", "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational",
                   "pcmf_phase_times", "pcmf_launch_count", "pcmf_destroy", "pcmf_generate_counts_device",
-                  "pcmf_device_free", "pcmf_device_to_host"]
+                  "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats", "pcmf_measure_fp64_tflops"]

@@ -87,6 +87,44 @@ def generate_counts_device(n, p, K_true, U, V, prob1=None, seed=0, device=0, row
     return DeviceCSR(device, n, p, nnz.value, rp.value, ci.value, vv.value)
 
 
+def csr_column_stats(X, device=0):
+    """Per-gene (sum x, sum x^2, nnz) over the local cells of a DeviceCSR or host CSR tuple (rowptr, colidx, val_f32, p)."""
+    L = _lib.lib()
+    if isinstance(X, DeviceCSR):
+        n, p, rp, ci, vv, on_dev, keep = X.n, X.p, X.rowptr, X.colidx, X.val, 1, None
+        device = X.device
+    else:
+        rp_, ci_, vv_, p = X
+        rp_ = np.ascontiguousarray(rp_, np.int64)
+        ci_ = np.ascontiguousarray(ci_, np.int32)
+        vv_ = np.ascontiguousarray(vv_, np.float32)
+        keep = (rp_, ci_, vv_)
+        n, on_dev = len(rp_) - 1, 0
+        rp, ci, vv = (x.ctypes.data_as(C.c_void_p) for x in keep)
+    s1, s2, cn = np.zeros(p), np.zeros(p), np.zeros(p)
+    err = C.create_string_buffer(512)
+    rc = L.pcmf_csr_column_stats(device, n, p, rp, ci, vv, on_dev, s1.ctypes.data_as(_lib.dp), s2.ctypes.data_as(_lib.dp),
+                                 cn.ctypes.data_as(_lib.dp), err, 512)
+    _lib.check(rc, err)
+    return s1, s2, cn
+
+
+def prior_S_from_stats(colsum, colsumsq, colnnz, n, K):
+    """pCMF.R:228-229 from per-gene sums: prior_S = 1 - exp(-sd_j / mean(X[X != 0])), sd with the n-1 estimator."""
+    var = (colsumsq - colsum ** 2 / n) / (n - 1)
+    sd = np.sqrt(np.maximum(var, 0.0))
+    prior_S = 1 - np.exp(-sd / (colsum.sum() / colnnz.sum()))
+    return np.repeat(prior_S[:, None], K, axis=1), prior_S
+
+
+def measure_fp64_tflops(device=0):
+    t = C.c_double(0)
+    rc = _lib.lib().pcmf_measure_fp64_tflops(device, C.byref(t))
+    if rc:
+        raise PcmfError(rc, "fp64 peak measurement failed")
+    return t.value
+
+
 class _Comm:
     """Sum all-reduce over torch.distributed for the cell-sharded run (one process per GPU).  The device buffer the
     library hands to the callback is wrapped zero-copy through __cuda_array_interface__."""
@@ -270,11 +308,14 @@ class Solver:
         except Exception:
             pass
 
-    def iterate(self, niter=1):
+    def iterate(self, niter=1, with_elbo=False):
+        """niter x (update_param, check_convergence, prepare_next_iterate); returns conv_crit[, elbo] per iteration."""
         crit = np.zeros(max(niter, 1))
+        elbo = np.zeros(max(niter, 1))
         err = C.create_string_buffer(512)
-        _lib.check(self.L.pcmf_iterate(self.h, int(niter), crit.ctypes.data_as(_lib.dp), err, 512), err)
-        return crit[:niter]
+        _lib.check(self.L.pcmf_iterate(self.h, int(niter), crit.ctypes.data_as(_lib.dp),
+                                       elbo.ctypes.data_as(_lib.dp) if with_elbo else None, err, 512), err)
+        return (crit[:niter], elbo[:niter]) if with_elbo else crit[:niter]
 
     def elbo(self, terms=False):
         e = C.c_double(0)

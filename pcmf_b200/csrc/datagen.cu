@@ -4,6 +4,7 @@
 // written straight into CSR (two passes: count, fill).  Philox counter-based streams keyed by the GLOBAL entry index,
 // so the matrix does not depend on the launch configuration or on how cells are sharded over GPUs.
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -123,5 +124,93 @@ extern "C" int pcmf_generate_counts_device(int device, int64_t n_local, int32_t 
     GK(cudaGetLastError());
     cudaFree(tmp); cudaFree(rc); cudaFree(dU); cudaFree(dV); cudaFree(dUr); cudaFree(dVr); if (dP) cudaFree(dP);
     *rowptr_dev = rp; *colidx_dev = ci; *val_dev = vv; *nnz_out = nnz;
+    return PCMF_OK;
+}
+
+
+// ---- per-gene statistics of a CSR matrix ---------------------------------------------------------------------
+namespace {
+__global__ void k_col_stats(int64_t n, const int64_t *rowptr, const int32_t *colidx, const float *val, double *s1, double *s2,
+                            double *cn) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nw)
+        for (int64_t e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) {
+            const int j = colidx[e];
+            const double x = (double)val[e];
+            atomicAdd(s1 + j, x); atomicAdd(s2 + j, x * x); atomicAdd(cn + j, x != 0.0 ? 1.0 : 0.0);
+        }
+}
+__global__ void k_dfma_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+}  // namespace
+
+extern "C" int pcmf_csr_column_stats(int device, int64_t n_local, int32_t p, const int64_t *rowptr, const int32_t *colidx,
+                                     const float *val_f32, int32_t on_device, double *colsum, double *colsumsq, double *colnnz,
+                                     char *errbuf, size_t errlen) {
+    if (!rowptr || !colidx || !val_f32 || !colsum || !colsumsq || !colnnz) {
+        if (errbuf && errlen) snprintf(errbuf, errlen, "bad argument to pcmf_csr_column_stats");
+        return PCMF_EINVAL;
+    }
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        if (errbuf && errlen) snprintf(errbuf, errlen, "no CUDA device available");
+        return PCMF_ECUDA;
+    }
+    GK(cudaSetDevice(device));
+    const int64_t *rp = rowptr; const int32_t *ci = colidx; const float *vv = val_f32;
+    int64_t *drp = nullptr; int32_t *dci = nullptr; float *dvv = nullptr;
+    if (!on_device) {
+        const int64_t nnz = rowptr[n_local];
+        GK(cudaMalloc(&drp, (size_t)(n_local + 1) * 8)); GK(cudaMalloc(&dci, (size_t)std::max<int64_t>(nnz, 1) * 4));
+        GK(cudaMalloc(&dvv, (size_t)std::max<int64_t>(nnz, 1) * 4));
+        GK(cudaMemcpy(drp, rowptr, (size_t)(n_local + 1) * 8, cudaMemcpyHostToDevice));
+        GK(cudaMemcpy(dci, colidx, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+        GK(cudaMemcpy(dvv, val_f32, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+        rp = drp; ci = dci; vv = dvv;
+    }
+    double *d = nullptr;
+    GK(cudaMalloc(&d, (size_t)p * 3 * 8));
+    GK(cudaMemset(d, 0, (size_t)p * 3 * 8));
+    const int grid = (int)std::min<int64_t>((n_local * 32 + 255) / 256, 148 * 32);
+    k_col_stats<<<grid, 256>>>(n_local, rp, ci, vv, d, d + p, d + 2 * (size_t)p);
+    GK(cudaMemcpy(colsum, d, (size_t)p * 8, cudaMemcpyDeviceToHost));
+    GK(cudaMemcpy(colsumsq, d + p, (size_t)p * 8, cudaMemcpyDeviceToHost));
+    GK(cudaMemcpy(colnnz, d + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d); if (drp) cudaFree(drp); if (dci) cudaFree(dci); if (dvv) cudaFree(dvv);
+    return PCMF_OK;
+}
+
+extern "C" int pcmf_measure_fp64_tflops(int device, double *tflops_out) {
+    char *errbuf = nullptr; size_t errlen = 0;
+    if (!tflops_out) return PCMF_EINVAL;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) return PCMF_ECUDA;
+    GK(cudaSetDevice(device));
+    cudaDeviceProp dp; GK(cudaGetDeviceProperties(&dp, device));
+    double *out = nullptr; GK(cudaMalloc(&out, 8));
+    cudaEvent_t e0, e1; GK(cudaEventCreate(&e0)); GK(cudaEventCreate(&e1));
+    const int blocks = dp.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    k_dfma_peak<<<blocks, threads>>>(out, 1024);   // warm-up
+    double best = 0;
+    for (int r = 0; r < 3; ++r) {
+        GK(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, threads>>>(out, iters);
+        GK(cudaEventRecord(e1));
+        GK(cudaEventSynchronize(e1));
+        float ms = 0; GK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops_out = best;
     return PCMF_OK;
 }

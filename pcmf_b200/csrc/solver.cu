@@ -682,17 +682,21 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
 
 void pcmf_destroy(pcmf_solver *s) { delete s; }
 
-int pcmf_iterate(pcmf_solver *s, int niter, double *conv_crit_out, char *errbuf, size_t errlen) {
+int pcmf_iterate(pcmf_solver *s, int niter, double *conv_crit_out, double *elbo_out, char *errbuf, size_t errlen) {
     return guarded(errbuf, errlen, [&] {
         if (!s) fail(PCMF_EINVAL, "null solver");
         CK(cudaSetDevice(s->device));
         for (int it = 0; it < niter; ++it) {
-            s->step(false);
+            // the data term of the ELBO of iterate t is a by-product of the E-step of iterate t+1 (same statistics)
+            const bool want = elbo_out && it > 0;
+            s->step(want);
+            if (want) elbo_out[it - 1] = s->last_nodata + s->h_scal[S_DATA];
             const double crit = s->opt.conv_mode == 0 ? s->h_scal[S_ABS_GAP] : s->h_scal[S_NORM_GAP];
             if (conv_crit_out) conv_crit_out[it] = crit;
             s->last_nodata = s->h_scal[S_ELBO_NODATA];
             s->iter++;
         }
+        if (elbo_out && niter > 0) elbo_out[niter - 1] = s->last_nodata + s->data_term_now();
     });
 }
 
