@@ -29,21 +29,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: n, p, K_true, K, prob1, target density, zi, sparse
-    "c4": dict(n=1_000_000, p=20_000, K_true=20, K=20, prob1=0.4, density=0.05, zi=True, sparse=True,
+    # Synthetic inputs follow the package's generative model (data_generation.R): X = Poisson(U V^T) * Bernoulli(prob1_j).
+    # `mean_rate` is the mean Poisson rate before drop-out; density ~= prob1 * P(Poisson > 0).  The sparse-V runs pass
+    # prob_S = prior_S = 0.5 explicitly, as the reference's own tests do (test-gap_factor_model.R:641-690): with the
+    # pCMF.R:228 heuristic ~99% of the genes have prior_S < sel_bound at 5% density and are masked out from iteration 0,
+    # and with mean counts ~1 the reference's spike-and-slab update zeroes every loading, which would leave the E-step
+    # with nothing to do.
+    "c4": dict(n=1_000_000, p=20_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=True, sparse=True,
                label="C4: 1M cells x 20k genes, ~5% nnz, ZI + sparse-V, K=20"),
-    "c3": dict(n=50_000, p=5_000, K_true=20, K=20, prob1=0.5, density=0.30, zi=True, sparse=True,
+    "c3": dict(n=50_000, p=5_000, K_true=20, K=20, prob1=0.3, mean_rate=20.0, zi=True, sparse=True,
                label="C3: 50k x 5k, ~30% nnz, ZI + sparse-V, K=20"),
-    "c2": dict(n=10_000, p=2_000, K_true=10, K=10, prob1=None, density=None, zi=False, sparse=False,
+    "c2": dict(n=10_000, p=2_000, K_true=10, K=10, prob1=None, mean_rate=20.0, zi=False, sparse=False,
                label="C2: 10k x 2k dense Gamma-Poisson, K=10"),
-    "tiny": dict(n=20_000, p=2_000, K_true=20, K=20, prob1=0.4, density=0.05, zi=True, sparse=True,
+    "c4gap": dict(n=1_000_000, p=20_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=False, sparse=False,
+                  label="C4 data, plain Gamma-Poisson (no ZI, no sparsity), K=20"),
+    "tiny": dict(n=20_000, p=2_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=True, sparse=True,
                  label="tiny: 20k x 2k, ~5% nnz, ZI + sparse-V, K=20 (smoke only)"),
 }
 
 
 def factor_matrices(cfg, seed):
     """U (n x K_true, 3 cell groups), V (p x K_true, 2 gene groups, 60% noise genes): SURVEY 8d / README.md:119-137.
-    U is rescaled by a constant calibrated on a row sample so that the realised density hits the target."""
+    U is rescaled so that the mean Poisson rate mean_ij (U V^T)_ij equals cfg['mean_rate']."""
     from pcmf_b200 import datagen
     rng = np.random.Generator(np.random.Philox(seed))
     n, p, Kt = cfg["n"], cfg["p"], cfg["K_true"]
@@ -52,17 +59,8 @@ def factor_matrices(cfg, seed):
     V = datagen.generate_factor_matrix(p, Kt, ngroup=2, average_signal=60.0, group_separation=0.8,
                                        distribution="exponential", shuffle_feature=True, prop_noise_feature=0.6,
                                        rng=rng)["factor_matrix"]
-    if cfg["density"] is not None:
-        keep = cfg["prob1"] if cfg["prob1"] is not None else 1.0
-        lam = U[:: max(1, n // 512)][:512] @ V.T
-        lo, hi = 1e-8, 1.0
-        for _ in range(60):   # density(c) = keep * mean(1 - exp(-c * lambda)) is increasing in c
-            mid = np.sqrt(lo * hi)
-            if keep * (1 - np.exp(-mid * lam)).mean() > cfg["density"]:
-                hi = mid
-            else:
-                lo = mid
-        U = U * np.sqrt(lo * hi)
+    mean_lam = float((U.mean(0) * V.mean(0)).sum())
+    U = U * (cfg["mean_rate"] / mean_lam)
     return U, V
 
 
@@ -138,8 +136,7 @@ def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None):
     a1, a2, b1, b2 = datagen.random_init(X, K, seed=seed + 1000)
     m = po.Model(X, K, cfg["zi"], cfg["sparse"])
     if cfg["sparse"]:
-        prob_S, prior_S = datagen.prior_S_heuristic(X, K)
-        m.init_sparse_param(0.5, prob_S, prior_S)
+        m.init_sparse_param(0.5, np.full((p, K), 0.5), np.full(p, 0.5))
     if cfg["zi"]:
         m.init_zi_param()
     m.init_variational_param(a1, a2, b1, b2)
@@ -188,6 +185,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=1500)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
+    ap.add_argument("--variant", type=int, default=0, help="experimental kernel variant bits")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -227,17 +225,12 @@ def main():
     # prior_S heuristic of the R wrapper (pCMF.R:228-229) from per-gene sums
     prob_S = prior_S = None
     if cfg["sparse"]:
-        s1, s2, cn = api.csr_column_stats(csr)
-        st = torch.tensor(np.stack([s1, s2, cn]), device="cuda")
-        if world > 1:
-            dist.all_reduce(st)
-        s1, s2, cn = st.cpu().numpy()
-        prob_S, prior_S = api.prior_S_from_stats(s1, s2, cn, n, K)
+        prob_S, prior_S = np.full((p, K), 0.5), np.full(p, 0.5)   # test-gap_factor_model.R:641-690
 
     stream = torch.cuda.current_stream()
     solver = pcmf_b200.Solver(csr, K, cfg["zi"], cfg["sparse"], seed=args.seed + 1000, prob_S=prob_S, prior_S=prior_S,
                               device=local, stream=stream.cuda_stream, comm=comm, n_global=n, row_offset=r0,
-                              iter_max=10 ** 6)
+                              iter_max=10 ** 6, kernel_variant=args.variant)
     # ---- warm-up, then exactly `steps` timed iterations (ELBO evaluated every iteration, as monitor=TRUE does)
     solver.iterate(args.warmup, with_elbo=True)
     ph0, l0 = solver.phase_times(), solver.launch_count()

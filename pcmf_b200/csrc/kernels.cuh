@@ -25,15 +25,31 @@ enum Scal : int {
 // guard block: min/max of ElogU / ElogV stored as ordered long long
 enum Guard : int { G_MINU = 0, G_MAXU, G_MINV, G_MAXV, G_COUNT };
 
-struct GuardView {
-    const long long *g;   // G_COUNT ordered ints
-};
-__device__ __forceinline__ bool need_exact(const long long *g) {
-    // gap_factor_model.cpp:483 (shift when max_k s_k >= 100) and internal.h:121-127 (floor below -100): the hoisted
-    // exp(ElogU)*exp(ElogV) form is only valid while neither guard can fire for any (i,j,k) of this rank.
-    const double mnU = dbl_from_ordered(g[G_MINU]), mxU = dbl_from_ordered(g[G_MAXU]);
-    const double mnV = dbl_from_ordered(g[G_MINV]), mxV = dbl_from_ordered(g[G_MAXV]);
-    return !(mxU + mxV < 99.0) || !(mnU + mnV > -99.0);
+// When may the multinomial weights be computed from the hoisted exponentials eu = exp(ElogU), ev = S o exp(ElogV)
+// (T_ij = eu_i . ev_j) instead of the reference's per-entry formula (gap_factor_model.cpp:481-487:
+// s_k = ElogU_ik + ElogV_jk, shift by max_k s_k only if it is >= 100, cexp floor 3e-44 below -100)?
+//   (1) no shift and no overflow: rowmax_i + max ElogV < 99 (resp. colmax_j + max ElogU), both below 700;
+//   (2) the floor only touches terms that are negligible: T >= 1e-26 (a floored term is <= 3.7e-44, so the two forms
+//       differ by < K * 3.7e-18 relative, below FP64 rounding), or every factor of the gene is masked (T == 0, r = 0);
+// anything else is recomputed with the exact formula for that entry only.
+struct PathFlags { bool force_exact; };
+__device__ __forceinline__ PathFlags path_flags(double own_min, double own_max, double other_min, double other_max) {
+    PathFlags f;
+    f.force_exact = !(own_max + other_max < 99.0) || !(own_max < 700.0) || !(other_max < 700.0);
+    (void)own_min; (void)other_min;
+    return f;
+}
+// exact multinomial terms of one entry: e_k = S_jk cexp(ElogU_ik + ElogV_jk - m), returns sum_k e_k (the shifted sum)
+template <int KP>
+__device__ __noinline__ double exact_terms(const double *__restrict__ elu, const double *__restrict__ elv,
+                                           const double *__restrict__ sd, int K, double *e) {
+    double m = -1e300;
+    for (int k = 0; k < K; ++k) { e[k] = elu[k] + elv[k]; m = fmax(m, e[k]); }
+    if (m < 100.0) m = 0.0;
+    double T = 0.0;
+    for (int k = 0; k < K; ++k) { e[k] = custom_exp(e[k] - m) * sd[k]; T += e[k]; }
+    for (int k = K; k < KP; ++k) e[k] = 0.0;
+    return T;
 }
 
 template <int KP>
@@ -93,18 +109,21 @@ struct RowArgs {
     const int32_t *colidx;
     const void *val;
     // V side (old stats)
-    const double *ev;      // p x KP: S o exp(ElogV)                      (fast path)
-    const double *evw;     // p x KP: ev o wS                              (fast path)
-    const double *ElogV;   // p x KP                                       (exact path)
-    const double *Sd;      // p x KP mask as double                        (exact path)
-    const double *wS;      // p x KP: prob_S o colw (or colw, or 1)        (exact path)
+    const double *ev;      // p x KP: S o exp(ElogV)
+    const double *evw;     // p x KP: ev o wS
+    const double *ElogV;   // p x KP                                       (exact fallback)
+    const double *Sd;      // p x KP mask as double                        (exact fallback)
+    const double *wS;      // p x KP: prob_S o colw (or colw, or 1)        (exact fallback)
+    const uint8_t *allmasked;   // p: 1 when S(j,.) is all zero (sparse models)
+    unsigned long long *dbg;    // [0] entries recomputed with the exact formula
     // U side, updated in place
     double *a1, *a2, *EU_new, *ElogU, *eu;
+    double2 *rowext;                 // n: (min_k, max_k) of ElogU per cell, read then refreshed
     const double *alpha1, *alpha2;   // K-vectors
     const double *rate_vec;          // KP: colsum(EV o prob_S) (non-ZI)   gap...cpp:531 / sparse...cpp:400
     const double *PV;                // n x KP: prob_D * (EV o prob_S) (ZI) zi...cpp:336 / zi_sparse...cpp:363
     int first_iter;                  // old iterate is Ones (gap_factor_model.cpp:72-75; never copied before iter 0)
-    const long long *guard_cur;      // guards of the stats being read
+    const long long *guard_cur;      // global extremes of the stats being read
     long long *guard_next;           // min/max of the new ElogU
     double *cs_eu, *cs_elog;         // KP each (atomic)
     double *usc;                     // 3 doubles (atomic): gap_d, gap_o, entropy of the local cells (all-reduced later)
@@ -116,56 +135,50 @@ struct RowArgs {
 // update_variational_gamma_param, factor U part (gap...cpp:530-532 and variants) + U_stats.
 template <int KP, typename VT>
 __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
-    const int lane = threadIdx.x & 31;
+    __shared__ double s_ex[8][KP];   // exact-path contributions of the warp's current cell
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
-    const int64_t warp0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int64_t warp0 = (int64_t)blockIdx.x * warps_per_block + w;
     const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
     const VT *__restrict__ val = static_cast<const VT *>(a.val);
-    const bool exact = need_exact(a.guard_cur);
+    const double gminV = dbl_from_ordered(a.guard_cur[G_MINV]), gmaxV = dbl_from_ordered(a.guard_cur[G_MAXV]);
+    const bool same_w = (a.evw == a.ev);
     UAcc acc[(KP + 31) / 32];
 
     for (int64_t i = warp0; i < a.n; i += nwarps) {
         double u[KP], r[KP];
-        load_vec<KP>((exact ? a.ElogU : a.eu) + i * KP, u);
+        load_vec<KP>(a.eu + i * KP, u);
 #pragma unroll
         for (int k = 0; k < KP; ++k) r[k] = 0.0;
+        for (int k = lane; k < KP; k += 32) s_ex[w][k] = 0.0;
+        __syncwarp();
+        const double2 ext = a.rowext[i];
+        const PathFlags pf = path_flags(ext.x, ext.y, gminV, gmaxV);
         const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
         for (int64_t e = e0 + lane; e < e1; e += 32) {
             const int j = __ldg(a.colidx + e);
             const double x = (double)__ldg(val + e);
-            if (!exact) {
-                double v[KP];
-                load_vec<KP>(a.ev + (int64_t)j * KP, v);
-                double T = 0.0;
+            double v[KP];
+            load_vec<KP>(a.ev + (int64_t)j * KP, v);
+            double T0 = 0.0, T1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < KP; ++k) T = fma(u[k], v[k], T);
-                const double q = x / (T > 0.0 ? T : 1.0);
-                if (a.evw != a.ev) load_vec<KP>(a.evw + (int64_t)j * KP, v);
+            for (int k = 0; k < KP; k += 2) { T0 = fma(u[k], v[k], T0); T1 = fma(u[k + 1], v[k + 1], T1); }
+            const double T = T0 + T1;
+            if (!pf.force_exact && T >= 1e-26) {
+                const double q = x / T;
+                if (!same_w) load_vec<KP>(a.evw + (int64_t)j * KP, v);
 #pragma unroll
                 for (int k = 0; k < KP; ++k) r[k] = fma(q, v[k], r[k]);
-            } else {
-                double s[KP], t[KP];
-                load_vec<KP>(a.ElogV + (int64_t)j * KP, s);
-                double m = -1e300;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
-                    s[k] += u[k];
-                    if (k < a.K) m = fmax(m, s[k]);
-                }
-                if (m < 100.0) m = 0.0;
-                load_vec<KP>(a.Sd + (int64_t)j * KP, t);
-                double T = 0.0;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
-                    s[k] = (k < a.K) ? custom_exp(s[k] - m) * t[k] : 0.0;
-                    T += s[k];
-                }
-                const double q = x / (T > 0.0 ? T : 1.0);
-                load_vec<KP>(a.wS + (int64_t)j * KP, t);
-#pragma unroll
-                for (int k = 0; k < KP; ++k) r[k] = fma(q * s[k], t[k], r[k]);
+            } else if (!a.allmasked[j]) {   // all-masked gene: T = 0, r_ijk = 0 (gap...cpp:487), nothing to add
+                atomicAdd(a.dbg, 1ull);
+                double ex[KP];
+                const double Tx = exact_terms<KP>(a.ElogU + i * KP, a.ElogV + (int64_t)j * KP, a.Sd + (int64_t)j * KP, a.K, ex);
+                const double q = x / (Tx > 0.0 ? Tx : 1.0);
+                for (int k = 0; k < a.K; ++k) atomicAdd(&s_ex[w][k], q * ex[k] * a.wS[(int64_t)j * KP + k]);
             }
         }
+        __syncwarp();
         // reduce over lanes; lane (k & 31) keeps component k
         double mine[(KP + 31) / 32], um[(KP + 31) / 32];
 #pragma unroll
@@ -173,23 +186,29 @@ __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
             const double t = warp_sum(r[k]);
             if ((k & 31) == lane) { mine[k >> 5] = t; um[k >> 5] = u[k]; }
         }
+        double emn = 1e300, emx = -1e300;
 #pragma unroll
         for (int c = 0; c < (KP + 31) / 32; ++c) {
             const int k = c * 32 + lane;
             if (k < a.K) {
                 const int64_t o = i * KP + k;
-                const double ez = exact ? mine[c] : um[c] * mine[c];
+                const double ez = um[c] * mine[c] + s_ex[w][k];
                 const double a1o = a.first_iter ? 1.0 : a.a1[o], a2o = a.first_iter ? 1.0 : a.a2[o];
                 const double a1n = a.alpha1[k] + ez;
                 const double a2n = a.alpha2[k] + (a.PV ? a.PV[o] : a.rate_vec[k]);
                 a.a1[o] = a1n;
                 a.a2[o] = a2n;
-                u_element(a1n, a2n, a1o, a2o, a.EU_new + o, a.ElogU + o, a.eu + o, acc[c]);
+                double el;
+                u_element(a1n, a2n, a1o, a2o, a.EU_new + o, &el, a.eu + o, acc[c]);
+                a.ElogU[o] = el;
+                emn = fmin(emn, el); emx = fmax(emx, el);
             }
         }
+        emn = warp_min(emn); emx = warp_max(emx);
+        if (lane == 0) a.rowext[i] = make_double2(emn, emx);
+        __syncwarp();
     }
     // flush per-lane partials
-    __shared__ double sh[32];
     double gd = 0, go = 0, en = 0, mn = 1e300, mx = -1e300;
 #pragma unroll
     for (int c = 0; c < (KP + 31) / 32; ++c) {
@@ -274,7 +293,10 @@ struct ColArgs {
     const void *val;
     const double *eu, *ElogU;         // n x KP
     const double *ev, *ElogV, *Sd;    // p x KP
-    const long long *guard;
+    const double2 *colext;            // p: (min_k, max_k) of ElogV per gene
+    const uint8_t *allmasked;         // p
+    unsigned long long *dbg;          // [1] entries recomputed with the exact formula
+    const long long *guard;           // global extremes (U part used)
     double *B1, *B2;                  // p x KP (plain stores: the block owns the gene)
     double *xlogT;                    // p
 };
@@ -283,27 +305,33 @@ __global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
     __shared__ double sh[4][KP];
     __shared__ double sh2[4][KP];
     __shared__ double shl[4];
+    __shared__ double sx1[KP], sx2[KP];   // exact-path contributions
     const VT *__restrict__ val = static_cast<const VT *>(a.val);
-    const bool exact = need_exact(a.guard);
+    const double gminU = dbl_from_ordered(a.guard[G_MINU]), gmaxU = dbl_from_ordered(a.guard[G_MAXU]);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int j = blockIdx.x; j < a.p; j += gridDim.x) {
-        double v[KP], b1[KP], b2[WITH_B2 ? KP : 1], msk[KP];
-        load_vec<KP>((exact ? a.ElogV : a.ev) + (int64_t)j * KP, v);
-        if (exact) load_vec<KP>(a.Sd + (int64_t)j * KP, msk);
+        double v[KP], b1[KP], b2[WITH_B2 ? KP : 1];
+        load_vec<KP>(a.ev + (int64_t)j * KP, v);
+        if (threadIdx.x < KP) { sx1[threadIdx.x] = 0.0; sx2[threadIdx.x] = 0.0; }
+        __syncthreads();
+        const double2 ext = a.colext[j];
+        const PathFlags pf = path_flags(ext.x, ext.y, gminU, gmaxU);
 #pragma unroll
         for (int k = 0; k < KP; ++k) { b1[k] = 0.0; if (WITH_B2) b2[k] = 0.0; }
         double lt = 0.0;
-        const int64_t e0 = a.colptr[j], e1 = a.colptr[j + 1];
+        // all-masked gene: every r_ijk is 0 (sparse...cpp:350-356), nothing to accumulate
+        const int64_t e0 = a.colptr[j], e1 = a.allmasked[j] ? a.colptr[j] : a.colptr[j + 1];
         for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
             const int64_t i = __ldg(a.rowidx + e);
             const double x = (double)__ldg(val + e);
             double u[KP];
-            if (!exact) {
-                load_vec<KP>(a.eu + i * KP, u);
-                double T = 0.0;
+            load_vec<KP>(a.eu + i * KP, u);
+            double T0 = 0.0, T1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < KP; ++k) T = fma(u[k], v[k], T);
-                const double q = x / (T > 0.0 ? T : 1.0);
+            for (int k = 0; k < KP; k += 2) { T0 = fma(u[k], v[k], T0); T1 = fma(u[k + 1], v[k + 1], T1); }
+            const double T = T0 + T1;
+            if (!pf.force_exact && T >= 1e-26) {
+                const double q = x / T;
                 if (WITH_LOGT) lt += x * log(T);
 #pragma unroll
                 for (int k = 0; k < KP; ++k) b1[k] = fma(q, u[k], b1[k]);
@@ -314,27 +342,14 @@ __global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
                     for (int k = 0; k < KP; ++k) b2[k] = fma(q * u[k], el[k], b2[k]);
                 }
             } else {
-                double el[KP];
-                load_vec<KP>(a.ElogU + i * KP, el);
-                double m = -1e300;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
-                    u[k] = el[k] + v[k];
-                    if (k < a.K) m = fmax(m, u[k]);
-                }
-                if (m < 100.0) m = 0.0;
-                double T = 0.0;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
-                    u[k] = (k < a.K) ? custom_exp(u[k] - m) * msk[k] : 0.0;
-                    T += u[k];
-                }
-                const double q = x / (T > 0.0 ? T : 1.0);
-                if (WITH_LOGT) lt += x * log(T);
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
-                    b1[k] = fma(q, u[k], b1[k]);
-                    if (WITH_B2) b2[k] = fma(q * u[k], el[k], b2[k]);
+                atomicAdd(a.dbg + 1, 1ull);
+                double ex[KP];
+                const double Tx = exact_terms<KP>(a.ElogU + i * KP, a.ElogV + (int64_t)j * KP, a.Sd + (int64_t)j * KP, a.K, ex);
+                const double q = x / (Tx > 0.0 ? Tx : 1.0);
+                if (WITH_LOGT) lt += x * log(Tx);
+                for (int k = 0; k < a.K; ++k) {
+                    atomicAdd(&sx1[k], q * ex[k]);
+                    if (WITH_B2) atomicAdd(&sx2[k], q * ex[k] * a.ElogU[i * KP + k]);
                 }
             }
         }
@@ -352,20 +367,18 @@ __global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
         __syncthreads();
         if (threadIdx.x < KP) {
             const int k = threadIdx.x;
-            double t = sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k];
             // fast path accumulated sum_i q eu_ik; e_ijk = eu_ik ev_jk
-            if (!exact) t *= __ldg(a.ev + (int64_t)j * KP + k);
-            a.B1[(int64_t)j * KP + k] = t;
-            if (WITH_B2) {
-                double t2 = sh2[0][k] + sh2[1][k] + sh2[2][k] + sh2[3][k];
-                if (!exact) t2 *= __ldg(a.ev + (int64_t)j * KP + k);
-                a.B2[(int64_t)j * KP + k] = t2;
-            }
+            const double evk = __ldg(a.ev + (int64_t)j * KP + k);
+            a.B1[(int64_t)j * KP + k] = (sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k]) * evk + sx1[k];
+            if (WITH_B2) a.B2[(int64_t)j * KP + k] = (sh2[0][k] + sh2[1][k] + sh2[2][k] + sh2[3][k]) * evk + sx2[k];
         }
         if (WITH_LOGT && threadIdx.x == 0) a.xlogT[j] = shl[0] + shl[1] + shl[2] + shl[3];
         __syncthreads();
     }
 }
+
+// (min_k, max_k) of a padded row-major matrix, one thread per row: per-cell / per-gene extremes for path_flags
+__global__ void k_row_extremes(int64_t rows, int K, int KP, const double *__restrict__ M, double2 *__restrict__ ext);
 
 // ------------------------------------------------------------------------------------------------------------
 // V-side M-step, one thread per (gene, factor): update_variational_gamma_param, factor V part
@@ -504,6 +517,7 @@ struct SparseArgs {
     int32_t *S;
     double *ev, *evw, *EVS, *wS;
     double *cs_evs;
+    uint8_t *allmasked;
     double *scal;
 };
 #ifdef PCMF_COMMON_KERNELS
@@ -518,6 +532,7 @@ __global__ void __launch_bounds__(128) k_sparse_genes(SparseArgs a) {
         const double cw = a.zi ? a.colw[j] : 1.0;
         const double lg = logit_clamped(pr);
         double rs = 0;
+        int any = 0;
         for (int k = 0; k < a.K; ++k) {
             const int64_t o = (int64_t)j * a.KP + k;
             double ps;
@@ -533,6 +548,7 @@ __global__ void __launch_bounds__(128) k_sparse_genes(SparseArgs a) {
                 ps = a.prob_S[o];
             }
             const int s = ps >= a.sel_bound;
+            any |= s;
             a.S[o] = s;
             a.Sd[o] = (double)s;
             const double evn = (double)s * exp(a.ElogV[o]);
@@ -544,6 +560,7 @@ __global__ void __launch_bounds__(128) k_sparse_genes(SparseArgs a) {
             atomicAdd(&scs[k], evs);
             rs += ps;
         }
+        a.allmasked[j] = any ? 0 : 1;
         const double prn = rs / a.K;
         a.prior_S[j] = prn;
         // likelihood::bernoulli_loglike_vec(prob_S, prior_S) with the intended gene index + bernoulli_loglike(prob_S, prob_S)
@@ -604,9 +621,12 @@ struct ZiAArgs {
     double *colsumP;             // p (atomic): colsum(prob_D) -> prior_D (zi...cpp:370-372)
     double *zsc;                 // 2 doubles (atomic): sum prob_D o UVt, sum P log P + (1-P) log(1-P)   (all-reduced later)
 };
-// Pass A: one thread per cell, genes streamed through shared memory in tiles of TJ.
+// Pass A: one thread per cell, genes streamed through shared memory in tiles of TJ, two genes per step.
+// Per (cell, gene): lambda = EU_i . EVS_j (K DFMA), P = expit(c_j - lambda) (fast_exp + fast_rcp, ~22 FP64 ops),
+// PV_i += P EVS_j (K DFMA).  The Bernoulli self term sum P log P + (1-P) log(1-P) = sum (1-P)(-z) - log(1+e^-z) keeps
+// a running product of (1+e^-z) and takes one log per ~hundred entries.
 template <int KP, int TJ>
-__global__ void __launch_bounds__(128) k_zi_pass_cells(ZiAArgs a) {
+__global__ void __launch_bounds__(128, 2) k_zi_pass_cells(ZiAArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_evs = reinterpret_cast<double *>(smem_raw);          // TJ x KP
     double *s_c = s_evs + TJ * KP;                                 // TJ
@@ -621,7 +641,7 @@ __global__ void __launch_bounds__(128) k_zi_pass_cells(ZiAArgs a) {
 #pragma unroll
     for (int k = 0; k < KP; ++k) { u[k] = 0.0; pv[k] = 0.0; }
     if (live) load_vec<KP>(a.EU + i * KP, u);
-    double sum_pl = 0, ent = 0;
+    double sum_pl = 0, ent_lin = 0, ent_log = 0, prod = 1.0;
     for (int j0 = 0; j0 < a.p; j0 += TJ) {
         __syncthreads();
         for (int t = threadIdx.x; t < TJ * KP; t += blockDim.x) {
@@ -638,36 +658,42 @@ __global__ void __launch_bounds__(128) k_zi_pass_cells(ZiAArgs a) {
         for (int jb = 0; jb < TJ; jb += 32) {
             if (j0 + jb >= a.p) break;
             const uint32_t bits = live ? a.bitT[(int64_t)((j0 + jb) >> 5) * a.n + i] : 0u;
-#pragma unroll 2
-            for (int c = 0; c < 32; ++c) {
-                const double *ev = s_evs + (jb + c) * KP;
-                double lam = 0.0;
+#pragma unroll 1
+            for (int c = 0; c < 32; c += 2) {
+                double v0[KP], v1[KP];
+                const double2 *e0 = reinterpret_cast<const double2 *>(s_evs + (jb + c) * KP);
+                const double2 *e1 = reinterpret_cast<const double2 *>(s_evs + (jb + c + 1) * KP);
+                double l0[4] = {0.0, 0.0, 0.0, 0.0}, l1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                 for (int k = 0; k < KP; k += 2) {
-                    const double2 t = *reinterpret_cast<const double2 *>(ev + k);
-                    lam = fma(u[k], t.x, lam);
-                    lam = fma(u[k + 1], t.y, lam);
+                    const double2 t0 = e0[k / 2], t1 = e1[k / 2];
+                    v0[k] = t0.x; v0[k + 1] = t0.y; v1[k] = t1.x; v1[k + 1] = t1.y;
+                    l0[k & 2] = fma(u[k], t0.x, l0[k & 2]); l0[(k & 2) + 1] = fma(u[k + 1], t0.y, l0[(k & 2) + 1]);
+                    l1[k & 2] = fma(u[k], t1.x, l1[k & 2]); l1[(k & 2) + 1] = fma(u[k + 1], t1.y, l1[(k & 2) + 1]);
                 }
-                const int f = live ? s_f[jb + c] : 3;
-                const double z = s_c[jb + c] - lam;
-                double pj;
-                if (f == 0) {
-                    if ((bits >> c) & 1u) pj = 1.0;
-                    else {
-                        pj = expit_clamped(z);
-                        // -bernoulli_loglike(prob_D, prob_D): sum over 0<P<1 of P log P + (1-P) log(1-P)
-                        //   = (1-P) * (-z) - log(1 + exp(-z))   with P = 1/(1+exp(-z))
-                        if (pj > 0.0 && pj < 1.0) ent += (1.0 - pj) * (-z) - log1p(exp(-z));
-                    }
-                } else pj = (f == 1) ? 1.0 : 0.0;
-                sum_pl = fma(pj, lam, sum_pl);                     // sum prob_D o UVt  (zi...cpp:182)
+                const double lam0 = (l0[0] + l0[1]) + (l0[2] + l0[3]), lam1 = (l1[0] + l1[1]) + (l1[2] + l1[3]);
+                const int f0 = live ? s_f[jb + c] : 3, f1 = live ? s_f[jb + c + 1] : 3;
+                const double z0 = s_c[jb + c] - lam0, z1 = s_c[jb + c + 1] - lam1;
+                double y0, y1;
+                bool in0, in1;
+                double p0 = fast_expit(z0, y0, in0), p1 = fast_expit(z1, y1, in1);
+                // exact entries: X != 0 -> 1 (zi...cpp:359-360); whole-gene shortcuts (zi...cpp:353-356)
+                const bool nz0 = (bits >> c) & 1u, nz1 = (bits >> (c + 1)) & 1u;
+                p0 = (f0 == 0) ? (nz0 ? 1.0 : p0) : ((f0 == 1) ? 1.0 : 0.0);
+                p1 = (f1 == 0) ? (nz1 ? 1.0 : p1) : ((f1 == 1) ? 1.0 : 0.0);
+                // -bernoulli_loglike(prob_D, prob_D) over 0 < P < 1 (1/(1+e^-z) is strictly inside (0,1) unless clamped)
+                const bool g0 = (f0 == 0) && !nz0 && in0;
+                const bool g1 = (f1 == 0) && !nz1 && in1;
+                ent_lin = fma(g0 ? (1.0 - p0) : 0.0, -z0, ent_lin);
+                ent_lin = fma(g1 ? (1.0 - p1) : 0.0, -z1, ent_lin);
+                prod *= (g0 ? y0 : 1.0) * (g1 ? y1 : 1.0);
+                sum_pl = fma(p0, lam0, sum_pl);                    // sum prob_D o UVt  (zi...cpp:182)
+                sum_pl = fma(p1, lam1, sum_pl);
 #pragma unroll
-                for (int k = 0; k < KP; k += 2) {
-                    const double2 t = *reinterpret_cast<const double2 *>(ev + k);
-                    pv[k] = fma(pj, t.x, pv[k]);
-                    pv[k + 1] = fma(pj, t.y, pv[k + 1]);
-                }
-                s_P[(w * 32 + c) * 33 + lane] = pj;
+                for (int k = 0; k < KP; ++k) pv[k] = fma(p1, v1[k], fma(p0, v0[k], pv[k]));
+                s_P[(w * 32 + c) * 33 + lane] = p0;
+                s_P[(w * 32 + c + 1) * 33 + lane] = p1;
+                if ((c & 6) == 6 && prod > 1e100) { ent_log += log(prod); prod = 1.0; }   // (1+e^30)^8 < 1e105
             }
             __syncwarp();
             double cs = 0.0;   // lane l sums gene (jb + l) over the warp's 32 cells
@@ -686,6 +712,93 @@ __global__ void __launch_bounds__(128) k_zi_pass_cells(ZiAArgs a) {
 #pragma unroll
         for (int k = 0; k < KP; k += 2) o[k / 2] = make_double2(pv[k], pv[k + 1]);
     }
+    double ent = ent_lin - (ent_log + log(prod));
+    sum_pl = block_sum(sum_pl, sh); ent = block_sum(ent, sh);
+    if (threadIdx.x == 0) { atomicAdd(a.zsc + 0, sum_pl); atomicAdd(a.zsc + 1, ent); }
+}
+
+// Variant 1 of pass A: one gene per step, the gene vector is re-read from shared memory for the PV update instead of
+// being cached -> ~half the registers, twice the resident warps (occupancy instead of ILP).
+template <int KP, int TJ>
+__global__ void __launch_bounds__(128, 3) k_zi_pass_cells_v1(ZiAArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_evs = reinterpret_cast<double *>(smem_raw);
+    double *s_c = s_evs + TJ * KP;
+    double *s_cs = s_c + TJ;
+    double *s_P = s_cs + 4 * TJ;
+    int *s_f = reinterpret_cast<int *>(s_P + 4 * 32 * 33);
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    double u[KP], pv[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { u[k] = 0.0; pv[k] = 0.0; }
+    if (live) load_vec<KP>(a.EU + i * KP, u);
+    double sum_pl = 0, ent_lin = 0, ent_log = 0, prod = 1.0;
+    for (int j0 = 0; j0 < a.p; j0 += TJ) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < TJ * KP; t += blockDim.x) {
+            const int jj = j0 + t / KP;
+            s_evs[t] = jj < a.p ? a.EVS[(int64_t)j0 * KP + t] : 0.0;
+        }
+        for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
+            const int jj = j0 + t;
+            s_c[t] = jj < a.p ? a.cz[jj] : 0.0;
+            s_f[t] = jj < a.p ? a.flag[jj] : 3;
+        }
+        for (int t = threadIdx.x; t < 4 * TJ; t += blockDim.x) s_cs[t] = 0.0;
+        __syncthreads();
+        for (int jb = 0; jb < TJ; jb += 32) {
+            if (j0 + jb >= a.p) break;
+            const uint32_t bits = live ? a.bitT[(int64_t)((j0 + jb) >> 5) * a.n + i] : 0u;
+#pragma unroll 2
+            for (int c = 0; c < 32; ++c) {
+                const double2 *e0 = reinterpret_cast<const double2 *>(s_evs + (jb + c) * KP);
+                double l0a = 0.0, l0b = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t0 = e0[k / 2];
+                    l0a = fma(u[k], t0.x, l0a); l0b = fma(u[k + 1], t0.y, l0b);
+                }
+                const double lam0 = l0a + l0b;
+                const int f0 = live ? s_f[jb + c] : 3;
+                const double z0 = s_c[jb + c] - lam0;
+                double y0;
+                bool in0;
+                double p0 = fast_expit(z0, y0, in0);
+                const bool nz0 = (bits >> c) & 1u;
+                p0 = (f0 == 0) ? (nz0 ? 1.0 : p0) : ((f0 == 1) ? 1.0 : 0.0);
+                const bool g0 = (f0 == 0) && !nz0 && in0;
+                ent_lin = fma(g0 ? (1.0 - p0) : 0.0, -z0, ent_lin);
+                prod *= (g0 ? y0 : 1.0);
+                sum_pl = fma(p0, lam0, sum_pl);
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t0 = e0[k / 2];
+                    pv[k] = fma(p0, t0.x, pv[k]); pv[k + 1] = fma(p0, t0.y, pv[k + 1]);
+                }
+                s_P[(w * 32 + c) * 33 + lane] = p0;
+                if ((c & 7) == 7 && prod > 1e100) { ent_log += log(prod); prod = 1.0; }
+            }
+            __syncwarp();
+            double cs = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) cs += s_P[(w * 32 + lane) * 33 + r];
+            __syncwarp();
+            s_cs[w * TJ + jb + lane] += cs;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
+            if (j0 + t < a.p) atomicAdd(a.colsumP + j0 + t, s_cs[t] + s_cs[TJ + t] + s_cs[2 * TJ + t] + s_cs[3 * TJ + t]);
+        }
+    }
+    if (live) {
+        double2 *o = reinterpret_cast<double2 *>(a.PV + i * KP);
+#pragma unroll
+        for (int k = 0; k < KP; k += 2) o[k / 2] = make_double2(pv[k], pv[k + 1]);
+    }
+    double ent = ent_lin - (ent_log + log(prod));
     sum_pl = block_sum(sum_pl, sh); ent = block_sum(ent, sh);
     if (threadIdx.x == 0) { atomicAdd(a.zsc + 0, sum_pl); atomicAdd(a.zsc + 1, ent); }
 }
@@ -700,19 +813,21 @@ struct ZiBArgs {
     const uint32_t *bitB;        // [ceil(n/32)][p]: bit r of word (ib, j) <-> X(32 ib + r, j) != 0
     double *tmpMat;              // p x KP (atomic): prob_D^T EU_new (zi...cpp:341, zi_sparse...:369)
 };
-// Pass B: one thread per gene, cells streamed through shared memory in tiles of TI (multiple of 32).
+// Pass B: one thread per TWO genes (j and j + 128), cells streamed through shared memory in tiles of TI (multiple
+// of 32); every broadcast shared-memory load of a cell's EU feeds four DFMAs.
 template <int KP, int TI>
-__global__ void __launch_bounds__(128) k_zi_pass_genes(ZiBArgs a) {
+__global__ void __launch_bounds__(128, 2) k_zi_pass_genes(ZiBArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_uz = reinterpret_cast<double *>(smem_raw);   // TI x KP
     double *s_un = s_uz + TI * KP;                         // TI x KP
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = j < a.p;
-    double v[KP], acc[KP];
+    const int jA = blockIdx.x * 256 + threadIdx.x, jB = jA + 128;
+    const bool liveA = jA < a.p, liveB = jB < a.p;
+    double vA[KP], vB[KP], accA[KP], accB[KP];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) { v[k] = 0.0; acc[k] = 0.0; }
-    double c = 0.0; int f = 3;
-    if (live) { load_vec<KP>(a.EVSz + (int64_t)j * KP, v); c = a.cz[j]; f = a.flag[j]; }
+    for (int k = 0; k < KP; ++k) { vA[k] = 0.0; vB[k] = 0.0; accA[k] = 0.0; accB[k] = 0.0; }
+    double cA = 0.0, cB = 0.0; int fA = 3, fB = 3;
+    if (liveA) { load_vec<KP>(a.EVSz + (int64_t)jA * KP, vA); cA = a.cz[jA]; fA = a.flag[jA]; }
+    if (liveB) { load_vec<KP>(a.EVSz + (int64_t)jB * KP, vB); cB = a.cz[jB]; fB = a.flag[jB]; }
     const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_chunk;
     const int64_t r1 = min(a.n, r0 + a.rows_per_chunk);
     for (int64_t i0 = r0; i0 < r1; i0 += TI) {
@@ -726,36 +841,97 @@ __global__ void __launch_bounds__(128) k_zi_pass_genes(ZiBArgs a) {
         __syncthreads();
         for (int ib = 0; ib < TI; ib += 32) {
             if (i0 + ib >= r1) break;
-            const uint32_t bits = live ? a.bitB[(int64_t)((i0 + ib) >> 5) * a.p + j] : 0u;
-#pragma unroll 4
+            const int64_t wrow = (i0 + ib) >> 5;
+            const uint32_t bitsA = liveA ? a.bitB[wrow * a.p + jA] : 0u;
+            const uint32_t bitsB = liveB ? a.bitB[wrow * a.p + jB] : 0u;
+#pragma unroll 2
             for (int r = 0; r < 32; ++r) {
-                const double *uz = s_uz + (ib + r) * KP;
-                const double *un = s_un + (ib + r) * KP;
-                double lam = 0.0;
+                const double2 *uz = reinterpret_cast<const double2 *>(s_uz + (ib + r) * KP);
+                const double2 *un = reinterpret_cast<const double2 *>(s_un + (ib + r) * KP);
+                double la0 = 0.0, la1 = 0.0, lb0 = 0.0, lb1 = 0.0;
 #pragma unroll
                 for (int k = 0; k < KP; k += 2) {
-                    const double2 t = *reinterpret_cast<const double2 *>(uz + k);
-                    lam = fma(v[k], t.x, lam);
-                    lam = fma(v[k + 1], t.y, lam);
+                    const double2 t = uz[k / 2];
+                    la0 = fma(vA[k], t.x, la0); la1 = fma(vA[k + 1], t.y, la1);
+                    lb0 = fma(vB[k], t.x, lb0); lb1 = fma(vB[k + 1], t.y, lb1);
                 }
-                double pj;
-                if (f == 0) pj = ((bits >> r) & 1u) ? 1.0 : expit_clamped(c - lam);
-                else pj = (f == 1) ? 1.0 : 0.0;
-                if (i0 + ib + r >= r1) pj = 0.0;
+                double y;
+                bool in_;
+                double pA = fast_expit(cA - (la0 + la1), y, in_), pB = fast_expit(cB - (lb0 + lb1), y, in_);
+                pA = (fA == 0) ? (((bitsA >> r) & 1u) ? 1.0 : pA) : ((fA == 1) ? 1.0 : 0.0);
+                pB = (fB == 0) ? (((bitsB >> r) & 1u) ? 1.0 : pB) : ((fB == 1) ? 1.0 : 0.0);
+                if (i0 + ib + r >= r1) { pA = 0.0; pB = 0.0; }
 #pragma unroll
                 for (int k = 0; k < KP; k += 2) {
-                    const double2 t = *reinterpret_cast<const double2 *>(un + k);
-                    acc[k] = fma(pj, t.x, acc[k]);
-                    acc[k + 1] = fma(pj, t.y, acc[k + 1]);
+                    const double2 t = un[k / 2];
+                    accA[k] = fma(pA, t.x, accA[k]); accA[k + 1] = fma(pA, t.y, accA[k + 1]);
+                    accB[k] = fma(pB, t.x, accB[k]); accB[k + 1] = fma(pB, t.y, accB[k + 1]);
                 }
             }
         }
     }
-    if (live) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k)
-            if (k < a.K) atomicAdd(a.tmpMat + (int64_t)j * KP + k, acc[k]);
+    for (int k = 0; k < KP; ++k) {
+        if (k < a.K) {
+            if (liveA) atomicAdd(a.tmpMat + (int64_t)jA * KP + k, accA[k]);
+            if (liveB) atomicAdd(a.tmpMat + (int64_t)jB * KP + k, accB[k]);
+        }
     }
+}
+
+// Variant 1 of pass B: one gene per thread (half the registers, twice the resident warps).
+template <int KP, int TI>
+__global__ void __launch_bounds__(128, 4) k_zi_pass_genes_v1(ZiBArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_uz = reinterpret_cast<double *>(smem_raw);
+    double *s_un = s_uz + TI * KP;
+    const int jA = blockIdx.x * 128 + threadIdx.x;
+    const bool liveA = jA < a.p;
+    double vA[KP], accA[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { vA[k] = 0.0; accA[k] = 0.0; }
+    double cA = 0.0; int fA = 3;
+    if (liveA) { load_vec<KP>(a.EVSz + (int64_t)jA * KP, vA); cA = a.cz[jA]; fA = a.flag[jA]; }
+    const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_chunk;
+    const int64_t r1 = min(a.n, r0 + a.rows_per_chunk);
+    for (int64_t i0 = r0; i0 < r1; i0 += TI) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < TI * KP; t += blockDim.x) {
+            const int64_t ii = i0 + t / KP;
+            const bool ok = ii < r1;
+            s_uz[t] = ok ? a.EUz[i0 * KP + t] : 0.0;
+            s_un[t] = ok ? a.EUn[i0 * KP + t] : 0.0;
+        }
+        __syncthreads();
+        for (int ib = 0; ib < TI; ib += 32) {
+            if (i0 + ib >= r1) break;
+            const uint32_t bitsA = liveA ? a.bitB[((i0 + ib) >> 5) * a.p + jA] : 0u;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                const double2 *uz = reinterpret_cast<const double2 *>(s_uz + (ib + r) * KP);
+                const double2 *un = reinterpret_cast<const double2 *>(s_un + (ib + r) * KP);
+                double la0 = 0.0, la1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t = uz[k / 2];
+                    la0 = fma(vA[k], t.x, la0); la1 = fma(vA[k + 1], t.y, la1);
+                }
+                double y;
+                bool in_;
+                double pA = fast_expit(cA - (la0 + la1), y, in_);
+                pA = (fA == 0) ? (((bitsA >> r) & 1u) ? 1.0 : pA) : ((fA == 1) ? 1.0 : 0.0);
+                if (i0 + ib + r >= r1) pA = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t = un[k / 2];
+                    accA[k] = fma(pA, t.x, accA[k]); accA[k + 1] = fma(pA, t.y, accA[k + 1]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+        if (k < a.K && liveA) atomicAdd(a.tmpMat + (int64_t)jA * KP + k, accA[k]);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -901,6 +1077,15 @@ __global__ void k_rowpad_to_colmajor_i32(int64_t rows, int K, int KP, const int3
         const int64_t r = o % rows;
         const int k = (int)(o / rows);
         dst[o] = src[r * KP + k];
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_row_extremes(int64_t rows, int K, int KP, const double *__restrict__ M, double2 *__restrict__ ext) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        double mn = 1e300, mx = -1e300;
+        for (int k = 0; k < K; ++k) { const double v = M[r * KP + k]; mn = fmin(mn, v); mx = fmax(mx, v); }
+        ext[r] = make_double2(mn, mx);
     }
 }
 #endif  // PCMF_COMMON_KERNELS

@@ -30,26 +30,34 @@ void launch_gene_pass(bool f32, int mode, const ColArgs &a, int grid, cudaStream
     else launch_gene_t<double>(mode, a, grid, st);
 }
 
-void launch_zi_cells(const ZiAArgs &a, cudaStream_t st) {
+void launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
     const size_t smem = sizeof(double) * (ZI_TJ * KP + ZI_TJ + 4 * ZI_TJ + 4 * 32 * 33) + sizeof(int) * ZI_TJ;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_pass_cells<KP, ZI_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_zi_pass_cells_v1<KP, ZI_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
     const int64_t grid = (a.n + 127) / 128;
-    k_zi_pass_cells<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
+    if (variant & 1) k_zi_pass_cells_v1<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
+    else k_zi_pass_cells<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
 }
 
-void launch_zi_genes(const ZiBArgs &a, int chunks, cudaStream_t st) {
+void launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
     const size_t smem = sizeof(double) * 2 * ZI_TI * KP;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_pass_genes<KP, ZI_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_zi_pass_genes_v1<KP, ZI_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    dim3 grid((a.p + 127) / 128, chunks);
-    k_zi_pass_genes<KP, ZI_TI><<<grid, 128, smem, st>>>(a);
+    if (variant & 2) {
+        dim3 grid((a.p + 127) / 128, chunks);
+        k_zi_pass_genes_v1<KP, ZI_TI><<<grid, 128, smem, st>>>(a);
+    } else {
+        dim3 grid((a.p + 255) / 256, chunks);
+        k_zi_pass_genes<KP, ZI_TI><<<grid, 128, smem, st>>>(a);
+    }
 }
 
 const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes};

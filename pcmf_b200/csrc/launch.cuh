@@ -11,8 +11,8 @@ struct Launchers {
     int KP;
     void (*estep_rows)(bool f32, const RowArgs &, int grid, int block, cudaStream_t);
     void (*gene_pass)(bool f32, int mode, const ColArgs &, int grid, cudaStream_t);
-    void (*zi_cells)(const ZiAArgs &, cudaStream_t);
-    void (*zi_genes)(const ZiBArgs &, int chunks, cudaStream_t);
+    void (*zi_cells)(const ZiAArgs &, int variant, cudaStream_t);
+    void (*zi_genes)(const ZiBArgs &, int chunks, int variant, cudaStream_t);
 };
 
 const Launchers *get_launchers_4();

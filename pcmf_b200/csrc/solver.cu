@@ -98,6 +98,9 @@ struct pcmf_solver {
     double *scal = nullptr;
     long long *guard[2] = {nullptr, nullptr};
     int gcur = 0;
+    double2 *rowext = nullptr, *colext = nullptr;
+    uint8_t *allmasked = nullptr;                   // per gene: every factor masked (sparse models)
+    unsigned long long *dbg = nullptr;              // [0] cells kernel, [1] gene kernel: entries that took the exact formula   // per-cell / per-gene (min_k, max_k) of E[log U] / E[log V]
     double *h_scal = nullptr;   // pinned
 
     // iteration state (algorithm.h:50-64)
@@ -148,7 +151,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { cudaFree((void *)rowptr); cudaFree((void *)colidx); cudaFree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1]};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -342,6 +345,9 @@ void pcmf_solver::alloc_state() {
     ar3 = dmalloc<double>(ar3_total); CK(cudaMemsetAsync(ar3, 0, ar3_total * 8, stream));
     scal = dmalloc<double>(S_COUNT); CK(cudaMemsetAsync(scal, 0, S_COUNT * 8, stream));
     guard[0] = dmalloc<long long>(G_COUNT); guard[1] = dmalloc<long long>(G_COUNT);
+    rowext = dmalloc<double2>(n); colext = dmalloc<double2>(p);
+    allmasked = dmalloc<uint8_t>(p); CK(cudaMemsetAsync(allmasked, 0, p, stream));
+    dbg = dmalloc<unsigned long long>(4); CK(cudaMemsetAsync(dbg, 0, 32, stream));
     k_init_guard<<<1, 32, 0, stream>>>(guard[0]); k_init_guard<<<1, 32, 0, stream>>>(guard[1]);
     CK(cudaMallocHost(&h_scal, sizeof(double) * S_COUNT));
     for (int i = 0; i < PH_COUNT; ++i) { CK(cudaEventCreate(&ev_a[i])); CK(cudaEventCreate(&ev_b[i])); }
@@ -460,16 +466,18 @@ void pcmf_solver::run_init_stats() {
         SparseArgs sa{};
         sa.p = p; sa.K = K; sa.KP = KP; sa.zi = zi; sa.update = 0; sa.sel_bound = opt.sel_bound; sa.EV = EV; sa.ElogV = ElogV;
         sa.colw = colw; sa.prob_S = prob_S; sa.Sd = Sd; sa.prior_S = prior_S; sa.S = S; sa.ev = ev; sa.evw = evw; sa.EVS = EVS;
-        sa.wS = wS; sa.cs_evs = csv + 128; sa.scal = scal;
+        sa.wS = wS; sa.cs_evs = csv + 128; sa.allmasked = allmasked; sa.scal = scal;
         k_sparse_genes<<<grid_for(p, 128), 128, 0, stream>>>(sa);
     }
-    launches += 2 + (sparse ? 1 : 0);
+    k_row_extremes<<<grid_for(n, 256), 256, 0, stream>>>(n, K, KP, ElogU, rowext);
+    k_row_extremes<<<grid_for(p, 256), 256, 0, stream>>>(p, K, KP, ElogV, colext);
+    launches += 4 + (sparse ? 1 : 0);
     if (zi) {
         // init_zi_param (zi_gap_factor_model.cpp:98-105): prob_D = (X > 0); realised as pass A with c_j = -inf
         ZiPrepArgs zp{p, 1, prior_D, Lg, cz, colw, flag, scal};
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
         ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc};
-        L->zi_cells(za, stream);
+        L->zi_cells(za, opt.kernel_variant, stream);
         launches += 2;
     }
     allreduce(ar1 + ar1_cseu, 64 + 64 + 4);
@@ -500,7 +508,7 @@ void pcmf_solver::step(bool want_data) {
     // 1. E-step, gene side (old statistics): B1 [+ B2 | xlogT for the ELBO data term of the previous iterate]
     begin(PH_GENE_E);
     {
-        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT};
+        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT};
         const int mode = !want_data ? GENE_B1 : (sparse ? GENE_B1_B2 : GENE_B1_LOGT);
         L->gene_pass(f32, mode, ca, std::min<int>(p, sms * 32), stream);
     }
@@ -510,7 +518,7 @@ void pcmf_solver::step(bool want_data) {
     {
         RowArgs ra{};
         ra.n = n; ra.K = K; ra.rowptr = rowptr; ra.colidx = colidx; ra.val = val_csr; ra.ev = ev; ra.evw = evw; ra.ElogV = ElogV;
-        ra.Sd = Sd; ra.wS = wS; ra.a1 = a1; ra.a2 = a2; ra.EU_new = EU[nxt]; ra.ElogU = ElogU; ra.eu = eu; ra.alpha1 = alpha1;
+        ra.Sd = Sd; ra.wS = wS; ra.allmasked = allmasked; ra.dbg = dbg; ra.a1 = a1; ra.a2 = a2; ra.EU_new = EU[nxt]; ra.ElogU = ElogU; ra.eu = eu; ra.rowext = rowext; ra.alpha1 = alpha1;
         ra.alpha2 = alpha2; ra.rate_vec = csv + 128; ra.PV = zi ? PV : nullptr; ra.first_iter = first_iter; ra.guard_cur = gc;
         ra.guard_next = gn; ra.cs_eu = ar1 + ar1_cseu; ra.cs_elog = ar1 + ar1_cselog; ra.usc = ar1 + ar1_usc;
         // colsum(EV o prob_S) of the OLD state: csv+128 is re-accumulated during this iteration, hyp+256 keeps the copy
@@ -526,12 +534,13 @@ void pcmf_solver::step(bool want_data) {
         ZiBArgs zb{};
         zb.n = n; zb.p = p; zb.K = K; zb.EUz = EU[cur]; zb.EUn = EU[nxt]; zb.EVSz = EVS; zb.cz = cz; zb.flag = flag; zb.bitB = bitB;
         zb.tmpMat = ar1 + ar1_tmp;
-        const int gx = (p + 127) / 128;
-        int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, (int64_t)(sms * 4 + gx - 1) / gx));
+        const int gx = (opt.kernel_variant & 2) ? (p + 127) / 128 : (p + 255) / 256;
+        // enough (gene block, cell chunk) CTAs for >= 16 full waves at 2 resident CTAs per SM: a 2.1-wave grid measured 29% slower
+        int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, (int64_t)(sms * 2 * 16 + gx - 1) / gx));
         int64_t rpc = (n + chunks - 1) / chunks; rpc = (rpc + 63) / 64 * 64;
         chunks = (int)((n + rpc - 1) / rpc);
         zb.rows_per_chunk = rpc;
-        L->zi_genes(zb, chunks, stream);
+        L->zi_genes(zb, chunks, opt.kernel_variant, stream);
         end(PH_ZI_B, 1);
     }
     // 4. all-reduce of the gene-side sums + U partials over the row shards
@@ -548,12 +557,13 @@ void pcmf_solver::step(bool want_data) {
         va.prob_S = prob_S; va.Sd = Sd; va.colw = colw; va.ev = ev; va.evw = evw; va.EVS = EVS; va.wS = wS; va.guard_next = gn;
         va.cs_ev = csv; va.cs_elogv = csv + 64; va.cs_evs = csv + 128; va.scal = scal;
         k_mstep_genes<<<grid_for(pK, 256), 256, 0, stream>>>(va);
+        k_row_extremes<<<grid_for(p, 256), 256, 0, stream>>>(p, K, KP, ElogV, colext);
     }
-    end(PH_MSTEP_V, 1);
+    end(PH_MSTEP_V, 2);
     // 6. spike-and-slab probabilities: second non-zero pass with the new statistics and the old mask
     if (sparse) {
         begin(PH_GENE_S);
-        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, gn, ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
+        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, dbg, gn, ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
         L->gene_pass(f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
         allreduce(ar2, 2 * pK);
         end(PH_GENE_S, 1);
@@ -562,7 +572,7 @@ void pcmf_solver::step(bool want_data) {
         SparseArgs sa{};
         sa.p = p; sa.K = K; sa.KP = KP; sa.zi = zi; sa.update = 1; sa.sel_bound = opt.sel_bound; sa.B1 = ar2 + ar2_B1; sa.B2 = ar2 + ar2_B2;
         sa.tmpMat = ar1 + ar1_tmp; sa.cs_eu = ar1 + ar1_cseu; sa.EV = EV; sa.ElogV = ElogV; sa.colw = colw; sa.prob_S = prob_S; sa.Sd = Sd;
-        sa.prior_S = prior_S; sa.S = S; sa.ev = ev; sa.evw = evw; sa.EVS = EVS; sa.wS = wS; sa.cs_evs = csv + 128; sa.scal = scal;
+        sa.prior_S = prior_S; sa.S = S; sa.ev = ev; sa.evw = evw; sa.EVS = EVS; sa.wS = wS; sa.cs_evs = csv + 128; sa.allmasked = allmasked; sa.scal = scal;
         k_sparse_genes<<<grid_for(p, 128), 128, 0, stream>>>(sa);
         end(PH_SPARSE, 1);
     }
@@ -573,7 +583,7 @@ void pcmf_solver::step(bool want_data) {
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
         k_refresh_weights<<<grid_for(pK, 256), 256, 0, stream>>>(p, K, KP, sparse, prob_S, colw, ev, wS, evw);
         ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc};
-        L->zi_cells(za, stream);
+        L->zi_cells(za, opt.kernel_variant, stream);
         allreduce(ar3, ar3_total);
         end(PH_ZI_A, 3);
     }
@@ -592,7 +602,7 @@ void pcmf_solver::step(bool want_data) {
 // ELBO data term of the current state (gap...cpp:301-313, sparse...cpp:194-212): one gene pass, nothing updated.
 double pcmf_solver::data_term_now() {
     const size_t pK = (size_t)p * KP;
-    ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, guard[gcur], ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
+    ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, dbg, guard[gcur], ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
     L->gene_pass(f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
     allreduce(ar2, ar2_total);
     CK(cudaMemsetAsync(scal + S_DATA, 0, 8, stream));
@@ -845,6 +855,17 @@ int pcmf_phase_times(pcmf_solver *s, const char **names, double *ms, int64_t *la
         if (names) names[c] = kPhaseNames[i];
         if (ms) ms[c] = s->ph_ms[i];
         if (launches) launches[c] = s->ph_launch[i];
+        ++c;
+    }
+    // diagnostics: number of non-zero entries that had to be recomputed with the exact (guarded) multinomial formula
+    unsigned long long h[4] = {0, 0, 0, 0};
+    cudaSetDevice(s->device);
+    cudaMemcpy(h, s->dbg, 32, cudaMemcpyDeviceToHost);
+    static const char *dn[2] = {"exact_fallback_entries_cells", "exact_fallback_entries_genes"};
+    for (int i = 0; i < 2 && c < cap; ++i) {
+        if (names) names[c] = dn[i];
+        if (ms) ms[c] = 0.0;
+        if (launches) launches[c] = (int64_t)h[i];
         ++c;
     }
     return c;

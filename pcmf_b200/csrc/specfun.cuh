@@ -73,6 +73,55 @@ __device__ __forceinline__ double gamma_entropy1(double p1, double p2, double ps
     return (1.0 - p1) * psi + p1 + lgamma(p1) - log(p2);
 }
 
+// ---- fast FP64 exp / reciprocal for the dense zero-inflation passes (the FP64 pipe is their roofline) --------
+// exp(x) for |x| <= 700: n = rint(x log2 e), r = x - n ln2 (two-term Cody-Waite), degree-12 Taylor in |r| <= 0.347
+// (truncation 1.7e-16) evaluated with Estrin's scheme (dependency depth 5 instead of 12: these kernels are bound by
+// FP64 dependent-issue latency, not by instruction count), result scaled by 2^n through the exponent field.
+__device__ __forceinline__ double fast_exp(double x) {
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to nearest integer in the low word
+    double t = fma(x, 1.4426950408889634074, MAGIC);
+    const int n = __double2loint(t);
+    t -= MAGIC;
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    const double r2 = r * r;
+    const double p01 = 1.0 + r;
+    const double p23 = fma(1.66666666666666666667e-01, r, 0.5);                           // 1/2! + r/3!
+    const double p45 = fma(8.33333333333333333333e-03, r, 4.16666666666666666667e-02);    // 1/4! + r/5!
+    const double p67 = fma(1.98412698412698412698e-04, r, 1.38888888888888888889e-03);    // 1/6! + r/7!
+    const double p89 = fma(2.75573192239858906526e-06, r, 2.48015873015873015873e-05);    // 1/8! + r/9!
+    const double pab = fma(2.50521083854417187751e-08, r, 2.75573192239858906526e-07);    // 1/10! + r/11!
+    const double r4 = r2 * r2;
+    const double q0 = fma(r2, p23, p01);
+    const double q1 = fma(r2, p67, p45);
+    const double q2 = fma(r2, pab, p89);
+    const double r8 = r4 * r4;
+    const double s0 = fma(r4, q1, q0);
+    const double s1 = fma(r4, 2.08767569878680989792e-09, q2);                            // + r^4 / 12!
+    const double p = fma(r8, s1, s0);
+    return p * __hiloint2double((n + 1023) << 20, 0);
+}
+// 1/y for normal y: MUFU.RCP64H seed (relative error e <= 2^-23) + one third-order step r (1 + e + e^2) (error e^3)
+__device__ __forceinline__ double fast_rcp(double y) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    const double e = fma(-y, r, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(r, e2, r);
+}
+// internal::expit (internal.h:151-155) with the fast primitives; also returns y = 1 + exp(-z) (1 when clamped) and
+// whether the result is strictly inside (0,1).  The |z| >= 30 clamps are tested on the exponent word (integer pipe).
+__device__ __forceinline__ double fast_expit(double z, double &y_out, bool &interior) {
+    const int hi = __double2hiint(z);
+    const bool big = (hi & 0x7fffffff) >= 0x403E0000;     // |z| >= 30 (30.0 = 0x403E000000000000), also NaN/inf
+    const double zc = big ? 0.0 : z;
+    const double y = 1.0 + fast_exp(-zc);
+    const double pr = fast_rcp(y);
+    interior = !big;
+    y_out = big ? 1.0 : y;
+    return big ? ((hi < 0) ? 0.0 : 1.0) : pr;
+}
+
 // ---- warp helpers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
