@@ -130,8 +130,13 @@ def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None):
         X *= rng.uniform(size=X.shape) < cfg["prob1"]
     X[X.sum(1) == 0, 0] = 1
     X[0, X.sum(0) == 0] = 1
-    if threads:
-        po.lib().orc_set_num_threads(int(threads))
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the baseline)
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except Exception:
+            threads = os.cpu_count() or 1
+    po.lib().orc_set_num_threads(int(threads))
     cores = po.lib().orc_num_threads()
     a1, a2, b1, b2 = datagen.random_init(X, K, seed=seed + 1000)
     m = po.Model(X, K, cfg["zi"], cfg["sparse"])

@@ -140,7 +140,10 @@ class _Comm:
         def cb(ctx, devptr, count, stream):
             try:
                 t = self._wrap(devptr, count)
-                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+                # order the collective on the library's stream: its producers were enqueued there, its consumers follow there
+                s = torch.cuda.ExternalStream(int(stream)) if stream else torch.cuda.default_stream()
+                with torch.cuda.stream(s):
+                    self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
                 self.calls += 1
                 self.bytes += count * 8
                 return 0

@@ -295,6 +295,8 @@ struct ColArgs {
     const double *ev, *ElogV, *Sd;    // p x KP
     const double2 *colext;            // p: (min_k, max_k) of ElogV per gene
     const uint8_t *allmasked;         // p
+    const uint8_t *reuse;             // p or null: 1 -> copy the gene's sums from B1_src/B2_src instead of recomputing
+    const double *B1_src, *B2_src;    // p x KP: this rank's sums from the previous sparse-probability pass
     unsigned long long *dbg;          // [1] entries recomputed with the exact formula
     const long long *guard;           // global extremes (U part used)
     double *B1, *B2;                  // p x KP (plain stores: the block owns the gene)
@@ -310,6 +312,15 @@ __global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
     const double gminU = dbl_from_ordered(a.guard[G_MINU]), gmaxU = dbl_from_ordered(a.guard[G_MAXU]);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int j = blockIdx.x; j < a.p; j += gridDim.x) {
+        if (a.reuse && a.reuse[j]) {
+            // same statistics, same mask row as the sparse-probability pass of the previous iteration
+            // (sparse...cpp:448-451 vs :350-356): the sums are identical, copy them
+            if (threadIdx.x < KP) {
+                a.B1[(int64_t)j * KP + threadIdx.x] = a.B1_src[(int64_t)j * KP + threadIdx.x];
+                if (WITH_B2) a.B2[(int64_t)j * KP + threadIdx.x] = a.B2_src[(int64_t)j * KP + threadIdx.x];
+            }
+            continue;
+        }
         double v[KP], b1[KP], b2[WITH_B2 ? KP : 1];
         load_vec<KP>(a.ev + (int64_t)j * KP, v);
         if (threadIdx.x < KP) { sx1[threadIdx.x] = 0.0; sx2[threadIdx.x] = 0.0; }
@@ -518,6 +529,7 @@ struct SparseArgs {
     double *ev, *evw, *EVS, *wS;
     double *cs_evs;
     uint8_t *allmasked;
+    uint8_t *unchanged;   // p: 1 when the gene's mask row S(j,.) did not change in this update
     double *scal;
 };
 #ifdef PCMF_COMMON_KERNELS
@@ -532,7 +544,7 @@ __global__ void __launch_bounds__(128) k_sparse_genes(SparseArgs a) {
         const double cw = a.zi ? a.colw[j] : 1.0;
         const double lg = logit_clamped(pr);
         double rs = 0;
-        int any = 0;
+        int any = 0, chg = 0;
         for (int k = 0; k < a.K; ++k) {
             const int64_t o = (int64_t)j * a.KP + k;
             double ps;
@@ -549,6 +561,7 @@ __global__ void __launch_bounds__(128) k_sparse_genes(SparseArgs a) {
             }
             const int s = ps >= a.sel_bound;
             any |= s;
+            chg |= (s != a.S[o]);
             a.S[o] = s;
             a.Sd[o] = (double)s;
             const double evn = (double)s * exp(a.ElogV[o]);
@@ -561,6 +574,7 @@ __global__ void __launch_bounds__(128) k_sparse_genes(SparseArgs a) {
             rs += ps;
         }
         a.allmasked[j] = any ? 0 : 1;
+        a.unchanged[j] = (a.update && !chg) ? 1 : 0;
         const double prn = rs / a.K;
         a.prior_S[j] = prn;
         // likelihood::bernoulli_loglike_vec(prob_S, prior_S) with the intended gene index + bernoulli_loglike(prob_S, prob_S)

@@ -99,6 +99,9 @@ struct pcmf_solver {
     long long *guard[2] = {nullptr, nullptr};
     int gcur = 0;
     double2 *rowext = nullptr, *colext = nullptr;
+    uint8_t *unchanged = nullptr;                   // per gene: mask row unchanged by the last sparse update
+    double *ar2keep = nullptr;                      // this rank's sparse-pass sums before the all-reduce (world > 1)
+    bool sparse_sums_valid = false;                 // ar2 / ar2keep hold the sums of the current statistics
     uint8_t *allmasked = nullptr;                   // per gene: every factor masked (sparse models)
     unsigned long long *dbg = nullptr;              // [0] cells kernel, [1] gene kernel: entries that took the exact formula   // per-cell / per-gene (min_k, max_k) of E[log U] / E[log V]
     double *h_scal = nullptr;   // pinned
@@ -151,7 +154,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { cudaFree((void *)rowptr); cudaFree((void *)colidx); cudaFree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -347,6 +350,8 @@ void pcmf_solver::alloc_state() {
     guard[0] = dmalloc<long long>(G_COUNT); guard[1] = dmalloc<long long>(G_COUNT);
     rowext = dmalloc<double2>(n); colext = dmalloc<double2>(p);
     allmasked = dmalloc<uint8_t>(p); CK(cudaMemsetAsync(allmasked, 0, p, stream));
+    unchanged = dmalloc<uint8_t>(p); CK(cudaMemsetAsync(unchanged, 0, p, stream));
+    if (opt.world > 1) ar2keep = dmalloc<double>(2 * (size_t)p * KP);
     dbg = dmalloc<unsigned long long>(4); CK(cudaMemsetAsync(dbg, 0, 32, stream));
     k_init_guard<<<1, 32, 0, stream>>>(guard[0]); k_init_guard<<<1, 32, 0, stream>>>(guard[1]);
     CK(cudaMallocHost(&h_scal, sizeof(double) * S_COUNT));
@@ -466,7 +471,7 @@ void pcmf_solver::run_init_stats() {
         SparseArgs sa{};
         sa.p = p; sa.K = K; sa.KP = KP; sa.zi = zi; sa.update = 0; sa.sel_bound = opt.sel_bound; sa.EV = EV; sa.ElogV = ElogV;
         sa.colw = colw; sa.prob_S = prob_S; sa.Sd = Sd; sa.prior_S = prior_S; sa.S = S; sa.ev = ev; sa.evw = evw; sa.EVS = EVS;
-        sa.wS = wS; sa.cs_evs = csv + 128; sa.allmasked = allmasked; sa.scal = scal;
+        sa.wS = wS; sa.cs_evs = csv + 128; sa.allmasked = allmasked; sa.unchanged = unchanged; sa.scal = scal;
         k_sparse_genes<<<grid_for(p, 128), 128, 0, stream>>>(sa);
     }
     k_row_extremes<<<grid_for(n, 256), 256, 0, stream>>>(n, K, KP, ElogU, rowext);
@@ -490,7 +495,7 @@ void pcmf_solver::run_init_stats() {
     read_scal();
     CK(cudaGetLastError());
     last_nodata = h_scal[S_ELBO_NODATA];
-    first_iter = true; have_pending = false;
+    first_iter = true; have_pending = false; sparse_sums_valid = false;
 }
 
 // One VEM iteration: model.update_param() (model.cpp:243-246) + the quantities check_convergence needs.
@@ -508,7 +513,10 @@ void pcmf_solver::step(bool want_data) {
     // 1. E-step, gene side (old statistics): B1 [+ B2 | xlogT for the ELBO data term of the previous iterate]
     begin(PH_GENE_E);
     {
-        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT};
+        const bool reuse = sparse && sparse_sums_valid;
+        const double *src = (opt.world > 1) ? ar2keep : ar2;
+        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, reuse ? unchanged : nullptr, src + ar2_B1,
+                   src + ar2_B2, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT};
         const int mode = !want_data ? GENE_B1 : (sparse ? GENE_B1_B2 : GENE_B1_LOGT);
         L->gene_pass(f32, mode, ca, std::min<int>(p, sms * 32), stream);
     }
@@ -563,16 +571,19 @@ void pcmf_solver::step(bool want_data) {
     // 6. spike-and-slab probabilities: second non-zero pass with the new statistics and the old mask
     if (sparse) {
         begin(PH_GENE_S);
-        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, dbg, gn, ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
+        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, gn, ar2 + ar2_B1,
+                   ar2 + ar2_B2, ar2 + ar2_xlogT};
         L->gene_pass(f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
+        if (opt.world > 1) CK(cudaMemcpyAsync(ar2keep, ar2, 2 * pK * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         allreduce(ar2, 2 * pK);
+        sparse_sums_valid = true;
         end(PH_GENE_S, 1);
         begin(PH_SPARSE);
         CK(cudaMemsetAsync(csv + 128, 0, 64 * 8, stream));
         SparseArgs sa{};
         sa.p = p; sa.K = K; sa.KP = KP; sa.zi = zi; sa.update = 1; sa.sel_bound = opt.sel_bound; sa.B1 = ar2 + ar2_B1; sa.B2 = ar2 + ar2_B2;
         sa.tmpMat = ar1 + ar1_tmp; sa.cs_eu = ar1 + ar1_cseu; sa.EV = EV; sa.ElogV = ElogV; sa.colw = colw; sa.prob_S = prob_S; sa.Sd = Sd;
-        sa.prior_S = prior_S; sa.S = S; sa.ev = ev; sa.evw = evw; sa.EVS = EVS; sa.wS = wS; sa.cs_evs = csv + 128; sa.allmasked = allmasked; sa.scal = scal;
+        sa.prior_S = prior_S; sa.S = S; sa.ev = ev; sa.evw = evw; sa.EVS = EVS; sa.wS = wS; sa.cs_evs = csv + 128; sa.allmasked = allmasked; sa.unchanged = unchanged; sa.scal = scal;
         k_sparse_genes<<<grid_for(p, 128), 128, 0, stream>>>(sa);
         end(PH_SPARSE, 1);
     }
@@ -602,7 +613,9 @@ void pcmf_solver::step(bool want_data) {
 // ELBO data term of the current state (gap...cpp:301-313, sparse...cpp:194-212): one gene pass, nothing updated.
 double pcmf_solver::data_term_now() {
     const size_t pK = (size_t)p * KP;
-    ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, dbg, guard[gcur], ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
+    ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, guard[gcur],
+                   ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
+    sparse_sums_valid = false;   // ar2 is overwritten with the (all-reduced) sums of a different mask
     L->gene_pass(f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
     allreduce(ar2, ar2_total);
     CK(cudaMemsetAsync(scal + S_DATA, 0, 8, stream));
