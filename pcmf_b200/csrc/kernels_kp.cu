@@ -1,5 +1,6 @@
 // One instantiation set of the K-templated kernels; compiled once per padded width with -DPCMF_KP=<n>.
 #include "launch.cuh"
+#include "zi_mma.cuh"
 
 #ifndef PCMF_KP
 #error "compile with -DPCMF_KP=<padded K>"
@@ -30,7 +31,44 @@ void launch_gene_pass(bool f32, int mode, const ColArgs &a, int grid, cudaStream
     else launch_gene_t<double>(mode, a, grid, st);
 }
 
+constexpr int MMA_MT = (KP <= 20) ? 4 : 2;          // 8-row tiles per warp in the DMMA ZI passes
+constexpr int MMA_TJ = 64;                           // genes per shared-memory tile, pass A
+constexpr int MMA_TI = 64;                          // cells per shared-memory tile, pass B
+constexpr int MMA_KS = KP / 4, MMA_NT = (KP + 7) / 8;
+
+template <int MT>
+void launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (2 * ((MMA_TJ / 8) * (MMA_KS + 2 * MMA_NT) * 32 + 2 * MMA_TJ) + MMA_TJ + 32);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    const int64_t grid = (a.n + 32 * MT - 1) / (32 * MT);
+    k_zi_cells_mma<KP, MT, MMA_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
+}
+template <int MT>
+void launch_zi_genes_mma_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * (MMA_KS + 2 * MMA_NT) * 32 + 32);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_genes_mma<KP, MT, MMA_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    dim3 grid((a.p + 32 * MT - 1) / (32 * MT), chunks);
+    k_zi_genes_mma<KP, MT, MMA_TI><<<grid, 128, smem, st>>>(a);
+}
+void launch_zi_cells_mma(const ZiAArgs &a, int variant, cudaStream_t st) {
+    if ((variant & 8) && MMA_MT == 4) launch_zi_cells_mma_t<2>(a, st);
+    else launch_zi_cells_mma_t<MMA_MT>(a, st);
+}
+void launch_zi_genes_mma(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
+    if ((variant & 8) && MMA_MT == 4) launch_zi_genes_mma_t<2>(a, chunks, st);
+    else launch_zi_genes_mma_t<MMA_MT>(a, chunks, st);
+}
+
 void launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
+    if (!(variant & 4)) { launch_zi_cells_mma(a, variant, st); return; }
     const size_t smem = sizeof(double) * (ZI_TJ * KP + ZI_TJ + 4 * ZI_TJ + 4 * 32 * 33) + sizeof(int) * ZI_TJ;
     static bool attr = false;
     if (!attr) {
@@ -44,6 +82,7 @@ void launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
 }
 
 void launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
+    if (!(variant & 4)) { launch_zi_genes_mma(a, chunks, variant, st); return; }
     const size_t smem = sizeof(double) * 2 * ZI_TI * KP;
     static bool attr = false;
     if (!attr) {
@@ -60,7 +99,9 @@ void launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st)
     }
 }
 
-const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes};
+int zi_genes_block(int variant) { return !(variant & 4) ? (((variant & 8) && MMA_MT == 4) ? 64 : 32 * MMA_MT) : ((variant & 2) ? 128 : 256); }
+
+const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes, zi_genes_block};
 
 }  // namespace
 

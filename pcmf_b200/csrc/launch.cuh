@@ -13,6 +13,7 @@ struct Launchers {
     void (*gene_pass)(bool f32, int mode, const ColArgs &, int grid, cudaStream_t);
     void (*zi_cells)(const ZiAArgs &, int variant, cudaStream_t);
     void (*zi_genes)(const ZiBArgs &, int chunks, int variant, cudaStream_t);
+    int (*zi_genes_block)(int variant);   // genes per CTA of the gene-side ZI pass (for the chunk count)
 };
 
 const Launchers *get_launchers_4();

@@ -542,7 +542,8 @@ void pcmf_solver::step(bool want_data) {
         ZiBArgs zb{};
         zb.n = n; zb.p = p; zb.K = K; zb.EUz = EU[cur]; zb.EUn = EU[nxt]; zb.EVSz = EVS; zb.cz = cz; zb.flag = flag; zb.bitB = bitB;
         zb.tmpMat = ar1 + ar1_tmp;
-        const int gx = (opt.kernel_variant & 2) ? (p + 127) / 128 : (p + 255) / 256;
+        const int gb = L->zi_genes_block(opt.kernel_variant);
+        const int gx = (p + gb - 1) / gb;
         // enough (gene block, cell chunk) CTAs for >= 16 full waves at 2 resident CTAs per SM: a 2.1-wave grid measured 29% slower
         int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, (int64_t)(sms * 2 * 16 + gx - 1) / gx));
         int64_t rpc = (n + chunks - 1) / chunks; rpc = (rpc + 63) / 64 * 64;
