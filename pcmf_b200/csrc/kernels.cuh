@@ -634,6 +634,7 @@ struct ZiAArgs {
     double *PV;                  // n x KP out: prob_D * EVS  (next iteration's a2, zi...cpp:336)
     double *colsumP;             // p (atomic): colsum(prob_D) -> prior_D (zi...cpp:370-372)
     double *zsc;                 // 2 doubles (atomic): sum prob_D o UVt, sum P log P + (1-P) log(1-P)   (all-reduced later)
+    double *pack;                // scratch: fragment-ordered gene records for the DMMA kernel (zi_mma.cuh)
 };
 // Pass A: one thread per cell, genes streamed through shared memory in tiles of TJ, two genes per step.
 // Per (cell, gene): lambda = EU_i . EVS_j (K DFMA), P = expit(c_j - lambda) (fast_exp + fast_rcp, ~22 FP64 ops),
@@ -826,6 +827,7 @@ struct ZiBArgs {
     const double *cz; const int32_t *flag;
     const uint32_t *bitB;        // [ceil(n/32)][p]: bit r of word (ib, j) <-> X(32 ib + r, j) != 0
     double *tmpMat;              // p x KP (atomic): prob_D^T EU_new (zi...cpp:341, zi_sparse...:369)
+    double *pack;                // scratch: fragment-ordered cell records for the DMMA kernel (zi_mma.cuh)
 };
 // Pass B: one thread per TWO genes (j and j + 128), cells streamed through shared memory in tiles of TI (multiple
 // of 32); every broadcast shared-memory load of a cell's EU feeds four DFMAs.

@@ -1,4 +1,5 @@
 // One instantiation set of the K-templated kernels; compiled once per padded width with -DPCMF_KP=<n>.
+#include <algorithm>
 #include "launch.cuh"
 #include "zi_mma.cuh"
 
@@ -36,39 +37,53 @@ constexpr int MMA_TJ = 64;                           // genes per shared-memory 
 constexpr int MMA_TI = 64;                          // cells per shared-memory tile, pass B
 constexpr int MMA_KS = KP / 4, MMA_NT = (KP + 7) / 8;
 
+inline int pack_grid(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 16)); }
+
 template <int MT>
-void launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
-    const size_t smem = sizeof(double) * (2 * ((MMA_TJ / 8) * (MMA_KS + 2 * MMA_NT) * 32 + 2 * MMA_TJ) + MMA_TJ + 32);
+int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
+    using R = ZiRec<KP, true>;
+    const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 2 * MMA_TJ + 64);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
+    const int64_t groups = (a.p + 7) / 8;
+    k_zi_pack<KP, true><<<pack_grid(groups * R::REC), 256, 0, st>>>(a.p, a.EVS, a.EVS, a.cz, a.flag, a.pack);
     const int64_t grid = (a.n + 32 * MT - 1) / (32 * MT);
     k_zi_cells_mma<KP, MT, MMA_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
+    return 2;
 }
 template <int MT>
-void launch_zi_genes_mma_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
-    const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * (MMA_KS + 2 * MMA_NT) * 32 + 32);
+int launch_zi_genes_mma_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
+    using R = ZiRec<KP, false>;
+    const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * R::REC + 64);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_genes_mma<KP, MT, MMA_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
+    const int64_t groups = (a.n + 7) / 8;
+    k_zi_pack<KP, false><<<pack_grid(groups * R::REC), 256, 0, st>>>(a.n, a.EUz, a.EUn, nullptr, nullptr, a.pack);
     dim3 grid((a.p + 32 * MT - 1) / (32 * MT), chunks);
     k_zi_genes_mma<KP, MT, MMA_TI><<<grid, 128, smem, st>>>(a);
+    return 2;
 }
-void launch_zi_cells_mma(const ZiAArgs &a, int variant, cudaStream_t st) {
-    if ((variant & 8) && MMA_MT == 4) launch_zi_cells_mma_t<2>(a, st);
-    else launch_zi_cells_mma_t<MMA_MT>(a, st);
+int launch_zi_cells_mma(const ZiAArgs &a, int variant, cudaStream_t st) {
+    if ((variant & 8) && MMA_MT == 4) return launch_zi_cells_mma_t<2>(a, st);
+    return launch_zi_cells_mma_t<MMA_MT>(a, st);
 }
-void launch_zi_genes_mma(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
-    if ((variant & 8) && MMA_MT == 4) launch_zi_genes_mma_t<2>(a, chunks, st);
-    else launch_zi_genes_mma_t<MMA_MT>(a, chunks, st);
+int launch_zi_genes_mma(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
+    if ((variant & 8) && MMA_MT == 4) return launch_zi_genes_mma_t<2>(a, chunks, st);
+    return launch_zi_genes_mma_t<MMA_MT>(a, chunks, st);
+}
+size_t zi_pack_doubles(int64_t rows, int cells_side) {
+    const int64_t groups = (rows + 7) / 8;
+    return (size_t)groups * (cells_side ? ZiRec<KP, false>::REC : ZiRec<KP, true>::REC);
 }
 
-void launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
-    if (!(variant & 4)) { launch_zi_cells_mma(a, variant, st); return; }
+int launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
+    if (!(variant & 4)) return launch_zi_cells_mma(a, variant, st);
     const size_t smem = sizeof(double) * (ZI_TJ * KP + ZI_TJ + 4 * ZI_TJ + 4 * 32 * 33) + sizeof(int) * ZI_TJ;
     static bool attr = false;
     if (!attr) {
@@ -79,10 +94,11 @@ void launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
     const int64_t grid = (a.n + 127) / 128;
     if (variant & 1) k_zi_pass_cells_v1<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
     else k_zi_pass_cells<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
+    return 1;
 }
 
-void launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
-    if (!(variant & 4)) { launch_zi_genes_mma(a, chunks, variant, st); return; }
+int launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
+    if (!(variant & 4)) return launch_zi_genes_mma(a, chunks, variant, st);
     const size_t smem = sizeof(double) * 2 * ZI_TI * KP;
     static bool attr = false;
     if (!attr) {
@@ -97,11 +113,12 @@ void launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st)
         dim3 grid((a.p + 255) / 256, chunks);
         k_zi_pass_genes<KP, ZI_TI><<<grid, 128, smem, st>>>(a);
     }
+    return 1;
 }
 
 int zi_genes_block(int variant) { return !(variant & 4) ? (((variant & 8) && MMA_MT == 4) ? 64 : 32 * MMA_MT) : ((variant & 2) ? 128 : 256); }
 
-const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes, zi_genes_block};
+const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes, zi_genes_block, zi_pack_doubles};
 
 }  // namespace
 

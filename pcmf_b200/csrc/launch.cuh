@@ -11,9 +11,10 @@ struct Launchers {
     int KP;
     void (*estep_rows)(bool f32, const RowArgs &, int grid, int block, cudaStream_t);
     void (*gene_pass)(bool f32, int mode, const ColArgs &, int grid, cudaStream_t);
-    void (*zi_cells)(const ZiAArgs &, int variant, cudaStream_t);
-    void (*zi_genes)(const ZiBArgs &, int chunks, int variant, cudaStream_t);
+    int (*zi_cells)(const ZiAArgs &, int variant, cudaStream_t);                // returns the number of launches
+    int (*zi_genes)(const ZiBArgs &, int chunks, int variant, cudaStream_t);    // returns the number of launches
     int (*zi_genes_block)(int variant);   // genes per CTA of the gene-side ZI pass (for the chunk count)
+    size_t (*zi_pack_doubles)(int64_t rows, int cells_side);   // scratch size of ZiAArgs::pack (0) / ZiBArgs::pack (1)
 };
 
 const Launchers *get_launchers_4();

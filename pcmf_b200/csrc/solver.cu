@@ -77,6 +77,7 @@ struct pcmf_solver {
     bool own_csr = false;
     int64_t *colptr = nullptr; int32_t *rowidx = nullptr; void *val_csc = nullptr;
     uint32_t *bitT = nullptr, *bitB = nullptr;
+    double *zpackA = nullptr, *zpackB = nullptr;   // fragment-ordered scratch of the DMMA ZI passes
     double *Lg = nullptr, *colsumX = nullptr, *colnnz = nullptr, *rowsumX = nullptr;
     double lgx_const = 0;
 
@@ -154,7 +155,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { cudaFree((void *)rowptr); cudaFree((void *)colidx); cudaFree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -325,7 +326,10 @@ void pcmf_solver::build_csc() {
 void pcmf_solver::alloc_state() {
     const size_t nK = (size_t)n * KP, pK = (size_t)p * KP;
     a1 = dmalloc<double>(nK); a2 = dmalloc<double>(nK); EU[0] = dmalloc<double>(nK); ElogU = dmalloc<double>(nK); eu = dmalloc<double>(nK);
-    if (zi) { EU[1] = dmalloc<double>(nK); PV = dmalloc<double>(nK); CK(cudaMemsetAsync(EU[1], 0, nK * 8, stream)); }
+    if (zi) {
+        EU[1] = dmalloc<double>(nK); PV = dmalloc<double>(nK); CK(cudaMemsetAsync(EU[1], 0, nK * 8, stream));
+        zpackA = dmalloc<double>(L->zi_pack_doubles(p, 0)); zpackB = dmalloc<double>(L->zi_pack_doubles(n, 1));
+    }
     b1 = dmalloc<double>(pK); b2 = dmalloc<double>(pK); EV = dmalloc<double>(pK); ElogV = dmalloc<double>(pK);
     ev = dmalloc<double>(pK); evw = dmalloc<double>(pK); EVS = dmalloc<double>(pK); wS = dmalloc<double>(pK);
     prob_S = dmalloc<double>(pK); Sd = dmalloc<double>(pK); S = dmalloc<int32_t>(pK); flag = dmalloc<int32_t>(p);
@@ -481,9 +485,8 @@ void pcmf_solver::run_init_stats() {
         // init_zi_param (zi_gap_factor_model.cpp:98-105): prob_D = (X > 0); realised as pass A with c_j = -inf
         ZiPrepArgs zp{p, 1, prior_D, Lg, cz, colw, flag, scal};
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
-        ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc};
-        L->zi_cells(za, opt.kernel_variant, stream);
-        launches += 2;
+        ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
+        launches += 1 + L->zi_cells(za, opt.kernel_variant, stream);
     }
     allreduce(ar1 + ar1_cseu, 64 + 64 + 4);
     if (zi) allreduce(ar3, ar3_total);
@@ -541,7 +544,7 @@ void pcmf_solver::step(bool want_data) {
         begin(PH_ZI_B);
         ZiBArgs zb{};
         zb.n = n; zb.p = p; zb.K = K; zb.EUz = EU[cur]; zb.EUn = EU[nxt]; zb.EVSz = EVS; zb.cz = cz; zb.flag = flag; zb.bitB = bitB;
-        zb.tmpMat = ar1 + ar1_tmp;
+        zb.tmpMat = ar1 + ar1_tmp; zb.pack = zpackB;
         const int gb = L->zi_genes_block(opt.kernel_variant);
         const int gx = (p + gb - 1) / gb;
         // enough (gene block, cell chunk) CTAs for >= 16 full waves at 2 resident CTAs per SM: a 2.1-wave grid measured 29% slower
@@ -549,8 +552,7 @@ void pcmf_solver::step(bool want_data) {
         int64_t rpc = (n + chunks - 1) / chunks; rpc = (rpc + 63) / 64 * 64;
         chunks = (int)((n + rpc - 1) / rpc);
         zb.rows_per_chunk = rpc;
-        L->zi_genes(zb, chunks, opt.kernel_variant, stream);
-        end(PH_ZI_B, 1);
+        end(PH_ZI_B, L->zi_genes(zb, chunks, opt.kernel_variant, stream));
     }
     // 4. all-reduce of the gene-side sums + U partials over the row shards
     begin(PH_AR1);
@@ -594,10 +596,10 @@ void pcmf_solver::step(bool want_data) {
         ZiPrepArgs zp{p, 0, prior_D, Lg, cz, colw, flag, scal};
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
         k_refresh_weights<<<grid_for(pK, 256), 256, 0, stream>>>(p, K, KP, sparse, prob_S, colw, ev, wS, evw);
-        ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc};
-        L->zi_cells(za, opt.kernel_variant, stream);
+        ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
+        const int nl = L->zi_cells(za, opt.kernel_variant, stream);
         allreduce(ar3, ar3_total);
-        end(PH_ZI_A, 3);
+        end(PH_ZI_A, 2 + nl);
     }
     // 8. hyper-parameters + scalars
     begin(PH_HYPER);

@@ -24,88 +24,125 @@
 
 namespace pcmf {
 
-__device__ const double kPow2Tab32[32] = {
-    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
-    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,
-    1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
-    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,
-    1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429, 1.718619298122478,
-    1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,
-    1.9571441241754002};
+__device__ const double kPow2Tab64[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572,
+    1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812, 1.189207115002721, 1.202156731452703,
+    1.215247359980469, 1.22848053610687, 1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303, 1.3542555469368927, 1.3690024229745905,
+    1.383909881963832, 1.3989796725383112, 1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, 1.5422108254079407, 1.559004400237837,
+    1.5759808451078865, 1.593142151342267, 1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062, 1.7562521603732995, 1.7753764925265212,
+    1.7947090750031072, 1.8142521755003989, 1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
 
-// exp(x) for |x| <= 700 with a 32-entry table of 2^(i/32) (shared memory): m = rint(32 x / ln 2), r = x - m ln2/32
-// (two-term Cody-Waite, |r| <= ln2/64 = 0.0108), degree-6 Taylor (truncation 3.6e-18), scaled through the exponent
-// field.  11 FP64 instructions instead of the 20 of fast_exp.
-__device__ __forceinline__ double fast_exp_tab(double x, const double *__restrict__ tab) {
+// exp(-z) for |z| < 30 with a 64-entry table of 2^(i/64) (shared memory): m = rint(-64 z / ln 2), r = -z - m ln2/64
+// (two-term Cody-Waite, |r| <= ln2/128 = 0.0054), degree-5 Taylor (truncation 3.5e-17), scaled through the exponent
+// field.  10 FP64 instructions (fast_exp: 20).  Arguments outside the range give garbage that the caller discards.
+// On this part the SM sub-partition's dispatch port is what the dense passes saturate (a DFMA holds it for 2 cycles, a
+// DMMA for 16, nothing else issues meanwhile -- scripts/ubench_zi_core.cu), so every instruction removed here counts.
+__device__ __forceinline__ double fast_exp_neg_tab(double z, const double *__restrict__ tab) {
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
-    double t = fma(x, 46.16624130844683, MAGIC);
+    double t = fma(z, -92.33248261689366, MAGIC);
     const int m = __double2loint(t);
     t -= MAGIC;
-    double r = fma(t, -0.02166084939249829, x);
-    r = fma(t, -7.247021293269686e-19, r);
-    double p = 1.38888888888888888889e-03;                  // 1/6!
-    p = fma(p, r, 8.33333333333333333333e-03);              // 1/5!
+    double r = fma(t, -0.010830424696249145, -z);
+    r = fma(t, -3.623510646634843e-19, r);
+    double p = 8.33333333333333333333e-03;                  // 1/5!
     p = fma(p, r, 4.16666666666666666667e-02);              // 1/4!
     p = fma(p, r, 1.66666666666666666667e-01);              // 1/3!
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    p *= tab[m & 31];
-    return __hiloint2double(__double2hiint(p) + ((m >> 5) << 20), __double2loint(p));
+    p *= tab[m & 63];
+    return __hiloint2double(__double2hiint(p) + ((m >> 6) << 20), __double2loint(p));
 }
-// internal::expit (internal.h:151-155), returns y = 1 + exp(-z) too (1 when clamped) and the (0,1)-interior flag
-__device__ __forceinline__ double fast_expit_tab(double z, const double *__restrict__ tab, double &y_out, bool &interior) {
+// internal::expit (internal.h:151-155): exactly 1 / 0 for z >= 30 / z <= -30.  `ov` is the value the entry takes when
+// `force` is set (X != 0, zi...cpp:359-360).  Also returns y = 1 + exp(-z) (garbage when clamped) and the clamp flag.
+__device__ __forceinline__ double fast_expit_tab(double z, const double *__restrict__ tab, bool force, double ov, double &y,
+                                                 bool &big) {
     const int hi = __double2hiint(z);
-    const bool big = (hi & 0x7fffffff) >= 0x403E0000;     // |z| >= 30, also NaN / inf
-    const double zc = big ? 0.0 : z;
-    const double y = 1.0 + fast_exp_tab(-zc, tab);
+    big = (hi & 0x7fffffff) >= 0x403E0000;                 // |z| >= 30, also NaN / inf
+    y = 1.0 + fast_exp_neg_tab(z, tab);
     const double pr = fast_rcp(y);
-    interior = !big;
-    y_out = big ? 1.0 : y;
-    return big ? ((hi < 0) ? 0.0 : 1.0) : pr;
+    const double sat = __hiloint2double((hi < 0) ? 0 : 0x3FF00000, 0);
+    return force ? ov : (big ? sat : pr);
 }
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
 }
 
-// Stage TR rows (multiple of 8) of a row-major [rows][KP] matrix into shared memory in fragment order:
-//   B1 fragments (first product, contraction over the K factors):   f1[(grp * KS + s) * 32 + lane] = M[8 grp + g][4 s + q]
-//   B2 fragments (second product, contraction over the 8 tile rows): f2[((grp * 2 + s') * NT + nt) * 32 + lane]
-//                                                                       = M[8 grp + 2 q + s'][8 nt + g]   (0 beyond KP)
-// Rows >= rows_valid_end read as 0.  The copies are asynchronous (cp.async, 8 bytes each, zero-filled when out of
-// range) so the next tile is staged while the current one is being consumed.
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+// ---- bulk (TMA) copy + mbarrier plumbing --------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
-template <int KP, int TR>
-__device__ __forceinline__ void stage_b1(const double *__restrict__ M, int64_t row0, int64_t rows_valid_end, double *f1) {
-    constexpr int KS = KP / 4;
-    for (int t = threadIdx.x; t < TR * KP; t += blockDim.x) {
-        const int row = t / KP, k = t - row * KP;
-        const int64_t gr = row0 + row;
-        const bool ok = gr < rows_valid_end;
-        const int grp = row >> 3, g = row & 7, s = k >> 2, q = k & 3;
-        cp_async8(f1 + (grp * KS + s) * 32 + g * 4 + q, ok ? M + gr * KP + k : M, ok);
-    }
-}
-template <int KP, int TR>
-__device__ __forceinline__ void stage_b2(const double *__restrict__ M, int64_t row0, int64_t rows_valid_end, double *f2) {
-    constexpr int NT = (KP + 7) / 8;
-    for (int t = threadIdx.x; t < TR * NT * 8; t += blockDim.x) {
-        const int row = t / (NT * 8), k = t - row * (NT * 8);
-        const int64_t gr = row0 + row;
-        const bool ok = gr < rows_valid_end && k < KP;
-        const int grp = row >> 3, rr = row & 7, q = rr >> 1, sp = rr & 1, nt = k >> 3, g = k & 7;
-        cp_async8(f2 + ((grp * 2 + sp) * NT + nt) * 32 + g * 4 + q, ok ? M + gr * KP + k : M, ok);
+// Fragment-ordered copy of a row-major [rows][KP] matrix, one record per group of 8 rows, so that a tile of the dense
+// passes is ONE contiguous bulk copy and every fragment load is a conflict-free 256-byte shared-memory read:
+//   record = [ f1: KS x 32 | f2: 2 x NT x 32 | (WITH_C) c: 8 | nzv: 8 ]
+//   f1[s][lane]      = M1[8 grp + g][4 s + q]               first product, contraction over the K factors
+//   f2[s'][nt][lane] = M2[8 grp + 2 q + s'][8 nt + g]       second product, contraction over the 8 rows (0 beyond KP)
+//   c / nzv: effective logit of the gene (+-1e300 for the whole-gene shortcuts, zi...cpp:353-356) and the value prob_D
+//   takes on its non-zero entries (zi...cpp:359-360).  Rows beyond `rows` are zero (c = -1e300 -> P = 0).
+template <int KP, bool WITH_C>
+struct ZiRec {
+    static constexpr int KS = KP / 4, NT = (KP + 7) / 8;
+    static constexpr int F1 = KS * 32, F2 = 2 * NT * 32, REC = F1 + F2 + (WITH_C ? 16 : 0);
+};
+template <int KP, bool WITH_C>
+__global__ void k_zi_pack(int64_t rows, const double *__restrict__ M1, const double *__restrict__ M2,
+                          const double *__restrict__ cz, const int32_t *__restrict__ flag, double *__restrict__ out) {
+    using R = ZiRec<KP, WITH_C>;
+    const int64_t ngroups = (rows + 7) >> 3, total = ngroups * R::REC;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t grp = idx / R::REC;
+        const int o = (int)(idx - grp * R::REC);
+        double v = 0.0;
+        if (o < R::F1) {
+            const int s = o >> 5, lane = o & 31, g = lane >> 2, q = lane & 3;
+            const int64_t row = grp * 8 + g;
+            if (row < rows) v = M1[row * KP + 4 * s + q];
+        } else if (o < R::F1 + R::F2) {
+            const int o2 = o - R::F1, lane = o2 & 31, g = lane >> 2, q = lane & 3;
+            const int t = o2 >> 5, sp = t / R::NT, nt = t - sp * R::NT;
+            const int64_t row = grp * 8 + 2 * q + sp;
+            const int k = 8 * nt + g;
+            if (row < rows && k < KP) v = M2[row * KP + k];
+        } else {
+            const int o3 = o - R::F1 - R::F2, e = o3 & 7;
+            const int64_t row = grp * 8 + e;
+            const int f = row < rows ? flag[row] : 2;
+            if (o3 < 8) v = (row < rows && f == 0) ? cz[row] : ((f == 1) ? 1e300 : -1e300);
+            else v = (f == 2) ? 0.0 : 1.0;
+        }
+        out[idx] = v;
     }
 }
 
@@ -115,15 +152,20 @@ __device__ __forceinline__ void stage_b2(const double *__restrict__ M, int64_t r
 // ------------------------------------------------------------------------------------------------------------
 template <int KP, int MT, int TJ>
 __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_cells_mma(ZiAArgs a) {
-    constexpr int KS = KP / 4, NT = (KP + 7) / 8, NG = TJ / 8;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int F1 = NG * KS * 32, F2 = NG * 2 * NT * 32, BUF = F1 + F2 + 2 * TJ;
-    double *s_buf = reinterpret_cast<double *>(smem_raw);       // 2 x [f1 | f2 | c | nzv], double buffered
-    double *s_cs = s_buf + 2 * BUF;                             // TJ: column sums of this CTA
-    double *s_tab = s_cs + TJ;                                  // 32
+    const double *__restrict__ pack = a.pack;
+    using R = ZiRec<KP, true>;
+    constexpr int KS = R::KS, NT = R::NT, NG = TJ / 8, BUF = NG * R::REC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_buf = reinterpret_cast<double *>(smem_raw);       // 2 x NG records, double buffered
+    double *s_cs = s_buf + 2 * BUF;                             // 2 x TJ: column sums of this CTA, double buffered
+    double *s_tab = s_cs + 2 * TJ;                              // 64
     __shared__ double sh[32];
+    __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    if (threadIdx.x < 32) s_tab[threadIdx.x] = kPow2Tab32[threadIdx.x];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
+    for (int t = threadIdx.x; t < 2 * TJ; t += blockDim.x) s_cs[t] = 0.0;
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
     const int64_t cell0 = (int64_t)blockIdx.x * (32 * MT) + w * (8 * MT);   // CTA = 4 warps x 8 MT cells
     double a1[MT][KS];
     bool live[MT];
@@ -139,39 +181,30 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
-    double sum_pl = 0, ent_lin = 0, ent_log = 0, prod = 1.0;
+    double ent_lin = 0, ent_log = 0, prod = 1.0;
     uint32_t bits[MT], bits_nx[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) { bits[mt] = 0u; bits_nx[mt] = live[mt] ? __ldg(a.bitT + (cell0 + mt * 8 + g)) : 0u; }
 
-    // tile staging: fragments by cp.async, per-gene constants by plain loads (TJ <= blockDim.x values per tile)
-    auto stage = [&](int j0, double *buf) {
-        stage_b1<KP, TJ>(a.EVS, j0, a.p, buf);
-        stage_b2<KP, TJ>(a.EVS, j0, a.p, buf + F1);
-        cp_async_commit();
-        for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
-            const int jj = j0 + t;
-            double c = -1e300, nzv = 0.0;
-            if (jj < a.p) {
-                const int f = a.flag[jj];
-                c = (f == 0) ? a.cz[jj] : ((f == 1) ? 1e300 : -1e300);     // zi...cpp:353-356 whole-gene shortcuts
-                nzv = (f == 2) ? 0.0 : 1.0;                                // zi...cpp:359-360
-            }
-            buf[F1 + F2 + t] = c; buf[F1 + F2 + TJ + t] = nzv;
-        }
+    const int ngroups = (a.p + 7) >> 3, ntiles = (ngroups + NG - 1) / NG;
+    auto issue = [&](int tile) {     // one thread: arm the barrier with the byte count, then one bulk copy
+        const int g0 = tile * NG, gn = min(NG, ngroups - g0);
+        const unsigned bytes = (unsigned)(gn * R::REC * sizeof(double));
+        mbar_expect_tx(&bar[tile & 1], bytes);
+        bulk_g2s(s_buf + (tile & 1) * BUF, pack + (int64_t)g0 * R::REC, bytes, &bar[tile & 1]);
     };
-    for (int t = threadIdx.x; t < TJ; t += blockDim.x) s_cs[t] = 0.0;
-    stage(0, s_buf);
-    int cur = 0;
-    for (int j0 = 0; j0 < a.p; j0 += TJ, cur ^= 1) {
-        const double *s_f1 = s_buf + cur * BUF, *s_f2 = s_f1 + F1, *s_c = s_f2 + F2, *s_nzv = s_c + TJ;
-        if (j0 + TJ < a.p) { stage(j0 + TJ, s_buf + (cur ^ 1) * BUF); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
+    if (threadIdx.x == 0) issue(0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int j0 = tile * TJ;
+        const double *buf = s_buf + (tile & 1) * BUF;
+        double *cs_buf = s_cs + (tile & 1) * TJ;
+        if (threadIdx.x == 0 && tile + 1 < ntiles) issue(tile + 1);
+        mbar_wait(&bar[tile & 1], (tile >> 1) & 1);
 #pragma unroll 1
         for (int grp = 0; grp < NG; ++grp) {
             const int jg = j0 + grp * 8;
             if (jg >= a.p) break;
+            const double *rec = buf + grp * R::REC;
             if ((grp & 3) == 0) {
                 // occupancy words of this 32-gene block were requested one block ahead; request the next block now
 #pragma unroll
@@ -185,30 +218,26 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             for (int mt = 0; mt < MT; ++mt) { d[mt][0] = 0.0; d[mt][1] = 0.0; }
 #pragma unroll
             for (int s = 0; s < KS; ++s) {
-                const double b = s_f1[(grp * KS + s) * 32 + lane];
+                const double b = rec[s * 32 + lane];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) dmma884(d[mt][0], d[mt][1], a1[mt][s], b);
             }
-            const double2 c2 = *reinterpret_cast<const double2 *>(s_c + grp * 8 + 2 * q);
-            const double2 n2 = *reinterpret_cast<const double2 *>(s_nzv + grp * 8 + 2 * q);
+            const double2 c2 = *reinterpret_cast<const double2 *>(rec + R::F1 + R::F2 + 2 * q);
+            const double2 n2 = *reinterpret_cast<const double2 *>(rec + R::F1 + R::F2 + 8 + 2 * q);
             const int sh0 = ((grp & 3) << 3) + 2 * q;
             double cs0 = 0.0, cs1 = 0.0;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const double lam0 = d[mt][0], lam1 = d[mt][1];
-                const double z0 = c2.x - lam0, z1 = c2.y - lam1;
-                double y0, y1; bool in0, in1;
-                double p0 = fast_expit_tab(z0, s_tab, y0, in0), p1 = fast_expit_tab(z1, s_tab, y1, in1);
+                const double z0 = c2.x - d[mt][0], z1 = c2.y - d[mt][1];
                 const bool nz0 = (bits[mt] >> sh0) & 1u, nz1 = (bits[mt] >> (sh0 + 1)) & 1u;
-                p0 = nz0 ? n2.x : p0; p1 = nz1 ? n2.y : p1;
+                double y0, y1; bool big0, big1;
+                double p0 = fast_expit_tab(z0, s_tab, nz0, n2.x, y0, big0), p1 = fast_expit_tab(z1, s_tab, nz1, n2.y, y1, big1);
                 p0 = live[mt] ? p0 : 0.0; p1 = live[mt] ? p1 : 0.0;
                 // -bernoulli_loglike(prob_D, prob_D) over 0 < P < 1: sum (1-P)(-z) - log(1 + e^-z)
-                const bool g0 = in0 && !nz0 && live[mt], g1 = in1 && !nz1 && live[mt];
-                ent_lin = fma(g0 ? (1.0 - p0) : 0.0, -z0, ent_lin);
-                ent_lin = fma(g1 ? (1.0 - p1) : 0.0, -z1, ent_lin);
+                const bool g0 = !big0 && !nz0 && live[mt], g1 = !big1 && !nz1 && live[mt];
+                ent_lin = fma(g0 ? (p0 - 1.0) : 0.0, z0, ent_lin);
+                ent_lin = fma(g1 ? (p1 - 1.0) : 0.0, z1, ent_lin);
                 prod *= (g0 ? y0 : 1.0) * (g1 ? y1 : 1.0);
-                sum_pl = fma(p0, lam0, sum_pl);                  // sum prob_D o UVt (zi...cpp:182)
-                sum_pl = fma(p1, lam1, sum_pl);
                 cs0 += p0; cs1 += p1;
                 d[mt][0] = p0; d[mt][1] = p1;
             }
@@ -217,7 +246,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             for (int sp = 0; sp < 2; ++sp)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    const double b = s_f2[((grp * 2 + sp) * NT + nt) * 32 + lane];
+                    const double b = rec[R::F1 + (sp * NT + nt) * 32 + lane];
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], d[mt][sp], b);
                 }
@@ -228,16 +257,18 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
                 cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
             }
             if (g == 0) {
-                atomicAdd(s_cs + grp * 8 + 2 * q, cs0);
-                atomicAdd(s_cs + grp * 8 + 2 * q + 1, cs1);
+                atomicAdd(cs_buf + grp * 8 + 2 * q, cs0);
+                atomicAdd(cs_buf + grp * 8 + 2 * q + 1, cs1);
             }
         }
-        __syncthreads();
+        __syncthreads();   // every warp is done with this buffer: it may be refilled, its column sums flushed
         for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
-            if (j0 + t < a.p) atomicAdd(a.colsumP + j0 + t, s_cs[t]);
-            s_cs[t] = 0.0;
+            if (j0 + t < a.p) atomicAdd(a.colsumP + j0 + t, cs_buf[t]);
+            cs_buf[t] = 0.0;
         }
     }
+    // epilogue: PV, and sum_ij prob_D_ij UVt_ij = sum_ik EU_ik PV_ik (zi...cpp:182)
+    double sum_pl = 0.0;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         if (!live[mt]) continue;
@@ -245,7 +276,11 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const int k = nt * 8 + 2 * q;
-            if (k < KP) *reinterpret_cast<double2 *>(a.PV + i * KP + k) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            if (k < KP) {
+                *reinterpret_cast<double2 *>(a.PV + i * KP + k) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                const double2 u = *reinterpret_cast<const double2 *>(a.EU + i * KP + k);
+                sum_pl = fma(u.x, acc[mt][nt][0], fma(u.y, acc[mt][nt][1], sum_pl));
+            }
         }
     }
     double ent = ent_lin - (ent_log + log(prod));
@@ -259,13 +294,17 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
 // ------------------------------------------------------------------------------------------------------------
 template <int KP, int MT, int TI>
 __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_genes_mma(ZiBArgs a) {
-    constexpr int KS = KP / 4, NT = (KP + 7) / 8, NG = TI / 8;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int F1 = NG * KS * 32, F2 = NG * 2 * NT * 32, BUF = F1 + F2;
-    double *s_buf = reinterpret_cast<double *>(smem_raw);       // 2 x [EUz first-product | EUn second-product fragments]
-    double *s_tab = s_buf + 2 * BUF;                            // 32
+    const double *__restrict__ pack = a.pack;
+    using R = ZiRec<KP, false>;
+    constexpr int KS = R::KS, NT = R::NT, NG = TI / 8, BUF = NG * R::REC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_buf = reinterpret_cast<double *>(smem_raw);       // 2 x NG records [EUz first-product | EUn second-product]
+    double *s_tab = s_buf + 2 * BUF;                            // 64
+    __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    if (threadIdx.x < 32) s_tab[threadIdx.x] = kPow2Tab32[threadIdx.x];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
     const int gene0 = blockIdx.x * (32 * MT) + w * (8 * MT);
     double a1[MT][KS], c[MT], nzv[MT];
     bool live[MT];
@@ -287,7 +326,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
-    const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_chunk;
+    const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_chunk;        // multiple of 64
     const int64_t r1 = min(a.n, r0 + a.rows_per_chunk);
     uint32_t bits[MT], bits_nx[MT];
 #pragma unroll
@@ -295,22 +334,26 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
         bits[mt] = 0u;
         bits_nx[mt] = (live[mt] && r0 < r1) ? __ldg(a.bitB + (r0 >> 5) * a.p + (gene0 + mt * 8 + g)) : 0u;
     }
-    auto stage = [&](int64_t i0, double *buf) {
-        stage_b1<KP, TI>(a.EUz, i0, r1, buf);
-        stage_b2<KP, TI>(a.EUn, i0, r1, buf + F1);
-        cp_async_commit();
+    const int64_t grp0 = r0 >> 3, grp1 = (r1 + 7) >> 3;
+    const int ntiles = (int)((grp1 - grp0 + NG - 1) / NG);
+    auto issue = [&](int tile) {
+        const int64_t g0 = grp0 + (int64_t)tile * NG;
+        const int gn = (int)min((int64_t)NG, grp1 - g0);
+        const unsigned bytes = (unsigned)(gn * R::REC * sizeof(double));
+        mbar_expect_tx(&bar[tile & 1], bytes);
+        bulk_g2s(s_buf + (tile & 1) * BUF, pack + g0 * R::REC, bytes, &bar[tile & 1]);
     };
-    if (r0 < r1) stage(r0, s_buf);
-    int cur = 0;
-    for (int64_t i0 = r0; i0 < r1; i0 += TI, cur ^= 1) {
-        const double *s_f1 = s_buf + cur * BUF, *s_f2 = s_f1 + F1;
-        if (i0 + TI < r1) { stage(i0 + TI, s_buf + (cur ^ 1) * BUF); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
+    if (threadIdx.x == 0 && ntiles > 0) issue(0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int64_t i0 = r0 + (int64_t)tile * TI;
+        const double *buf = s_buf + (tile & 1) * BUF;
+        if (threadIdx.x == 0 && tile + 1 < ntiles) issue(tile + 1);
+        mbar_wait(&bar[tile & 1], (tile >> 1) & 1);
 #pragma unroll 1
         for (int grp = 0; grp < NG; ++grp) {
             const int64_t ig = i0 + grp * 8;
             if (ig >= r1) break;
+            const double *rec = buf + grp * R::REC;
             if ((grp & 3) == 0) {
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -323,30 +366,28 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             for (int mt = 0; mt < MT; ++mt) { d[mt][0] = 0.0; d[mt][1] = 0.0; }
 #pragma unroll
             for (int s = 0; s < KS; ++s) {
-                const double b = s_f1[(grp * KS + s) * 32 + lane];
+                const double b = rec[s * 32 + lane];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) dmma884(d[mt][0], d[mt][1], a1[mt][s], b);
             }
             const int sh0 = ((grp & 3) << 3) + 2 * q;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                double y; bool in_;
-                double p0 = fast_expit_tab(c[mt] - d[mt][0], s_tab, y, in_);
-                double p1 = fast_expit_tab(c[mt] - d[mt][1], s_tab, y, in_);
-                p0 = ((bits[mt] >> sh0) & 1u) ? nzv[mt] : p0;
-                p1 = ((bits[mt] >> (sh0 + 1)) & 1u) ? nzv[mt] : p1;
-                d[mt][0] = p0; d[mt][1] = p1;      // cells beyond the chunk have EU_new = 0 in the staged tile
+                double y; bool big;
+                const double p0 = fast_expit_tab(c[mt] - d[mt][0], s_tab, (bits[mt] >> sh0) & 1u, nzv[mt], y, big);
+                const double p1 = fast_expit_tab(c[mt] - d[mt][1], s_tab, (bits[mt] >> (sh0 + 1)) & 1u, nzv[mt], y, big);
+                d[mt][0] = p0; d[mt][1] = p1;      // cells beyond n have EU_new = 0 in the packed records
             }
 #pragma unroll
             for (int sp = 0; sp < 2; ++sp)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    const double b = s_f2[((grp * 2 + sp) * NT + nt) * 32 + lane];
+                    const double b = rec[R::F1 + (sp * NT + nt) * 32 + lane];
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], d[mt][sp], b);
                 }
         }
-        __syncthreads();   // every warp is done with this buffer before it is staged again
+        __syncthreads();   // every warp is done with this buffer before it is refilled
     }
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
