@@ -79,7 +79,9 @@ typedef struct {
     double epsilon;            /* default 1e-2 */
     int32_t additional_iter;   /* default 10 */
     int32_t conv_mode;         /* 0 absolute gap, 1 normalised gap (algorithm.h:412-450); 2 is PCMF_EUNSUPPORTED */
-    int32_t monitor;           /* record the ELBO every iteration (algorithm.h:391-397); norm/abs gap always recorded */
+    int32_t monitor;           /* 1: record ELBO, log-likelihood and deviance every iteration like monitor=TRUE does
+                                * (algorithm.h:391-397); 2: ELBO only (extension: skips the two extra passes);
+                                * 0: none.  norm/abs gap are always recorded */
     int32_t reorder_factor;    /* order factors by deviance after the loop (model.cpp:137-187) */
     int32_t ninit;             /* multi-init (wrapper_gap_factor.h:296-350) */
     int32_t iter_init;
@@ -153,7 +155,13 @@ int pcmf_iterate(pcmf_solver *s, int niter, double *conv_crit_out, double *elbo_
  * terms (nullable): 11 doubles in the order gammaU, entU, gammaV, entV, bernS_prior, bernS_self, bernD_prior,
  * bernD_self, sumUVt, data, lgammaX */
 int pcmf_elbo(pcmf_solver *s, double *elbo_out, double *terms, char *errbuf, size_t errlen);
-/* variational_em_algo::order_factor (algorithm_variational_EM.h:189-192) */
+/* multi-init (wrapper_gap_factor.h:296-350, wrapper_sparse_gap_factor.h:328-387): options.ninit runs of
+ * options.iter_init iterations from successive random initialisations, keeps the run with the smallest loss (sic) and
+ * leaves the solver at iteration iter_init of that run; pcmf_optimize then continues.  The per-iteration vectors of
+ * `res` hold the kept run's first iter_init entries. */
+int pcmf_multi_init(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen);
+/* variational_em_algo::order_factor (algorithm_variational_EM.h:189-192): greedy ordering by partial deviance
+ * (model.cpp:137-187) + reorder_factor; permutes every K-indexed array of the state. */
 int pcmf_order_factor(pcmf_solver *s, char *errbuf, size_t errlen);
 /* monitors (gap_factor_model.cpp:278-284, :329-341 and variants): any pointer may be NULL */
 int pcmf_monitors(pcmf_solver *s, double *loglikelihood, double *deviance, double *exp_deviance,

@@ -295,6 +295,19 @@ void orc_destroy(orc_model *m) {
     free(m->S); free(m->factor_order); free(m);
 }
 void orc_seed(orc_model *m, uint32_t seed) { orc_rng_seed(&m->rng, seed); }
+/* `my_model = tmp_model` of the multi-init loop (wrapper_gap_factor.h:339-345): deep copy of every member, including
+ * the `old` iterates.  Both models must have been created with the same kind and sizes. */
+void orc_copy_state(orc_model *dst, const orc_model *src) {
+    long np = (long)src->n * src->p, nK = (long)src->n * src->K, pK = (long)src->p * src->K;
+#define CPY(f, l) if (src->f) memcpy(dst->f, src->f, sizeof(*src->f) * (size_t)(l));
+    CPY(UVt, np) CPY(T, np) CPY(EU, nK) CPY(ElogU, nK) CPY(EV, pK) CPY(ElogV, pK)
+    CPY(a1, nK) CPY(a2, nK) CPY(a1o, nK) CPY(a2o, nK) CPY(b1, pK) CPY(b2, pK) CPY(b1o, pK) CPY(b2o, pK)
+    CPY(alpha1, nK) CPY(alpha2, nK) CPY(alpha1o, nK) CPY(alpha2o, nK) CPY(beta1, pK) CPY(beta2, pK) CPY(beta1o, pK) CPY(beta2o, pK)
+    CPY(EZ_i, pK) CPY(EZ_j, nK) CPY(prob_D, np) CPY(prior_D, src->p) CPY(freq_D, src->p) CPY(prob_S, pK) CPY(prior_S, src->p)
+    CPY(S, pK) CPY(factor_order, src->K)
+#undef CPY
+    dst->sel_bound = src->sel_bound;
+}
 
 /* field access for the test harness */
 double *orc_field(orc_model *m, const char *name, long *len) {

@@ -72,6 +72,8 @@ def lib():
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_seed.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_copy_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_copy_state.restype = None
         L.orc_field.restype = dp
         L.orc_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
         L.orc_field_S.restype = ip
@@ -247,6 +249,10 @@ class Model:
     def exp_deviance(self):
         return self.L.orc_exp_deviance(self.h)
 
+    def copy_from(self, other):
+        """my_model = tmp_model (wrapper_gap_factor.h:339-345)."""
+        self.L.orc_copy_state(self.h, other.h)
+
     def order_factor(self):
         self.L.orc_order_factor(self.h)
 
@@ -272,21 +278,42 @@ class Model:
 
 def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True, iter_max=1000, iter_min=500,
         epsilon=1e-2, additional_iter=10, conv_mode=1, reorder_factor=True, seed=None,
-        a1=None, a2=None, b1=None, b2=None, prob_S=None, prior_S=None):
-    """Single-init restatement of wrapper_gap_factor.h:164-393 / wrapper_sparse_gap_factor.h:176-435 (init order of
-    :389-417), returning a dict shaped like the reference's R list."""
+        a1=None, a2=None, b1=None, b2=None, prob_S=None, prior_S=None, ninit=1, iter_init=100):
+    """Restatement of wrapper_gap_factor.h:164-393 / wrapper_sparse_gap_factor.h:176-435 (init order of :389-417,
+    multi-init loop of :296-350 / :328-387), returning a dict shaped like the reference's R list."""
     m = Model(X, K, zero_inflation, sparsity)
-    if seed is not None:
-        m.seed(seed)
-    if sparsity:
-        m.init_sparse_param(sel_bound, prob_S, prior_S)
-    if zero_inflation:
-        m.init_zi_param()
-    if a1 is not None:
-        m.init_variational_param(a1, a2, b1, b2)
+
+    def init(mod):
+        if sparsity:
+            mod.init_sparse_param(sel_bound, prob_S, prior_S)
+        if zero_inflation:
+            mod.init_zi_param()
+        if a1 is not None:
+            mod.init_variational_param(a1, a2, b1, b2)
+        else:
+            mod.init_random()
+
+    head = None
+    if ninit > 1:
+        tmp = Model(X, K, zero_inflation, sparsity)      # one RNG stream for every run (the wrapper's `rng`)
+        if seed is not None:
+            tmp.seed(seed)
+        best_loss = None
+        for nrun in range(ninit):
+            init(tmp)
+            c = tmp.optimize(iter_init, iter_init, 1e-6, additional_iter, conv_mode, monitor, iter_start=0)
+            if nrun == 0 or c["loss"] < best_loss:           # sic: keeps the SMALLEST loss (wrapper_gap_factor.h:342)
+                best_loss, head = c["loss"], c
+                m.copy_from(tmp)
+        conv = m.optimize(iter_max, iter_min, epsilon, additional_iter, conv_mode, monitor, iter_start=iter_init)
+        for k, v in head.items():                           # entries < iter_init are the kept run's (copied members)
+            if isinstance(v, np.ndarray) and k in conv:
+                conv[k][:len(v)] = v
     else:
-        m.init_random()
-    conv = m.optimize(iter_max, iter_min, epsilon, additional_iter, conv_mode, monitor)
+        if seed is not None:
+            m.seed(seed)
+        init(m)
+        conv = m.optimize(iter_max, iter_min, epsilon, additional_iter, conv_mode, monitor)
     if reorder_factor:
         m.order_factor()
     st = m.state()

@@ -74,6 +74,7 @@ def lib():
     L.pcmf_iterate.argtypes = [C.c_void_p, C.c_int, dp, dp] + err
     L.pcmf_elbo.argtypes = [C.c_void_p, dp, dp] + err
     L.pcmf_order_factor.argtypes = [C.c_void_p] + err
+    L.pcmf_multi_init.argtypes = [C.c_void_p, C.POINTER(Result)] + err
     L.pcmf_monitors.argtypes = [C.c_void_p, dp, dp, dp] + err
     L.pcmf_get_output.argtypes = [C.c_void_p, C.POINTER(Result)] + err
     L.pcmf_set_variational.argtypes = [C.c_void_p, dp, dp, dp, dp] + err
@@ -89,7 +90,7 @@ def lib():
     L.pcmf_measure_fp64_tflops.argtypes = [C.c_int, dp]
     L.pcmf_device_free.argtypes = [C.c_int, C.c_void_p]
     L.pcmf_device_to_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
-    for name in ("pcmf_fit", "pcmf_create", "pcmf_optimize", "pcmf_iterate", "pcmf_elbo", "pcmf_order_factor",
+    for name in ("pcmf_fit", "pcmf_create", "pcmf_optimize", "pcmf_iterate", "pcmf_elbo", "pcmf_order_factor", "pcmf_multi_init",
                  "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational", "pcmf_phase_times",
                  "pcmf_generate_counts_device", "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats",
                  "pcmf_measure_fp64_tflops"):
@@ -105,6 +106,6 @@ def check(rc, errbuf):
 
 # every symbol include/pcmf_b200.h declares (tests check the library exports them all)
 HEADER_SYMBOLS = ["pcmf_version", "pcmf_device_count", "pcmf_fit", "pcmf_create", "pcmf_optimize", "pcmf_iterate",
-                  "pcmf_elbo", "pcmf_order_factor", "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational",
+                  "pcmf_elbo", "pcmf_order_factor", "pcmf_multi_init", "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational",
                   "pcmf_phase_times", "pcmf_launch_count", "pcmf_destroy", "pcmf_generate_counts_device",
                   "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats", "pcmf_measure_fp64_tflops"]

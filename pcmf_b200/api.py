@@ -246,7 +246,7 @@ class Solver:
         o = Options()
         o.K, o.zero_inflation, o.sparsity, o.sel_bound = int(K), int(self.zi), int(self.sparse), float(sel_bound)
         o.iter_max, o.iter_min, o.epsilon, o.additional_iter = int(iter_max), int(iter_min), float(epsilon), int(additional_iter)
-        o.conv_mode, o.monitor, o.reorder_factor, o.ninit, o.iter_init = int(conv_mode), int(bool(monitor)), int(bool(reorder_factor)), int(ninit), int(iter_init)
+        o.conv_mode, o.monitor, o.reorder_factor, o.ninit, o.iter_init = int(conv_mode), int(monitor), int(bool(reorder_factor)), int(ninit), int(iter_init)
         o.has_seed, o.seed = (0, 0) if seed is None else (1, int(seed) & 0xFFFFFFFF)
         o.verbose, o.device = int(bool(verbose)), int(device)
         o.stream = stream
@@ -372,24 +372,31 @@ class Solver:
         _lib.check(self.L.pcmf_get_output(self.h, C.byref(r), err, 512), err)
         return bufs
 
-    def optimize(self):
-        r, bufs = self._result_buffers(False, vectors=True)
-        err = C.create_string_buffer(512)
-        _lib.check(self.L.pcmf_optimize(self.h, C.byref(r), err, 512), err)
+    def _conv_dict(self, r, bufs):
         nb = r.nb_iter
         out = {"nb_iter": int(nb), "converged": bool(r.converged), "loss": r.loss, "seconds_iter": r.seconds_iter}
-        for nm in ("conv_crit", "norm_gap", "abs_gap", "optim_criterion"):
+        for nm in ("conv_crit", "norm_gap", "abs_gap", "optim_criterion", "loglikelihood", "deviance"):
             out[nm] = bufs[nm][:nb].copy()
         return out
+
+    def optimize(self, multi_init=False):
+        """algorithm::optimize; with multi_init=True the multi-init loop of the wrapper runs first (the per-iteration
+        vectors then start with the kept run's first iter_init entries)."""
+        r, bufs = self._result_buffers(False, vectors=True)
+        err = C.create_string_buffer(512)
+        if multi_init:
+            _lib.check(self.L.pcmf_multi_init(self.h, C.byref(r), err, 512), err)
+        _lib.check(self.L.pcmf_optimize(self.h, C.byref(r), err, 512), err)
+        return self._conv_dict(r, bufs)
 
     def order_factor(self):
         err = C.create_string_buffer(512)
         _lib.check(self.L.pcmf_order_factor(self.h, err, 512), err)
 
-    def monitors(self):
-        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    def monitors(self, loglikelihood=True):
+        a, b, c = C.c_double(float("nan")), C.c_double(0), C.c_double(0)
         err = C.create_string_buffer(512)
-        _lib.check(self.L.pcmf_monitors(self.h, C.byref(a), C.byref(b), C.byref(c), err, 512), err)
+        _lib.check(self.L.pcmf_monitors(self.h, C.byref(a) if loglikelihood else None, C.byref(b), C.byref(c), err, 512), err)
         return {"loglikelihood": a.value, "deviance": b.value, "exp_dev": c.value}
 
     def phase_times(self):
@@ -415,8 +422,6 @@ def _run(X, K, zero_inflation, sparsity, sel_bound=0.5, U=None, V=None, verbose=
     if prob_D is not None or prior_D is not None:
         raise PcmfError(_lib.EUNSUPPORTED, "warm-starting from a dense prob_D matrix is not supported: the GPU path "
                                            "never materialises prob_D (pCMF() never passes it either)")
-    if ninit and ninit > 1:
-        raise PcmfError(_lib.EUNSUPPORTED, "ninit > 1 (multi-init) is not implemented yet")
     del ncores  # kept for signature compatibility (omp_set_num_threads in the reference); the GPU path ignores it
     progress = None
     if verbose:
@@ -427,19 +432,10 @@ def _run(X, K, zero_inflation, sparsity, sel_bound=0.5, U=None, V=None, verbose=
                alpha1=alpha1, alpha2=alpha2, beta1=beta1, beta2=beta2, prob_S=prob_S, prior_S=prior_S, progress=progress,
                **gpu)
     try:
-        conv = s.optimize()
-        exp_dev = float("nan")
+        conv = s.optimize(multi_init=bool(ninit and ninit > 1))     # wrapper_gap_factor.h:296-350, :379
         if reorder_factor:
-            try:
-                s.order_factor()
-            except PcmfError as e:
-                if e.code != _lib.EUNSUPPORTED:
-                    raise
-        try:
-            exp_dev = s.monitors()["exp_dev"]
-        except PcmfError as e:
-            if e.code != _lib.EUNSUPPORTED:
-                raise
+            s.order_factor()                                        # :382-385
+        exp_dev = s.monitors(loglikelihood=False)["exp_dev"]        # algorithm.h:367
         o = s.get_output(want_prob_D=return_prob_D)
     finally:
         s.close()
@@ -458,8 +454,8 @@ def _run(X, K, zero_inflation, sparsity, sel_bound=0.5, U=None, V=None, verbose=
     res["loss"] = conv["loss"]
     res["exp_dev"] = exp_dev
     if monitor:
-        res["monitor"] = {"norm_gap": conv["norm_gap"], "abs_gap": conv["abs_gap"],
-                          "optim_criterion": conv["optim_criterion"]}                      # algorithm.h:369-376
+        res["monitor"] = {k: conv[k] for k in ("norm_gap", "abs_gap", "loglikelihood", "deviance",
+                                               "optim_criterion")}                         # algorithm.h:369-376
     res["seed"] = seed                                                                     # wrapper_gap_factor.h:391
     res["factor_order"] = o["factor_order"]
     return res

@@ -122,7 +122,10 @@ struct RowArgs {
     const double *alpha1, *alpha2;   // K-vectors
     const double *rate_vec;          // KP: colsum(EV o prob_S) (non-ZI)   gap...cpp:531 / sparse...cpp:400
     const double *PV;                // n x KP: prob_D * (EV o prob_S) (ZI) zi...cpp:336 / zi_sparse...cpp:363
-    int first_iter;                  // old iterate is Ones (gap_factor_model.cpp:72-75; never copied before iter 0)
+    int first_iter;                  // 1: old iterate is Ones (gap_factor_model.cpp:72-75; never copied before iter 0)
+                                     // 2: old iterate is a1_old0 / a2_old0 (first iteration of a later multi-init run:
+                                     //    the old copy still holds the previous run's last iterate, wrapper_gap_factor.h:296-350)
+    const double *a1_old0, *a2_old0;
     const long long *guard_cur;      // global extremes of the stats being read
     long long *guard_next;           // min/max of the new ElogU
     double *cs_eu, *cs_elog;         // KP each (atomic)
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
             if (k < a.K) {
                 const int64_t o = i * KP + k;
                 const double ez = um[c] * mine[c] + s_ex[w][k];
-                const double a1o = a.first_iter ? 1.0 : a.a1[o], a2o = a.first_iter ? 1.0 : a.a2[o];
+                const double a1o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a1_old0[o] : a.a1[o]);
+                const double a2o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a2_old0[o] : a.a2[o]);
                 const double a1n = a.alpha1[k] + ez;
                 const double a2n = a.alpha2[k] + (a.PV ? a.PV[o] : a.rate_vec[k]);
                 a.a1[o] = a1n;
@@ -410,6 +414,7 @@ struct VArgs {
     long long *guard_next;
     double *cs_ev, *cs_elogv, *cs_evs;    // KP each
     double *scal;
+    const double *b1_old0, *b2_old0;      // first_iter == 2 (see RowArgs)
 };
 #ifdef PCMF_COMMON_KERNELS
 __global__ void __launch_bounds__(256) k_mstep_genes(VArgs a) {
@@ -435,8 +440,8 @@ __global__ void __launch_bounds__(256) k_mstep_genes(VArgs a) {
                 if (a.sparse) data += ps * cw * (a.B2[o] + a.ElogV[o] * a.B1[o]);
                 else if (k == 0) data += cw * a.xlogT[j];
             }
-            b1o = a.first_iter ? 1.0 : a.b1[o];
-            b2o = a.first_iter ? 1.0 : a.b2[o];
+            b1o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.b1_old0[o] : a.b1[o]);
+            b2o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.b2_old0[o] : a.b2[o]);
             b1n = a.beta1[k] + ps * cw * a.B1[o];
             b2n = a.beta2[k] + ps * (a.zi ? a.tmpMat[o] : a.cs_eu[k]);
             a.b1[o] = b1n;
@@ -1033,22 +1038,24 @@ __global__ void k_build_bitmaps(int64_t n, int32_t p, const int64_t *rowptr, con
     }
 }
 #endif  // PCMF_COMMON_KERNELS
-// per-gene constants: sum_i lgamma(X_ij + 1) (ELBO, gap...cpp:319-323), nnz count and sum of the gene (init, freq_D)
+// per-gene constants: sum_i lgamma(X_ij + 1) (ELBO, gap...cpp:319-323), nnz count and sum of the gene (init, freq_D),
+// sum_i X_ij log X_ij - X_ij (poisson_loglike(X, X) of the deviance monitors, likelihood.h:149-155)
 template <typename VT>
 __global__ void k_gene_constants(int32_t p, const int64_t *colptr, const void *val_, double *Lg, double *colsumX,
-                                 double *colnnz) {
+                                 double *colnnz, double *xlogx) {
     const VT *val = static_cast<const VT *>(val_);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
     for (int j = warp; j < p; j += nw) {
-        double lg = 0, sx = 0, cn = 0;
+        double lg = 0, sx = 0, cn = 0, xl = 0;
         for (int64_t e = colptr[j] + lane; e < colptr[j + 1]; e += 32) {
             const double x = (double)val[e];
             lg += lgamma(x + 1.0); sx += x; cn += (x != 0.0) ? 1.0 : 0.0;
+            xl += x * custom_log(x) - x;
         }
-        lg = warp_sum(lg); sx = warp_sum(sx); cn = warp_sum(cn);
-        if (lane == 0) { Lg[j] = lg; colsumX[j] = sx; colnnz[j] = cn; }
+        lg = warp_sum(lg); sx = warp_sum(sx); cn = warp_sum(cn); xl = warp_sum(xl);
+        if (lane == 0) { Lg[j] = lg; colsumX[j] = sx; colnnz[j] = cn; xlogx[j] = xl; }
     }
 }
 template <typename VT>
@@ -1064,6 +1071,140 @@ __global__ void k_row_sums(int64_t n, const int64_t *rowptr, const void *val_, d
         if (lane == 0) rowsumX[i] = s;
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Monitors and factor ordering.  Everything the reference evaluates on the dense n x p rate
+// matrix UVt (or prob_D o UVt) splits into a sum over the non-zeros of X -- sum x clog(rate) -- and the total rate,
+// which has a closed form (gap...cpp:298) or comes out of the dense ZI pass (sum prob_D o UVt).
+// ------------------------------------------------------------------------------------------------------------
+// Non-zero pass over CSC, one block per gene: lambda_ij = EU_i . EVS_j.
+//   out[0] += w_j sum_i x clog(w_j lambda)    rate prob_D o UVt of deviance / exp_deviance (zi...cpp:218-245); w_j is
+//                                             prob_D on the gene's non-zeros (1, or 0 under the prior_D == 0 shortcut)
+//   out[1] += sum_i x clog(lambda)            rate UVt of loglikelihood (gap...cpp:278-284, likelihood.h:197-212)
+//   out[2] += sum_i lambda                    non-zero part of sum UVt
+//   out[3] += #non-zeros with w_j = 0         log(prob_D) = -inf in zi_poisson_loglike (likelihood.h:206)
+struct LamArgs {
+    int32_t p; int K;
+    const int64_t *colptr; const int32_t *rowidx; const void *val;
+    const double *EU;        // n x KP
+    const double *EVS;       // p x KP
+    const int32_t *flag;     // p or null (non-ZI)
+    double *out;             // 4 doubles (atomic)
+};
+template <int KP, typename VT>
+__global__ void __launch_bounds__(128) k_gene_loglam(LamArgs a) {
+    __shared__ double sh[32];
+    const VT *__restrict__ val = static_cast<const VT *>(a.val);
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    for (int j = blockIdx.x; j < a.p; j += gridDim.x) {
+        double v[KP];
+        load_vec<KP>(a.EVS + (int64_t)j * KP, v);
+        const double w = (a.flag && a.flag[j] == 2) ? 0.0 : 1.0;
+        double s1 = 0, s2 = 0;
+        const int64_t e0 = a.colptr[j], e1 = a.colptr[j + 1];
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int64_t i = __ldg(a.rowidx + e);
+            const double x = (double)__ldg(val + e);
+            double u[KP];
+            load_vec<KP>(a.EU + i * KP, u);
+            double l0 = 0.0, l1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; k += 2) { l0 = fma(u[k], v[k], l0); l1 = fma(u[k + 1], v[k + 1], l1); }
+            const double lam = l0 + l1;
+            s1 += x * custom_log(lam);
+            s2 += lam;
+        }
+        t0 += w * s1; t1 += s1; t2 += s2;
+        if (w == 0.0 && threadIdx.x == 0) t3 += (double)(e1 - e0);
+    }
+    t0 = block_sum(t0, sh); t1 = block_sum(t1, sh); t2 = block_sum(t2, sh); t3 = block_sum(t3, sh);
+    if (threadIdx.x == 0) { atomicAdd(a.out + 0, t0); atomicAdd(a.out + 1, t1); atomicAdd(a.out + 2, t2); atomicAdd(a.out + 3, t3); }
+}
+
+// One round of the greedy factor ordering (model.cpp:137-187): for every factor c not chosen yet,
+//   out[c] += sum_nnz x clog(w_j (base_ij + EU_ic EVS_jc)),   base_ij = sum_{k chosen} EU_ik EVS_jk
+// which is the non-zero part of poisson_loglike(X, rate restricted to chosen + c) in partial_deviance
+// (gap...cpp:420-450, zi...:264-286, sparse...:294-319, zi_sparse...:288-313).
+struct OrderArgs {
+    int32_t p; int K;
+    const int64_t *colptr; const int32_t *rowidx; const void *val;
+    const double *EU, *EVS; const int32_t *flag;
+    const double *chosen;    // KP doubles: 1 when the factor is already chosen
+    double *out;             // KP doubles (atomic)
+};
+template <int KP, typename VT>
+__global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
+    __shared__ double sacc[KP];
+    __shared__ double sch[KP];
+    const VT *__restrict__ val = static_cast<const VT *>(a.val);
+    if (threadIdx.x < KP) { sacc[threadIdx.x] = 0.0; sch[threadIdx.x] = threadIdx.x < a.K ? a.chosen[threadIdx.x] : 1.0; }
+    __syncthreads();
+    double acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+    for (int j = blockIdx.x; j < a.p; j += gridDim.x) {
+        if (a.flag && a.flag[j] == 2) continue;     // rate 0 on the whole gene: clog(0) = 0
+        double v[KP];
+        load_vec<KP>(a.EVS + (int64_t)j * KP, v);
+        const int64_t e0 = a.colptr[j], e1 = a.colptr[j + 1];
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int64_t i = __ldg(a.rowidx + e);
+            const double x = (double)__ldg(val + e);
+            double u[KP];
+            load_vec<KP>(a.EU + i * KP, u);
+            double base = 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) { u[k] *= v[k]; base = fma(u[k], sch[k], base); }
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (sch[k] == 0.0) acc[k] = fma(x, custom_log(base + u[k]), acc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const double t = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0 && t != 0.0) atomicAdd(&sacc[k], t);
+    }
+    __syncthreads();
+    if (threadIdx.x < a.K && sacc[threadIdx.x] != 0.0) atomicAdd(a.out + threadIdx.x, sacc[threadIdx.x]);
+}
+
+#ifdef PCMF_COMMON_KERNELS
+// likelihood::gamma_loglike(X, p1, p2) summed (likelihood.h:85-88): p1 log p2 + (p1 - 1) log X - p2 X - lgamma(p1)
+__global__ void k_gamma_loglike(int64_t rows, int K, int KP, const double *X, const double *p1, const double *p2, double *out) {
+    __shared__ double sh[32];
+    double t = 0;
+    const int64_t total = rows * KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        if ((int)(o % KP) >= K) continue;
+        t += p1[o] * log(p2[o]) + (p1[o] - 1.0) * log(X[o]) - p2[o] * X[o] - lgamma(p1[o]);
+    }
+    t = block_sum(t, sh);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+}
+// out[k] += sum_r A(r,k) B(r,k)
+__global__ void k_dot_cols(int64_t rows, int K, int KP, const double *A, const double *B, double *out) {
+    __shared__ double sacc[64];
+    if (threadIdx.x < 64) sacc[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int64_t total = rows * KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % KP);
+        if (k < K) atomicAdd(&sacc[k], A[o] * B[o]);
+    }
+    __syncthreads();
+    if (threadIdx.x < K) atomicAdd(out + threadIdx.x, sacc[threadIdx.x]);
+}
+// dst(:, c) = src(:, order[c]) -- Eigen's `M *= perm` with perm.indices()[c] = order[c] (gap...cpp:344-366)
+template <typename T>
+__global__ void k_permute_cols(int64_t rows, int K, int KP, const int32_t *order, const T *src, T *dst) {
+    const int64_t total = rows * KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % KP);
+        dst[o] = k < K ? src[o - k + order[k]] : src[o];
+    }
+}
+#endif  // PCMF_COMMON_KERNELS
 
 // column-major (R / Eigen) <-> padded row-major
 #ifdef PCMF_COMMON_KERNELS

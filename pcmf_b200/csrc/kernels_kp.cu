@@ -77,6 +77,25 @@ int launch_zi_genes_mma(const ZiBArgs &a, int chunks, int variant, cudaStream_t 
     if ((variant & 8) && MMA_MT == 4) return launch_zi_genes_mma_t<2>(a, chunks, st);
     return launch_zi_genes_mma_t<MMA_MT>(a, chunks, st);
 }
+void launch_zi_loglik(const ZiAArgs &a, double *out, cudaStream_t st) {
+    using R = ZiRec<KP, true>;
+    const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 2 * MMA_TJ + 64);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_loglik_mma<KP, MMA_MT, MMA_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    const int64_t grid = (a.n + 32 * MMA_MT - 1) / (32 * MMA_MT);
+    k_zi_loglik_mma<KP, MMA_MT, MMA_TJ><<<(unsigned)grid, 128, smem, st>>>(a, out);
+}
+void launch_gene_loglam(bool f32, const LamArgs &a, int grid, cudaStream_t st) {
+    if (f32) k_gene_loglam<KP, float><<<grid, 128, 0, st>>>(a);
+    else k_gene_loglam<KP, double><<<grid, 128, 0, st>>>(a);
+}
+void launch_gene_order(bool f32, const OrderArgs &a, int grid, cudaStream_t st) {
+    if (f32) k_gene_order<KP, float><<<grid, 128, 0, st>>>(a);
+    else k_gene_order<KP, double><<<grid, 128, 0, st>>>(a);
+}
 size_t zi_pack_doubles(int64_t rows, int cells_side) {
     const int64_t groups = (rows + 7) / 8;
     return (size_t)groups * (cells_side ? ZiRec<KP, false>::REC : ZiRec<KP, true>::REC);
@@ -118,7 +137,8 @@ int launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) 
 
 int zi_genes_block(int variant) { return !(variant & 4) ? (((variant & 8) && MMA_MT == 4) ? 64 : 32 * MMA_MT) : ((variant & 2) ? 128 : 256); }
 
-const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes, zi_genes_block, zi_pack_doubles};
+const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes, zi_genes_block, zi_pack_doubles,
+                         launch_zi_loglik, launch_gene_loglam, launch_gene_order};
 
 }  // namespace
 

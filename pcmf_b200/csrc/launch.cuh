@@ -14,7 +14,10 @@ struct Launchers {
     int (*zi_cells)(const ZiAArgs &, int variant, cudaStream_t);                // returns the number of launches
     int (*zi_genes)(const ZiBArgs &, int chunks, int variant, cudaStream_t);    // returns the number of launches
     int (*zi_genes_block)(int variant);   // genes per CTA of the gene-side ZI pass (for the chunk count)
-    size_t (*zi_pack_doubles)(int64_t rows, int cells_side);   // scratch size of ZiAArgs::pack (0) / ZiBArgs::pack (1)
+    size_t (*zi_pack_doubles)(int64_t rows, int cells_side);
+    void (*zi_loglik)(const ZiAArgs &, double *out, cudaStream_t);            // zero part of zi_poisson_loglike (monitor)
+    void (*gene_loglam)(bool f32, const LamArgs &, int grid, cudaStream_t);   // deviance / log-likelihood non-zero pass
+    void (*gene_order)(bool f32, const OrderArgs &, int grid, cudaStream_t);  // one round of the greedy factor ordering   // scratch size of ZiAArgs::pack (0) / ZiBArgs::pack (1)
 };
 
 const Launchers *get_launchers_4();

@@ -80,6 +80,14 @@ struct pcmf_solver {
     double *zpackA = nullptr, *zpackB = nullptr;   // fragment-ordered scratch of the DMMA ZI passes
     double *Lg = nullptr, *colsumX = nullptr, *colnnz = nullptr, *rowsumX = nullptr;
     double lgx_const = 0;
+    double *xlogx = nullptr;            // per gene: sum_i x log x - x
+    double ll_XX = 0, ll_Xmean = 0;     // poisson_loglike(X, X), poisson_loglike_vec(X, colmean(X)): constants of the deviance monitors
+    double *mon = nullptr;              // monitor / ordering scratch: 8 + 64 + 64 doubles
+    int32_t *d_order = nullptr;         // K
+    double *old0[4] = {nullptr, nullptr, nullptr, nullptr};   // multi-init: previous run's last a1, a2, b1, b2
+    int first_mode = 1;                 // value of first_iter for the first iteration (1: old = Ones, 2: old = old0)
+    std::mt19937 rng;                   // one stream for all random initialisations (wrapper_gap_factor.h:277-284)
+    unsigned long long rng_consumed = 0;
 
     // U side (n x KP)
     double *a1 = nullptr, *a2 = nullptr, *EU[2] = {nullptr, nullptr}, *ElogU = nullptr, *eu = nullptr, *PV = nullptr;
@@ -110,6 +118,7 @@ struct pcmf_solver {
     // iteration state (algorithm.h:50-64)
     int iter = 0;
     bool first_iter = true, converged = false;
+    pcmf_init init_copy{};              // the caller's warm-start pointers (multi-init re-initialises from them)
     int nb_iter_stab = 0;
     double last_nodata = 0;        // ELBO without its data term, state after the last update
     bool have_pending = false;     // the ELBO of iteration (iter-1) still waits for its data term
@@ -127,11 +136,20 @@ struct pcmf_solver {
     void setup_problem(const pcmf_problem &pr);
     void build_csc();
     void alloc_state();
-    void init_state(const pcmf_init *in);
+    void init_state(const pcmf_init *in, bool reinit = false);
     void run_init_stats();
     void allreduce(double *ptr, size_t count);
     void step(bool want_data);
     double data_term_now();
+    struct Mon { double loglik, deviance, exp_dev; };
+    Mon monitors_now(bool want_loglik);
+    void order_factor_now();
+    void multi_init(pcmf_result *res);
+    struct Saved { std::vector<std::pair<void *, size_t>> arrays; std::vector<void *> copies; int cur, gcur; bool first_iter, sparse_sums_valid, have_pending;
+                   double last_nodata; std::vector<double> h; int iter, first_mode; };
+    std::vector<std::pair<void *, size_t>> state_arrays();
+    void save_state(Saved &sv);
+    void restore_state(const Saved &sv);
     void begin(Phase ph) { CK(cudaEventRecord(ev_a[ph], stream)); }
     void end(Phase ph, int nl) { CK(cudaEventRecord(ev_b[ph], stream)); ph_used[ph] = true; ph_launch[ph] += nl; launches += nl; }
     void collect_phase_times() {
@@ -155,7 +173,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { cudaFree((void *)rowptr); cudaFree((void *)colidx); cudaFree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3]};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -301,11 +319,12 @@ void pcmf_solver::build_csc() {
     cudaFree(tmp); cudaFree(rowids); cudaFree(perm_in); cudaFree(perm_out); cudaFree(keys_out);
 
     Lg = dmalloc<double>(p); colsumX = dmalloc<double>(p); colnnz = dmalloc<double>(p); rowsumX = dmalloc<double>(n);
+    xlogx = dmalloc<double>(p);
     if (f32) {
-        k_gene_constants<float><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz);
+        k_gene_constants<float><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz, xlogx);
         k_row_sums<float><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
     } else {
-        k_gene_constants<double><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz);
+        k_gene_constants<double><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz, xlogx);
         k_row_sums<double><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
     }
     if (zi) {
@@ -315,11 +334,20 @@ void pcmf_solver::build_csc() {
         k_build_bitmaps<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, p, rowptr, colidx, bitT, bitB);
     }
     // gene constants are sums over cells -> all-reduce across the row shards
-    allreduce(Lg, p); allreduce(colsumX, p); allreduce(colnnz, p);
-    std::vector<double> h(p);
+    allreduce(Lg, p); allreduce(colsumX, p); allreduce(colnnz, p); allreduce(xlogx, p);
+    std::vector<double> h(p), hx(p), hs(p);
     CK(cudaMemcpyAsync(h.data(), Lg, sizeof(double) * p, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hx.data(), xlogx, sizeof(double) * p, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hs.data(), colsumX, sizeof(double) * p, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     lgx_const = 0; for (double x : h) lgx_const += x;
+    // constants of deviance / exp_deviance (gap...cpp:329-341): poisson_loglike(X, X) and poisson_loglike_vec(X, colmean X)
+    ll_XX = -lgx_const; ll_Xmean = -lgx_const;
+    for (int j = 0; j < p; ++j) {
+        ll_XX += hx[j];
+        const double m = hs[j] / (double)n_global;
+        ll_Xmean += hs[j] * (m > 0 ? std::log(m) : 0.0) - (double)n_global * m;
+    }
     CK(cudaGetLastError());
 }
 
@@ -356,6 +384,7 @@ void pcmf_solver::alloc_state() {
     allmasked = dmalloc<uint8_t>(p); CK(cudaMemsetAsync(allmasked, 0, p, stream));
     unchanged = dmalloc<uint8_t>(p); CK(cudaMemsetAsync(unchanged, 0, p, stream));
     if (opt.world > 1) ar2keep = dmalloc<double>(2 * (size_t)p * KP);
+    mon = dmalloc<double>(8 + 64 + 64); d_order = dmalloc<int32_t>(64);
     dbg = dmalloc<unsigned long long>(4); CK(cudaMemsetAsync(dbg, 0, 32, stream));
     k_init_guard<<<1, 32, 0, stream>>>(guard[0]); k_init_guard<<<1, 32, 0, stream>>>(guard[1]);
     CK(cudaMallocHost(&h_scal, sizeof(double) * S_COUNT));
@@ -379,7 +408,7 @@ void pcmf_solver::download_colmajor(const double *src, int64_t rows, double *hos
     cudaFree(tmp);
 }
 
-void pcmf_solver::init_state(const pcmf_init *in) {
+void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
     const pcmf_init none{};
     if (!in) in = &none;
     // ---- argument consistency, with the reference's messages (wrapper_gap_factor.h:215-258)
@@ -392,17 +421,22 @@ void pcmf_solver::init_state(const pcmf_init *in) {
         fail(PCMF_EINVAL, "You should supply initial values for all alpha1, alpha2, beta1, beta2 or for none of them");
 
     // hyper-parameters: Ones (gap_factor_model.cpp:56-59) unless given
-    std::vector<double> h(4 * 64, 1.0);
-    if (nhy == 4) {
-        for (int k = 0; k < K; ++k) { h[k] = in->alpha1[k]; h[64 + k] = in->alpha2[k]; h[128 + k] = in->beta1[k]; h[192 + k] = in->beta2[k]; }
+    // a later multi-init run starts from the hyper-parameters the previous run ended with (the reference re-uses one
+    // model object, wrapper_gap_factor.h:299-301: update_prior_gamma_param then reads log(alpha2) of that run)
+    if (!reinit || nhy == 4) {
+        std::vector<double> h(4 * 64, 1.0);
+        if (nhy == 4) {
+            for (int k = 0; k < K; ++k) { h[k] = in->alpha1[k]; h[64 + k] = in->alpha2[k]; h[128 + k] = in->beta1[k]; h[192 + k] = in->beta2[k]; }
+        }
+        CK(cudaMemcpyAsync(hyp, h.data(), sizeof(double) * 4 * 64, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
     }
-    CK(cudaMemcpyAsync(hyp, h.data(), sizeof(double) * 4 * 64, cudaMemcpyHostToDevice, stream));
-    CK(cudaStreamSynchronize(stream));
 
     // sparse parameters first (wrapper_sparse_gap_factor.h:390-394)
-    std::mt19937 rng(opt.has_seed ? opt.seed : (uint32_t)std::chrono::system_clock::now().time_since_epoch().count());
+    // every draw comes from ONE stream, positioned by the number of draws consumed so far, so that a cell-sharded run
+    // and successive multi-init runs see the same numbers as a single process would
     auto unif = [](std::mt19937 &g) { return ((double)g() + 0.5) / 4294967296.0; };
-    int64_t draws_before_U = 0;
+    std::mt19937 base = rng; base.discard(rng_consumed);
     if (sparse) {
         if (in->prob_S && in->prior_S) {
             upload_colmajor(in->prob_S, p, prob_S, 0.0);
@@ -410,12 +444,13 @@ void pcmf_solver::init_state(const pcmf_init *in) {
         } else {
             // init_sparse_param(sel_bound, rng): uniform prob_S (sparse_gap_factor_model.cpp:71-88)
             std::vector<double> ps((size_t)p * K), pr(p);
+            std::mt19937 gs = base;
             for (int j = 0; j < p; ++j) {
                 double s = 0;
-                for (int k = 0; k < K; ++k) { const double u = unif(rng); ps[j + (size_t)k * p] = u; s += u; }
+                for (int k = 0; k < K; ++k) { const double u = unif(gs); ps[j + (size_t)k * p] = u; s += u; }
                 pr[j] = s / K;
             }
-            draws_before_U = (int64_t)p * K;
+            base.discard((unsigned long long)p * K); rng_consumed += (unsigned long long)p * K;
             upload_colmajor(ps.data(), p, prob_S, 0.0);
             CK(cudaMemcpy(prior_S, pr.data(), sizeof(double) * p, cudaMemcpyHostToDevice));
         }
@@ -435,17 +470,17 @@ void pcmf_solver::init_state(const pcmf_init *in) {
         CK(cudaMemcpy(rs.data(), rowsumX, sizeof(double) * n, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(cs.data(), colsumX, sizeof(double) * p, cudaMemcpyDeviceToHost));
         std::vector<double> A((size_t)n * K), B((size_t)p * K);
-        std::mt19937 gu = rng; gu.discard((unsigned long long)row_offset * K);
+        std::mt19937 gu = base; gu.discard((unsigned long long)row_offset * K);
         for (int64_t i = 0; i < n; ++i) {
             const double rate = std::sqrt((double)K / (rs[i] / p));
             for (int k = 0; k < K; ++k) A[i + (size_t)k * n] = -std::log(unif(gu)) / rate;
         }
-        std::mt19937 gv = rng; gv.discard((unsigned long long)n_global * K);
+        std::mt19937 gv = base; gv.discard((unsigned long long)n_global * K);
         for (int j = 0; j < p; ++j) {
             const double rate = std::sqrt((double)K / (cs[j] / (double)n_global));
             for (int k = 0; k < K; ++k) B[j + (size_t)k * p] = -std::log(unif(gv)) / rate;
         }
-        (void)draws_before_U;
+        rng_consumed += (unsigned long long)(n_global + p) * K;
         upload_colmajor(A.data(), n, a1, 1.0); upload_colmajor(B.data(), p, b1, 1.0);
         k_fill<<<grid_for(n * KP, 256), 256, 0, stream>>>(a2, n * KP, 1.0);
         k_fill<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(b2, (int64_t)p * KP, 1.0);
@@ -530,7 +565,7 @@ void pcmf_solver::step(bool want_data) {
         RowArgs ra{};
         ra.n = n; ra.K = K; ra.rowptr = rowptr; ra.colidx = colidx; ra.val = val_csr; ra.ev = ev; ra.evw = evw; ra.ElogV = ElogV;
         ra.Sd = Sd; ra.wS = wS; ra.allmasked = allmasked; ra.dbg = dbg; ra.a1 = a1; ra.a2 = a2; ra.EU_new = EU[nxt]; ra.ElogU = ElogU; ra.eu = eu; ra.rowext = rowext; ra.alpha1 = alpha1;
-        ra.alpha2 = alpha2; ra.rate_vec = csv + 128; ra.PV = zi ? PV : nullptr; ra.first_iter = first_iter; ra.guard_cur = gc;
+        ra.alpha2 = alpha2; ra.rate_vec = csv + 128; ra.PV = zi ? PV : nullptr; ra.first_iter = first_iter ? first_mode : 0; ra.a1_old0 = old0[0]; ra.a2_old0 = old0[1]; ra.guard_cur = gc;
         ra.guard_next = gn; ra.cs_eu = ar1 + ar1_cseu; ra.cs_elog = ar1 + ar1_cselog; ra.usc = ar1 + ar1_usc;
         // colsum(EV o prob_S) of the OLD state: csv+128 is re-accumulated during this iteration, hyp+256 keeps the copy
         ra.rate_vec = hyp + 256;
@@ -562,7 +597,7 @@ void pcmf_solver::step(bool want_data) {
     begin(PH_MSTEP_V);
     {
         VArgs va{};
-        va.p = p; va.K = K; va.KP = KP; va.sparse = sparse; va.zi = zi; va.first_iter = first_iter; va.want_data = want_data;
+        va.p = p; va.K = K; va.KP = KP; va.sparse = sparse; va.zi = zi; va.first_iter = first_iter ? first_mode : 0; va.b1_old0 = old0[2]; va.b2_old0 = old0[3]; va.want_data = want_data;
         va.stats_only = 0; va.B1 = ar1 + ar1_B1; va.B2 = ar1 + ar1_B2; va.xlogT = ar1 + ar1_xlogT; va.tmpMat = ar1 + ar1_tmp;
         va.cs_eu = ar1 + ar1_cseu; va.beta1 = beta1; va.beta2 = beta2; va.b1 = b1; va.b2 = b2; va.EV = EV; va.ElogV = ElogV;
         va.prob_S = prob_S; va.Sd = Sd; va.colw = colw; va.ev = ev; va.evw = evw; va.EVS = EVS; va.wS = wS; va.guard_next = gn;
@@ -627,6 +662,202 @@ double pcmf_solver::data_term_now() {
     launches += 2;
     read_scal();
     return h_scal[S_DATA];
+}
+
+// Monitors of the current state.  rate = UVt (gap, sparse) or prob_D o UVt (ZI variants):
+//   deviance      -2 (pl(X, rate) - pl(X, X))                 gap...cpp:329-333, zi...:218-229, sparse...:231-235
+//   exp_deviance  (pl(X, rate) - pl_vec(X, colmean)) / (pl(X, X) - pl_vec(X, colmean))   gap...cpp:336-341 and variants
+//   loglikelihood gap...cpp:278-284, zi...:160-167, sparse...:151-157, zi_sparse...:171-178
+// pl(X, rate) = sum_nnz x clog(rate) - sum_ij rate - sum lgamma(x + 1): one non-zero pass + the total rate, which is
+// the closed form of gap...cpp:298 or, for ZI, sum prob_D o UVt of the last dense pass.
+pcmf_solver::Mon pcmf_solver::monitors_now(bool want_loglik) {
+    CK(cudaMemsetAsync(mon, 0, 8 * sizeof(double), stream));
+    LamArgs la{p, K, colptr, rowidx, val_csc, EU[cur], EVS, zi ? flag : nullptr, mon};
+    L->gene_loglam(f32, la, std::min<int>(p, sms * 32), stream);
+    launches += 1;
+    if (want_loglik) {
+        k_gamma_loglike<<<grid_for(n * KP, 256), 256, 0, stream>>>(n, K, KP, EU[cur], a1, a2, mon + 4);
+        k_gamma_loglike<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, EV, b1, b2, mon + 6);
+        launches += 2;
+        if (zi) {
+            ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
+            L->zi_loglik(za, mon + 5, stream);
+            launches += 1;
+        }
+    }
+    allreduce(mon, 6);    // [0..3] non-zero sums, [4] Gamma term of U, [5] zero part: sums over the local cells; [6] is replicated
+    double h[8];
+    CK(cudaMemcpyAsync(h, mon, sizeof h, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const double sum_rate = zi ? h_scal[S_SUM_PUVT] : h_scal[S_SUMUVT_CLOSED];
+    const double r1 = h[0] - sum_rate - lgx_const;
+    Mon m;
+    m.deviance = -2.0 * (r1 - ll_XX);
+    m.exp_dev = (r1 - ll_Xmean) / (ll_XX - ll_Xmean);
+    m.loglik = NAN;
+    if (want_loglik) {
+        double ll;
+        if (!zi) ll = h[1] - h_scal[S_SUMUVT_CLOSED] - lgx_const;
+        else {
+            // zi_poisson_loglike (likelihood.h:197-212): non-zeros log(prob_D) + pl1(x, lambda), zeros log(1 - P + P e^-lambda)
+            ll = h[1] - h[2] - lgx_const + h[5];
+            if (h[3] > 0) ll = -INFINITY;    // log(prob_D) with prob_D = 0 on a non-zero entry (prior_D == 0 shortcut)
+            ll += h_scal[S_BERND_SELF];
+        }
+        ll += h[4] + h[6];
+        if (sparse) ll += h_scal[S_BERNS_SELF];
+        m.loglik = ll;
+    }
+    return m;
+}
+
+// variational_em_algo::order_factor (algorithm_variational_EM.h:189-192): greedy forward selection on the partial deviance
+// (model.cpp:137-187), then reorder_factor (gap...cpp:344-366, sparse...cpp:250-275).  One non-zero pass per round
+// evaluates every remaining candidate; the total-rate part of each candidate is a sum of per-factor totals.
+void pcmf_solver::order_factor_now() {
+    // per-factor totals t_k = sum_ij [prob_D_ij] EU_ik EVS_jk
+    std::vector<double> tk(64, 0.0), hsum(64);
+    CK(cudaMemsetAsync(mon + 8, 0, 128 * sizeof(double), stream));
+    if (zi) {
+        k_dot_cols<<<grid_for(n * KP, 256), 256, 0, stream>>>(n, K, KP, EU[cur], PV, mon + 8);   // sum_i EU_ik (prob_D EVS)_ik
+        allreduce(mon + 8, K);
+        CK(cudaMemcpyAsync(tk.data(), mon + 8, sizeof(double) * K, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    } else {
+        // closed form: colsum(EU)_k colsum(EVS)_k, both maintained by the iteration (all-reduced) -- gap...cpp:298
+        CK(cudaMemcpyAsync(tk.data(), ar1 + ar1_cseu, sizeof(double) * K, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hsum.data(), csv + 128, sizeof(double) * K, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (int k = 0; k < K; ++k) tk[k] *= hsum[k];
+    }
+    launches += zi ? 1 : 0;
+    std::vector<int> left, chosen;
+    for (int k = 0; k < K; ++k) left.push_back(k);
+    std::vector<double> mask(64, 0.0), out(64);
+    double base_total = 0;
+    for (int k = 0; k < K; ++k) {
+        CK(cudaMemsetAsync(mon + 8, 0, 64 * sizeof(double), stream));
+        CK(cudaMemcpyAsync(mon + 72, mask.data(), 64 * sizeof(double), cudaMemcpyHostToDevice, stream));
+        OrderArgs oa{p, K, colptr, rowidx, val_csc, EU[cur], EVS, zi ? flag : nullptr, mon + 72, mon + 8};
+        L->gene_order(f32, oa, std::min<int>(p, sms * 32), stream);
+        launches += 1;
+        allreduce(mon + 8, K);
+        CK(cudaMemcpyAsync(out.data(), mon + 8, sizeof(double) * K, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        double val_min = -1; int ind_min = 0; size_t ind_left = 0;
+        for (size_t ind = 0; ind < left.size(); ++ind) {
+            const int c = left[ind];
+            const double r1 = out[c] - (base_total + tk[c]) - lgx_const;
+            const double res = -2.0 * (r1 - ll_XX);
+            if (ind == 0) { val_min = res; ind_min = c; ind_left = ind; }          // model.cpp:161-165
+            if (res < val_min) { val_min = res; ind_min = c; ind_left = ind; }     // model.cpp:168-172
+        }
+        chosen.push_back(ind_min);
+        left.erase(left.begin() + ind_left);
+        mask[ind_min] = 1.0; base_total += tk[ind_min];
+    }
+    for (int k = 0; k < K; ++k) factor_order[k] = chosen[k];
+    // reorder_factor: column c of every K-indexed matrix becomes old column factor_order[c]
+    std::vector<int32_t> ord(64, 0);
+    for (int k = 0; k < K; ++k) ord[k] = chosen[k];
+    CK(cudaMemcpyAsync(d_order, ord.data(), sizeof(int32_t) * 64, cudaMemcpyHostToDevice, stream));
+    const int64_t big = std::max<int64_t>(n, p);
+    double *tmp = dmalloc<double>((size_t)big * KP);
+    auto perm_d = [&](double *A, int64_t rows, int kp) {
+        if (!A) return;
+        k_permute_cols<double><<<grid_for(rows * kp, 256), 256, 0, stream>>>(rows, K, kp, d_order, A, tmp);
+        CK(cudaMemcpyAsync(A, tmp, sizeof(double) * rows * kp, cudaMemcpyDeviceToDevice, stream));
+    };
+    for (double *A : {a1, a2, EU[0], EU[1], ElogU, eu, PV}) perm_d(A, n, KP);
+    for (double *A : {b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd}) perm_d(A, p, KP);
+    for (int v = 0; v < 5; ++v) perm_d(hyp + 64 * v, 1, 64);
+    for (int v = 0; v < 3; ++v) perm_d(csv + 64 * v, 1, 64);
+    perm_d(ar1 + ar1_cseu, 1, 64); perm_d(ar1 + ar1_cselog, 1, 64);
+    k_permute_cols<int32_t><<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, d_order, S, reinterpret_cast<int32_t *>(tmp));
+    CK(cudaMemcpyAsync(S, tmp, sizeof(int32_t) * (size_t)p * KP, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(tmp);
+    sparse_sums_valid = false;   // the cached gene-pass sums are in the old column order
+    CK(cudaGetLastError());
+}
+
+// ---- multi-init (wrapper_gap_factor.h:296-350, wrapper_sparse_gap_factor.h:328-387) ---------------------------
+std::vector<std::pair<void *, size_t>> pcmf_solver::state_arrays() {
+    const size_t nK = (size_t)n * KP * 8, pK = (size_t)p * KP * 8;
+    std::vector<std::pair<void *, size_t>> v;
+    for (double *A : {a1, a2, EU[0], EU[1], ElogU, eu, PV}) if (A) v.push_back({A, nK});
+    for (double *A : {b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd}) if (A) v.push_back({A, pK});
+    v.push_back({S, (size_t)p * KP * 4}); v.push_back({flag, (size_t)p * 4});
+    for (double *A : {prior_S, prior_D, cz, colw}) v.push_back({A, (size_t)p * 8});
+    v.push_back({hyp, 5 * 64 * 8}); v.push_back({csv, 3 * 64 * 8});
+    v.push_back({ar1, ar1_total * 8}); v.push_back({ar2, ar2_total * 8}); v.push_back({ar3, ar3_total * 8});
+    if (ar2keep) v.push_back({ar2keep, 2 * pK});
+    v.push_back({scal, S_COUNT * 8}); v.push_back({guard[0], G_COUNT * 8}); v.push_back({guard[1], G_COUNT * 8});
+    v.push_back({rowext, (size_t)n * 16}); v.push_back({colext, (size_t)p * 16});
+    v.push_back({allmasked, (size_t)p}); v.push_back({unchanged, (size_t)p});
+    return v;
+}
+void pcmf_solver::save_state(Saved &sv) {
+    if (sv.copies.empty()) {
+        sv.arrays = state_arrays();
+        for (auto &a : sv.arrays) { void *q = nullptr; CK(cudaMalloc(&q, std::max<size_t>(a.second, 1))); sv.copies.push_back(q); }
+    }
+    for (size_t i = 0; i < sv.arrays.size(); ++i)
+        CK(cudaMemcpyAsync(sv.copies[i], sv.arrays[i].first, sv.arrays[i].second, cudaMemcpyDeviceToDevice, stream));
+    sv.cur = cur; sv.gcur = gcur; sv.first_iter = first_iter; sv.sparse_sums_valid = sparse_sums_valid; sv.have_pending = have_pending;
+    sv.last_nodata = last_nodata; sv.h.assign(h_scal, h_scal + S_COUNT); sv.iter = iter; sv.first_mode = first_mode;
+    CK(cudaStreamSynchronize(stream));
+}
+void pcmf_solver::restore_state(const Saved &sv) {
+    for (size_t i = 0; i < sv.arrays.size(); ++i)
+        CK(cudaMemcpyAsync(sv.arrays[i].first, sv.copies[i], sv.arrays[i].second, cudaMemcpyDeviceToDevice, stream));
+    cur = sv.cur; gcur = sv.gcur; first_iter = sv.first_iter; sparse_sums_valid = sv.sparse_sums_valid; have_pending = sv.have_pending;
+    last_nodata = sv.last_nodata; std::copy(sv.h.begin(), sv.h.end(), h_scal); iter = sv.iter; first_mode = sv.first_mode;
+    CK(cudaStreamSynchronize(stream));
+}
+
+// Runs `ninit` initialisations for `iter_init` iterations each and keeps the one with the SMALLEST loss (sic:
+// `tmp_loss < best_loss` although the loss is the ELBO, wrapper_gap_factor.h:342), leaving the solver in the kept
+// run's state at iteration iter_init so that pcmf_optimize continues from there (my_model = tmp_model, :339-345).
+// Reference details kept: the per-iteration vectors of the kept run stay in `res` for iterations < iter_init; the
+// first iteration of runs after the first measures its gap against the previous run's last iterate (the `old` copies
+// are never reset); with explicit a1..b2 / U,V the reference perturbs by max(U, V)/K, reading U and V even when only
+// a1..b2 were given (undefined behaviour there) -- here explicit initial values are re-used unperturbed unless U, V
+// were given.
+void pcmf_solver::multi_init(pcmf_result *res) {
+    const pcmf_options saved_opt = opt;
+    opt.iter_max = saved_opt.iter_init; opt.iter_min = saved_opt.iter_init; opt.epsilon = 1e-6;   // set_iter(iter_init, iter_init, 1e-6)
+    opt.progress = nullptr;                                                                     // set_verbosity(false)
+    const size_t nK = (size_t)n * KP * 8, pK = (size_t)p * KP * 8;
+    Saved best;
+    std::vector<std::vector<double>> best_vec(6);
+    double *vecs[6] = {res->conv_crit, res->norm_gap, res->abs_gap, res->optim_criterion, res->loglikelihood, res->deviance};
+    double best_loss = 0;
+    for (int run = 0; run < saved_opt.ninit; ++run) {
+        if (run > 0) {
+            // the reference's m_*old members still hold the previous run's last iterate
+            if (!old0[0]) { old0[0] = dmalloc<double>(nK / 8); old0[1] = dmalloc<double>(nK / 8); old0[2] = dmalloc<double>(pK / 8); old0[3] = dmalloc<double>(pK / 8); }
+            CK(cudaMemcpyAsync(old0[0], a1, nK, cudaMemcpyDeviceToDevice, stream)); CK(cudaMemcpyAsync(old0[1], a2, nK, cudaMemcpyDeviceToDevice, stream));
+            CK(cudaMemcpyAsync(old0[2], b1, pK, cudaMemcpyDeviceToDevice, stream)); CK(cudaMemcpyAsync(old0[3], b2, pK, cudaMemcpyDeviceToDevice, stream));
+            first_mode = 2;
+            init_state(&init_copy, true);   // init_sparse_param / init_zi_param / init_random with the continuing stream
+        }
+        iter = 0;                        // set_current_iter(0)
+        char err[512] = {0};
+        const int rc = pcmf_optimize(this, res, err, sizeof err);
+        if (rc != PCMF_OK) fail(rc, "%s", err);
+        const double loss = res->loss;
+        if (run == 0 || loss < best_loss) {
+            best_loss = loss;
+            save_state(best);
+            for (int v = 0; v < 6; ++v) if (vecs[v]) best_vec[v].assign(vecs[v], vecs[v] + saved_opt.iter_init);
+        }
+    }
+    restore_state(best);
+    for (int v = 0; v < 6; ++v) if (vecs[v]) std::copy(best_vec[v].begin(), best_vec[v].end(), vecs[v]);
+    for (void *q : best.copies) cudaFree(q);
+    opt = saved_opt;                     // set_iter(iter_min, iter_max, epsilon); set_verbosity(verbose)
+    first_mode = 1;
 }
 
 // ================================================================================================================
@@ -699,6 +930,8 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
         if (!s->L) fail(PCMF_EUNSUPPORTED, "no kernels compiled for padded K = %d", s->KP);
         s->setup_problem(*prob);
         s->alloc_state();
+        if (init) s->init_copy = *init;
+        s->rng.seed(s->opt.has_seed ? s->opt.seed : (uint32_t)std::chrono::system_clock::now().time_since_epoch().count());
         s->init_state(init);
     });
     if (rc != PCMF_OK) { delete s; s = nullptr; }
@@ -733,6 +966,7 @@ int pcmf_optimize(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen)
         const pcmf_options &o = s->opt;
         const double t0 = now_s();
         s->converged = false;
+        s->nb_iter_stab = 0;     // local to optimize() in the reference (algorithm.h:161)
         // algorithm.h:158-210
         int pending = -1;   // iteration whose ELBO still lacks its data term
         while (s->iter < o.iter_max && !s->converged) {
@@ -746,6 +980,11 @@ int pcmf_optimize(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen)
             if (want && res->optim_criterion) res->optim_criterion[pending] = s->last_nodata + s->h_scal[S_DATA];
             s->last_nodata = s->h_scal[S_ELBO_NODATA];
             pending = it;
+            if (o.monitor == 1 && (res->loglikelihood || res->deviance)) {   // algorithm.h:391-397
+                const pcmf_solver::Mon m = s->monitors_now(res->loglikelihood != nullptr);
+                if (res->loglikelihood) res->loglikelihood[it] = m.loglik;
+                if (res->deviance) res->deviance[it] = m.deviance;
+            }
             const double ag = s->h_scal[S_ABS_GAP], ng = s->h_scal[S_NORM_GAP];
             const double crit = o.conv_mode == 0 ? ag : ng;   // algorithm.h:417-423
             if (res->conv_crit) res->conv_crit[it] = crit;
@@ -795,15 +1034,27 @@ int pcmf_set_variational(pcmf_solver *s, const double *a1, const double *a2, con
 int pcmf_order_factor(pcmf_solver *s, char *errbuf, size_t errlen) {
     return guarded(errbuf, errlen, [&] {
         if (!s) fail(PCMF_EINVAL, "null solver");
-        fail(PCMF_EUNSUPPORTED, "order_factor is not implemented yet (SURVEY 8f rank 2)");
+        CK(cudaSetDevice(s->device));
+        s->order_factor_now();
     });
 }
 
 int pcmf_monitors(pcmf_solver *s, double *loglikelihood, double *deviance, double *exp_deviance, char *errbuf, size_t errlen) {
     return guarded(errbuf, errlen, [&] {
         if (!s) fail(PCMF_EINVAL, "null solver");
-        (void)loglikelihood; (void)deviance; (void)exp_deviance;
-        fail(PCMF_EUNSUPPORTED, "monitors are not implemented yet (SURVEY 8f rank 1)");
+        CK(cudaSetDevice(s->device));
+        const pcmf_solver::Mon m = s->monitors_now(loglikelihood != nullptr);
+        if (loglikelihood) *loglikelihood = m.loglik;
+        if (deviance) *deviance = m.deviance;
+        if (exp_deviance) *exp_deviance = m.exp_dev;
+    });
+}
+
+int pcmf_multi_init(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        if (!s || !res) fail(PCMF_EINVAL, "null solver/result");
+        CK(cudaSetDevice(s->device));
+        s->multi_init(res);
     });
 }
 
@@ -896,16 +1147,11 @@ int pcmf_fit(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_init 
     int rc = pcmf_create(prob, opt, init, &s, errbuf, errlen);
     if (rc != PCMF_OK) return rc;
     res->seconds_setup = now_s() - t0;
-    if (opt->ninit > 1) {
-        pcmf_destroy(s);
-        if (errbuf && errlen) snprintf(errbuf, errlen, "ninit > 1 (multi-init) is not implemented yet (SURVEY 8f rank 4)");
-        return PCMF_EUNSUPPORTED;
-    }
-    rc = pcmf_optimize(s, res, errbuf, errlen);
-    if (rc == PCMF_OK) {
-        res->exp_dev = NAN;
-        rc = pcmf_get_output(s, res, errbuf, errlen);
-    }
+    if (opt->ninit > 1) rc = pcmf_multi_init(s, res, errbuf, errlen);                                 // wrapper_gap_factor.h:296-350
+    if (rc == PCMF_OK) rc = pcmf_optimize(s, res, errbuf, errlen);                                      // :379
+    if (rc == PCMF_OK && opt->reorder_factor) rc = pcmf_order_factor(s, errbuf, errlen);               // :382-385
+    if (rc == PCMF_OK) rc = pcmf_monitors(s, nullptr, nullptr, &res->exp_dev, errbuf, errlen);          // algorithm.h:367
+    if (rc == PCMF_OK) rc = pcmf_get_output(s, res, errbuf, errlen);                                    // :389-392
     pcmf_destroy(s);
     res->seconds_total = now_s() - t0;
     return rc;

@@ -289,6 +289,97 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Zero-entry part of likelihood::zi_poisson_loglike (likelihood.h:197-212), monitor only:
+//   sum over X_ij == 0 of log(1 - P_ij + P_ij exp(-lambda_ij)),  P the current prob_D, lambda = UVt.
+// Same tiles as pass A (it reuses pass A's packed gene records), first product only.  With y = 1 + e^-z, P = 1/y:
+//   1 - P + P e^-lambda = ((y - 1) + e^-lambda) / y;  clamped entries give -lambda (P = 1) or 0 (P = 0).
+// ------------------------------------------------------------------------------------------------------------
+template <int KP, int MT, int TJ>
+__global__ void __launch_bounds__(128, (KP <= 20) ? 3 : 2) k_zi_loglik_mma(ZiAArgs a, double *out) {
+    const double *__restrict__ pack = a.pack;
+    using R = ZiRec<KP, true>;
+    constexpr int KS = R::KS, NG = TJ / 8, BUF = NG * R::REC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_buf = reinterpret_cast<double *>(smem_raw);
+    double *s_tab = s_buf + 2 * BUF + 2 * TJ;
+    __shared__ double sh[32];
+    __shared__ uint64_t bar[2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    const int64_t cell0 = (int64_t)blockIdx.x * (32 * MT) + w * (8 * MT);
+    double a1[MT][KS];
+    bool live[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int64_t i = cell0 + mt * 8 + g;
+        live[mt] = i < a.n;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) a1[mt][s] = live[mt] ? __ldg(a.EU + i * KP + 4 * s + q) : 0.0;
+    }
+    double lin = 0, lg = 0, pn = 1.0, pd = 1.0;
+    uint32_t bits[MT];
+    const int ngroups = (a.p + 7) >> 3, ntiles = (ngroups + NG - 1) / NG;
+    auto issue = [&](int tile) {
+        const int g0 = tile * NG, gn = min(NG, ngroups - g0);
+        const unsigned bytes = (unsigned)(gn * R::REC * sizeof(double));
+        mbar_expect_tx(&bar[tile & 1], bytes);
+        bulk_g2s(s_buf + (tile & 1) * BUF, pack + (int64_t)g0 * R::REC, bytes, &bar[tile & 1]);
+    };
+    if (threadIdx.x == 0) issue(0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int j0 = tile * TJ;
+        const double *buf = s_buf + (tile & 1) * BUF;
+        if (threadIdx.x == 0 && tile + 1 < ntiles) issue(tile + 1);
+        mbar_wait(&bar[tile & 1], (tile >> 1) & 1);
+#pragma unroll 1
+        for (int grp = 0; grp < NG; ++grp) {
+            const int jg = j0 + grp * 8;
+            if (jg >= a.p) break;
+            const double *rec = buf + grp * R::REC;
+            if ((grp & 3) == 0) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    bits[mt] = live[mt] ? __ldg(a.bitT + (int64_t)(jg >> 5) * a.n + (cell0 + mt * 8 + g)) : 0xffffffffu;
+            }
+            double d[MT][2];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) { d[mt][0] = 0.0; d[mt][1] = 0.0; }
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                const double b = rec[s * 32 + lane];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) dmma884(d[mt][0], d[mt][1], a1[mt][s], b);
+            }
+            const double2 c2 = *reinterpret_cast<const double2 *>(rec + R::F1 + R::F2 + 2 * q);
+            const int sh0 = ((grp & 3) << 3) + 2 * q;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double lam = d[mt][e], z = (e ? c2.y : c2.x) - lam;
+                    const bool zero = !((bits[mt] >> (sh0 + e)) & 1u);      // dead rows carry all-ones words
+                    const int hi = __double2hiint(z);
+                    const bool big = (hi & 0x7fffffff) >= 0x403E0000;
+                    const double em = fast_exp_neg_tab(z, s_tab);               // y - 1
+                    const double el = fast_exp_neg_tab(fmin(lam, 690.0), s_tab);
+                    const bool in_ = zero && !big;
+                    pn *= in_ ? (em + el) : 1.0;
+                    pd *= in_ ? (1.0 + em) : 1.0;
+                    lin -= (zero && big && hi >= 0) ? lam : 0.0;
+                }
+            if (pn > 1e100 || pn < 1e-100) { lg += log(pn); pn = 1.0; }
+            if (pd > 1e100) { lg -= log(pd); pd = 1.0; }
+        }
+        __syncthreads();
+    }
+    double t = lin + lg + log(pn) - log(pd);
+    t = block_sum(t, sh);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Pass B: rows = genes (8 MT per warp), columns = cells of this CTA's chunk streamed through shared memory.
 // Output tmpMat = prob_D^T . EU_new (p x KP), prob_D recomputed from the triple saved when it was defined.
 // ------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,105 @@
+"""GPU parity of the components around the iteration through the C ABI, against the oracle:
+monitors (log-likelihood, deviance, explained deviance), the greedy factor ordering + reorder, and the multi-init loop.
+Tolerance: 1e-8 relative on scalars (north_star allows 1e-6), exact equality on the chosen factor order."""
+import numpy as np
+import pytest
+
+import pcmf_b200
+from oracle import pyoracle as po
+from pcmf_b200 import datagen
+from tests.test_gpu_parity import IDS, MODELS, compare_state, make_pair, problem, relerr
+
+pytestmark = pytest.mark.gpu
+
+RUN = {(False, False): pcmf_b200.run_gap_factor, (True, False): pcmf_b200.run_zi_gap_factor,
+       (False, True): pcmf_b200.run_sparse_gap_factor, (True, True): pcmf_b200.run_zi_sparse_gap_factor}
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+@pytest.mark.parametrize("K", [3, 20])
+def test_monitors_match_oracle(zi, sparse, K):
+    """loglikelihood / deviance / exp_deviance of the state after 0, 1 and 4 iterations."""
+    X = problem(21, 150, 90, K_true=5)
+    m, s = make_pair(X, K, zi, sparse)
+    done = 0
+    for upto in (0, 1, 4):
+        for _ in range(upto - done):
+            m.update_param()
+            m.prepare_next_iterate()
+        s.iterate(upto - done)
+        done = upto
+        g = s.monitors()
+        for name, ref in (("loglikelihood", m.loglikelihood()), ("deviance", m.deviance()), ("exp_dev", m.exp_deviance())):
+            assert abs(g[name] - ref) < 1e-8 * max(1.0, abs(ref)), (upto, name, g[name], ref)
+    s.close()
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+def test_order_factor_matches_oracle(zi, sparse):
+    """Same greedy order, and every K-indexed array permuted like reorder_factor does; the solver stays consistent
+    (one more iteration after the reorder still matches)."""
+    X = problem(22, 120, 70, K_true=5)
+    K = 5
+    m, s = make_pair(X, K, zi, sparse)
+    for _ in range(5):
+        m.update_param()
+        m.prepare_next_iterate()
+    s.iterate(5)
+    m.order_factor()
+    s.order_factor()
+    o = s.get_output()
+    assert list(o["factor_order"]) == list(m.get("factor_order"))
+    assert sorted(o["factor_order"]) == list(range(K))
+    compare_state(m, s, zi, sparse, "after reorder")
+    ref_dev = m.exp_deviance()
+    assert abs(s.monitors(loglikelihood=False)["exp_dev"] - ref_dev) < 1e-8 * max(1.0, abs(ref_dev))
+    m.update_param()
+    m.prepare_next_iterate()
+    s.iterate(1)
+    compare_state(m, s, zi, sparse, "iteration after reorder")
+    s.close()
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+def test_run_with_monitor_and_reorder(zi, sparse):
+    """The full default call shape (monitor=TRUE, reorder_factor=TRUE): per-iteration log-likelihood and deviance
+    vectors, exp_dev and the reordered factors."""
+    X = problem(23, 90, 50)
+    K = 4
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=9)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=25, iter_min=5, epsilon=1e-2, additional_iter=3, a1=a1, a2=a2, b1=b1, b2=b2)
+    ref = po.run(X, K, zi, sparse, monitor=True, reorder_factor=True, prob_S=prob_S, prior_S=prior_S, **kw)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    res = RUN[(zi, sparse)](X, K, verbose=False, monitor=True, reorder_factor=True, **kw)
+    assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    for k in ("loglikelihood", "deviance", "optim_criterion", "norm_gap"):
+        assert relerr(res["monitor"][k], ref["monitor"][k]) < 1e-6, k
+    assert abs(res["exp_dev"] - ref["exp_dev"]) < 1e-8
+    assert list(res["factor_order"]) == list(ref["factor_order"])
+    for grp in ("variational_params", "hyper_params", "factor"):
+        for k in res[grp]:
+            assert relerr(res[grp][k], ref[grp][k]) < 1e-6, (grp, k)
+    if sparse:
+        assert (res["sparse_param"]["S"] == ref["sparse_param"]["S"]).all()
+
+
+@pytest.mark.parametrize("zi,sparse", [(False, False), (True, True)], ids=["gap", "zi_sparse"])
+def test_multi_init_matches_oracle(zi, sparse):
+    """ninit = 3 seeded random initialisations of iter_init = 6 iterations, smallest loss kept (sic), then optimize
+    continues from iteration iter_init: same kept run, same trajectory, same per-iteration vectors."""
+    X = problem(24, 70, 40)
+    K = 3
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=20, iter_min=8, epsilon=1e-2, additional_iter=3, seed=77, ninit=3, iter_init=6)
+    ref = po.run(X, K, zi, sparse, monitor=True, reorder_factor=False, prob_S=prob_S, prior_S=prior_S, **kw)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    res = RUN[(zi, sparse)](X, K, verbose=False, monitor=True, reorder_factor=False, **kw)
+    assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    assert relerr(res["convergence"]["conv_crit"], ref["convergence"]["conv_crit"]) < 1e-6
+    assert relerr(res["monitor"]["optim_criterion"], ref["monitor"]["optim_criterion"]) < 1e-6
+    assert abs(res["loss"] - ref["loss"]) < 1e-6 * abs(ref["loss"])
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
