@@ -179,6 +179,17 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def ncu_traffic(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    workload (profiles/r01_ncu_traffic.json, written by profiles/ncu_traffic.py); {} when there is none."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(config, {})
+    except Exception:
+        return {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,24 +280,44 @@ def main():
     # algorithmic bytes per launch, this rank
     b_cells = 8 * nnz_local + 8 * (nl + 1) + w * K * nl * (1 + 2 + 5 + (1 if zi else 0)) + w * K * p * (2 if (zi or sparse) else 1)
     b_genes = 8 * nnz_local + 8 * (p + 1) + w * K * nl * (2 if sparse else 1) + w * K * p * (1 + (2 if sparse else 1))
+    # The non-zero passes read one or two 8K-byte factor rows per non-zero through L2 (gene table p x K for the cell
+    # pass, cell table n x K for the gene passes); that gather, not the HBM stream of X, is what bounds them, so the
+    # measured gather bandwidth of this device is reported next to the HBM figure.
+    gather_gene_tab = api.measure_gather_gbs(p, local)
+    gather_cell_tab = api.measure_gather_gbs(nl, local)
+    traffic = ncu_traffic(args.config)
     kernels = []
-    for name, byts in (("estep_cells_mstep_u", b_cells), ("estep_genes", b_genes)):
+    nz_rows = {"estep_cells_mstep_u": (b_cells, (2 if (zi or sparse) else 1), gather_gene_tab),
+               "estep_genes": (b_genes, 1, gather_cell_tab)}
+    if sparse:
+        nz_rows["sparse_gene_pass"] = (b_genes, 2, gather_cell_tab)
+    for name, (byts, nvec, gpk) in nz_rows.items():
         t = per[name][0]
+        gb = 8.0 * K * nvec * nnz_local
         kernels.append({"kernel": name, "ms": t, "share": t * args.steps / ms if ms else None, "bound": "hbm",
                         "algorithmic_bytes": byts, "achieved": byts / (t * 1e-3) / 1e9 if t > 0 else None,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": (byts / (t * 1e-3) / 1e9 / hbm_peak) if t > 0 else None})
+                        "peak": hbm_peak, "unit": "GB/s", "frac": (byts / (t * 1e-3) / 1e9 / hbm_peak) if t > 0 else None,
+                        "traffic": traffic.get(name),
+                        "gathered_bytes": gb, "gather_achieved": gb / (t * 1e-3) / 1e9 if t > 0 else None,
+                        "gather_peak_measured": gpk, "gather_frac": (gb / (t * 1e-3) / 1e9 / gpk) if t > 0 else None,
+                        "note": "estep_genes copies the sums of genes whose mask row did not change (no gather for those)"
+                                if name == "estep_genes" and sparse else None})
     fp64_peak = api.measure_fp64_tflops(local)
+    dmma_peak = api.measure_fp64_mma_tflops(local)
     if zi:
-        # dense ZI passes: 2 contractions of length K per entry (4K flop) + expit; FP64-pipe bound
+        # dense ZI passes: 2 contractions of length K per entry (4K flop) + expit, on the FP64 tensor pipe (DMMA)
         for name in ("zi_pass_cells", "zi_pass_genes"):
             t = per[name][0]
             fl = 4.0 * K * nl * p
-            kernels.append({"kernel": name, "ms": t, "share": t * args.steps / ms, "bound": "fp64", "algorithmic_flops": fl,
-                            "achieved": fl / (t * 1e-3) / 1e12 if t > 0 else None, "peak": fp64_peak, "unit": "TFLOP/s",
-                            "frac": (fl / (t * 1e-3) / 1e12 / fp64_peak) if t > 0 else None})
-    dom = max(kernels[:2], key=lambda k: k["ms"])
-    roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": None, "kernel": dom["kernel"], "peak_source": peak_src, "ms_per_launch": dom["ms"]}
+            kernels.append({"kernel": name, "ms": t, "share": t * args.steps / ms, "bound": "tensor", "algorithmic_flops": fl,
+                            "achieved": fl / (t * 1e-3) / 1e12 if t > 0 else None, "peak": dmma_peak, "unit": "TFLOP/s",
+                            "frac": (fl / (t * 1e-3) / 1e12 / dmma_peak) if t > 0 else None, "traffic": traffic.get(name),
+                            "peak_source": "FP64 DMMA m8n8k4 microbenchmark run by this bench (MEASURED_PEAKS.json holds no FP64 "
+                                           "figure; FP64 has no tcgen05 kind)"})
+    dom = max(kernels, key=lambda k: k["ms"])
+    roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
+                "traffic": dom.get("traffic"), "kernel": dom["kernel"], "ms_per_launch": dom["ms"],
+                "peak_source": dom.get("peak_source", peak_src)}
     phases = {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in per.items()}
     solver.close()
 
@@ -303,7 +334,7 @@ def main():
         Xh = (hrp.numpy(), hci.numpy(), hvv.numpy(), p)
         fn = {(False, False): pcmf_b200.run_gap_factor, (True, False): pcmf_b200.run_zi_gap_factor,
               (False, True): pcmf_b200.run_sparse_gap_factor, (True, True): pcmf_b200.run_zi_sparse_gap_factor}[(zi, sparse)]
-        kw = dict(verbose=False, monitor=True, iter_max=args.steps, iter_min=args.steps, epsilon=0.0, reorder_factor=False,
+        kw = dict(verbose=False, monitor=2, iter_max=args.steps, iter_min=args.steps, epsilon=0.0, reorder_factor=False,
                   seed=args.seed + 1000, device=local, comm=comm, n_global=n, row_offset=r0, return_prob_D=False)
         if sparse:
             kw.update(prob_S=prob_S, prior_S=prior_S)
@@ -341,7 +372,7 @@ def main():
                            "l2": "inputs larger than L2 (CSR+CSC %.1f GB per rank); no explicit flush" % (16e-9 * nnz_local),
                            "generator_seconds": t_gen},
                 "roofline": roofline, "kernels": kernels, "phases": phases, "cpu_baseline": cb, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clk, "fp64_peak_tflops_measured": fp64_peak,
+                "gpu_launches": int(launches), "clocks": clk, "fp64_peak_tflops_measured": fp64_peak, "fp64_dmma_peak_tflops_measured": dmma_peak,
                 "elbo_last": float(elbo[-1]), "conv_crit_last": float(crit[-1])}
         print(json.dumps(line))
     if world > 1:

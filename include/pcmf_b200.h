@@ -195,6 +195,11 @@ int pcmf_csr_column_stats(int device, int64_t n_local, int32_t p, const int64_t 
 /* Measured FP64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA microbenchmark, ~50 ms): the
  * roofline denominator of the dense zero-inflation passes, which are FP64-pipe bound, not HBM bound. */
 int pcmf_measure_fp64_tflops(int device, double *tflops_out);
+/* Same for the FP64 tensor pipe (mma.sync m8n8k4 DMMA), which the dense zero-inflation passes run on. */
+int pcmf_measure_fp64_mma_tflops(int device, double *tflops_out);
+/* Measured gather bandwidth (GB/s) of 160-byte K-vector rows out of a `rows`-row FP64 table: the ceiling of the E-step
+ * non-zero passes, which read one or two such rows per non-zero through L2. */
+int pcmf_measure_gather_gbs(int device, int64_t rows, double *gbs_out);
 int pcmf_device_free(int device, void *ptr);
 /* copy device CSR arrays to host buffers (bench e2e leg) */
 int pcmf_device_to_host(int device, void *dst_host, const void *src_dev, size_t bytes);

@@ -88,12 +88,14 @@ def lib():
                                               lp] + err
     L.pcmf_csr_column_stats.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, dp, dp, dp] + err
     L.pcmf_measure_fp64_tflops.argtypes = [C.c_int, dp]
+    L.pcmf_measure_fp64_mma_tflops.argtypes = [C.c_int, dp]
+    L.pcmf_measure_gather_gbs.argtypes = [C.c_int, C.c_int64, dp]
     L.pcmf_device_free.argtypes = [C.c_int, C.c_void_p]
     L.pcmf_device_to_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
     for name in ("pcmf_fit", "pcmf_create", "pcmf_optimize", "pcmf_iterate", "pcmf_elbo", "pcmf_order_factor", "pcmf_multi_init",
                  "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational", "pcmf_phase_times",
                  "pcmf_generate_counts_device", "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats",
-                 "pcmf_measure_fp64_tflops"):
+                 "pcmf_measure_fp64_tflops", "pcmf_measure_fp64_mma_tflops", "pcmf_measure_gather_gbs"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -108,4 +110,5 @@ def check(rc, errbuf):
 HEADER_SYMBOLS = ["pcmf_version", "pcmf_device_count", "pcmf_fit", "pcmf_create", "pcmf_optimize", "pcmf_iterate",
                   "pcmf_elbo", "pcmf_order_factor", "pcmf_multi_init", "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational",
                   "pcmf_phase_times", "pcmf_launch_count", "pcmf_destroy", "pcmf_generate_counts_device",
-                  "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats", "pcmf_measure_fp64_tflops"]
+                  "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats", "pcmf_measure_fp64_tflops",
+                  "pcmf_measure_fp64_mma_tflops", "pcmf_measure_gather_gbs"]

@@ -125,6 +125,24 @@ def measure_fp64_tflops(device=0):
     return t.value
 
 
+def measure_fp64_mma_tflops(device=0):
+    """FP64 tensor-pipe (DMMA) throughput in TFLOP/s, measured on the device."""
+    v = C.c_double(0)
+    rc = _lib.lib().pcmf_measure_fp64_mma_tflops(int(device), C.byref(v))
+    if rc != _lib.OK:
+        raise PcmfError(rc, "pcmf_measure_fp64_mma_tflops failed")
+    return v.value
+
+
+def measure_gather_gbs(rows, device=0):
+    """Gather bandwidth (GB/s) of 160-byte rows out of a `rows`-row table: ceiling of the E-step non-zero passes."""
+    v = C.c_double(0)
+    rc = _lib.lib().pcmf_measure_gather_gbs(int(device), int(rows), C.byref(v))
+    if rc != _lib.OK:
+        raise PcmfError(rc, "pcmf_measure_gather_gbs failed")
+    return v.value
+
+
 class _Comm:
     """Sum all-reduce over torch.distributed for the cell-sharded run (one process per GPU).  The device buffer the
     library hands to the callback is wrapped zero-copy through __cuda_array_interface__."""

@@ -214,3 +214,99 @@ extern "C" int pcmf_measure_fp64_tflops(int device, double *tflops_out) {
     *tflops_out = best;
     return PCMF_OK;
 }
+
+// ---- roofline denominators measured on the device the bench runs on --------------------------------------------------
+namespace {
+__global__ void k_dmma_peak(double *out, int iters) {
+    double d[8][2];
+    for (int i = 0; i < 8; ++i) { d[i][0] = threadIdx.x * 1e-9; d[i][1] = i; }
+    const double a = 1.0000001, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(d[i][0]), "+d"(d[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+    for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+// every thread gathers rows idx[e] of a (rows x 20) FP64 table with 16-byte loads, like the E-step non-zero passes
+__global__ void k_gather_peak(const int32_t *__restrict__ idx, int64_t nidx, const double *__restrict__ tab, double *out) {
+    double acc = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nidx; e += stride) {
+        const double2 *q = reinterpret_cast<const double2 *>(tab + (int64_t)__ldg(idx + e) * 20);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { const double2 t = __ldg(q + k); acc = fma(t.x, t.y, acc); }
+    }
+    if (acc == 12345.678) out[0] = acc;
+}
+__global__ void k_fill_idx(int32_t *idx, int64_t nidx, int32_t rows) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nidx; e += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t s = (uint64_t)e * 0x9E3779B97F4A7C15ull + 0x2545F4914F6CDD1Dull;
+        s ^= s >> 29; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 32;
+        idx[e] = (int32_t)(s % (uint64_t)rows);
+    }
+}
+}  // namespace
+
+// FP64 tensor-pipe (DMMA m8n8k4) throughput in TFLOP/s: the roofline denominator of the DMMA zero-inflation passes.
+extern "C" int pcmf_measure_fp64_mma_tflops(int device, double *tflops_out) {
+    char *errbuf = nullptr; size_t errlen = 0;
+    if (!tflops_out) return PCMF_EINVAL;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) return PCMF_ECUDA;
+    GK(cudaSetDevice(device));
+    cudaDeviceProp dp; GK(cudaGetDeviceProperties(&dp, device));
+    double *out = nullptr; GK(cudaMalloc(&out, 8));
+    cudaEvent_t e0, e1; GK(cudaEventCreate(&e0)); GK(cudaEventCreate(&e1));
+    const int blocks = dp.multiProcessorCount * 4, threads = 256, iters = 1 << 13;
+    k_dmma_peak<<<blocks, threads>>>(out, 256);
+    double best = 0;
+    for (int r = 0; r < 3; ++r) {
+        GK(cudaEventRecord(e0));
+        k_dmma_peak<<<blocks, threads>>>(out, iters);
+        GK(cudaEventRecord(e1));
+        GK(cudaEventSynchronize(e1));
+        float ms = 0; GK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 512.0 * 8.0 * iters * ((double)blocks * threads / 32.0) / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops_out = best;
+    return PCMF_OK;
+}
+
+// Gather bandwidth in GB/s of 160-byte K-vector rows out of a table of `rows` rows (L2-resident for the p x K gene
+// table, larger than L2 for the n x K cell table): the ceiling of the E-step non-zero passes, which read one or two
+// such rows per non-zero entry through L2.
+extern "C" int pcmf_measure_gather_gbs(int device, int64_t rows, double *gbs_out) {
+    char *errbuf = nullptr; size_t errlen = 0;
+    if (!gbs_out || rows <= 0) return PCMF_EINVAL;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) return PCMF_ECUDA;
+    GK(cudaSetDevice(device));
+    cudaDeviceProp dp; GK(cudaGetDeviceProperties(&dp, device));
+    const int64_t nidx = 100000000;
+    int32_t *idx = nullptr; double *tab = nullptr, *out = nullptr;
+    GK(cudaMalloc(&idx, nidx * 4)); GK(cudaMalloc(&tab, rows * 20 * 8)); GK(cudaMalloc(&out, 8));
+    GK(cudaMemset(tab, 0, rows * 20 * 8));
+    const int blocks = dp.multiProcessorCount * 16;
+    k_fill_idx<<<blocks, 256>>>(idx, nidx, (int32_t)rows);
+    cudaEvent_t e0, e1; GK(cudaEventCreate(&e0)); GK(cudaEventCreate(&e1));
+    k_gather_peak<<<blocks, 256>>>(idx, nidx, tab, out);
+    double best = 0;
+    for (int r = 0; r < 3; ++r) {
+        GK(cudaEventRecord(e0));
+        k_gather_peak<<<blocks, 256>>>(idx, nidx, tab, out);
+        GK(cudaEventRecord(e1));
+        GK(cudaEventSynchronize(e1));
+        float ms = 0; GK(cudaEventElapsedTime(&ms, e0, e1));
+        const double gbs = (double)nidx * 160.0 / (ms * 1e-3) / 1e9;
+        if (gbs > best) best = gbs;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(idx); cudaFree(tab); cudaFree(out);
+    *gbs_out = best;
+    return PCMF_OK;
+}
