@@ -12,15 +12,26 @@
  * columns j with per-thread private accumulators reduced at the end, K `exp` per (i,j))
  * and its quirks.  Compiled `gcc -O2 -fopenmp` like an R package.
  *
- * PARITY STATUS: "parity unpinned" end to end.  The reference itself cannot be built in
- * this environment (needs R + Rcpp + RcppEigen + BH; none present, no network) and its own
- * tests pin no U/V/ELBO values (test_gap_factor_algo.cpp:123-126 assert shapes only, on
- * unseeded data).  What IS pinned (tests/test_oracle_primitives.py): the reference's
- * known-answer tests for the primitives -- digammaInv 7.8834286312 / 22026.9657929151
- * (test_internal.cpp:35-41), logit/expit clamps (:58-80), custom_log (:51-56),
- * variance (:43-49), Bregman-Poisson 23.57360306 (test_probability.cpp:119-135),
- * Egamma/ElogGamma/entropy identities (:38-108), likelihood identities
- * (test_likelihood.cpp:39-172) -- plus scipy cross-checks of digamma/trigamma/lgamma.
+ * PARITY STATUS: PINNED against the reference itself.  R, Rcpp, Eigen and Boost are absent
+ * from this image, so the reference's package cannot be built as such; instead its OWN model
+ * and algorithm sources (pkg/src/{model,gap_factor_model,zi_gap_factor_model,
+ * sparse_gap_factor_model,zi_sparse_gap_factor_model}.cpp, algorithm*.h, utils/*.h) are
+ * compiled where they lie against small stand-in headers (oracle/shim/: an eager dense
+ * matrix class covering the Eigen expression forms those files use, a list-shaped Rcpp
+ * stub, digamma/trigamma and mt19937 distributions for Boost) into
+ * oracle/_ref/libpcmf_ref.so (`make -C oracle ref`).  tests/test_ref_build.py runs this
+ * oracle and that build side by side -- whole driver, all four models, monitors, stopping
+ * rule, factor ordering, seeded random init -- and they agree to 1e-10 relative (observed
+ * ~1e-14); tests/golden/ref_*.npz are outputs of that build, committed so the check travels
+ * (tests/test_golden_vectors.py, tests/test_gpu_golden.py).  Caveat, stated where it
+ * applies: the linear algebra underneath the reference's formulas is the stand-in's, not
+ * Eigen's (summation order differs; vectors have no static orientation).
+ * Also pinned (tests/test_oracle_primitives.py): the reference's known-answer tests for the
+ * primitives -- digammaInv 7.8834286312 / 22026.9657929151 (test_internal.cpp:35-41),
+ * logit/expit clamps (:58-80), custom_log (:51-56), variance (:43-49), Bregman-Poisson
+ * 23.57360306 (test_probability.cpp:119-135), Egamma/ElogGamma/entropy identities (:38-108),
+ * likelihood identities (test_likelihood.cpp:39-172) -- plus scipy cross-checks of
+ * digamma/trigamma/lgamma.
  *
  * Third-party arithmetic restated here (absent from /root/reference):
  *   boost::math::digamma / trigamma (package BH, version unpinned by DESCRIPTION:22):
@@ -29,11 +40,14 @@
  *     and uses a minimax rational, the two agree to a few ulp (checked against scipy).
  *   boost::random mt19937 + gamma_distribution (BH, unpinned, no test pins the stream):
  *     NOT reproduced; orc_init_random uses MT19937 + inversion for the shape-1 Gamma
- *     (an exponential).  Parity tests inject a1,a2,b1,b2 explicitly instead.
+ *     (an exponential), the same rule as oracle/shim/boost/random and the library, so seeded
+ *     random inits coincide across the three.  Most parity tests inject a1,a2,b1,b2 explicitly.
  *
  * Deliberate deviation: likelihood::bernoulli_loglike_vec (likelihood.h:296-313) reads out
- * of bounds in the reference (prob(i,j) on a row vector); we implement the intended term
- * sum_ij P_ij log(pi_j) + (1-P_ij) log(1-pi_j) gated on 0<pi_j<1.
+ * of bounds in the reference (prob(i,j) on a row vector) and, in the sparse call
+ * (sparse_gap_factor_model.cpp:172), uses the prior of GENE k for FACTOR k; we implement the intended
+ * term sum_ij P_ij log(pi_j) + (1-P_ij) log(1-pi_j) gated on 0<pi_j<1.  The tests
+ * compare the sparse ELBO with the reference build up to exactly that term (tests/refcmp.py).
  */
 #include <math.h>
 #include <stdint.h>

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Generates tests/golden/ref_<model>.npz: outputs of the REFERENCE ITSELF -- its own C++ classes compiled from
+/root/reference/pkg/src against the stand-in headers of oracle/shim/ (oracle/_ref/libpcmf_ref.so, `make -C oracle ref`)
+-- on small seeded inputs with an explicit initialisation.  The fixtures travel with the repo, /root/reference does
+not; tests/test_golden_vectors.py pins the CPU oracle (and tests/test_gpu_golden.py the CUDA path) against them.
+
+Run from the repo root, only where /root/reference exists:  python tests/golden/make_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyref  # noqa: E402
+from pcmf_b200 import datagen  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = {"gap": (False, False), "zi": (True, False), "sparse": (False, True), "zi_sparse": (True, True)}
+
+
+def inputs(name):
+    """Deterministic inputs of a case: X from the package's generative model, a1..b2 random, prior_S heuristic."""
+    seed = {"gap": 31, "zi": 32, "sparse": 33, "zi_sparse": 34}[name]
+    X, _, _ = datagen.simulate(48, 36, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=seed)
+    K = 3
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=seed + 100)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    if name in ("sparse", "zi_sparse"):
+        # The reference's sparse ELBO reads prior_S of gene k as the prior of FACTOR k (likelihood.h:307 called from
+        # sparse_gap_factor_model.cpp:172) and becomes NaN as soon as one of the first K genes has a prior
+        # of exactly 0 or 1.  Put K genes whose prior stays strictly inside (0, 1) first, so that the reference's value
+        # is finite and the fixture pins every other term of the sparse ELBO.
+        from oracle import pyoracle as po
+        m = po.Model(X, K, name == "zi_sparse", True)
+        m.init_sparse_param(0.5, prob_S, prior_S)
+        if name == "zi_sparse":
+            m.init_zi_param()
+        m.init_variational_param(a1, a2, b1, b2)
+        lo, hi = prior_S.copy(), prior_S.copy()
+        for _ in range(14):
+            m.update_param()
+            m.prepare_next_iterate()
+            pr = m.get("prior_S")
+            lo, hi = np.minimum(lo, pr), np.maximum(hi, pr)
+        good = [j for j in range(X.shape[1]) if lo[j] > 0.0 and hi[j] < 1.0]
+        assert len(good) >= K, "no gene keeps an interior prior"
+        perm = good[:K] + [j for j in range(X.shape[1]) if j not in good[:K]]
+        X, b1, b2, prob_S, prior_S = X[:, perm], b1[perm], b2[perm], prob_S[perm], prior_S[perm]
+    return X, K, a1, a2, b1, b2, prob_S, prior_S
+
+
+def main():
+    pyref.build()
+    for name, (zi, sparse) in CASES.items():
+        X, K, a1, a2, b1, b2, prob_S, prior_S = inputs(name)
+        kw = dict(iter_max=12, iter_min=4, epsilon=1e-2, additional_iter=2, a1=a1, a2=a2, b1=b1, b2=b2, reorder_factor=True)
+        if sparse:
+            kw.update(prob_S=prob_S, prior_S=prior_S)
+        r = pyref.run(X, K, zi, sparse, **kw)
+        flat = {"X": X, "K": np.array(K), "in_a1": a1, "in_a2": a2, "in_b1": b1, "in_b2": b2, "in_prob_S": prob_S,
+                "in_prior_S": prior_S, "loss": np.array(r["loss"]), "exp_dev": np.array(r["exp_dev"]),
+                "nb_iter": np.array(r["convergence"]["nb_iter"]), "converged": np.array(r["convergence"]["converged"])}
+        for g in ("variational_params", "hyper_params", "stats", "sparse_param", "ZI_param", "monitor"):
+            for k, v in r.get(g, {}).items():
+                flat["%s.%s" % (g, k)] = np.asarray(v)
+        flat["convergence.conv_crit"] = np.asarray(r["convergence"]["conv_crit"])
+        np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % name), **flat)
+        print(name, "nb_iter", r["convergence"]["nb_iter"], "loss", r["loss"], "exp_dev", r["exp_dev"])
+
+
+if __name__ == "__main__":
+    main()
