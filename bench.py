@@ -117,7 +117,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None):
+def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None, warmup=0):
     """The oracle (dense OpenMP restatement of the reference) on the first `max_rows` cells of the same workload."""
     from oracle import pyoracle as po
     from pcmf_b200 import datagen
@@ -146,13 +146,14 @@ def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None):
         m.init_zi_param()
     m.init_variational_param(a1, a2, b1, b2)
     times = []
-    for _ in range(iters):
+    for it in range(warmup + iters):
         t0 = time.perf_counter()
         m.update_param()
         m.elbo()
         m.gap_between_iterates()
         m.prepare_next_iterate()
-        times.append(time.perf_counter() - t0)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
     t_iter = float(np.mean(times))
     full = (1.0 / t_iter) * (ns / n)
     return {"value": full, "unit": "iter/s", "cores": int(cores), "kind": "port",
@@ -167,15 +168,22 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     U, V = factor_matrices(cfg, args.seed)
-    iters = max(1, min(args.steps, 3))
-    cb = cpu_baseline(cfg, U, V, args.seed, args.cpu_rows, iters)
+    # K timed + W warm-up steps, each on the bounded cell sample; rows are reduced if the run would exceed a few minutes
+    iters, warm = max(1, args.steps), max(0, args.warmup)
+    rows = args.cpu_rows
+    if (iters + warm) > 20:
+        rows = max(200, int(rows * 20 / (iters + warm)))
+    cb = cpu_baseline(cfg, U, V, args.seed, rows, iters, warmup=warm)
     line = {"impl": "reference", "metric": "VEM iterations/sec", "value": cb["value"], "unit": "iter/s", "n_gpus": args.gpus,
-            "steps": iters, "warmup": 0, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong",
+            "steps": iters, "warmup": warm, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["label"], "model": "zi_sparse_gap" if cfg["zi"] and cfg["sparse"] else "gap"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference binary unbuildable here (needs R/Rcpp/RcppEigen/BH); this is the oracle port on the host cores"}
+            "note": "the reference's R package cannot be built here (no R/Rcpp/Eigen/Boost). Its own sources do compile against "
+                    "stand-in headers (oracle/_ref, used to pin parity at 1e-10), but that build's linear algebra is not Eigen's "
+                    "and runs ~2x slower than this C port of the same loops, so the port is what is timed (the faster, "
+                    "conservative baseline); all host cores, dense n x p loops exactly as the reference runs them"}
     print(json.dumps(line))
 
 
