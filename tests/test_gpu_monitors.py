@@ -16,7 +16,7 @@ RUN = {(False, False): pcmf_b200.run_gap_factor, (True, False): pcmf_b200.run_zi
 
 
 @pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
-@pytest.mark.parametrize("K", [3, 20])
+@pytest.mark.parametrize("K", [3, 20, 30])
 def test_monitors_match_oracle(zi, sparse, K):
     """loglikelihood / deviance / exp_deviance of the state after 0, 1 and 4 iterations."""
     X = problem(21, 150, 90, K_true=5)

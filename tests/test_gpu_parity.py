@@ -58,7 +58,9 @@ def compare_state(m, s, zi, sparse, tag):
 
 
 @pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
-@pytest.mark.parametrize("n,p,K", [(60, 45, 3), (97, 130, 20), (40, 33, 5)])
+# K = 3, 20, 5, 10, 14, 30, 64 -> padded widths 4, 20, 8, 12, 16, 32, 64: every compiled kernel set (BASELINE config 5 sweeps K)
+@pytest.mark.parametrize("n,p,K", [(60, 45, 3), (97, 130, 20), (40, 33, 5), (70, 90, 10), (66, 70, 14), (75, 140, 30),
+                                   (131, 100, 64)])
 def test_free_running_iterations_match_oracle(zi, sparse, n, p, K):
     X = problem(3, n, p)
     m, s = make_pair(X, K, zi, sparse)
