@@ -43,6 +43,8 @@ CONFIGS = {
                label="C2: 10k x 2k dense Gamma-Poisson, K=10"),
     "c4gap": dict(n=1_000_000, p=20_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=False, sparse=False,
                   label="C4 data, plain Gamma-Poisson (no ZI, no sparsity), K=20"),
+    "c4s8": dict(n=125_000, p=20_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=True, sparse=True,
+                 label="one 8-GPU shard of C4 on one GPU: 125k cells x 20k genes (kernel tuning only)"),
     "tiny": dict(n=20_000, p=2_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=True, sparse=True,
                  label="tiny: 20k x 2k, ~5% nnz, ZI + sparse-V, K=20 (smoke only)"),
 }

@@ -50,8 +50,14 @@ int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
     }
     const int64_t groups = (a.p + 7) / 8;
     k_zi_pack<KP, true><<<pack_grid(groups * R::REC), 256, 0, st>>>(a.p, a.EVS, a.EVS, a.cz, a.flag, a.pack);
-    const int64_t grid = (a.n + 32 * MT - 1) / (32 * MT);
-    k_zi_cells_mma<KP, MT, MMA_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
+    const int64_t gx = (a.n + 32 * MT - 1) / (32 * MT);
+    // at least ~8 waves of CTAs (3 resident per SM): split the gene tiles over blockIdx.y when there are few cell blocks
+    const int ntiles = (int)((groups + MMA_TJ / 8 - 1) / (MMA_TJ / 8));
+    int gy = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles / 8, (148 * 3 * 8 + gx - 1) / gx));
+    if (gx >= 148 * 3 * 8) gy = 1;
+    if (gy > 1) cudaMemsetAsync(a.PV, 0, sizeof(double) * (size_t)a.n * KP, st);
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    k_zi_cells_mma<KP, MT, MMA_TJ><<<grid, 128, smem, st>>>(a);
     return 2;
 }
 template <int MT>

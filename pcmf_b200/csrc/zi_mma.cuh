@@ -184,18 +184,26 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     double ent_lin = 0, ent_log = 0, prod = 1.0;
     uint32_t bits[MT], bits_nx[MT];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) { bits[mt] = 0u; bits_nx[mt] = live[mt] ? __ldg(a.bitT + (cell0 + mt * 8 + g)) : 0u; }
+    for (int mt = 0; mt < MT; ++mt) { bits[mt] = 0u; bits_nx[mt] = 0u; }
 
-    const int ngroups = (a.p + 7) >> 3, ntiles = (ngroups + NG - 1) / NG;
-    auto issue = [&](int tile) {     // one thread: arm the barrier with the byte count, then one bulk copy
-        const int g0 = tile * NG, gn = min(NG, ngroups - g0);
+    // gene range of this CTA: blockIdx.y splits the gene tiles when there are too few cell blocks to fill the machine
+    // for many waves (cell-sharded runs); PV and the scalars are then accumulated atomically over the chunks
+    const int ngroups = (a.p + 7) >> 3, ntiles_all = (ngroups + NG - 1) / NG;
+    const int tiles_per_chunk = (ntiles_all + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int tile_first = (int)blockIdx.y * tiles_per_chunk;
+    const int ntiles = max(0, min(ntiles_all, tile_first + tiles_per_chunk) - tile_first);
+    auto issue = [&](int t) {        // one thread: arm the barrier with the byte count, then one bulk copy
+        const int g0 = (tile_first + t) * NG, gn = min(NG, ngroups - g0);
         const unsigned bytes = (unsigned)(gn * R::REC * sizeof(double));
-        mbar_expect_tx(&bar[tile & 1], bytes);
-        bulk_g2s(s_buf + (tile & 1) * BUF, pack + (int64_t)g0 * R::REC, bytes, &bar[tile & 1]);
+        mbar_expect_tx(&bar[t & 1], bytes);
+        bulk_g2s(s_buf + (t & 1) * BUF, pack + (int64_t)g0 * R::REC, bytes, &bar[t & 1]);
     };
-    if (threadIdx.x == 0) issue(0);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+        bits_nx[mt] = (live[mt] && ntiles > 0) ? __ldg(a.bitT + (int64_t)((tile_first * TJ) >> 5) * a.n + (cell0 + mt * 8 + g)) : 0u;
+    if (threadIdx.x == 0 && ntiles > 0) issue(0);
     for (int tile = 0; tile < ntiles; ++tile) {
-        const int j0 = tile * TJ;
+        const int j0 = (tile_first + tile) * TJ;
         const double *buf = s_buf + (tile & 1) * BUF;
         double *cs_buf = s_cs + (tile & 1) * TJ;
         if (threadIdx.x == 0 && tile + 1 < ntiles) issue(tile + 1);
@@ -277,7 +285,8 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
         for (int nt = 0; nt < NT; ++nt) {
             const int k = nt * 8 + 2 * q;
             if (k < KP) {
-                *reinterpret_cast<double2 *>(a.PV + i * KP + k) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                if (gridDim.y == 1) *reinterpret_cast<double2 *>(a.PV + i * KP + k) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                else { atomicAdd(a.PV + i * KP + k, acc[mt][nt][0]); atomicAdd(a.PV + i * KP + k + 1, acc[mt][nt][1]); }
                 const double2 u = *reinterpret_cast<const double2 *>(a.EU + i * KP + k);
                 sum_pl = fma(u.x, acc[mt][nt][0], fma(u.y, acc[mt][nt][1], sum_pl));
             }
