@@ -130,6 +130,9 @@ struct RowArgs {
     long long *guard_next;           // min/max of the new ElogU
     double *cs_eu, *cs_elog;         // KP each (atomic)
     double *usc;                     // 3 doubles (atomic): gap_d, gap_o, entropy of the local cells (all-reduced later)
+    // stored multinomial weights (k_estep_rows_q): q_ij = x_ij / T_ij written by the gene passes in CSC order
+    const uint32_t *csr2csc;         // nnz: CSC position of every CSR entry
+    const double *qcsc;              // nnz: q in CSC order; NaN marks an entry that needs the exact formula
 };
 
 // E-step, cell side + fused U-side M-step.  One warp per cell; lanes stride over the cell's non-zeros.
@@ -237,6 +240,100 @@ __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
     }
 }
 
+// Same pass when the gene passes have left q_ij = x_ij / T_ij for every non-zero (CSC order): the cell side is then a
+// pure SpMM, EZ_j(i,.) = eu_i o sum_j q_ij evw_j -- one gathered K-vector per non-zero instead of two (ev for T, evw for
+// the sum), no division, half the registers.  q is read through the CSR -> CSC position map; a NaN marks an entry whose
+// weights need the reference's guarded formula (exact_terms), recomputed here exactly as k_estep_rows does.
+// Used for the ZI / sparse models (evw != ev); the plain model gathers one vector either way.
+template <int KP, typename VT>
+__global__ void __launch_bounds__(256, 2) k_estep_rows_q(RowArgs a) {
+    __shared__ double s_ex[8][KP];
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t warp0 = (int64_t)blockIdx.x * warps_per_block + w;
+    const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
+    const VT *__restrict__ val = static_cast<const VT *>(a.val);
+    UAcc acc[(KP + 31) / 32];
+
+    for (int64_t i = warp0; i < a.n; i += nwarps) {
+        double r[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) r[k] = 0.0;
+        for (int k = lane; k < KP; k += 32) s_ex[w][k] = 0.0;
+        __syncwarp();
+        const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const int j = __ldg(a.colidx + e);
+            const double q = __ldg(a.qcsc + __ldg(a.csr2csc + e));
+            if (q == q) {
+                double v[KP];
+                load_vec<KP>(a.evw + (int64_t)j * KP, v);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) r[k] = fma(q, v[k], r[k]);
+            } else if (!a.allmasked[j]) {
+                atomicAdd(a.dbg, 1ull);
+                const double x = (double)__ldg(val + e);
+                double ex[KP];
+                const double Tx = exact_terms<KP>(a.ElogU + i * KP, a.ElogV + (int64_t)j * KP, a.Sd + (int64_t)j * KP, a.K, ex);
+                const double qx = x / (Tx > 0.0 ? Tx : 1.0);
+                for (int k = 0; k < a.K; ++k) atomicAdd(&s_ex[w][k], qx * ex[k] * a.wS[(int64_t)j * KP + k]);
+            }
+        }
+        __syncwarp();
+        double mine[(KP + 31) / 32];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const double t = warp_sum(r[k]);
+            if ((k & 31) == lane) mine[k >> 5] = t;
+        }
+        double emn = 1e300, emx = -1e300;
+#pragma unroll
+        for (int c = 0; c < (KP + 31) / 32; ++c) {
+            const int k = c * 32 + lane;
+            if (k < a.K) {
+                const int64_t o = i * KP + k;
+                const double ez = a.eu[o] * mine[c] + s_ex[w][k];
+                const double a1o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a1_old0[o] : a.a1[o]);
+                const double a2o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a2_old0[o] : a.a2[o]);
+                const double a1n = a.alpha1[k] + ez;
+                const double a2n = a.alpha2[k] + (a.PV ? a.PV[o] : a.rate_vec[k]);
+                a.a1[o] = a1n;
+                a.a2[o] = a2n;
+                double el;
+                u_element(a1n, a2n, a1o, a2o, a.EU_new + o, &el, a.eu + o, acc[c]);
+                a.ElogU[o] = el;
+                emn = fmin(emn, el); emx = fmax(emx, el);
+            }
+        }
+        emn = warp_min(emn); emx = warp_max(emx);
+        if (lane == 0) a.rowext[i] = make_double2(emn, emx);
+        __syncwarp();
+    }
+    double gd = 0, go = 0, en = 0, mn = 1e300, mx = -1e300;
+#pragma unroll
+    for (int c = 0; c < (KP + 31) / 32; ++c) {
+        const int k = c * 32 + lane;
+        if (k < a.K) {
+            atomicAdd(a.cs_eu + k, acc[c].cs_eu);
+            atomicAdd(a.cs_elog + k, acc[c].cs_elog);
+        }
+        gd += acc[c].gap_d; go += acc[c].gap_o; en += acc[c].ent;
+        mn = fmin(mn, acc[c].mn); mx = fmax(mx, acc[c].mx);
+    }
+    gd = block_sum(gd, sh); go = block_sum(go, sh); en = block_sum(en, sh);
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (threadIdx.x == 0) {
+        atomicAdd(a.usc + 0, gd);
+        atomicAdd(a.usc + 1, go);
+        atomicAdd(a.usc + 2, en);
+    }
+    if (lane == 0 && mn <= mx) {
+        atomicMin(a.guard_next + G_MINU, dbl_ordered(mn));
+        atomicMax(a.guard_next + G_MAXU, dbl_ordered(mx));
+    }
+}
+
 // init: statistics of given (a1, a2) without an E-step (gap_factor_model.cpp:119, 140, 170: U_stats()).
 struct UInitArgs {
     int64_t n; int K, KP;
@@ -305,6 +402,7 @@ struct ColArgs {
     const long long *guard;           // global extremes (U part used)
     double *B1, *B2;                  // p x KP (plain stores: the block owns the gene)
     double *xlogT;                    // p
+    double *qout;                     // nnz or null: q_ij = x_ij / T_ij of every entry visited, CSC order (NaN: exact-formula entry)
 };
 template <int KP, typename VT, bool WITH_B2, bool WITH_LOGT>
 __global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
@@ -336,6 +434,8 @@ __global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
         double lt = 0.0;
         // all-masked gene: every r_ijk is 0 (sparse...cpp:350-356), nothing to accumulate
         const int64_t e0 = a.colptr[j], e1 = a.allmasked[j] ? a.colptr[j] : a.colptr[j + 1];
+        if (a.qout && a.allmasked[j])
+            for (int64_t e = e0 + threadIdx.x; e < a.colptr[j + 1]; e += blockDim.x) a.qout[e] = 0.0;
         for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
             const int64_t i = __ldg(a.rowidx + e);
             const double x = (double)__ldg(val + e);
@@ -347,6 +447,7 @@ __global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
             const double T = T0 + T1;
             if (!pf.force_exact && T >= 1e-26) {
                 const double q = x / T;
+                if (a.qout) a.qout[e] = q;
                 if (WITH_LOGT) lt += x * log(T);
 #pragma unroll
                 for (int k = 0; k < KP; ++k) b1[k] = fma(q, u[k], b1[k]);
@@ -358,6 +459,7 @@ __global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
                 }
             } else {
                 atomicAdd(a.dbg + 1, 1ull);
+                if (a.qout) a.qout[e] = __longlong_as_double(0x7ff8000000000000LL);   // NaN: the cell pass takes the exact formula too
                 double ex[KP];
                 const double Tx = exact_terms<KP>(a.ElogU + i * KP, a.ElogV + (int64_t)j * KP, a.Sd + (int64_t)j * KP, a.K, ex);
                 const double q = x / (Tx > 0.0 ? Tx : 1.0);

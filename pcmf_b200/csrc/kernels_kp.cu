@@ -15,6 +15,12 @@ constexpr int ZI_TJ = 128;                       // genes per shared-memory tile
 constexpr int ZI_TI = (KP <= 32) ? 64 : 32;      // cells per shared-memory tile in the gene-threaded ZI pass
 
 void launch_estep_rows(bool f32, const RowArgs &a, int grid, int block, cudaStream_t st) {
+    if (a.qcsc && a.evw != a.ev) {
+        // stored-q variant: twice the resident warps, so twice the grid
+        if (f32) k_estep_rows_q<KP, float><<<grid * 2, block, 0, st>>>(a);
+        else k_estep_rows_q<KP, double><<<grid * 2, block, 0, st>>>(a);
+        return;
+    }
     if (f32) k_estep_rows<KP, float><<<grid, block, 0, st>>>(a);
     else k_estep_rows<KP, double><<<grid, block, 0, st>>>(a);
 }

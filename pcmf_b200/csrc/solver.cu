@@ -78,6 +78,8 @@ struct pcmf_solver {
     int64_t *colptr = nullptr; int32_t *rowidx = nullptr; void *val_csc = nullptr;
     uint32_t *bitT = nullptr, *bitB = nullptr;
     double *zpackA = nullptr, *zpackB = nullptr;   // fragment-ordered scratch of the DMMA ZI passes
+    uint32_t *csr2csc = nullptr;                   // nnz: CSC position of every CSR entry (stored-q cell pass)
+    double *qcsc = nullptr;                        // nnz: q_ij = x_ij / T_ij left by the gene passes, CSC order
     double *Lg = nullptr, *colsumX = nullptr, *colnnz = nullptr, *rowsumX = nullptr;
     double lgx_const = 0;
     double *xlogx = nullptr;            // per gene: sum_i x log x - x
@@ -173,7 +175,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { cudaFree((void *)rowptr); cudaFree((void *)colidx); cudaFree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3]};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3]};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -203,6 +205,10 @@ __global__ void k_gather_csc(int64_t nnz, const int64_t *perm, const int32_t *ro
         rowidx[t] = rowids[e];
         val_csc[t] = val[e];
     }
+}
+__global__ void k_invert_perm(int64_t nnz, const int64_t *perm, uint32_t *inv) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (int64_t)gridDim.x * blockDim.x)
+        inv[perm[t]] = (uint32_t)t;
 }
 __global__ void k_colptr_from_sorted(int64_t nnz, int32_t p, const int32_t *keys, int64_t *colptr) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= p; j += gridDim.x * blockDim.x) {
@@ -313,6 +319,12 @@ void pcmf_solver::build_csc() {
     } else {
         val_csc = dmalloc<double>(nnz);
         k_gather_csc<double><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, (const double *)val_csr, rowidx, (double *)val_csc);
+    }
+    // ZI / sparse models: the gene passes leave q_ij in CSC order and the cell pass reads it back through this map
+    if ((zi || sparse) && nnz < 0xffffffffLL && !(opt.kernel_variant & 16)) {
+        csr2csc = dmalloc<uint32_t>(nnz);
+        k_invert_perm<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, csr2csc);
+        qcsc = dmalloc<double>(nnz);
     }
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
@@ -554,7 +566,7 @@ void pcmf_solver::step(bool want_data) {
         const bool reuse = sparse && sparse_sums_valid;
         const double *src = (opt.world > 1) ? ar2keep : ar2;
         ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, reuse ? unchanged : nullptr, src + ar2_B1,
-                   src + ar2_B2, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT};
+                   src + ar2_B2, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc};
         const int mode = !want_data ? GENE_B1 : (sparse ? GENE_B1_B2 : GENE_B1_LOGT);
         L->gene_pass(f32, mode, ca, std::min<int>(p, sms * 32), stream);
     }
@@ -566,7 +578,7 @@ void pcmf_solver::step(bool want_data) {
         ra.n = n; ra.K = K; ra.rowptr = rowptr; ra.colidx = colidx; ra.val = val_csr; ra.ev = ev; ra.evw = evw; ra.ElogV = ElogV;
         ra.Sd = Sd; ra.wS = wS; ra.allmasked = allmasked; ra.dbg = dbg; ra.a1 = a1; ra.a2 = a2; ra.EU_new = EU[nxt]; ra.ElogU = ElogU; ra.eu = eu; ra.rowext = rowext; ra.alpha1 = alpha1;
         ra.alpha2 = alpha2; ra.rate_vec = csv + 128; ra.PV = zi ? PV : nullptr; ra.first_iter = first_iter ? first_mode : 0; ra.a1_old0 = old0[0]; ra.a2_old0 = old0[1]; ra.guard_cur = gc;
-        ra.guard_next = gn; ra.cs_eu = ar1 + ar1_cseu; ra.cs_elog = ar1 + ar1_cselog; ra.usc = ar1 + ar1_usc;
+        ra.guard_next = gn; ra.csr2csc = csr2csc; ra.qcsc = qcsc; ra.cs_eu = ar1 + ar1_cseu; ra.cs_elog = ar1 + ar1_cselog; ra.usc = ar1 + ar1_usc;
         // colsum(EV o prob_S) of the OLD state: csv+128 is re-accumulated during this iteration, hyp+256 keeps the copy
         ra.rate_vec = hyp + 256;
         const int block = 256;
@@ -610,7 +622,7 @@ void pcmf_solver::step(bool want_data) {
     if (sparse) {
         begin(PH_GENE_S);
         ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, gn, ar2 + ar2_B1,
-                   ar2 + ar2_B2, ar2 + ar2_xlogT};
+                   ar2 + ar2_B2, ar2 + ar2_xlogT, qcsc};
         L->gene_pass(f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
         if (opt.world > 1) CK(cudaMemcpyAsync(ar2keep, ar2, 2 * pK * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         allreduce(ar2, 2 * pK);
@@ -652,7 +664,7 @@ void pcmf_solver::step(bool want_data) {
 double pcmf_solver::data_term_now() {
     const size_t pK = (size_t)p * KP;
     ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, guard[gcur],
-                   ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT};
+                   ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT, qcsc};
     sparse_sums_valid = false;   // ar2 is overwritten with the (all-reduced) sums of a different mask
     L->gene_pass(f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
     allreduce(ar2, ar2_total);
@@ -813,6 +825,7 @@ void pcmf_solver::restore_state(const Saved &sv) {
         CK(cudaMemcpyAsync(sv.arrays[i].first, sv.copies[i], sv.arrays[i].second, cudaMemcpyDeviceToDevice, stream));
     cur = sv.cur; gcur = sv.gcur; first_iter = sv.first_iter; sparse_sums_valid = sv.sparse_sums_valid; have_pending = sv.have_pending;
     last_nodata = sv.last_nodata; std::copy(sv.h.begin(), sv.h.end(), h_scal); iter = sv.iter; first_mode = sv.first_mode;
+    sparse_sums_valid = false;   // the stored q of the non-zeros belong to the last run, not to the restored one
     CK(cudaStreamSynchronize(stream));
 }
 
