@@ -8,11 +8,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -43,6 +45,20 @@ struct Err : std::runtime_error {
         if (e_ != cudaSuccess) fail(PCMF_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
                                     cudaGetErrorString(e_));                                             \
     } while (0)
+
+// PCMF_TIMING=1 prints the wall-clock of the set-up stages (synchronising the stream at each mark)
+struct StageTimer {
+    cudaStream_t st; bool on; double t;
+    explicit StageTimer(cudaStream_t s) : st(s), on(getenv("PCMF_TIMING") != nullptr), t(0) { if (on) { cudaStreamSynchronize(st); t = mark_now(); } }
+    static double mark_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const double n = mark_now();
+        fprintf(stderr, "[pcmf timing] %-28s %8.1f ms\n", what, (n - t) * 1e3);
+        t = n;
+    }
+};
 
 double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -236,6 +252,18 @@ __global__ void k_refresh_weights(int32_t p, int K, int KP, int sparse, const do
         wS[o] = w; evw[o] = ev[o] * w;
     }
 }
+// random_init_model_param (gap_factor_model.cpp:159-168): shape-1 Gamma with rate sqrt(K / mean) by inversion of
+// u = (r + 0.5) / 2^32, mean = sums[row] / denom; pads are 1
+__global__ void k_init_gamma_rows(int64_t rows, int K, int KP, const uint32_t *raw, const double *sums, double denom, double *dst) {
+    const int64_t total = rows * KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % KP);
+        const int64_t r = o / KP;
+        if (k >= K) { dst[o] = 1.0; continue; }
+        const double rate = sqrt((double)K / (sums[r] / denom));
+        dst[o] = -log(((double)raw[r * K + k] + 0.5) / 4294967296.0) / rate;
+    }
+}
 __global__ void k_vec_scale(double *dst, const double *src, int64_t n, double s) {
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) dst[o] = src[o] * s;
 }
@@ -263,6 +291,7 @@ void pcmf_solver::setup_problem(const pcmf_problem &pr) {
             CK(cudaMemcpyAsync(vv, f32 ? (const void *)pr.csr_val_f32 : (const void *)pr.csr_val_f64,
                                (f32 ? sizeof(float) : sizeof(double)) * nnz, cudaMemcpyHostToDevice, stream));
             rowptr = rp; colidx = ci; val_csr = vv; own_csr = true;
+            StageTimer th(stream); th.t -= 0; th.mark("H2D of the CSR arrays (wait)");
         }
     } else {
         // dense R matrix (wrapper_gap_factor.h:204-211) -> CSR on the host, two column-major sweeps
@@ -299,17 +328,24 @@ void pcmf_solver::setup_problem(const pcmf_problem &pr) {
 }
 
 void pcmf_solver::build_csc() {
+    StageTimer tm(stream);
     // CSR -> CSC by a stable radix sort on the gene index (rows stay ascending inside a gene -> deterministic sums)
-    int32_t *rowids = dmalloc<int32_t>(nnz);
-    int64_t *perm_in = dmalloc<int64_t>(nnz), *perm_out = dmalloc<int64_t>(nnz);
-    int32_t *keys_out = dmalloc<int32_t>(nnz);
-    k_expand_rows<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, rowids, perm_in);
+    // one scratch block for all the temporaries of the sort (one cudaMalloc / cudaFree instead of ten)
     int end_bit = 1; while ((1ll << end_bit) < (int64_t)p) ++end_bit;
     size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, colidx, keys_out, perm_in, perm_out, nnz, 0, end_bit, stream));
-    void *tmp = nullptr;
-    CK(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 1)));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (const int64_t *)nullptr,
+                                       (int64_t *)nullptr, nnz, 0, end_bit, stream));
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t o_rowids = 0, o_pin = o_rowids + up(4 * (size_t)nnz), o_pout = o_pin + up(8 * (size_t)nnz),
+                 o_keys = o_pout + up(8 * (size_t)nnz), o_tmp = o_keys + up(4 * (size_t)nnz), scratch_bytes = o_tmp + up(tmp_bytes);
+    unsigned char *scratch = dmalloc<unsigned char>(scratch_bytes);
+    int32_t *rowids = reinterpret_cast<int32_t *>(scratch + o_rowids);
+    int64_t *perm_in = reinterpret_cast<int64_t *>(scratch + o_pin), *perm_out = reinterpret_cast<int64_t *>(scratch + o_pout);
+    int32_t *keys_out = reinterpret_cast<int32_t *>(scratch + o_keys);
+    void *tmp = scratch + o_tmp;
+    k_expand_rows<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, rowids, perm_in);
     CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, colidx, keys_out, perm_in, perm_out, nnz, 0, end_bit, stream));
+    tm.mark("csc: expand + radix sort");
     colptr = dmalloc<int64_t>(p + 1);
     rowidx = dmalloc<int32_t>(nnz);
     k_colptr_from_sorted<<<grid_for(p + 1, 256), 256, 0, stream>>>(nnz, p, keys_out, colptr);
@@ -328,8 +364,9 @@ void pcmf_solver::build_csc() {
     }
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
-    cudaFree(tmp); cudaFree(rowids); cudaFree(perm_in); cudaFree(perm_out); cudaFree(keys_out);
+    cudaFree(scratch);
 
+    tm.mark("csc: gather + maps + frees");
     Lg = dmalloc<double>(p); colsumX = dmalloc<double>(p); colnnz = dmalloc<double>(p); rowsumX = dmalloc<double>(n);
     xlogx = dmalloc<double>(p);
     if (f32) {
@@ -339,12 +376,14 @@ void pcmf_solver::build_csc() {
         k_gene_constants<double><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz, xlogx);
         k_row_sums<double><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
     }
+    tm.mark("gene/cell constants");
     if (zi) {
         const size_t wT = (size_t)((p + 31) / 32) * n, wB = (size_t)((n + 31) / 32) * p;
         bitT = dmalloc<uint32_t>(wT); bitB = dmalloc<uint32_t>(wB);
         CK(cudaMemsetAsync(bitT, 0, wT * 4, stream)); CK(cudaMemsetAsync(bitB, 0, wB * 4, stream));
         k_build_bitmaps<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, p, rowptr, colidx, bitT, bitB);
     }
+    tm.mark("occupancy bitmaps");
     // gene constants are sums over cells -> all-reduce across the row shards
     allreduce(Lg, p); allreduce(colsumX, p); allreduce(colnnz, p); allreduce(xlogx, p);
     std::vector<double> h(p), hx(p), hs(p);
@@ -478,22 +517,22 @@ void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
     } else {
         // random_init_model_param (gap_factor_model.cpp:147-174): a1(i,.) ~ Gamma(1, rate sqrt(K / rowmean_i)),
         // b1(j,.) ~ Gamma(1, rate sqrt(K / colmean_j)); one MT19937 stream, cells first (in global order) then genes.
-        std::vector<double> rs(n), cs(p);
-        CK(cudaMemcpy(rs.data(), rowsumX, sizeof(double) * n, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(cs.data(), colsumX, sizeof(double) * p, cudaMemcpyDeviceToHost));
-        std::vector<double> A((size_t)n * K), B((size_t)p * K);
+        // The raw 32-bit draws come off the single host stream in order; the inversion -log(u) / rate runs on the device,
+        // straight into the padded row-major layout (row / column sums of X are already there).
+        auto draw = [&](std::mt19937 g, int64_t rows, const double *sums, double denom, double *dst) {
+            std::vector<uint32_t> raw((size_t)rows * K);
+            for (size_t e = 0; e < raw.size(); ++e) raw[e] = (uint32_t)g();
+            uint32_t *d_raw = dmalloc<uint32_t>(raw.size());
+            CK(cudaMemcpyAsync(d_raw, raw.data(), raw.size() * 4, cudaMemcpyHostToDevice, stream));
+            k_init_gamma_rows<<<grid_for(rows * KP, 256), 256, 0, stream>>>(rows, K, KP, d_raw, sums, denom, dst);
+            CK(cudaStreamSynchronize(stream));
+            cudaFree(d_raw);
+        };
         std::mt19937 gu = base; gu.discard((unsigned long long)row_offset * K);
-        for (int64_t i = 0; i < n; ++i) {
-            const double rate = std::sqrt((double)K / (rs[i] / p));
-            for (int k = 0; k < K; ++k) A[i + (size_t)k * n] = -std::log(unif(gu)) / rate;
-        }
+        draw(gu, n, rowsumX, (double)p, a1);
         std::mt19937 gv = base; gv.discard((unsigned long long)n_global * K);
-        for (int j = 0; j < p; ++j) {
-            const double rate = std::sqrt((double)K / (cs[j] / (double)n_global));
-            for (int k = 0; k < K; ++k) B[j + (size_t)k * p] = -std::log(unif(gv)) / rate;
-        }
+        draw(gv, p, colsumX, (double)n_global, b1);
         rng_consumed += (unsigned long long)(n_global + p) * K;
-        upload_colmajor(A.data(), n, a1, 1.0); upload_colmajor(B.data(), p, b1, 1.0);
         k_fill<<<grid_for(n * KP, 256), 256, 0, stream>>>(a2, n * KP, 1.0);
         k_fill<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(b2, (int64_t)p * KP, 1.0);
     }
@@ -941,11 +980,15 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
         s->K = opt->K; s->KP = padded_K(opt->K); s->zi = opt->zero_inflation != 0; s->sparse = opt->sparsity != 0;
         s->L = get_launchers(s->KP);
         if (!s->L) fail(PCMF_EUNSUPPORTED, "no kernels compiled for padded K = %d", s->KP);
+        StageTimer tm(s->stream);
         s->setup_problem(*prob);
+        tm.mark("setup_problem (total)");
         s->alloc_state();
+        tm.mark("alloc_state");
         if (init) s->init_copy = *init;
         s->rng.seed(s->opt.has_seed ? s->opt.seed : (uint32_t)std::chrono::system_clock::now().time_since_epoch().count());
         s->init_state(init);
+        tm.mark("init_state");
     });
     if (rc != PCMF_OK) { delete s; s = nullptr; }
     if (out) *out = s;
