@@ -43,6 +43,8 @@ CONFIGS = {
                label="C2: 10k x 2k dense Gamma-Poisson, K=10"),
     "c4gap": dict(n=1_000_000, p=20_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=False, sparse=False,
                   label="C4 data, plain Gamma-Poisson (no ZI, no sparsity), K=20"),
+    **{"c5k%d" % k: dict(n=200_000, p=10_000, K_true=20, K=k, prob1=0.05, mean_rate=20.0, zi=True, sparse=False,
+                         label="C5: 200k x 10k, ~5%% nnz, ZI, K=%d (latent-dimension sweep)" % k) for k in (2, 10, 30, 64)},
     "c4s8": dict(n=125_000, p=20_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=True, sparse=True,
                  label="one 8-GPU shard of C4 on one GPU: 125k cells x 20k genes (kernel tuning only)"),
     "tiny": dict(n=20_000, p=2_000, K_true=20, K=20, prob1=0.05, mean_rate=20.0, zi=True, sparse=True,
