@@ -702,13 +702,20 @@ void pcmf_solver::step(bool want_data) {
 // ELBO data term of the current state (gap...cpp:301-313, sparse...cpp:194-212): one gene pass, nothing updated.
 double pcmf_solver::data_term_now() {
     const size_t pK = (size_t)p * KP;
-    ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, guard[gcur],
-                   ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT, qcsc};
-    sparse_sums_valid = false;   // ar2 is overwritten with the (all-reduced) sums of a different mask
+    // Sparse models: for genes whose mask row did not change in the last spike-and-slab update the sums of that
+    // update's gene pass (same statistics, same mask) are exactly the ones needed -- copy them, recompute the others.
+    // The result goes to the B1 / B2 / xlogT slots of the first reduction buffer (free between iterations), so the cached
+    // sums stay valid for the next E-step.
+    const bool reuse = sparse && sparse_sums_valid;
+    const double *src = (opt.world > 1) ? ar2keep : ar2;
+    ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, reuse ? unchanged : nullptr,
+               reuse ? src + ar2_B1 : nullptr, reuse ? src + ar2_B2 : nullptr, dbg, guard[gcur],
+               ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc};
     L->gene_pass(f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
-    allreduce(ar2, ar2_total);
+    allreduce(ar1 + ar1_B1, pK);
+    allreduce(ar1 + ar1_B2, pK + p);
     CK(cudaMemsetAsync(scal + S_DATA, 0, 8, stream));
-    DataArgs da{p, K, KP, sparse, zi, ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT, ElogV, prob_S, colw, scal};
+    DataArgs da{p, K, KP, sparse, zi, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, ElogV, prob_S, colw, scal};
     k_data_term<<<grid_for(pK, 256), 256, 0, stream>>>(da);
     launches += 2;
     read_scal();
