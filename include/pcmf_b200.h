@@ -108,6 +108,9 @@ typedef struct {
     const double *a1, *a2, *b1, *b2;             /* -> init_variational_param (gap_factor_model.cpp:113-123) */
     const double *alpha1, *alpha2, *beta1, *beta2; /* K-vectors (the reference's n x K / p x K with identical rows) */
     const double *prob_S, *prior_S;              /* p x K, p -> init_sparse_param (sparse_gap_factor_model.cpp:96-104) */
+    const double *prob_D, *prior_D;              /* n_local x p (dense), p -> init_zi_param(prob_D, prior_D)
+                                                  * (zi_gap_factor_model.cpp:110-114; both or neither).  The dense matrix is
+                                                  * only held until the first zero-inflation update replaces it */
 } pcmf_init;
 
 /* Caller-allocated outputs (NULL = not wanted); column-major; U-side sizes are for the LOCAL rows.

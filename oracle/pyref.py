@@ -44,6 +44,7 @@ def lib():
         L.ref_init_sparse.argtypes = [C.c_void_p, C.c_double, dp, dp, C.c_int, C.c_int]
         L.ref_init_sparse_random.argtypes = [C.c_void_p, C.c_double]
         L.ref_init_zi.argtypes = [C.c_void_p]
+        L.ref_init_zi_given.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
         L.ref_init_variational.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int]
         for nm in ("ref_init_random", "ref_optimize", "ref_order_factor", "ref_output"):
             getattr(L, nm).argtypes = [C.c_void_p]
@@ -99,8 +100,13 @@ class RefModel:
             b, bp = _f(prior_S)
             self._ck(self.L.ref_init_sparse(self.h, float(sel_bound), ap, bp, self.p, self.K))
 
-    def init_zi_param(self):
-        self._ck(self.L.ref_init_zi(self.h))
+    def init_zi_param(self, prob_D=None, prior_D=None):
+        if prob_D is None:
+            self._ck(self.L.ref_init_zi(self.h))
+        else:
+            a, ap = _f(prob_D)
+            b, bp = _f(prior_D)
+            self._ck(self.L.ref_init_zi_given(self.h, ap, bp, self.n, self.p))
 
     def init_variational_param(self, a1, a2, b1, b2):
         arrs = [_f(x) for x in (a1, a2, b1, b2)]
@@ -159,14 +165,14 @@ class RefModel:
 
 def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True, iter_max=1000, iter_min=500, epsilon=1e-2,
         additional_iter=10, conv_mode=1, reorder_factor=True, seed=None, a1=None, a2=None, b1=None, b2=None,
-        prob_S=None, prior_S=None):
+        prob_S=None, prior_S=None, prob_D=None, prior_D=None):
     m = RefModel(X, K, zero_inflation, sparsity, monitor, iter_max, iter_min, epsilon, additional_iter, conv_mode)
     if seed is not None:
         m.seed(seed)
     if sparsity:                                   # wrapper_sparse_gap_factor.h:389-394
         m.init_sparse_param(sel_bound, prob_S, prior_S)
     if zero_inflation:                             # :395-399
-        m.init_zi_param()
+        m.init_zi_param(prob_D, prior_D)
     if a1 is not None:                             # :402-403
         m.init_variational_param(a1, a2, b1, b2)
     else:                                          # :410-411

@@ -34,6 +34,7 @@ struct IRunner {
     virtual void init_sparse(double sel_bound, const MatrixXd &prob_S, const VectorXd &prior_S) = 0;
     virtual void init_sparse_random(double sel_bound, myRandom::RNGType &rng) = 0;
     virtual void init_zi() = 0;
+    virtual void init_zi_given(const MatrixXd &prob_D, const VectorXd &prior_D) = 0;
     virtual void init_variational(const MatrixXd &a1, const MatrixXd &a2, const MatrixXd &b1, const MatrixXd &b2) = 0;
     virtual void init_random(myRandom::RNGType &rng) = 0;
     virtual void optimize() = 0;
@@ -48,6 +49,7 @@ struct Runner : IRunner {
     void init_sparse(double sb, const MatrixXd &ps, const VectorXd &pr) override { algo.init_sparse_param_gap(sb, ps, pr); }
     void init_sparse_random(double sb, myRandom::RNGType &rng) override { algo.init_sparse_param_gap(sb, rng); }
     void init_zi() override { algo.init_zi_param_gap(); }
+    void init_zi_given(const MatrixXd &pd, const VectorXd &pr) override { algo.init_zi_param_gap(pd, pr); }
     void init_variational(const MatrixXd &a1, const MatrixXd &a2, const MatrixXd &b1, const MatrixXd &b2) override {
         algo.init_variational_param_gap(a1, a2, b1, b2);
     }
@@ -103,6 +105,9 @@ int ref_init_sparse(void *hv, double sel_bound, const double *prob_S, const doub
 }
 int ref_init_sparse_random(void *hv, double sel_bound) { GUARD(h->r->init_sparse_random(sel_bound, h->rng)) }
 int ref_init_zi(void *hv) { GUARD(h->r->init_zi()) }
+int ref_init_zi_given(void *hv, const double *prob_D, const double *prior_D, int n, int p) {
+    GUARD(h->r->init_zi_given(mat(prob_D, n, p), mat(prior_D, p, 1)))
+}
 int ref_init_variational(void *hv, const double *a1, const double *a2, const double *b1, const double *b2, int n, int p, int K) {
     GUARD(h->r->init_variational(mat(a1, n, K), mat(a2, n, K), mat(b1, p, K), mat(b2, p, K)))
 }

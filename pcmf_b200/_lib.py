@@ -36,7 +36,7 @@ class Options(C.Structure):
 
 class Init(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("U", "V", "a1", "a2", "b1", "b2", "alpha1", "alpha2", "beta1", "beta2",
-                                          "prob_S", "prior_S")]
+                                          "prob_S", "prior_S", "prob_D", "prior_D")]
 
 
 class Result(C.Structure):

@@ -253,8 +253,8 @@ class Solver:
     def __init__(self, X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, iter_max=1000, iter_min=500,
                  epsilon=1e-2, additional_iter=10, conv_mode=1, monitor=True, reorder_factor=False, ninit=1, iter_init=100,
                  seed=None, verbose=False, U=None, V=None, a1=None, a2=None, b1=None, b2=None, alpha1=None, alpha2=None,
-                 beta1=None, beta2=None, prob_S=None, prior_S=None, device=0, stream=None, comm=None, n_global=None,
-                 row_offset=0, progress=None, kernel_variant=0):
+                 beta1=None, beta2=None, prob_S=None, prior_S=None, prob_D=None, prior_D=None, device=0, stream=None,
+                 comm=None, n_global=None, row_offset=0, progress=None, kernel_variant=0):
         self.L = _lib.lib()
         self.h = None
         pr, self._keep, n, p = _as_problem(X, n_global, row_offset)
@@ -312,6 +312,13 @@ class Solver:
                 raise PcmfError(_lib.EINVAL, "Wrong dimension for prob_S and/or prior_S input matrix/vector")
             k.append(pv)
             ini.prior_S = pv.ctypes.data_as(C.c_void_p)
+        if self.zi and prob_D is not None and prior_D is not None:      # wrapper_gap_factor.h:352-356
+            put("prob_D", prob_D, (n, p), "prob_D and/or prior_D")
+            pd = np.ascontiguousarray(np.asarray(prior_D, np.float64).reshape(-1))
+            if pd.shape != (p,):
+                raise PcmfError(_lib.EINVAL, "Wrong dimension for prob_D and/or prior_D input matrix/vector")
+            k.append(pd)
+            ini.prior_D = pd.ctypes.data_as(C.c_void_p)
         h = C.c_void_p()
         err = C.create_string_buffer(512)
         rc = self.L.pcmf_create(C.byref(pr), C.byref(o), C.byref(ini), C.byref(h), err, 512)
@@ -437,9 +444,6 @@ def _run(X, K, zero_inflation, sparsity, sel_bound=0.5, U=None, V=None, verbose=
         raise PcmfError(_lib.EINVAL, "FixMe not implemented yet")               # wrapper_gap_factor.h:370
     if init_mode != "random":
         raise PcmfError(_lib.EINVAL, "`init_mode` input parameter should be 'random' or 'nmf'")   # :372
-    if prob_D is not None or prior_D is not None:
-        raise PcmfError(_lib.EUNSUPPORTED, "warm-starting from a dense prob_D matrix is not supported: the GPU path "
-                                           "never materialises prob_D (pCMF() never passes it either)")
     del ncores  # kept for signature compatibility (omp_set_num_threads in the reference); the GPU path ignores it
     progress = None
     if verbose:
@@ -447,8 +451,8 @@ def _run(X, K, zero_inflation, sparsity, sel_bound=0.5, U=None, V=None, verbose=
     s = Solver(X, K, zero_inflation, sparsity, sel_bound=sel_bound, iter_max=iter_max, iter_min=iter_min, epsilon=epsilon,
                additional_iter=additional_iter, conv_mode=conv_mode, monitor=monitor, reorder_factor=reorder_factor,
                ninit=ninit, iter_init=iter_init, seed=seed, verbose=verbose, U=U, V=V, a1=a1, a2=a2, b1=b1, b2=b2,
-               alpha1=alpha1, alpha2=alpha2, beta1=beta1, beta2=beta2, prob_S=prob_S, prior_S=prior_S, progress=progress,
-               **gpu)
+               alpha1=alpha1, alpha2=alpha2, beta1=beta1, beta2=beta2, prob_S=prob_S, prior_S=prior_S, prob_D=prob_D,
+               prior_D=prior_D, progress=progress, **gpu)
     try:
         conv = s.optimize(multi_init=bool(ninit and ninit > 1))     # wrapper_gap_factor.h:296-350, :379
         if reorder_factor:

@@ -1308,6 +1308,78 @@ __global__ void k_permute_cols(int64_t rows, int K, int KP, const int32_t *order
 }
 #endif  // PCMF_COMMON_KERNELS
 
+// ------------------------------------------------------------------------------------------------------------
+// Warm start from an explicit dense prob_D (init_zi_param(prob_D, prior_D), zi_gap_factor_model.cpp:110-114).  The
+// matrix only lives until the first zero-inflation update overwrites it with the closed form, so these plain kernels
+// run once or twice per fit: they replace the DMMA passes while prob_D is an arbitrary n x p matrix (column-major).
+// ------------------------------------------------------------------------------------------------------------
+#ifdef PCMF_COMMON_KERNELS
+// values of the non-zeros weighted by prob_D (the multinomial sums are linear in x, zi...cpp:316-322), and
+// sum_ij prob_D_ij lgamma(X_ij + 1) (zi...cpp:207-212)
+template <typename VT>
+__global__ void k_weight_vals_csr(int64_t n, const int64_t *rowptr, const int32_t *colidx, const void *val_, const double *P,
+                                  double *out, double *lgx) {
+    const VT *val = static_cast<const VT *>(val_);
+    __shared__ double sh[32];
+    double lg = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nw)
+        for (int64_t e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) {
+            const double x = (double)val[e], w = P[i + (int64_t)colidx[e] * n];
+            out[e] = w * x;
+            lg += w * lgamma(x + 1.0);
+        }
+    lg = block_sum(lg, sh);
+    if (threadIdx.x == 0 && lgx) atomicAdd(lgx, lg);
+}
+template <typename VT>
+__global__ void k_weight_vals_csc(int32_t p, int64_t n, const int64_t *colptr, const int32_t *rowidx, const void *val_,
+                                  const double *P, double *out) {
+    const VT *val = static_cast<const VT *>(val_);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < p; j += nw)
+        for (int64_t e = colptr[j] + lane; e < colptr[j + 1]; e += 32) out[e] = P[rowidx[e] + (int64_t)j * n] * (double)val[e];
+}
+// "pass A" on an explicit P: PV = P EVS, colsum(P), sum P o UVt, sum_{0<P<1} P log P + (1-P) log(1-P); thread per cell
+__global__ void k_dense_zi_cells(int64_t n, int32_t p, int K, int KP, const double *P, const double *EU, const double *EVS,
+                                 double *PV, double *colsumP, double *zsc) {
+    __shared__ double sh[32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    double u[64], pv[64];
+    for (int k = 0; k < K; ++k) { u[k] = live ? EU[i * KP + k] : 0.0; pv[k] = 0.0; }
+    double spl = 0, ent = 0;
+    for (int j = 0; j < p; ++j) {
+        const double pj = live ? P[i + (int64_t)j * n] : 0.0;
+        double lam = 0;
+        for (int k = 0; k < K; ++k) { const double v = EVS[(int64_t)j * KP + k]; lam = fma(u[k], v, lam); pv[k] = fma(pj, v, pv[k]); }
+        spl = fma(pj, lam, spl);
+        if (pj > 0.0 && pj < 1.0) ent += pj * log(pj) + (1.0 - pj) * log(1.0 - pj);
+        const double cs = warp_sum(pj);
+        if ((threadIdx.x & 31) == 0) atomicAdd(colsumP + j, cs);
+    }
+    if (live) for (int k = 0; k < KP; ++k) PV[i * KP + k] = k < K ? pv[k] : 0.0;
+    spl = block_sum(spl, sh); ent = block_sum(ent, sh);
+    if (threadIdx.x == 0) { atomicAdd(zsc + 0, spl); atomicAdd(zsc + 1, ent); }
+}
+// "pass B" on an explicit P: tmpMat += P^T EU_new; thread per gene
+__global__ void k_dense_zi_genes(int64_t n, int32_t p, int K, int KP, const double *P, const double *EUn, double *tmpMat) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    double acc[64];
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double pj = P[i + (int64_t)j * n];
+        for (int k = 0; k < K; ++k) acc[k] = fma(pj, EUn[i * KP + k], acc[k]);
+    }
+    for (int k = 0; k < K; ++k) tmpMat[(int64_t)j * KP + k] += acc[k];
+}
+#endif  // PCMF_COMMON_KERNELS
+
 // column-major (R / Eigen) <-> padded row-major
 #ifdef PCMF_COMMON_KERNELS
 __global__ void k_colmajor_to_rowpad(int64_t rows, int K, int KP, const double *src, double *dst, double padval) {

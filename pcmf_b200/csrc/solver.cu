@@ -94,6 +94,9 @@ struct pcmf_solver {
     int64_t *colptr = nullptr; int32_t *rowidx = nullptr; void *val_csc = nullptr;
     uint32_t *bitT = nullptr, *bitB = nullptr;
     double *zpackA = nullptr, *zpackB = nullptr;   // fragment-ordered scratch of the DMMA ZI passes
+    // explicit dense prob_D of a warm start: held until the first zero-inflation update (init_zi_param(prob_D, prior_D))
+    double *Pexp = nullptr, *valw_csr = nullptr, *valw_csc = nullptr;
+    bool explicitP = false, freq_ones = false;
     uint32_t *csr2csc = nullptr;                   // nnz: CSC position of every CSR entry (stored-q cell pass)
     double *qcsc = nullptr;                        // nnz: q_ij = x_ij / T_ij left by the gene passes, CSC order
     double *Lg = nullptr, *colsumX = nullptr, *colnnz = nullptr, *rowsumX = nullptr;
@@ -191,7 +194,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { cudaFree((void *)rowptr); cudaFree((void *)colidx); cudaFree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3]};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3]};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -472,6 +475,19 @@ void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
         fail(PCMF_EINVAL, "You should supply initial values for all alpha1, alpha2, beta1, beta2 or for none of them");
 
     // hyper-parameters: Ones (gap_factor_model.cpp:56-59) unless given
+    if ((in->prob_D != nullptr) != (in->prior_D != nullptr))
+        fail(PCMF_EINVAL, "You should supply initial values for both prob_D and prior_D or for neither of them");
+    if (zi && in->prob_D) {
+        // init_zi_param(prob_D, prior_D) (zi...cpp:110-114): the given prior is overwritten by colmean(prob_D) in the
+        // update_hyper_param that every initialisation ends with (zi...cpp:146-151, :370-372); freq_D keeps its
+        // constructor value Ones (zi...cpp:57)
+        if (Pexp) { cudaFree(Pexp); cudaFree(valw_csr); cudaFree(valw_csc); }
+        Pexp = dmalloc<double>((size_t)n * p); valw_csr = dmalloc<double>(nnz); valw_csc = dmalloc<double>(nnz);
+        CK(cudaMemcpyAsync(Pexp, in->prob_D, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, stream));
+        explicitP = true; freq_ones = true;
+    } else {
+        explicitP = false;
+    }
     // a later multi-init run starts from the hyper-parameters the previous run ended with (the reference re-uses one
     // model object, wrapper_gap_factor.h:299-301: update_prior_gamma_param then reads log(alpha2) of that run)
     if (!reinit || nhy == 4) {
@@ -567,7 +583,23 @@ void pcmf_solver::run_init_stats() {
     k_row_extremes<<<grid_for(n, 256), 256, 0, stream>>>(n, K, KP, ElogU, rowext);
     k_row_extremes<<<grid_for(p, 256), 256, 0, stream>>>(p, K, KP, ElogV, colext);
     launches += 4 + (sparse ? 1 : 0);
-    if (zi) {
+    if (zi && explicitP) {
+        // explicit prob_D: no gene shortcut applies (flag 0, weight 1), the weights of the non-zeros go into the values
+        CK(cudaMemsetAsync(flag, 0, p * 4, stream));
+        k_fill<<<grid_for(p, 256), 256, 0, stream>>>(colw, p, 1.0);
+        k_fill<<<grid_for(p, 256), 256, 0, stream>>>(cz, p, 0.0);
+        k_refresh_weights<<<grid_for(pK, 256), 256, 0, stream>>>(p, K, KP, sparse, prob_S, colw, ev, wS, evw);
+        if (f32) {
+            k_weight_vals_csr<float><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, val_csr, Pexp, valw_csr, scal + S_LGX);
+            k_weight_vals_csc<float><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, n, colptr, rowidx, val_csc, Pexp, valw_csc);
+        } else {
+            k_weight_vals_csr<double><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, val_csr, Pexp, valw_csr, scal + S_LGX);
+            k_weight_vals_csc<double><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, n, colptr, rowidx, val_csc, Pexp, valw_csc);
+        }
+        k_dense_zi_cells<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, p, K, KP, Pexp, EU[cur], EVS, PV, ar3 + ar3_csP, ar3 + ar3_zsc);
+        allreduce(scal + S_LGX, 1);
+        launches += 6;
+    } else if (zi) {
         // init_zi_param (zi_gap_factor_model.cpp:98-105): prob_D = (X > 0); realised as pass A with c_j = -inf
         ZiPrepArgs zp{p, 1, prior_D, Lg, cz, colw, flag, scal};
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
@@ -599,22 +631,25 @@ void pcmf_solver::step(bool want_data) {
     if (zi) CK(cudaMemsetAsync(ar3, 0, ar3_total * 8, stream));
     k_init_guard<<<1, 32, 0, stream>>>(gn);
 
+    // first iteration after a warm start from an explicit prob_D: the non-zeros carry prob_D_ij x_ij (FP64 values)
+    const void *v_csr = explicitP ? (const void *)valw_csr : val_csr, *v_csc = explicitP ? (const void *)valw_csc : val_csc;
+    const bool v_f32 = explicitP ? false : f32;
     // 1. E-step, gene side (old statistics): B1 [+ B2 | xlogT for the ELBO data term of the previous iterate]
     begin(PH_GENE_E);
     {
         const bool reuse = sparse && sparse_sums_valid;
         const double *src = (opt.world > 1) ? ar2keep : ar2;
-        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, reuse ? unchanged : nullptr, src + ar2_B1,
+        ColArgs ca{p, K, colptr, rowidx, v_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, reuse ? unchanged : nullptr, src + ar2_B1,
                    src + ar2_B2, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc};
         const int mode = !want_data ? GENE_B1 : (sparse ? GENE_B1_B2 : GENE_B1_LOGT);
-        L->gene_pass(f32, mode, ca, std::min<int>(p, sms * 32), stream);
+        L->gene_pass(v_f32, mode, ca, std::min<int>(p, sms * 32), stream);
     }
     end(PH_GENE_E, 1);
     // 2. E-step, cell side + U-side M-step (in place)
     begin(PH_ROWS);
     {
         RowArgs ra{};
-        ra.n = n; ra.K = K; ra.rowptr = rowptr; ra.colidx = colidx; ra.val = val_csr; ra.ev = ev; ra.evw = evw; ra.ElogV = ElogV;
+        ra.n = n; ra.K = K; ra.rowptr = rowptr; ra.colidx = colidx; ra.val = v_csr; ra.ev = ev; ra.evw = evw; ra.ElogV = ElogV;
         ra.Sd = Sd; ra.wS = wS; ra.allmasked = allmasked; ra.dbg = dbg; ra.a1 = a1; ra.a2 = a2; ra.EU_new = EU[nxt]; ra.ElogU = ElogU; ra.eu = eu; ra.rowext = rowext; ra.alpha1 = alpha1;
         ra.alpha2 = alpha2; ra.rate_vec = csv + 128; ra.PV = zi ? PV : nullptr; ra.first_iter = first_iter ? first_mode : 0; ra.a1_old0 = old0[0]; ra.a2_old0 = old0[1]; ra.guard_cur = gc;
         ra.guard_next = gn; ra.csr2csc = csr2csc; ra.qcsc = qcsc; ra.cs_eu = ar1 + ar1_cseu; ra.cs_elog = ar1 + ar1_cselog; ra.usc = ar1 + ar1_usc;
@@ -622,7 +657,7 @@ void pcmf_solver::step(bool want_data) {
         ra.rate_vec = hyp + 256;
         const int block = 256;
         const int64_t warps = std::min<int64_t>(n, (int64_t)sms * 8 * 8);
-        L->estep_rows(f32, ra, (int)((warps + 7) / 8), block, stream);
+        L->estep_rows(v_f32, ra, (int)((warps + 7) / 8), block, stream);
     }
     end(PH_ROWS, 1);
     // 3. ZI: prob_D^T EU_new with prob_D recomputed from the triple saved when it was defined
@@ -638,7 +673,12 @@ void pcmf_solver::step(bool want_data) {
         int64_t rpc = (n + chunks - 1) / chunks; rpc = (rpc + 63) / 64 * 64;
         chunks = (int)((n + rpc - 1) / rpc);
         zb.rows_per_chunk = rpc;
-        end(PH_ZI_B, L->zi_genes(zb, chunks, opt.kernel_variant, stream));
+        if (explicitP) {
+            k_dense_zi_genes<<<(p + 127) / 128, 128, 0, stream>>>(n, p, K, KP, Pexp, EU[nxt], ar1 + ar1_tmp);
+            end(PH_ZI_B, 1);
+        } else {
+            end(PH_ZI_B, L->zi_genes(zb, chunks, opt.kernel_variant, stream));
+        }
     }
     // 4. all-reduce of the gene-side sums + U partials over the row shards
     begin(PH_AR1);
@@ -660,9 +700,9 @@ void pcmf_solver::step(bool want_data) {
     // 6. spike-and-slab probabilities: second non-zero pass with the new statistics and the old mask
     if (sparse) {
         begin(PH_GENE_S);
-        ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, gn, ar2 + ar2_B1,
+        ColArgs ca{p, K, colptr, rowidx, v_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, gn, ar2 + ar2_B1,
                    ar2 + ar2_B2, ar2 + ar2_xlogT, qcsc};
-        L->gene_pass(f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
+        L->gene_pass(v_f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
         if (opt.world > 1) CK(cudaMemcpyAsync(ar2keep, ar2, 2 * pK * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         allreduce(ar2, 2 * pK);
         sparse_sums_valid = true;
@@ -697,6 +737,12 @@ void pcmf_solver::step(bool want_data) {
     read_scal();
     collect_phase_times();
     cur = nxt; gcur = 1 - gcur; first_iter = false;
+    if (explicitP) {   // the zero-inflation update of this iteration replaced the explicit matrix by the closed form
+        explicitP = false;
+        sparse_sums_valid = false;   // the cached gene sums and the stored q carried the explicit weights
+        cudaFree(Pexp); cudaFree(valw_csr); cudaFree(valw_csc);
+        Pexp = valw_csr = valw_csc = nullptr;
+    }
 }
 
 // ELBO data term of the current state (gap...cpp:301-313, sparse...cpp:194-212): one gene pass, nothing updated.
@@ -708,10 +754,10 @@ double pcmf_solver::data_term_now() {
     // sums stay valid for the next E-step.
     const bool reuse = sparse && sparse_sums_valid;
     const double *src = (opt.world > 1) ? ar2keep : ar2;
-    ColArgs ca{p, K, colptr, rowidx, val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, reuse ? unchanged : nullptr,
-               reuse ? src + ar2_B1 : nullptr, reuse ? src + ar2_B2 : nullptr, dbg, guard[gcur],
+    ColArgs ca{p, K, colptr, rowidx, explicitP ? (const void *)valw_csc : val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked,
+               reuse ? unchanged : nullptr, reuse ? src + ar2_B1 : nullptr, reuse ? src + ar2_B2 : nullptr, dbg, guard[gcur],
                ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc};
-    L->gene_pass(f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
+    L->gene_pass(explicitP ? false : f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
     allreduce(ar1 + ar1_B1, pK);
     allreduce(ar1 + ar1_B2, pK + p);
     CK(cudaMemsetAsync(scal + S_DATA, 0, 8, stream));
@@ -729,6 +775,7 @@ double pcmf_solver::data_term_now() {
 // pl(X, rate) = sum_nnz x clog(rate) - sum_ij rate - sum lgamma(x + 1): one non-zero pass + the total rate, which is
 // the closed form of gap...cpp:298 or, for ZI, sum prob_D o UVt of the last dense pass.
 pcmf_solver::Mon pcmf_solver::monitors_now(bool want_loglik) {
+    if (explicitP) fail(PCMF_EUNSUPPORTED, "monitors are not available before the first iteration of a run warm-started from a dense prob_D");
     CK(cudaMemsetAsync(mon, 0, 8 * sizeof(double), stream));
     LamArgs la{p, K, colptr, rowidx, val_csc, EU[cur], EVS, zi ? flag : nullptr, mon};
     L->gene_loglam(f32, la, std::min<int>(p, sms * 32), stream);
@@ -1156,12 +1203,15 @@ int pcmf_get_output(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errle
             if (res->prior_prob_D) CK(cudaMemcpy(res->prior_prob_D, s->prior_D, sizeof(double) * p, cudaMemcpyDeviceToHost));
             if (res->freq_D) {
                 double *tmp = dmalloc<double>(p);
-                k_vec_scale<<<s->grid_for(p, 256), 256, 0, s->stream>>>(tmp, s->colnnz, p, 1.0 / (double)s->n_global);
+                if (s->freq_ones) k_fill<<<s->grid_for(p, 256), 256, 0, s->stream>>>(tmp, p, 1.0);   // never set when prob_D is given (zi...cpp:57, :110-114)
+                else k_vec_scale<<<s->grid_for(p, 256), 256, 0, s->stream>>>(tmp, s->colnnz, p, 1.0 / (double)s->n_global);
                 CK(cudaMemcpyAsync(res->freq_D, tmp, sizeof(double) * p, cudaMemcpyDeviceToHost, s->stream));
                 CK(cudaStreamSynchronize(s->stream));
                 cudaFree(tmp);
             }
-            if (res->prob_D) {
+            if (res->prob_D && s->explicitP) {
+                CK(cudaMemcpy(res->prob_D, s->Pexp, sizeof(double) * n * p, cudaMemcpyDeviceToHost));
+            } else if (res->prob_D) {
                 // prob_D is defined by the triple saved at the last ZI update: EU[cur] (the EU of that update), EVS, cz/flag
                 double *tmp = dmalloc<double>((size_t)n * p);
                 ProbDArgs pa{n, p, K, s->KP, s->EU[s->cur], s->EVS, s->cz, s->flag, s->bitT, tmp};

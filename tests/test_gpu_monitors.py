@@ -103,3 +103,42 @@ def test_multi_init_matches_oracle(zi, sparse):
     assert abs(res["loss"] - ref["loss"]) < 1e-6 * abs(ref["loss"])
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
+
+
+@pytest.mark.parametrize("sparse", [False, True], ids=["zi", "zi_sparse"])
+def test_warm_start_from_dense_prob_D_matches_oracle(sparse):
+    """run_zi_*_gap_factor(..., prob_D = <dense n x p>, prior_D = <p>) as the reference's R tests call it
+    (test-gap_factor_model.R:303-317): init_zi_param(prob_D, prior_D), first iteration on the explicit matrix, closed
+    form from then on; freq_D keeps its constructor value (ones)."""
+    X = problem(25, 64, 48)
+    K = 4
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=12)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    rng = np.random.default_rng(3)
+    PD, prD = rng.uniform(0.05, 0.95, X.shape), np.full(X.shape[1], 0.5)
+    kw = dict(iter_max=15, iter_min=4, epsilon=1e-2, additional_iter=2, a1=a1, a2=a2, b1=b1, b2=b2, prob_D=PD, prior_D=prD)
+    ref = po.run(X, K, True, sparse, monitor=True, reorder_factor=False, prob_S=prob_S, prior_S=prior_S, **kw)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    res = RUN[(True, sparse)](X, K, verbose=False, monitor=True, reorder_factor=False, **kw)
+    assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    assert relerr(res["convergence"]["conv_crit"], ref["convergence"]["conv_crit"]) < 1e-6
+    for k in ("optim_criterion", "loglikelihood", "deviance"):
+        assert relerr(res["monitor"][k], ref["monitor"][k]) < 1e-6, k
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
+    assert np.abs(res["ZI_param"]["prob_D"] - ref["ZI_param"]["prob_D"]).max() < 1e-8
+    assert (res["ZI_param"]["freq_D"] == 1.0).all() and (ref["ZI_param"]["freq_D"] == 1.0).all()
+    # state right after the initialisation: the explicit matrix is what get_output returns, ELBO matches
+    m = po.Model(X, K, True, sparse)
+    if sparse:
+        m.init_sparse_param(0.5, prob_S, prior_S)
+    m.init_zi_param(PD, prD)
+    m.init_variational_param(a1, a2, b1, b2)
+    s = pcmf_b200.Solver(X, K, True, sparse, a1=a1, a2=a2, b1=b1, b2=b2, prob_D=PD, prior_D=prD,
+                         **(dict(prob_S=prob_S, prior_S=prior_S) if sparse else {}))
+    assert abs(s.elbo() - m.elbo()) < 1e-8 * abs(m.elbo())
+    o = s.get_output()
+    assert np.abs(o["prob_D"] - PD).max() == 0.0
+    assert relerr(o["prior_prob_D"], m.get("prior_D")) < 1e-12
+    s.close()

@@ -86,3 +86,30 @@ def test_seeded_random_init_matches_reference_build(zi, sparse):
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(orc["variational_params"][k], ref["variational_params"][k]) < TOL, k
     assert relerr(orc["convergence"]["conv_crit"], ref["convergence"]["conv_crit"]) < TOL
+
+
+@pytest.mark.parametrize("sparse", [False, True], ids=["zi", "zi_sparse"])
+def test_dense_prob_D_warm_start_matches_reference_build(sparse):
+    """init_zi_param(prob_D, prior_D) (zi_gap_factor_model.cpp:110-114) as the reference's R tests use it
+    (test-gap_factor_model.R:303-317)."""
+    X, _, _ = datagen.simulate(40, 30, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=41)
+    K = 3
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=42)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    rng = np.random.default_rng(5)
+    PD, prD = rng.uniform(0.05, 0.95, X.shape), np.full(X.shape[1], 0.5)
+    kw = dict(iter_max=10, iter_min=3, additional_iter=2, a1=a1, a2=a2, b1=b1, b2=b2, reorder_factor=False, prob_D=PD, prior_D=prD)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    ref = pyref.run(X, K, True, sparse, **kw)
+    orc = po.run(X, K, True, sparse, **kw)
+    assert orc["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    assert relerr(orc["convergence"]["conv_crit"], ref["convergence"]["conv_crit"]) < TOL
+    for k in ("loglikelihood", "deviance"):
+        assert relerr(orc["monitor"][k], ref["monitor"][k]) < TOL, k
+    if not sparse:
+        assert relerr(orc["monitor"]["optim_criterion"], ref["monitor"]["optim_criterion"]) < TOL
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(orc["variational_params"][k], ref["variational_params"][k]) < TOL, k
+    assert np.abs(orc["ZI_param"]["prob_D"] - ref["ZI_param"]["prob_D"]).max() < TOL
+    assert (ref["ZI_param"]["freq_D"] == 1.0).all() and (orc["ZI_param"]["freq_D"] == 1.0).all()
