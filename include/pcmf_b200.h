@@ -78,7 +78,7 @@ typedef struct {
     int32_t iter_min;          /* default iter_max/2 (pCMF.R:203-205) */
     double epsilon;            /* default 1e-2 */
     int32_t additional_iter;   /* default 10 */
-    int32_t conv_mode;         /* 0 absolute gap, 1 normalised gap (algorithm.h:412-450); 2 is PCMF_EUNSUPPORTED */
+    int32_t conv_mode;         /* 0 absolute gap, 1 normalised gap, 2 RV coefficient (algorithm.h:412-450, gap...cpp:265-269) */
     int32_t monitor;           /* 1: record ELBO, log-likelihood and deviance every iteration like monitor=TRUE does
                                 * (algorithm.h:391-397); 2: ELBO only (extension: skips the two extra passes);
                                 * 0: none.  norm/abs gap are always recorded */

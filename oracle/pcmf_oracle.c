@@ -15,7 +15,7 @@
  * PARITY STATUS: PINNED against the reference itself.  R, Rcpp, Eigen and Boost are absent
  * from this image, so the reference's package cannot be built as such; instead its OWN model
  * and algorithm sources (pkg/src/{model,gap_factor_model,zi_gap_factor_model,
- * sparse_gap_factor_model,zi_sparse_gap_factor_model}.cpp, algorithm*.h, utils/*.h) are
+ * sparse_gap_factor_model,zi_sparse_gap_factor_model}.cpp, algorithm.h, algorithm_variational_EM.h and the headers under utils) are
  * compiled where they lie against small stand-in headers (oracle/shim/: an eager dense
  * matrix class covering the Eigen expression forms those files use, a list-shaped Rcpp
  * stub, digamma/trigamma and mt19937 distributions for Boost) into
@@ -887,6 +887,33 @@ void orc_order_factor(orc_model *m) {
     if (m->sparse) { permute_cols_i(m->S, p, K, o); permute_cols_d(m->prob_S, p, K, o); }
 }
 
+/* matrix::rv_coeff (utils/matrix.h:100-104): trace(A A' B B') / sqrt(trace(A A' A A') trace(B B' B B')).  The reference
+ * forms the n x n products; trace(A A' B B') = ||A' B||_F^2, so K x K Gram matrices give the same number. */
+static double rv_coeff(const double *A, const double *B, int rows, int K) {
+    double num = 0, da = 0, db = 0;
+    for (int k = 0; k < K; k++)
+        for (int l = 0; l < K; l++) {
+            double ab = 0, aa = 0, bb = 0;
+            for (int r = 0; r < rows; r++) {
+                ab += A[r + (long)k * rows] * B[r + (long)l * rows];
+                aa += A[r + (long)k * rows] * A[r + (long)l * rows];
+                bb += B[r + (long)k * rows] * B[r + (long)l * rows];
+            }
+            num += ab * ab; da += aa * aa; db += bb * bb;
+        }
+    return num / sqrt(da * db);
+}
+/* gap_factor_model::custom_conv_criterion (gap_factor_model.cpp:265-269), conv_mode = 2 */
+double orc_custom_conv_criterion(orc_model *m) {
+    long nK = (long)m->n * m->K, pK = (long)m->p * m->K;
+    double *uo = (double *)malloc(8 * (size_t)nK), *vo = (double *)malloc(8 * (size_t)pK);
+    for (long e = 0; e < nK; e++) uo[e] = m->a1o[e] / m->a2o[e];
+    for (long e = 0; e < pK; e++) vo[e] = m->b1o[e] / m->b2o[e];
+    double r1 = rv_coeff(m->EU, uo, m->n, m->K), r2 = rv_coeff(m->EV, vo, m->p, m->K);
+    free(uo); free(vo);
+    return 1 - (r1 < r2 ? r1 : r2);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* iteration driver: algorithm.h:158-210 (optimize), :391-397 (monitor), :412-450         */
 /* (check_convergence), :402-404 (optim_criterion).  Per-iteration vectors must hold      */
@@ -909,7 +936,8 @@ int orc_optimize(orc_model *m, int iter_max, int iter_min, double epsilon, int a
         orc_gap_between_iterates(m, &abs_gap, &norm_gap);
         if (conv_mode == 0) conv_crit[iter] = abs_gap;
         else if (conv_mode == 1) conv_crit[iter] = norm_gap;
-        else return -1;   /* conv_mode 2 (RV coefficient, O(n^2)) is out of scope; pCMF() hard-codes 1 (pCMF.R:212) */
+        else if (conv_mode == 2) conv_crit[iter] = orc_custom_conv_criterion(m);   /* algorithm.h:424-425 */
+        else return -1;   /* algorithm.h:427 */
         if (monitor) { if (abs_gap_v) abs_gap_v[iter] = abs_gap; if (norm_gap_v) norm_gap_v[iter] = norm_gap; }
         if (fabs(conv_crit[iter]) < epsilon) nb_iter_stab++; else nb_iter_stab = 0;
         if (nb_iter_stab > additional_iter && iter > iter_min) converged = 1;

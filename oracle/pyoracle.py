@@ -268,7 +268,7 @@ class Model:
         nb = self.L.orc_optimize(self.h, int(iter_max), int(iter_min), float(epsilon), int(additional_iter),
                                  int(conv_mode), int(bool(monitor)), C.byref(it), C.byref(conv), C.byref(loss), *ptrs)
         if nb < 0:
-            raise ValueError("`conv_mode` parameter should take value in {0,1} (2 is out of scope)")
+            raise ValueError("`conv_mode` parameter should take value in {0,1,2}")
         out = {"nb_iter": nb, "converged": bool(conv.value), "loss": loss.value, "conv_crit": v[0][:nb]}
         if monitor:
             out.update(abs_gap=v[1][:nb], norm_gap=v[2][:nb], loglikelihood=v[3][:nb], optim_criterion=v[4][:nb],

@@ -1380,6 +1380,29 @@ __global__ void k_dense_zi_genes(int64_t n, int32_t p, int K, int KP, const doub
 }
 #endif  // PCMF_COMMON_KERNELS
 
+#ifdef PCMF_COMMON_KERNELS
+// conv_mode = 2: Gram matrices for matrix::rv_coeff (utils/matrix.h:100-104) of (A, B), rows x KP each:
+// out[0..K^2) += A'B, out[K^2..2K^2) += A'A, out[2K^2..3K^2) += B'B (K <= 64); trace(A A' B B') = ||A'B||_F^2
+__global__ void k_rv_gram(int64_t rows, int K, int KP, const double *A, const double *B, double *out) {
+    const int kl = blockIdx.y * blockDim.y + threadIdx.y;     // (k, l) pair
+    if (kl >= K * K) return;
+    const int k = kl / K, l = kl % K;
+    double ab = 0, aa = 0, bb = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const double ak = A[r * KP + k], al = A[r * KP + l], bk = B[r * KP + k], bl = B[r * KP + l];
+        ab = fma(ak, bl, ab); aa = fma(ak, al, aa); bb = fma(bk, bl, bb);
+    }
+    ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+    if (threadIdx.x == 0) { atomicAdd(out + kl, ab); atomicAdd(out + K * K + kl, aa); atomicAdd(out + 2 * K * K + kl, bb); }
+}
+// dst = num / den element-wise (E[U] of the previous iterate from a1_old / a2_old), pads 0
+__global__ void k_ratio(int64_t rows, int K, int KP, const double *num, const double *den, double *dst) {
+    const int64_t total = rows * KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x)
+        dst[o] = ((int)(o % KP) < K) ? num[o] / den[o] : 0.0;
+}
+#endif  // PCMF_COMMON_KERNELS
+
 // column-major (R / Eigen) <-> padded row-major
 #ifdef PCMF_COMMON_KERNELS
 __global__ void k_colmajor_to_rowpad(int64_t rows, int K, int KP, const double *src, double *dst, double padval) {

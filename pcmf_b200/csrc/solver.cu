@@ -97,6 +97,11 @@ struct pcmf_solver {
     // explicit dense prob_D of a warm start: held until the first zero-inflation update (init_zi_param(prob_D, prior_D))
     double *Pexp = nullptr, *valw_csr = nullptr, *valw_csc = nullptr;
     bool explicitP = false, freq_ones = false;
+    // conv_mode = 2 (RV coefficient, gap_factor_model.cpp:265-269): E[U], E[V] of the previous iterate are kept
+    bool keep_old = false;
+    double *EVold = nullptr, *rvbuf = nullptr;
+    double rv_crit = 0;
+    double rv_criterion();
     uint32_t *csr2csc = nullptr;                   // nnz: CSC position of every CSR entry (stored-q cell pass)
     double *qcsc = nullptr;                        // nnz: q_ij = x_ij / T_ij left by the gene passes, CSC order
     double *Lg = nullptr, *colsumX = nullptr, *colnnz = nullptr, *rowsumX = nullptr;
@@ -194,7 +199,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { cudaFree((void *)rowptr); cudaFree((void *)colidx); cudaFree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3]};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3]};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -408,6 +413,9 @@ void pcmf_solver::build_csc() {
 void pcmf_solver::alloc_state() {
     const size_t nK = (size_t)n * KP, pK = (size_t)p * KP;
     a1 = dmalloc<double>(nK); a2 = dmalloc<double>(nK); EU[0] = dmalloc<double>(nK); ElogU = dmalloc<double>(nK); eu = dmalloc<double>(nK);
+    keep_old = opt.conv_mode == 2;
+    if (keep_old) { EVold = dmalloc<double>((size_t)p * KP); rvbuf = dmalloc<double>(6 * 64 * 64); }
+    if (keep_old && !zi) { EU[1] = dmalloc<double>(nK); CK(cudaMemsetAsync(EU[1], 0, nK * 8, stream)); }
     if (zi) {
         EU[1] = dmalloc<double>(nK); PV = dmalloc<double>(nK); CK(cudaMemsetAsync(EU[1], 0, nK * 8, stream));
         zpackA = dmalloc<double>(L->zi_pack_doubles(p, 0)); zpackB = dmalloc<double>(L->zi_pack_doubles(n, 1));
@@ -624,7 +632,7 @@ void pcmf_solver::step(bool want_data) {
     const size_t pK = (size_t)p * KP;
     double *alpha1 = hyp, *alpha2 = hyp + 64, *beta1 = hyp + 128, *beta2 = hyp + 192;
     long long *gc = guard[gcur], *gn = guard[1 - gcur];
-    const int nxt = zi ? 1 - cur : cur;
+    const int nxt = (zi || keep_old) ? 1 - cur : cur;
     CK(cudaMemsetAsync(scal, 0, S_COUNT * 8, stream));
     CK(cudaMemsetAsync(csv, 0, 3 * 64 * 8, stream));
     CK(cudaMemsetAsync(ar1 + ar1_tmp, 0, (ar1_core - ar1_tmp) * 8, stream));   // tmpMat, cs_eu, cs_elog, usc
@@ -686,6 +694,7 @@ void pcmf_solver::step(bool want_data) {
     end(PH_AR1, 0);
     // 5. V-side M-step
     begin(PH_MSTEP_V);
+    if (keep_old) CK(cudaMemcpyAsync(EVold, EV, sizeof(double) * pK, cudaMemcpyDeviceToDevice, stream));
     {
         VArgs va{};
         va.p = p; va.K = K; va.KP = KP; va.sparse = sparse; va.zi = zi; va.first_iter = first_iter ? first_mode : 0; va.b1_old0 = old0[2]; va.b2_old0 = old0[3]; va.want_data = want_data;
@@ -734,7 +743,24 @@ void pcmf_solver::step(bool want_data) {
                  ar3 + ar3_csP, prior_D, ar1 + ar1_usc, ar3 + ar3_zsc, lgx_const, scal};
     k_hyper<<<1, 256, 0, stream>>>(ha);
     end(PH_HYPER, 2);
+    if (keep_old) {
+        if (first_iter) {
+            // the old iterate is a1_old / a2_old: Ones / Ones, or the previous multi-init run's last iterate
+            if (first_mode == 2) k_ratio<<<grid_for(n * KP, 256), 256, 0, stream>>>(n, K, KP, old0[0], old0[1], EU[cur]);
+            else k_ratio<<<grid_for(n * KP, 256), 256, 0, stream>>>(n, K, KP, a1, a1, EU[cur]);
+            if (first_mode == 2) k_ratio<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, old0[2], old0[3], EVold);
+            else k_ratio<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, b1, b1, EVold);
+        }
+        CK(cudaMemsetAsync(rvbuf, 0, sizeof(double) * 6 * 64 * 64, stream));
+        dim3 blk(32, 8);
+        dim3 gu((unsigned)std::min<int64_t>((n + 31) / 32, sms * 4), (K * K + 7) / 8), gv((unsigned)std::min<int64_t>((p + 31) / 32, sms * 4), (K * K + 7) / 8);
+        k_rv_gram<<<gu, blk, 0, stream>>>(n, K, KP, EU[nxt], EU[cur], rvbuf);
+        k_rv_gram<<<gv, blk, 0, stream>>>(p, K, KP, EV, EVold, rvbuf + 3 * 64 * 64);
+        allreduce(rvbuf, 3 * (size_t)K * K);
+        launches += 2;
+    }
     read_scal();
+    if (keep_old) rv_crit = rv_criterion();
     collect_phase_times();
     cur = nxt; gcur = 1 - gcur; first_iter = false;
     if (explicitP) {   // the zero-inflation update of this iteration replaced the explicit matrix by the closed form
@@ -966,6 +992,19 @@ void pcmf_solver::multi_init(pcmf_result *res) {
     first_mode = 1;
 }
 
+// gap_factor_model::custom_conv_criterion (gap_factor_model.cpp:265-269): 1 - min(RV(EU, EU_old), RV(EV, EV_old))
+double pcmf_solver::rv_criterion() {
+    std::vector<double> h(6 * 64 * 64);
+    CK(cudaMemcpyAsync(h.data(), rvbuf, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    auto rv = [&](const double *g) {
+        double num = 0, da = 0, db = 0;
+        for (int e = 0; e < K * K; ++e) { num += g[e] * g[e]; da += g[K * K + e] * g[K * K + e]; db += g[2 * K * K + e] * g[2 * K * K + e]; }
+        return num / std::sqrt(da * db);
+    };
+    return 1.0 - std::min(rv(h.data()), rv(h.data() + 3 * 64 * 64));
+}
+
 // ================================================================================================================
 // C ABI
 // ================================================================================================================
@@ -996,8 +1035,6 @@ void check_options(const pcmf_problem *prob, const pcmf_options *opt) {
         fail(PCMF_EINVAL, "Input parameter sel_bound should be a real value between 0 and 1");
     // algorithm.h:427
     if (opt->conv_mode < 0 || opt->conv_mode > 2) fail(PCMF_EINVAL, "`conv_mode` parameter should take value in {0,1,2}");
-    if (opt->conv_mode == 2)
-        fail(PCMF_EUNSUPPORTED, "conv_mode = 2 (RV coefficient, O(n^2)) is out of scope; pCMF() always uses conv_mode = 1");
 }
 }  // namespace
 
@@ -1060,7 +1097,7 @@ int pcmf_iterate(pcmf_solver *s, int niter, double *conv_crit_out, double *elbo_
             const bool want = elbo_out && it > 0;
             s->step(want);
             if (want) elbo_out[it - 1] = s->last_nodata + s->h_scal[S_DATA];
-            const double crit = s->opt.conv_mode == 0 ? s->h_scal[S_ABS_GAP] : s->h_scal[S_NORM_GAP];
+            const double crit = s->opt.conv_mode == 0 ? s->h_scal[S_ABS_GAP] : (s->opt.conv_mode == 1 ? s->h_scal[S_NORM_GAP] : s->rv_crit);
             if (conv_crit_out) conv_crit_out[it] = crit;
             s->last_nodata = s->h_scal[S_ELBO_NODATA];
             s->iter++;
@@ -1096,7 +1133,7 @@ int pcmf_optimize(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen)
                 if (res->deviance) res->deviance[it] = m.deviance;
             }
             const double ag = s->h_scal[S_ABS_GAP], ng = s->h_scal[S_NORM_GAP];
-            const double crit = o.conv_mode == 0 ? ag : ng;   // algorithm.h:417-423
+            const double crit = o.conv_mode == 0 ? ag : (o.conv_mode == 1 ? ng : s->rv_crit);   // algorithm.h:417-425
             if (res->conv_crit) res->conv_crit[it] = crit;
             if (res->abs_gap) res->abs_gap[it] = ag;
             if (res->norm_gap) res->norm_gap[it] = ng;

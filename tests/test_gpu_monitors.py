@@ -142,3 +142,23 @@ def test_warm_start_from_dense_prob_D_matches_oracle(sparse):
     assert np.abs(o["prob_D"] - PD).max() == 0.0
     assert relerr(o["prior_prob_D"], m.get("prior_D")) < 1e-12
     s.close()
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+def test_rv_coefficient_convergence_mode(zi, sparse):
+    """conv_mode = 2: 1 - min(RV(EU, EU_old), RV(EV, EV_old)) (gap_factor_model.cpp:265-269, utils/matrix.h:100-104) as the
+    stopping criterion; the gaps are still monitored (algorithm.h:432-437)."""
+    X = problem(26, 70, 44)
+    K = 4
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=13)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=30, iter_min=4, epsilon=2e-3, additional_iter=2, conv_mode=2, a1=a1, a2=a2, b1=b1, b2=b2)
+    ref = po.run(X, K, zi, sparse, monitor=True, reorder_factor=False, prob_S=prob_S, prior_S=prior_S, **kw)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    res = RUN[(zi, sparse)](X, K, verbose=False, monitor=True, reorder_factor=False, **kw)
+    assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    assert res["convergence"]["converged"] == ref["convergence"]["converged"]
+    assert np.abs(res["convergence"]["conv_crit"] - ref["convergence"]["conv_crit"]).max() < 1e-10   # 1 - RV: absolute
+    assert relerr(res["monitor"]["norm_gap"], ref["monitor"]["norm_gap"]) < 1e-6
+    assert res["convergence"]["conv_mode"] == 2

@@ -113,3 +113,21 @@ def test_dense_prob_D_warm_start_matches_reference_build(sparse):
         assert relerr(orc["variational_params"][k], ref["variational_params"][k]) < TOL, k
     assert np.abs(orc["ZI_param"]["prob_D"] - ref["ZI_param"]["prob_D"]).max() < TOL
     assert (ref["ZI_param"]["freq_D"] == 1.0).all() and (orc["ZI_param"]["freq_D"] == 1.0).all()
+
+
+@pytest.mark.parametrize("zi,sparse", [(False, False), (True, True)], ids=["gap", "zi_sparse"])
+def test_rv_coefficient_criterion_matches_reference_build(zi, sparse):
+    """conv_mode = 2 through the reference's own custom_conv_criterion / matrix::rv_coeff (n x n products there,
+    K x K Gram matrices in the oracle)."""
+    X, _, _ = datagen.simulate(40, 30, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=41)
+    K = 3
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=42)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=12, iter_min=3, additional_iter=2, epsilon=1e-3, conv_mode=2, a1=a1, a2=a2, b1=b1, b2=b2, reorder_factor=False)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    ref = pyref.run(X, K, zi, sparse, **kw)
+    orc = po.run(X, K, zi, sparse, **kw)
+    assert orc["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    assert np.abs(orc["convergence"]["conv_crit"] - ref["convergence"]["conv_crit"]).max() < 1e-12
+    assert relerr(orc["monitor"]["norm_gap"], ref["monitor"]["norm_gap"]) < TOL
