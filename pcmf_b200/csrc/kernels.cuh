@@ -839,92 +839,6 @@ __global__ void __launch_bounds__(128, 2) k_zi_pass_cells(ZiAArgs a) {
     if (threadIdx.x == 0) { atomicAdd(a.zsc + 0, sum_pl); atomicAdd(a.zsc + 1, ent); }
 }
 
-// Variant 1 of pass A: one gene per step, the gene vector is re-read from shared memory for the PV update instead of
-// being cached -> ~half the registers, twice the resident warps (occupancy instead of ILP).
-template <int KP, int TJ>
-__global__ void __launch_bounds__(128, 3) k_zi_pass_cells_v1(ZiAArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_evs = reinterpret_cast<double *>(smem_raw);
-    double *s_c = s_evs + TJ * KP;
-    double *s_cs = s_c + TJ;
-    double *s_P = s_cs + 4 * TJ;
-    int *s_f = reinterpret_cast<int *>(s_P + 4 * 32 * 33);
-    __shared__ double sh[32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < a.n;
-    double u[KP], pv[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) { u[k] = 0.0; pv[k] = 0.0; }
-    if (live) load_vec<KP>(a.EU + i * KP, u);
-    double sum_pl = 0, ent_lin = 0, ent_log = 0, prod = 1.0;
-    for (int j0 = 0; j0 < a.p; j0 += TJ) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < TJ * KP; t += blockDim.x) {
-            const int jj = j0 + t / KP;
-            s_evs[t] = jj < a.p ? a.EVS[(int64_t)j0 * KP + t] : 0.0;
-        }
-        for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
-            const int jj = j0 + t;
-            s_c[t] = jj < a.p ? a.cz[jj] : 0.0;
-            s_f[t] = jj < a.p ? a.flag[jj] : 3;
-        }
-        for (int t = threadIdx.x; t < 4 * TJ; t += blockDim.x) s_cs[t] = 0.0;
-        __syncthreads();
-        for (int jb = 0; jb < TJ; jb += 32) {
-            if (j0 + jb >= a.p) break;
-            const uint32_t bits = live ? a.bitT[(int64_t)((j0 + jb) >> 5) * a.n + i] : 0u;
-#pragma unroll 2
-            for (int c = 0; c < 32; ++c) {
-                const double2 *e0 = reinterpret_cast<const double2 *>(s_evs + (jb + c) * KP);
-                double l0a = 0.0, l0b = 0.0;
-#pragma unroll
-                for (int k = 0; k < KP; k += 2) {
-                    const double2 t0 = e0[k / 2];
-                    l0a = fma(u[k], t0.x, l0a); l0b = fma(u[k + 1], t0.y, l0b);
-                }
-                const double lam0 = l0a + l0b;
-                const int f0 = live ? s_f[jb + c] : 3;
-                const double z0 = s_c[jb + c] - lam0;
-                double y0;
-                bool in0;
-                double p0 = fast_expit(z0, y0, in0);
-                const bool nz0 = (bits >> c) & 1u;
-                p0 = (f0 == 0) ? (nz0 ? 1.0 : p0) : ((f0 == 1) ? 1.0 : 0.0);
-                const bool g0 = (f0 == 0) && !nz0 && in0;
-                ent_lin = fma(g0 ? (1.0 - p0) : 0.0, -z0, ent_lin);
-                prod *= (g0 ? y0 : 1.0);
-                sum_pl = fma(p0, lam0, sum_pl);
-#pragma unroll
-                for (int k = 0; k < KP; k += 2) {
-                    const double2 t0 = e0[k / 2];
-                    pv[k] = fma(p0, t0.x, pv[k]); pv[k + 1] = fma(p0, t0.y, pv[k + 1]);
-                }
-                s_P[(w * 32 + c) * 33 + lane] = p0;
-                if ((c & 7) == 7 && prod > 1e100) { ent_log += log(prod); prod = 1.0; }
-            }
-            __syncwarp();
-            double cs = 0.0;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) cs += s_P[(w * 32 + lane) * 33 + r];
-            __syncwarp();
-            s_cs[w * TJ + jb + lane] += cs;
-        }
-        __syncthreads();
-        for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
-            if (j0 + t < a.p) atomicAdd(a.colsumP + j0 + t, s_cs[t] + s_cs[TJ + t] + s_cs[2 * TJ + t] + s_cs[3 * TJ + t]);
-        }
-    }
-    if (live) {
-        double2 *o = reinterpret_cast<double2 *>(a.PV + i * KP);
-#pragma unroll
-        for (int k = 0; k < KP; k += 2) o[k / 2] = make_double2(pv[k], pv[k + 1]);
-    }
-    double ent = ent_lin - (ent_log + log(prod));
-    sum_pl = block_sum(sum_pl, sh); ent = block_sum(ent, sh);
-    if (threadIdx.x == 0) { atomicAdd(a.zsc + 0, sum_pl); atomicAdd(a.zsc + 1, ent); }
-}
-
 struct ZiBArgs {
     int64_t n; int32_t p; int K;
     int64_t rows_per_chunk;
@@ -1000,61 +914,6 @@ __global__ void __launch_bounds__(128, 2) k_zi_pass_genes(ZiBArgs a) {
             if (liveB) atomicAdd(a.tmpMat + (int64_t)jB * KP + k, accB[k]);
         }
     }
-}
-
-// Variant 1 of pass B: one gene per thread (half the registers, twice the resident warps).
-template <int KP, int TI>
-__global__ void __launch_bounds__(128, 4) k_zi_pass_genes_v1(ZiBArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_uz = reinterpret_cast<double *>(smem_raw);
-    double *s_un = s_uz + TI * KP;
-    const int jA = blockIdx.x * 128 + threadIdx.x;
-    const bool liveA = jA < a.p;
-    double vA[KP], accA[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) { vA[k] = 0.0; accA[k] = 0.0; }
-    double cA = 0.0; int fA = 3;
-    if (liveA) { load_vec<KP>(a.EVSz + (int64_t)jA * KP, vA); cA = a.cz[jA]; fA = a.flag[jA]; }
-    const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_chunk;
-    const int64_t r1 = min(a.n, r0 + a.rows_per_chunk);
-    for (int64_t i0 = r0; i0 < r1; i0 += TI) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < TI * KP; t += blockDim.x) {
-            const int64_t ii = i0 + t / KP;
-            const bool ok = ii < r1;
-            s_uz[t] = ok ? a.EUz[i0 * KP + t] : 0.0;
-            s_un[t] = ok ? a.EUn[i0 * KP + t] : 0.0;
-        }
-        __syncthreads();
-        for (int ib = 0; ib < TI; ib += 32) {
-            if (i0 + ib >= r1) break;
-            const uint32_t bitsA = liveA ? a.bitB[((i0 + ib) >> 5) * a.p + jA] : 0u;
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-                const double2 *uz = reinterpret_cast<const double2 *>(s_uz + (ib + r) * KP);
-                const double2 *un = reinterpret_cast<const double2 *>(s_un + (ib + r) * KP);
-                double la0 = 0.0, la1 = 0.0;
-#pragma unroll
-                for (int k = 0; k < KP; k += 2) {
-                    const double2 t = uz[k / 2];
-                    la0 = fma(vA[k], t.x, la0); la1 = fma(vA[k + 1], t.y, la1);
-                }
-                double y;
-                bool in_;
-                double pA = fast_expit(cA - (la0 + la1), y, in_);
-                pA = (fA == 0) ? (((bitsA >> r) & 1u) ? 1.0 : pA) : ((fA == 1) ? 1.0 : 0.0);
-                if (i0 + ib + r >= r1) pA = 0.0;
-#pragma unroll
-                for (int k = 0; k < KP; k += 2) {
-                    const double2 t = un[k / 2];
-                    accA[k] = fma(pA, t.x, accA[k]); accA[k + 1] = fma(pA, t.y, accA[k + 1]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < KP; ++k)
-        if (k < a.K && liveA) atomicAdd(a.tmpMat + (int64_t)jA * KP + k, accA[k]);
 }
 
 // ------------------------------------------------------------------------------------------------------------

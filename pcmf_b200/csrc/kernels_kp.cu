@@ -119,12 +119,10 @@ int launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_pass_cells<KP, ZI_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_zi_pass_cells_v1<KP, ZI_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
     const int64_t grid = (a.n + 127) / 128;
-    if (variant & 1) k_zi_pass_cells_v1<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
-    else k_zi_pass_cells<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
+    k_zi_pass_cells<KP, ZI_TJ><<<(unsigned)grid, 128, smem, st>>>(a);
     return 1;
 }
 
@@ -134,20 +132,14 @@ int launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) 
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_pass_genes<KP, ZI_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_zi_pass_genes_v1<KP, ZI_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    if (variant & 2) {
-        dim3 grid((a.p + 127) / 128, chunks);
-        k_zi_pass_genes_v1<KP, ZI_TI><<<grid, 128, smem, st>>>(a);
-    } else {
-        dim3 grid((a.p + 255) / 256, chunks);
-        k_zi_pass_genes<KP, ZI_TI><<<grid, 128, smem, st>>>(a);
-    }
+    dim3 grid((a.p + 255) / 256, chunks);
+    k_zi_pass_genes<KP, ZI_TI><<<grid, 128, smem, st>>>(a);
     return 1;
 }
 
-int zi_genes_block(int variant) { return !(variant & 4) ? (((variant & 8) && MMA_MT == 4) ? 64 : 32 * MMA_MT) : ((variant & 2) ? 128 : 256); }
+int zi_genes_block(int variant) { return !(variant & 4) ? (((variant & 8) && MMA_MT == 4) ? 64 : 32 * MMA_MT) : 256; }
 
 const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes, zi_genes_block, zi_pack_doubles,
                          launch_zi_loglik, launch_gene_loglam, launch_gene_order};
