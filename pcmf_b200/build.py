@@ -34,7 +34,7 @@ def _run(cmd):
 
 def build(force=False, verbose=False, ptxas_info=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("kernels.cuh", "specfun.cuh", "launch.cuh")] + \
+    headers = sorted(os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")) + \
               [os.path.join(os.path.dirname(HERE), "include", "pcmf_b200.h")]
     jobs = []
     objs = []

@@ -48,7 +48,7 @@ inline int pack_grid(int64_t total) { return (int)std::max<int64_t>(1, std::min<
 template <int MT>
 int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
     using R = ZiRec<KP, true>;
-    const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 2 * MMA_TJ + 64);
+    const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 8 * MMA_TJ + 64);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -157,13 +157,14 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     constexpr int KS = R::KS, NT = R::NT, NG = TJ / 8, BUF = NG * R::REC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_buf = reinterpret_cast<double *>(smem_raw);       // 2 x NG records, double buffered
-    double *s_cs = s_buf + 2 * BUF;                             // 2 x TJ: column sums of this CTA, double buffered
-    double *s_tab = s_cs + 2 * TJ;                              // 64
+    double *s_cs = s_buf + 2 * BUF;                             // 2 x 4 x TJ: per-warp column sums, double buffered (plain stores:
+                                                                //   a shared-memory FP64 atomicAdd is a CAS spin loop)
+    double *s_tab = s_cs + 8 * TJ;                              // 64
     __shared__ double sh[32];
     __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
-    for (int t = threadIdx.x; t < 2 * TJ; t += blockDim.x) s_cs[t] = 0.0;
+    for (int t = threadIdx.x; t < 8 * TJ; t += blockDim.x) s_cs[t] = 0.0;
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     const int64_t cell0 = (int64_t)blockIdx.x * (32 * MT) + w * (8 * MT);   // CTA = 4 warps x 8 MT cells
@@ -192,20 +193,25 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     const int tiles_per_chunk = (ntiles_all + (int)gridDim.y - 1) / (int)gridDim.y;
     const int tile_first = (int)blockIdx.y * tiles_per_chunk;
     const int ntiles = max(0, min(ntiles_all, tile_first + tiles_per_chunk) - tile_first);
+    // every CTA walks its tiles in a rotated order (start = blockIdx.x mod ntiles): the resident CTAs then flush their
+    // column sums to different genes instead of all hammering the same TJ addresses at the same moment
+    const int rot = ntiles > 0 ? (int)(blockIdx.x % (unsigned)ntiles) : 0;
+    auto tile_id = [&](int t) { const int u = t + rot; return tile_first + (u >= ntiles ? u - ntiles : u); };
     auto issue = [&](int t) {        // one thread: arm the barrier with the byte count, then one bulk copy
-        const int g0 = (tile_first + t) * NG, gn = min(NG, ngroups - g0);
+        const int g0 = tile_id(t) * NG, gn = min(NG, ngroups - g0);
         const unsigned bytes = (unsigned)(gn * R::REC * sizeof(double));
         mbar_expect_tx(&bar[t & 1], bytes);
         bulk_g2s(s_buf + (t & 1) * BUF, pack + (int64_t)g0 * R::REC, bytes, &bar[t & 1]);
     };
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
-        bits_nx[mt] = (live[mt] && ntiles > 0) ? __ldg(a.bitT + (int64_t)((tile_first * TJ) >> 5) * a.n + (cell0 + mt * 8 + g)) : 0u;
+        bits_nx[mt] = (live[mt] && ntiles > 0) ? __ldg(a.bitT + (int64_t)((tile_id(0) * TJ) >> 5) * a.n + (cell0 + mt * 8 + g)) : 0u;
     if (threadIdx.x == 0 && ntiles > 0) issue(0);
     for (int tile = 0; tile < ntiles; ++tile) {
-        const int j0 = (tile_first + tile) * TJ;
+        const int j0 = tile_id(tile) * TJ;
+        const int j0_next = tile + 1 < ntiles ? tile_id(tile + 1) * TJ : a.p;
         const double *buf = s_buf + (tile & 1) * BUF;
-        double *cs_buf = s_cs + (tile & 1) * TJ;
+        double *cs_buf = s_cs + (tile & 1) * 4 * TJ;
         if (threadIdx.x == 0 && tile + 1 < ntiles) issue(tile + 1);
         mbar_wait(&bar[tile & 1], (tile >> 1) & 1);
 #pragma unroll 1
@@ -218,7 +224,9 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     bits[mt] = bits_nx[mt];
-                    bits_nx[mt] = (live[mt] && jg + 32 < a.p) ? __ldg(a.bitT + (int64_t)((jg + 32) >> 5) * a.n + (cell0 + mt * 8 + g)) : 0u;
+                    // next 32-gene block: in this tile if it has one (the last tile may be partial), else the next tile's first
+                    const int jn = (grp + 4 < NG && jg + 32 < a.p) ? jg + 32 : j0_next;
+                    bits_nx[mt] = (live[mt] && jn < a.p) ? __ldg(a.bitT + (int64_t)(jn >> 5) * a.n + (cell0 + mt * 8 + g)) : 0u;
                 }
             }
             double d[MT][2];
@@ -264,15 +272,12 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
                 cs0 += __shfl_xor_sync(0xffffffffu, cs0, o);
                 cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
             }
-            if (g == 0) {
-                atomicAdd(cs_buf + grp * 8 + 2 * q, cs0);
-                atomicAdd(cs_buf + grp * 8 + 2 * q + 1, cs1);
-            }
+            if (g == 0) *reinterpret_cast<double2 *>(cs_buf + w * TJ + grp * 8 + 2 * q) = make_double2(cs0, cs1);
         }
         __syncthreads();   // every warp is done with this buffer: it may be refilled, its column sums flushed
         for (int t = threadIdx.x; t < TJ; t += blockDim.x) {
-            if (j0 + t < a.p) atomicAdd(a.colsumP + j0 + t, cs_buf[t]);
-            cs_buf[t] = 0.0;
+            if (j0 + t < a.p) atomicAdd(a.colsumP + j0 + t, (cs_buf[t] + cs_buf[TJ + t]) + (cs_buf[2 * TJ + t] + cs_buf[3 * TJ + t]));
+            cs_buf[t] = 0.0; cs_buf[TJ + t] = 0.0; cs_buf[2 * TJ + t] = 0.0; cs_buf[3 * TJ + t] = 0.0;
         }
     }
     // epilogue: PV, and sum_ij prob_D_ij UVt_ij = sum_ik EU_ik PV_ik (zi...cpp:182)
