@@ -52,15 +52,18 @@ __device__ __noinline__ double exact_terms(const double *__restrict__ elu, const
     return T;
 }
 
+// One padded K-vector (32-byte aligned, KP a multiple of 4) with 256-bit loads -- LDG.E.256, new on sm_100.  The gather of
+// these rows is what bounds the non-zero passes; measured (scripts/ubench_gather256.cu) the same random 160-byte rows come
+// in at 9.1 TB/s with 256-bit loads against 6.4 TB/s with 128-bit ones from an L2-resident table (6.8-7.6 vs 6.2 TB/s
+// from a table larger than L2): the limit was the number of requests, not the bytes.
 template <int KP>
 __device__ __forceinline__ void load_vec(const double *__restrict__ p, double (&r)[KP]) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
+    static_assert(KP % 4 == 0, "padded factor widths are multiples of 4");
 #pragma unroll
-    for (int i = 0; i < KP / 2; ++i) {
-        const double2 t = __ldg(q + i);
-        r[2 * i] = t.x;
-        r[2 * i + 1] = t.y;
-    }
+    for (int i = 0; i < KP / 4; ++i)
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(r[4 * i]), "=d"(r[4 * i + 1]), "=d"(r[4 * i + 2]), "=d"(r[4 * i + 3])
+                     : "l"(p + 4 * i));
 }
 
 __device__ __forceinline__ double block_sum(double v, double *sh /* >= 32 doubles */) {
