@@ -299,21 +299,25 @@ def main():
     gather_cell_tab = api.measure_gather_gbs(nl, local)
     traffic = ncu_traffic(args.config)
     kernels = []
-    nz_rows = {"estep_cells_mstep_u": (b_cells, (2 if (zi or sparse) else 1), gather_gene_tab),
-               "estep_genes": (b_genes, 1, gather_cell_tab)}
+    # gathered bytes per non-zero: the cell pass of the ZI / sparse models reads one K-vector (evw) plus the stored q of the
+    # entry (a 32-byte sector) and its 4-byte CSR->CSC position; the plain model reads ev and recomputes T; the gene passes
+    # read eu (+ ElogU when the spike-and-slab sums are wanted)
+    stored_q = zi or sparse
+    nz_rows = {"estep_cells_mstep_u": (b_cells, (8.0 * K + 36.0) if stored_q else 8.0 * K, gather_gene_tab),
+               "estep_genes": (b_genes, None if sparse else 8.0 * K, gather_cell_tab)}
     if sparse:
-        nz_rows["sparse_gene_pass"] = (b_genes, 2, gather_cell_tab)
-    for name, (byts, nvec, gpk) in nz_rows.items():
+        nz_rows["sparse_gene_pass"] = (b_genes, 16.0 * K, gather_cell_tab)
+    for name, (byts, per_nnz, gpk) in nz_rows.items():
         t = per[name][0]
-        gb = 8.0 * K * nvec * nnz_local
+        gb = per_nnz * nnz_local if per_nnz else None
         kernels.append({"kernel": name, "ms": t, "share": t * args.steps / ms if ms else None, "bound": "hbm",
                         "algorithmic_bytes": byts, "achieved": byts / (t * 1e-3) / 1e9 if t > 0 else None,
                         "peak": hbm_peak, "unit": "GB/s", "frac": (byts / (t * 1e-3) / 1e9 / hbm_peak) if t > 0 else None,
                         "traffic": traffic.get(name),
-                        "gathered_bytes": gb, "gather_achieved": gb / (t * 1e-3) / 1e9 if t > 0 else None,
-                        "gather_peak_measured": gpk, "gather_frac": (gb / (t * 1e-3) / 1e9 / gpk) if t > 0 else None,
-                        "note": "estep_genes copies the sums of genes whose mask row did not change (no gather for those)"
-                                if name == "estep_genes" and sparse else None})
+                        "gathered_bytes": gb, "gather_achieved": gb / (t * 1e-3) / 1e9 if (gb and t > 0) else None,
+                        "gather_peak_measured": gpk, "gather_frac": (gb / (t * 1e-3) / 1e9 / gpk) if (gb and t > 0) else None,
+                        "note": "steady state: genes whose mask row did not change copy the sums of the previous spike-and-slab "
+                                "pass, so only a few genes are gathered for" if name == "estep_genes" and sparse else None})
     fp64_peak = api.measure_fp64_tflops(local)
     dmma_peak = api.measure_fp64_mma_tflops(local)
     if zi:

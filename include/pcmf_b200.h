@@ -204,6 +204,9 @@ int pcmf_measure_fp64_mma_tflops(int device, double *tflops_out);
  * non-zero passes, which read one or two such rows per non-zero through L2. */
 int pcmf_measure_gather_gbs(int device, int64_t rows, double *gbs_out);
 int pcmf_device_free(int device, void *ptr);
+/* The library keeps the device memory a finished fit releases for the next fit of the process;
+ * this returns all of it to the driver. */
+int pcmf_release_cached_memory(void);
 /* copy device CSR arrays to host buffers (bench e2e leg) */
 int pcmf_device_to_host(int device, void *dst_host, const void *src_dev, size_t bytes);
 

@@ -111,4 +111,4 @@ HEADER_SYMBOLS = ["pcmf_version", "pcmf_device_count", "pcmf_fit", "pcmf_create"
                   "pcmf_elbo", "pcmf_order_factor", "pcmf_multi_init", "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational",
                   "pcmf_phase_times", "pcmf_launch_count", "pcmf_destroy", "pcmf_generate_counts_device",
                   "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats", "pcmf_measure_fp64_tflops",
-                  "pcmf_measure_fp64_mma_tflops", "pcmf_measure_gather_gbs"]
+                  "pcmf_measure_fp64_mma_tflops", "pcmf_measure_gather_gbs", "pcmf_release_cached_memory"]

@@ -231,14 +231,18 @@ __global__ void k_dmma_peak(double *out, int iters) {
     for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1];
     if (s == 12345.678) out[0] = s;
 }
-// every thread gathers rows idx[e] of a (rows x 20) FP64 table with 16-byte loads, like the E-step non-zero passes
+// every thread gathers rows idx[e] of a (rows x 20) FP64 table with 256-bit loads, like the E-step non-zero passes
 __global__ void k_gather_peak(const int32_t *__restrict__ idx, int64_t nidx, const double *__restrict__ tab, double *out) {
     double acc = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nidx; e += stride) {
-        const double2 *q = reinterpret_cast<const double2 *>(tab + (int64_t)__ldg(idx + e) * 20);
+        const double *row = tab + (int64_t)__ldg(idx + e) * 20;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) { const double2 t = __ldg(q + k); acc = fma(t.x, t.y, acc); }
+        for (int k = 0; k < 5; ++k) {      // 256-bit loads, like load_vec in kernels.cuh
+            double a, b, c, d;
+            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(row + 4 * k));
+            acc = fma(a, b, acc); acc = fma(c, d, acc);
+        }
     }
     if (acc == 12345.678) out[0] = acc;
 }
