@@ -14,7 +14,8 @@ OBJ = os.path.join(HERE, "_build")
 SO = os.path.join(HERE, "libpcmf_b200.so")
 KPS = [4, 8, 12, 16, 20, 32, 64]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+# PCMF_EXTRA_NVCC="-DPCMF_GENE_MINB=3 ..." adds flags for kernel tuning experiments
+FLAGS = os.environ.get("PCMF_EXTRA_NVCC", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++"]
 
 

@@ -407,8 +407,11 @@ struct ColArgs {
     double *xlogT;                    // p
     double *qout;                     // nnz or null: q_ij = x_ij / T_ij of every entry visited, CSC order (NaN: exact-formula entry)
 };
+#ifndef PCMF_GENE_MINB
+#define PCMF_GENE_MINB 2
+#endif
 template <int KP, typename VT, bool WITH_B2, bool WITH_LOGT>
-__global__ void __launch_bounds__(128) k_gene_pass(ColArgs a) {
+__global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
     __shared__ double sh[4][KP];
     __shared__ double sh2[4][KP];
     __shared__ double shl[4];
