@@ -268,10 +268,11 @@ __global__ void __launch_bounds__(256, 2) k_estep_rows_q(RowArgs a) {
         const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
         for (int64_t e = e0 + lane; e < e1; e += 32) {
             const int j = __ldg(a.colidx + e);
-            const double q = __ldg(a.qcsc + __ldg(a.csr2csc + e));
+            const uint32_t t = __ldg(a.csr2csc + e);
+            double v[KP];
+            load_vec<KP>(a.evw + (int64_t)j * KP, v);      // requested together with q, not after it (latency bound)
+            const double q = __ldg(a.qcsc + t);
             if (q == q) {
-                double v[KP];
-                load_vec<KP>(a.evw + (int64_t)j * KP, v);
 #pragma unroll
                 for (int k = 0; k < KP; ++k) r[k] = fma(q, v[k], r[k]);
             } else if (!a.allmasked[j]) {
@@ -445,8 +446,11 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
         for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
             const int64_t i = __ldg(a.rowidx + e);
             const double x = (double)__ldg(val + e);
-            double u[KP];
+            // both rows of the cell are requested before anything is consumed: the pass is bound by the latency of these
+            // gathers, and a second request issued only once T is known would double it
+            double u[KP], el[WITH_B2 ? KP : 1];
             load_vec<KP>(a.eu + i * KP, u);
+            if (WITH_B2) load_vec<KP>(a.ElogU + i * KP, reinterpret_cast<double (&)[KP]>(el));
             double T0 = 0.0, T1 = 0.0;
 #pragma unroll
             for (int k = 0; k < KP; k += 2) { T0 = fma(u[k], v[k], T0); T1 = fma(u[k + 1], v[k + 1], T1); }
@@ -458,8 +462,6 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
 #pragma unroll
                 for (int k = 0; k < KP; ++k) b1[k] = fma(q, u[k], b1[k]);
                 if (WITH_B2) {
-                    double el[KP];
-                    load_vec<KP>(a.ElogU + i * KP, el);
 #pragma unroll
                     for (int k = 0; k < KP; ++k) b2[k] = fma(q * u[k], el[k], b2[k]);
                 }
