@@ -10,11 +10,11 @@ using namespace pcmf;
 template <int KP, int MT, int MODE, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_core(double *out, int ngroups) {
     constexpr int KS = KP / 4, NT = (KP + 7) / 8, NG = 8;
-    __shared__ double s_f1[NG * KS * 32], s_f2[NG * 2 * NT * 32], s_tab[32];
+    __shared__ double s_f1[NG * KS * 32], s_f2[NG * 2 * NT * 32], s_tab[64];
     const int lane = threadIdx.x & 31, q = lane & 3;
     for (int t = threadIdx.x; t < NG * KS * 32; t += blockDim.x) s_f1[t] = 1e-3 * (t % 17);
     for (int t = threadIdx.x; t < NG * 2 * NT * 32; t += blockDim.x) s_f2[t] = 1e-3 * (t % 13);
-    if (threadIdx.x < 32) s_tab[threadIdx.x] = kPow2Tab32[threadIdx.x];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
     __syncthreads();
     double a1[MT][KS], c[MT], acc[MT][NT][2];
     for (int mt = 0; mt < MT; ++mt) { c[mt] = 0.5 + mt; for (int s = 0; s < KS; ++s) a1[mt][s] = 1e-2 * (lane + s + mt); }
@@ -41,12 +41,9 @@ __global__ void __launch_bounds__(128, MINB) k_core(double *out, int ngroups) {
             const int sh0 = ((grp & 3) << 3) + 2 * q;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                double y; bool in_;
-                double p0 = fast_expit_tab(c[mt] - d[mt][0], s_tab, y, in_);
-                double p1 = fast_expit_tab(c[mt] - d[mt][1], s_tab, y, in_);
-                p0 = ((bits >> sh0) & 1u) ? 1.0 : p0;
-                p1 = ((bits >> (sh0 + 1)) & 1u) ? 1.0 : p1;
-                d[mt][0] = p0; d[mt][1] = p1;
+                double y; bool big;
+                d[mt][0] = fast_expit_tab(c[mt] - d[mt][0], s_tab, (bits >> sh0) & 1u, 1.0, y, big);
+                d[mt][1] = fast_expit_tab(c[mt] - d[mt][1], s_tab, (bits >> (sh0 + 1)) & 1u, 1.0, y, big);
             }
         }
         if (MODE & 4) {
