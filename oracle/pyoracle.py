@@ -278,7 +278,7 @@ class Model:
 
 def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True, iter_max=1000, iter_min=500,
         epsilon=1e-2, additional_iter=10, conv_mode=1, reorder_factor=True, seed=None,
-        a1=None, a2=None, b1=None, b2=None, prob_S=None, prior_S=None, ninit=1, iter_init=100, prob_D=None, prior_D=None):
+        a1=None, a2=None, b1=None, b2=None, prob_S=None, prior_S=None, ninit=1, iter_init=100, prob_D=None, prior_D=None, U=None, V=None):
     """Restatement of wrapper_gap_factor.h:164-393 / wrapper_sparse_gap_factor.h:176-435 (init order of :389-417,
     multi-init loop of :296-350 / :328-387), returning a dict shaped like the reference's R list."""
     m = Model(X, K, zero_inflation, sparsity)
@@ -288,7 +288,9 @@ def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True,
             mod.init_sparse_param(sel_bound, prob_S, prior_S)
         if zero_inflation:
             mod.init_zi_param(prob_D, prior_D)       # both given or the default (wrapper_gap_factor.h:352-356)
-        if a1 is not None:
+        if U is not None:
+            mod.init_from_factor(U, V)             # wrapper_gap_factor.h:353-354
+        elif a1 is not None:
             mod.init_variational_param(a1, a2, b1, b2)
         else:
             mod.init_random()

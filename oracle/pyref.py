@@ -46,6 +46,7 @@ def lib():
         L.ref_init_zi.argtypes = [C.c_void_p]
         L.ref_init_zi_given.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
         L.ref_init_variational.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int]
+        L.ref_init_factor.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int, C.c_int]
         for nm in ("ref_init_random", "ref_optimize", "ref_order_factor", "ref_output"):
             getattr(L, nm).argtypes = [C.c_void_p]
         L.ref_get.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, dp, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -115,6 +116,11 @@ class RefModel:
     def init_random(self):
         self._ck(self.L.ref_init_random(self.h))
 
+    def init_from_factor(self, U, V):
+        a, ap = _f(U)
+        b, bp = _f(V)
+        self._ck(self.L.ref_init_factor(self.h, ap, bp, self.n, self.p, self.K))
+
     def optimize(self):
         self._ck(self.L.ref_optimize(self.h))
 
@@ -165,7 +171,7 @@ class RefModel:
 
 def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True, iter_max=1000, iter_min=500, epsilon=1e-2,
         additional_iter=10, conv_mode=1, reorder_factor=True, seed=None, a1=None, a2=None, b1=None, b2=None,
-        prob_S=None, prior_S=None, prob_D=None, prior_D=None):
+        prob_S=None, prior_S=None, prob_D=None, prior_D=None, U=None, V=None):
     m = RefModel(X, K, zero_inflation, sparsity, monitor, iter_max, iter_min, epsilon, additional_iter, conv_mode)
     if seed is not None:
         m.seed(seed)
@@ -173,7 +179,9 @@ def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True,
         m.init_sparse_param(sel_bound, prob_S, prior_S)
     if zero_inflation:                             # :395-399
         m.init_zi_param(prob_D, prior_D)
-    if a1 is not None:                             # :402-403
+    if U is not None:                              # :400-401
+        m.init_from_factor(U, V)
+    elif a1 is not None:                           # :402-403
         m.init_variational_param(a1, a2, b1, b2)
     else:                                          # :410-411
         m.init_random()

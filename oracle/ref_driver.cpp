@@ -37,6 +37,7 @@ struct IRunner {
     virtual void init_zi_given(const MatrixXd &prob_D, const VectorXd &prior_D) = 0;
     virtual void init_variational(const MatrixXd &a1, const MatrixXd &a2, const MatrixXd &b1, const MatrixXd &b2) = 0;
     virtual void init_random(myRandom::RNGType &rng) = 0;
+    virtual void init_factor(const MatrixXd &U, const MatrixXd &V) = 0;
     virtual void optimize() = 0;
     virtual void order_factor() = 0;
     virtual void output(Rcpp::List &l) = 0;
@@ -54,6 +55,7 @@ struct Runner : IRunner {
         algo.init_variational_param_gap(a1, a2, b1, b2);
     }
     void init_random(myRandom::RNGType &rng) override { algo.init_random(rng); }
+    void init_factor(const MatrixXd &U, const MatrixXd &V) override { algo.init(U, V); }     // wrapper_gap_factor.h:353-354
     void optimize() override { algo.optimize(); }
     void order_factor() override { algo.order_factor(); }
     void output(Rcpp::List &l) override { algo.get_output(l); }
@@ -112,6 +114,7 @@ int ref_init_variational(void *hv, const double *a1, const double *a2, const dou
     GUARD(h->r->init_variational(mat(a1, n, K), mat(a2, n, K), mat(b1, p, K), mat(b2, p, K)))
 }
 int ref_init_random(void *hv) { GUARD(h->r->init_random(h->rng)) }
+int ref_init_factor(void *hv, const double *U, const double *V, int n, int p, int K) { GUARD(h->r->init_factor(mat(U, n, K), mat(V, p, K))) }
 int ref_optimize(void *hv) { GUARD(h->r->optimize()) }
 int ref_order_factor(void *hv) { GUARD(h->r->order_factor()) }
 int ref_output(void *hv) { GUARD(h->out = Rcpp::List(); h->r->output(h->out)) }

@@ -162,3 +162,21 @@ def test_rv_coefficient_convergence_mode(zi, sparse):
     assert np.abs(res["convergence"]["conv_crit"] - ref["convergence"]["conv_crit"]).max() < 1e-10   # 1 - RV: absolute
     assert relerr(res["monitor"]["norm_gap"], ref["monitor"]["norm_gap"]) < 1e-6
     assert res["convergence"]["conv_mode"] == 2
+
+
+@pytest.mark.parametrize("zi,sparse", [(False, False), (True, True)], ids=["gap", "zi_sparse"])
+def test_init_from_factor_matches_oracle(zi, sparse):
+    """run_*(X, K, U = ..., V = ...): init_from_factor (gap_factor_model.cpp:135-144)."""
+    X = problem(27, 60, 40)
+    K = 3
+    rng = np.random.default_rng(8)
+    U, V = rng.exponential(1.0, (60, K)) + 0.05, rng.exponential(1.0, (40, K)) + 0.05
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=8, iter_min=8, U=U, V=V)
+    ref = po.run(X, K, zi, sparse, monitor=True, reorder_factor=False, prob_S=prob_S, prior_S=prior_S, **kw)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    res = RUN[(zi, sparse)](X, K, verbose=False, monitor=True, reorder_factor=False, **kw)
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
+    assert relerr(res["monitor"]["optim_criterion"], ref["monitor"]["optim_criterion"]) < 1e-6

@@ -131,3 +131,22 @@ def test_rv_coefficient_criterion_matches_reference_build(zi, sparse):
     assert orc["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
     assert np.abs(orc["convergence"]["conv_crit"] - ref["convergence"]["conv_crit"]).max() < 1e-12
     assert relerr(orc["monitor"]["norm_gap"], ref["monitor"]["norm_gap"]) < TOL
+
+
+@pytest.mark.parametrize("zi,sparse", [(False, False), (True, True)], ids=["gap", "zi_sparse"])
+def test_init_from_factor_matches_reference_build(zi, sparse):
+    """U, V supplied: init_from_factor (gap_factor_model.cpp:135-144) -- a1 = U, b1 = V, unit rates, then the four
+    post-steps."""
+    X, _, _ = datagen.simulate(40, 30, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=43)
+    K = 3
+    rng = np.random.default_rng(8)
+    U, V = rng.exponential(1.0, (40, K)) + 0.05, rng.exponential(1.0, (30, K)) + 0.05
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=8, iter_min=8, U=U, V=V, reorder_factor=False)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    ref = pyref.run(X, K, zi, sparse, **kw)
+    orc = po.run(X, K, zi, sparse, **kw)
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(orc["variational_params"][k], ref["variational_params"][k]) < TOL, k
+    assert relerr(orc["convergence"]["conv_crit"], ref["convergence"]["conv_crit"]) < TOL
