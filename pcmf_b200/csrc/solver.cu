@@ -270,6 +270,35 @@ void pcmf_solver::allreduce(double *ptr, size_t count) {
 
 // ---- preprocessing kernels local to this TU ------------------------------------------------------------------
 namespace {
+// dense column-major block (n x nb) -> per-cell non-zero counts; flag is raised when a value is not exact in FP32
+template <typename T>
+__global__ void k_dense_count(int64_t n, int64_t nb, const T *X, int64_t *cnt, int *flag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = 0; bool bad = false;
+        for (int64_t j = 0; j < nb; ++j) {
+            const double x = (double)X[i + j * n];
+            if (x != 0.0) { ++c; bad |= ((double)(float)x != x); }
+        }
+        cnt[i] += c;
+        if (bad) atomicOr(flag, 1);
+    }
+}
+// second sweep: write (gene, value) of every non-zero at the cell's running position (genes ascending within a cell)
+template <typename T>
+__global__ void k_dense_fill(int64_t n, int64_t nb, int32_t j0, const T *X, int64_t *pos, int32_t *colidx, void *val, int f32) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t e = pos[i];
+        for (int64_t j = 0; j < nb; ++j) {
+            const double x = (double)X[i + j * n];
+            if (x != 0.0) {
+                colidx[e] = j0 + (int32_t)j;
+                if (f32) static_cast<float *>(val)[e] = (float)x; else static_cast<double *>(val)[e] = x;
+                ++e;
+            }
+        }
+        pos[i] = e;
+    }
+}
 __global__ void k_expand_rows(int64_t n, const int64_t *rowptr, int32_t *rowids, int64_t *perm) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -357,34 +386,49 @@ void pcmf_solver::setup_problem(const pcmf_problem &pr) {
             StageTimer th(stream); th.t -= 0; th.mark("H2D of the CSR arrays (wait)");
         }
     } else {
-        // dense R matrix (wrapper_gap_factor.h:204-211) -> CSR on the host, two column-major sweeps
-        std::vector<int64_t> rp(n + 1, 0);
-        bool fits32 = true;
-        auto at = [&](int64_t i, int64_t j) -> double {
-            return pr.dense_f64 ? pr.dense_f64[i + j * n] : (double)pr.dense_i32[i + j * n];
+        // dense R matrix (wrapper_gap_factor.h:204-211), INTSXP or REALSXP, column-major: uploaded as it is and turned into
+        // CSR on the device (count per cell, scan, fill in ascending gene order); column blocks bound the staging buffer
+        const int64_t colblk = std::max<int64_t>(1, std::min<int64_t>(p, (int64_t)(2ull << 30) / std::max<int64_t>(1, n * 8)));
+        const size_t esz = pr.dense_f64 ? 8 : 4;
+        unsigned char *stage = dmalloc<unsigned char>((size_t)n * colblk * esz);
+        int64_t *cnt = dmalloc<int64_t>(n + 1);
+        int *d_flag = dmalloc<int>(1);
+        CK(cudaMemsetAsync(cnt, 0, sizeof(int64_t) * (n + 1), stream));
+        CK(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+        auto upload = [&](int64_t j0, int64_t nb) {
+            const unsigned char *src = pr.dense_f64 ? (const unsigned char *)(pr.dense_f64 + j0 * n) : (const unsigned char *)(pr.dense_i32 + j0 * n);
+            CK(cudaMemcpyAsync(stage, src, (size_t)n * nb * esz, cudaMemcpyHostToDevice, stream));
         };
-        for (int64_t j = 0; j < p; ++j)
-            for (int64_t i = 0; i < n; ++i) {
-                const double x = at(i, j);
-                if (x != 0.0) { rp[i + 1]++; if ((double)(float)x != x) fits32 = false; }
-            }
-        for (int64_t i = 0; i < n; ++i) rp[i + 1] += rp[i];
-        nnz = rp[n];
-        f32 = fits32;
-        std::vector<int32_t> ci(nnz);
-        std::vector<float> vf(f32 ? nnz : 0);
-        std::vector<double> vd(f32 ? 0 : nnz);
-        std::vector<int64_t> pos(rp.begin(), rp.end() - 1);
-        for (int64_t j = 0; j < p; ++j)
-            for (int64_t i = 0; i < n; ++i) {
-                const double x = at(i, j);
-                if (x != 0.0) { const int64_t e = pos[i]++; ci[e] = (int32_t)j; if (f32) vf[e] = (float)x; else vd[e] = x; }
-            }
-        int64_t *drp = dmalloc<int64_t>(n + 1); int32_t *dci = dmalloc<int32_t>(nnz);
+        for (int64_t j0 = 0; j0 < p; j0 += colblk) {          // pass 1: non-zeros per cell, FP32-exactness of the values
+            const int64_t nb = std::min(colblk, (int64_t)p - j0);
+            upload(j0, nb);
+            if (pr.dense_f64) k_dense_count<double><<<grid_for(n, 256), 256, 0, stream>>>(n, nb, (const double *)stage, cnt + 1, d_flag);
+            else k_dense_count<int32_t><<<grid_for(n, 256), 256, 0, stream>>>(n, nb, (const int32_t *)stage, cnt + 1, d_flag);
+        }
+        int64_t *drp = dmalloc<int64_t>(n + 1);
+        {
+            size_t tb = 0;
+            CK(cub::DeviceScan::InclusiveSum(nullptr, tb, cnt, drp, (int)(n + 1), stream));
+            void *tmp = dmalloc<unsigned char>(tb);
+            CK(cub::DeviceScan::InclusiveSum(tmp, tb, cnt, drp, (int)(n + 1), stream));
+            CK(cudaStreamSynchronize(stream));
+            dfree(tmp);
+        }
+        int h_flag = 0;
+        CK(cudaMemcpy(&nnz, drp + n, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        f32 = h_flag == 0;
+        int32_t *dci = dmalloc<int32_t>(nnz);
         void *dv = f32 ? (void *)dmalloc<float>(nnz) : (void *)dmalloc<double>(nnz);
-        CK(cudaMemcpy(drp, rp.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dci, ci.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dv, f32 ? (const void *)vf.data() : (const void *)vd.data(), (f32 ? 4 : 8) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(cnt, drp, sizeof(int64_t) * n, cudaMemcpyDeviceToDevice, stream));   // running write position per cell
+        for (int64_t j0 = 0; j0 < p; j0 += colblk) {          // pass 2: fill
+            const int64_t nb = std::min(colblk, (int64_t)p - j0);
+            if (colblk < p) upload(j0, nb);
+            if (pr.dense_f64) k_dense_fill<double><<<grid_for(n, 256), 256, 0, stream>>>(n, nb, (int32_t)j0, (const double *)stage, cnt, dci, dv, f32 ? 1 : 0);
+            else k_dense_fill<int32_t><<<grid_for(n, 256), 256, 0, stream>>>(n, nb, (int32_t)j0, (const int32_t *)stage, cnt, dci, dv, f32 ? 1 : 0);
+        }
+        CK(cudaStreamSynchronize(stream));
+        dfree(stage); dfree(cnt); dfree(d_flag);
         rowptr = drp; colidx = dci; val_csr = dv; own_csr = true;
     }
     build_csc();
