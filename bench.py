@@ -375,7 +375,7 @@ def main():
         csr.free()
 
     cb = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:      # the CPU baseline is reported at N = 1 only
         cb = cpu_baseline(cfg, U, V, args.seed, args.cpu_rows, 2)
 
     if rank == 0:

@@ -3,8 +3,6 @@
 #include <Rcpp.h>
 #include "pcmf_b200_shim.h"
 
-using Eigen::MatrixXd;
-using Eigen::VectorXd;
 
 // [[Rcpp::export]]
 SEXP run_zi_sparse_gap_factor(SEXP X, int K, double sel_bound = 0.5,
