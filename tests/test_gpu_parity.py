@@ -273,3 +273,21 @@ def test_full_size_c4_properties():
     assert ph["exact_fallback_entries_cells"][1] < 0.02 * 2 * csr.nnz
     s.close()
     csr.free()
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+@pytest.mark.parametrize("n,p,K", [(9, 5, 2), (33, 7, 1), (5, 40, 3)])
+def test_degenerate_shapes_match_oracle(zi, sparse, n, p, K):
+    """Shapes smaller than every tile (fewer genes than one 8-gene group, fewer cells than one warp, K = 1)."""
+    rng = np.random.default_rng(100 + n + p)
+    X = rng.poisson(2.0, (n, p)).astype(float) * (rng.uniform(size=(n, p)) < 0.7)
+    X[X.sum(1) == 0, 0] = 1
+    X[0, X.sum(0) == 0] = 1
+    m, s = make_pair(X, K, zi, sparse)
+    for it in range(4):
+        m.update_param()
+        s.iterate(1)
+        compare_state(m, s, zi, sparse, "iter %d" % it)
+        assert abs(s.elbo() - m.elbo()) < RTOL * abs(m.elbo())
+        m.prepare_next_iterate()
+    s.close()
