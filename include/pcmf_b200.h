@@ -51,7 +51,7 @@ typedef int (*pcmf_allreduce_fn)(void *ctx, void *devptr, size_t count, void *st
  * Return non-zero to stop (-> PCMF_EINTERRUPT). */
 typedef int (*pcmf_progress_fn)(void *ctx, int iter, double conv_crit);
 
-/* The count matrix held by THIS process: all p genes of n_local cells (rows).  Exactly one of the three
+/* The count matrix held by THIS process: all p genes of n_local cells (rows).  Exactly one of the four
  * representations is non-NULL.  Reference: SEXP X, INTSXP or REALSXP n x p column-major
  * (wrapper_gap_factor.h:204-211), copied into the model (model.cpp:83). */
 typedef struct {
@@ -66,6 +66,12 @@ typedef struct {
     const float *csr_val_f32;  /* nnz (counts are exact in FP32 up to 2^24), or NULL */
     const double *csr_val_f64; /* nnz, or NULL */
     int32_t csr_on_device;     /* 1: the three CSR arrays are device pointers on options.device */
+    /* Matrix::dgCMatrix as R holds it (slots @p, @i, @x), host memory: compressed columns (genes), 0-based int32
+     * cell indices, double values; explicit zeros are dropped.  Converted to the cell-major CSR on the device.
+     * (The reference only accepts a base matrix, wrapper_gap_factor.h:204-211) */
+    const int32_t *csc_colptr; /* p+1, or NULL */
+    const int32_t *csc_rowidx; /* nnz */
+    const double *csc_val_f64; /* nnz */
 } pcmf_problem;
 
 /* Mirrors the scalar arguments of run_*_gap_factor (pkg/R/RcppExports.R:212 etc.) + GPU plumbing. */
@@ -189,12 +195,13 @@ int pcmf_generate_counts_device(int device, int64_t n_local, int32_t p, int32_t 
                                 const double *V, const double *prob1, uint64_t seed, int64_t row_offset,
                                 int64_t **rowptr_dev, int32_t **colidx_dev, float **val_dev, int64_t *nnz_out,
                                 char *errbuf, size_t errlen);
-/* Per-gene sums over the LOCAL cells of a CSR matrix (host or device resident): sum_i x, sum_i x^2, #non-zeros.
- * Host outputs of length p.  This is what the R wrapper's prior_S heuristic needs (pCMF.R:228-229:
- * 1 - exp(-sd_j / mean(X[X != 0]))) when X never exists as a dense matrix. */
+/* Per-gene statistics over the LOCAL cells of a CSR matrix (host or device resident): sum_i x, sum_i x^2, #non-zeros
+ * and (colmax, may be NULL) the largest count.  Host outputs of length p.  This is what the R wrapper's prior_S
+ * heuristic (pCMF.R:228-229: 1 - exp(-sd_j / mean(X[X != 0]))) and prefilter() (prefiltering.R:127-146: column max,
+ * share of non-null entries, the same sd heuristic) need when X never exists as a dense matrix.  Counts are >= 0. */
 int pcmf_csr_column_stats(int device, int64_t n_local, int32_t p, const int64_t *rowptr, const int32_t *colidx,
                           const float *val_f32, int32_t on_device, double *colsum, double *colsumsq, double *colnnz,
-                          char *errbuf, size_t errlen);
+                          double *colmax, char *errbuf, size_t errlen);
 /* Measured FP64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA microbenchmark, ~50 ms): the
  * roofline denominator of the dense zero-inflation passes, which are FP64-pipe bound, not HBM bound. */
 int pcmf_measure_fp64_tflops(int device, double *tflops_out);

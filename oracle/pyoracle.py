@@ -338,3 +338,22 @@ def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True,
         res["monitor"] = {k: conv[k] for k in ("norm_gap", "abs_gap", "loglikelihood", "deviance", "optim_criterion")}
     res["factor_order"] = m.get("factor_order")
     return res
+
+
+def prefilter(X, prop=0.05, quant_max=1.0, presel=False, threshold=0.2):
+    """pkg/R/prefiltering.R:127-146 restated column by column (the R code is four apply() calls over the dense matrix):
+    crit1 :130, crit2 :132, crit3 :134 (quantile type 7), crit4 :137-140.  Checker only."""
+    X = np.asarray(X, float)
+    n, p = X.shape
+    xmax = np.array([X[:, j].max() for j in range(p)])
+    nnz = np.array([(X[:, j] != 0).sum() for j in range(p)])
+    srt = np.sort(xmax)                                    # quantile(type = 7): h = (p - 1) q, linear between order statistics
+    h = (p - 1) * quant_max
+    lo = int(np.floor(h))
+    q = srt[lo] + (h - lo) * (srt[min(lo + 1, p - 1)] - srt[lo])
+    keep = (xmax > 0) & (nnz >= prop * n) & (xmax <= q)
+    if presel:
+        nzmean = X[X != 0].sum() / (X != 0).sum()
+        sd = np.array([np.sqrt(((X[:, j] - X[:, j].mean()) ** 2).sum() / (n - 1)) for j in range(p)])
+        keep &= (1 - np.exp(-sd / nzmean)) > threshold
+    return keep

@@ -21,7 +21,8 @@ class Problem(C.Structure):
     _fields_ = [("n_local", C.c_int64), ("n_global", C.c_int64), ("row_offset", C.c_int64), ("p", C.c_int32),
                 ("dense_f64", C.c_void_p), ("dense_i32", C.c_void_p), ("csr_rowptr", C.c_void_p),
                 ("csr_colidx", C.c_void_p), ("csr_val_f32", C.c_void_p), ("csr_val_f64", C.c_void_p),
-                ("csr_on_device", C.c_int32)]
+                ("csr_on_device", C.c_int32),
+                ("csc_colptr", C.c_void_p), ("csc_rowidx", C.c_void_p), ("csc_val_f64", C.c_void_p)]
 
 
 class Options(C.Structure):
@@ -86,7 +87,7 @@ def lib():
     L.pcmf_generate_counts_device.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, dp, dp, dp, C.c_uint64, C.c_int64,
                                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                               lp] + err
-    L.pcmf_csr_column_stats.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, dp, dp, dp] + err
+    L.pcmf_csr_column_stats.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, dp, dp, dp, dp] + err
     L.pcmf_measure_fp64_tflops.argtypes = [C.c_int, dp]
     L.pcmf_measure_fp64_mma_tflops.argtypes = [C.c_int, dp]
     L.pcmf_measure_gather_gbs.argtypes = [C.c_int, C.c_int64, dp]

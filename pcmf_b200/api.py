@@ -87,13 +87,17 @@ def generate_counts_device(n, p, K_true, U, V, prob1=None, seed=0, device=0, row
     return DeviceCSR(device, n, p, nnz.value, rp.value, ci.value, vv.value)
 
 
-def csr_column_stats(X, device=0):
-    """Per-gene (sum x, sum x^2, nnz) over the local cells of a DeviceCSR or host CSR tuple (rowptr, colidx, val_f32, p)."""
+def csr_column_stats(X, device=0, with_max=False):
+    """Per-gene (sum x, sum x^2, nnz[, max]) over the local cells of a DeviceCSR, a scipy sparse matrix or a host CSR
+    tuple (rowptr, colidx, val, p), computed on the GPU."""
     L = _lib.lib()
     if isinstance(X, DeviceCSR):
         n, p, rp, ci, vv, on_dev, keep = X.n, X.p, X.rowptr, X.colidx, X.val, 1, None
         device = X.device
     else:
+        if _sp is not None and _sp.issparse(X):
+            Xc = X.tocsr()
+            X = (Xc.indptr, Xc.indices, Xc.data, Xc.shape[1])
         rp_, ci_, vv_, p = X
         rp_ = np.ascontiguousarray(rp_, np.int64)
         ci_ = np.ascontiguousarray(ci_, np.int32)
@@ -101,12 +105,42 @@ def csr_column_stats(X, device=0):
         keep = (rp_, ci_, vv_)
         n, on_dev = len(rp_) - 1, 0
         rp, ci, vv = (x.ctypes.data_as(C.c_void_p) for x in keep)
-    s1, s2, cn = np.zeros(p), np.zeros(p), np.zeros(p)
+    s1, s2, cn, mx = np.zeros(p), np.zeros(p), np.zeros(p), np.zeros(p)
     err = C.create_string_buffer(512)
     rc = L.pcmf_csr_column_stats(device, n, p, rp, ci, vv, on_dev, s1.ctypes.data_as(_lib.dp), s2.ctypes.data_as(_lib.dp),
-                                 cn.ctypes.data_as(_lib.dp), err, 512)
+                                 cn.ctypes.data_as(_lib.dp), mx.ctypes.data_as(_lib.dp), err, 512)
     _lib.check(rc, err)
-    return s1, s2, cn
+    return (s1, s2, cn, mx) if with_max else (s1, s2, cn)
+
+
+def prefilter(X, prop=0.05, quant_max=1, presel=False, threshold=0.2, device=0):
+    """pkg/R/prefiltering.R:110-146: boolean vector over the genes (columns) that are kept.
+
+    crit1 max > 0; crit2 at least prop * n non-null entries; crit3 max <= quantile(max over genes, quant_max) (R's default
+    type-7 quantile = numpy's linear interpolation); crit4 (presel) 1 - exp(-sd_j / mean(X[X != 0])) > threshold.
+    A dense matrix is reduced with numpy the way the R function uses apply(); sparse / device-resident inputs (which the
+    R function cannot take) get their per-gene statistics from one GPU pass over the non-zeros."""
+    for name, v in (("prop", prop), ("quant_max", quant_max), ("threshold", threshold)):
+        if not np.isscalar(v) or not (0 <= v <= 1):
+            raise PcmfError(_lib.EINVAL, "`%s` should be a [0,1]-valued number" % name)
+    if isinstance(X, DeviceCSR) or (_sp is not None and _sp.issparse(X)) or isinstance(X, tuple):
+        s1, s2, cn, mx = csr_column_stats(X, device=device, with_max=True)
+        n = X.n if isinstance(X, DeviceCSR) else (X.shape[0] if not isinstance(X, tuple) else len(X[0]) - 1)
+        var = (s2 - s1 ** 2 / n) / (n - 1)
+        sd = np.sqrt(np.maximum(var, 0.0))
+        nzmean = s1.sum() / cn.sum()
+    else:
+        A = np.asarray(X)
+        if A.ndim != 2:
+            raise PcmfError(_lib.EINVAL, "`X` should be a matrix or a data.frame or an array")
+        n = A.shape[0]
+        mx, cn = A.max(axis=0), (A != 0).sum(axis=0)
+        sd = A.std(axis=0, ddof=1) if presel else None
+        nzmean = A[A != 0].mean() if presel else None
+    kept = (mx > 0) & (cn >= prop * n) & (mx <= np.quantile(mx, quant_max))
+    if presel:
+        kept &= (1 - np.exp(-sd / nzmean)) > threshold
+    return kept
 
 
 def prior_S_from_stats(colsum, colsumsq, colnnz, n, K):
@@ -191,8 +225,19 @@ def _as_problem(X, n_global=None, row_offset=0):
         n, p = X.n, X.p
         pr.csr_rowptr, pr.csr_colidx, pr.csr_val_f32, pr.csr_on_device = X.rowptr, X.colidx, X.val, 1
         keep.append(X)
+    elif _sp is not None and _sp.issparse(X) and X.format == "csc" and X.nnz < 2 ** 31 and X.shape[0] < 2 ** 31 - 1:
+        # compressed columns = Matrix::dgCMatrix (slots p, i, x): handed over as it is, CSR is built on the device
+        n, p = X.shape
+        cp = np.ascontiguousarray(X.indptr, np.int32)
+        ri = np.ascontiguousarray(X.indices, np.int32)
+        xv = np.ascontiguousarray(X.data, np.float64)
+        pr.csc_colptr, pr.csc_rowidx, pr.csc_val_f64 = (a.ctypes.data_as(C.c_void_p) for a in (cp, ri, xv))
+        keep += [cp, ri, xv]
     elif _sp is not None and _sp.issparse(X):
         Xc = X.tocsr()
+        if Xc.nnz and (Xc.data == 0).any():      # explicit zeros must not count as X != 0
+            Xc = Xc.copy()
+            Xc.eliminate_zeros()
         n, p = Xc.shape
         rp = np.ascontiguousarray(Xc.indptr, np.int64)
         ci = np.ascontiguousarray(Xc.indices, np.int32)
@@ -539,9 +584,11 @@ def pCMF(X, K, zero_inflation=True, sparsity=True, sel_bound=0.5, verbose=True, 
     # prior_S <- 1-exp(-apply(X,2,sd)/mean(X[X!=0])); prob_S <- matrix(rep(prior_S, K), ncol=K)   (pCMF.R:228-229)
     from .datagen import prior_S_heuristic
     if isinstance(X, DeviceCSR) or (_sp is not None and _sp.issparse(X)):
-        raise PcmfError(_lib.EUNSUPPORTED, "pCMF() with sparsity=TRUE needs a dense X for the prior_S heuristic; "
-                                           "call run_*sparse_gap_factor with prob_S / prior_S for CSR inputs")
-    prob_S, prior_S = prior_S_heuristic(np.asarray(X), K)
+        # X never exists as a dense matrix: the same heuristic from per-gene sums taken in one GPU pass over the non-zeros
+        s1, s2, cn = csr_column_stats(X, device=gpu.get("device", 0))
+        prob_S, prior_S = prior_S_from_stats(s1, s2, cn, X.n if isinstance(X, DeviceCSR) else X.shape[0], K)
+    else:
+        prob_S, prior_S = prior_S_heuristic(np.asarray(X), K)
     if not zero_inflation:
         return run_sparse_gap_factor(X, K, sel_bound=sel_bound, prob_S=prob_S, prior_S=prior_S, **common)
     return run_zi_sparse_gap_factor(X, K, sel_bound=sel_bound, prob_S=prob_S, prior_S=prior_S, **common)

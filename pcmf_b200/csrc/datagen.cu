@@ -131,7 +131,7 @@ extern "C" int pcmf_generate_counts_device(int device, int64_t n_local, int32_t 
 // ---- per-gene statistics of a CSR matrix ---------------------------------------------------------------------
 namespace {
 __global__ void k_col_stats(int64_t n, const int64_t *rowptr, const int32_t *colidx, const float *val, double *s1, double *s2,
-                            double *cn) {
+                            double *cn, double *mx) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -140,6 +140,8 @@ __global__ void k_col_stats(int64_t n, const int64_t *rowptr, const int32_t *col
             const int j = colidx[e];
             const double x = (double)val[e];
             atomicAdd(s1 + j, x); atomicAdd(s2 + j, x * x); atomicAdd(cn + j, x != 0.0 ? 1.0 : 0.0);
+            // counts are >= 0: the bit pattern of a non-negative double orders like the integer
+            if (x > 0.0) atomicMax(reinterpret_cast<unsigned long long *>(mx + j), (unsigned long long)__double_as_longlong(x));
         }
 }
 __global__ void k_dfma_peak(double *out, int iters) {
@@ -155,7 +157,7 @@ __global__ void k_dfma_peak(double *out, int iters) {
 
 extern "C" int pcmf_csr_column_stats(int device, int64_t n_local, int32_t p, const int64_t *rowptr, const int32_t *colidx,
                                      const float *val_f32, int32_t on_device, double *colsum, double *colsumsq, double *colnnz,
-                                     char *errbuf, size_t errlen) {
+                                     double *colmax, char *errbuf, size_t errlen) {
     if (!rowptr || !colidx || !val_f32 || !colsum || !colsumsq || !colnnz) {
         if (errbuf && errlen) snprintf(errbuf, errlen, "bad argument to pcmf_csr_column_stats");
         return PCMF_EINVAL;
@@ -178,13 +180,14 @@ extern "C" int pcmf_csr_column_stats(int device, int64_t n_local, int32_t p, con
         rp = drp; ci = dci; vv = dvv;
     }
     double *d = nullptr;
-    GK(cudaMalloc(&d, (size_t)p * 3 * 8));
-    GK(cudaMemset(d, 0, (size_t)p * 3 * 8));
+    GK(cudaMalloc(&d, (size_t)p * 4 * 8));
+    GK(cudaMemset(d, 0, (size_t)p * 4 * 8));
     const int grid = (int)std::min<int64_t>((n_local * 32 + 255) / 256, 148 * 32);
-    k_col_stats<<<grid, 256>>>(n_local, rp, ci, vv, d, d + p, d + 2 * (size_t)p);
+    k_col_stats<<<grid, 256>>>(n_local, rp, ci, vv, d, d + p, d + 2 * (size_t)p, d + 3 * (size_t)p);
     GK(cudaMemcpy(colsum, d, (size_t)p * 8, cudaMemcpyDeviceToHost));
     GK(cudaMemcpy(colsumsq, d + p, (size_t)p * 8, cudaMemcpyDeviceToHost));
     GK(cudaMemcpy(colnnz, d + 2 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToHost));
+    if (colmax) GK(cudaMemcpy(colmax, d + 3 * (size_t)p, (size_t)p * 8, cudaMemcpyDeviceToHost));
     cudaFree(d); if (drp) cudaFree(drp); if (dci) cudaFree(dci); if (dvv) cudaFree(dvv);
     return PCMF_OK;
 }

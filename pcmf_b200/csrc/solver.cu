@@ -120,6 +120,58 @@ struct BlockCache {
 };
 BlockCache &block_cache() { static BlockCache c; return c; }
 
+// Device -> user memory through two pinned staging chunks: the DMA of chunk c+1 overlaps the host copy of chunk c, and
+// the host copy (which pays the first-touch page faults of the caller's freshly allocated result arrays) runs on several
+// threads.  Measured need: at C4 the result is ~1 GB and a plain cudaMemcpy into pageable memory ran at ~4 GB/s.
+struct HostStager {
+    static constexpr size_t CH = (size_t)32 << 20;
+    std::mutex mu;
+    void *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    int nthreads() const { return (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency())); }
+    static void par_for(size_t bytes, int T, const std::function<void(size_t, size_t)> &f) {
+        size_t per = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) {
+            size_t lo = per * t, hi = std::min(bytes, lo + per);
+            if (lo < hi) th.emplace_back(f, lo, hi);
+        }
+        f(0, std::min(bytes, per));
+        for (auto &x : th) x.join();
+    }
+    void d2h(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+        if (bytes < ((size_t)4 << 20)) {
+            CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            return;
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        if (!buf[0]) {
+            for (int i = 0; i < 2; ++i) { CK(cudaHostAlloc(&buf[i], CH, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+        }
+        const int T = nthreads();
+        const size_t nch = (bytes + CH - 1) / CH;
+        auto drain = [&](size_t c) {
+            CK(cudaEventSynchronize(ev[c & 1]));
+            const size_t off = c * CH, len = std::min(CH, bytes - off);
+            char *d = static_cast<char *>(dst) + off; const char *b = static_cast<const char *>(buf[c & 1]);
+            par_for(len, T, [=](size_t lo, size_t hi) { std::memcpy(d + lo, b + lo, hi - lo); });
+        };
+        for (size_t c = 0; c < nch; ++c) {
+            const size_t off = c * CH, len = std::min(CH, bytes - off);
+            CK(cudaMemcpyAsync(buf[c & 1], static_cast<const char *>(src) + off, len, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ev[c & 1], st));
+            if (c > 0) drain(c - 1);
+        }
+        drain(nch - 1);
+    }
+    void release() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (int i = 0; i < 2; ++i) if (buf[i]) { cudaFreeHost(buf[i]); cudaEventDestroy(ev[i]); buf[i] = nullptr; }
+    }
+};
+HostStager &host_stager() { static HostStager h; return h; }
+
 template <typename T>
 T *dmalloc(size_t count) {
     return static_cast<T *>(block_cache().get(std::max<size_t>(count, 1) * sizeof(T)));
@@ -314,6 +366,33 @@ __global__ void k_gather_csc(int64_t nnz, const int64_t *perm, const int32_t *ro
         val_csc[t] = val[e];
     }
 }
+// dgCMatrix input: sort keys (cell index; explicit zeros get the key n and fall off the end), gene index per entry
+__global__ void k_csc_keys(int32_t p, int64_t n, const int32_t *colptr, const int32_t *rowidx, const double *x, int32_t *keys,
+                           int32_t *colids, int64_t *perm, int *flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    bool bad = false, oob = false;
+    for (int64_t j = warp; j < p; j += nw)
+        for (int64_t e = colptr[j] + lane; e < colptr[j + 1]; e += 32) {
+            const double v = x[e];
+            const int32_t r = rowidx[e];
+            oob |= (r < 0 || r >= n);
+            keys[e] = (v != 0.0 && r >= 0 && r < n) ? r : (int32_t)n;
+            colids[e] = (int32_t)j; perm[e] = e;
+            bad |= ((double)(float)v != v);
+        }
+    if (bad) atomicOr(flag, 1);
+    if (oob) atomicOr(flag, 2);
+}
+template <typename VT>
+__global__ void k_gather_csr_from_csc(int64_t nnz, const int64_t *perm, const int32_t *colids, const double *x, int32_t *colidx, VT *val) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = perm[t];
+        colidx[t] = colids[e];
+        val[t] = (VT)x[e];
+    }
+}
 __global__ void k_invert_perm(int64_t nnz, const int64_t *perm, uint32_t *inv) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (int64_t)gridDim.x * blockDim.x)
         inv[perm[t]] = (uint32_t)t;
@@ -356,6 +435,36 @@ __global__ void k_init_gamma_rows(int64_t rows, int K, int KP, const uint32_t *r
         dst[o] = -log(((double)raw[r * K + k] + 0.5) / 4294967296.0) / rate;
     }
 }
+// init_zi_param (zi_gap_factor_model.cpp:98-105) sets prob_D = (X > 0), so the dense cell pass collapses onto the
+// non-zeros: PV_i = sum_{j in nz(i)} EVS_j, sum prob_D o UVt = sum_i EU_i . PV_i, the Bernoulli self term is 0 and
+// colsum(prob_D)_j = nnz_j (k_zi_init_colsum).  One warp per cell, lane k owns factor k, four gathers in flight.
+__global__ void __launch_bounds__(256) k_zi_init_cells(int64_t n, int KP, const int64_t *rowptr, const int32_t *colidx, const double *EU,
+                                                       const double *EVS, double *PV, double *zsc) {
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double spl = 0;
+    for (int64_t i = w0; i < n; i += nw) {
+        const int64_t e0 = rowptr[i], e1 = rowptr[i + 1];
+        for (int k = lane; k < KP; k += 32) {
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            int64_t e = e0;
+            for (; e + 4 <= e1; e += 4) {
+                const int32_t j0 = colidx[e], j1 = colidx[e + 1], j2 = colidx[e + 2], j3 = colidx[e + 3];
+                a0 += EVS[(size_t)j0 * KP + k]; a1 += EVS[(size_t)j1 * KP + k]; a2 += EVS[(size_t)j2 * KP + k]; a3 += EVS[(size_t)j3 * KP + k];
+            }
+            for (; e < e1; ++e) a0 += EVS[(size_t)colidx[e] * KP + k];
+            const double pv = (a0 + a1) + (a2 + a3);
+            PV[(size_t)i * KP + k] = pv;
+            spl += EU[(size_t)i * KP + k] * pv;
+        }
+    }
+    spl = block_sum(spl, sh);
+    if (threadIdx.x == 0) atomicAdd(zsc, spl);
+}
+__global__ void k_zi_init_colsum(int32_t p, const int64_t *colptr, double *colsumP) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) colsumP[j] = (double)(colptr[j + 1] - colptr[j]);
+}
 __global__ void k_vec_scale(double *dst, const double *src, int64_t n, double s) {
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) dst[o] = src[o] * s;
 }
@@ -364,9 +473,49 @@ __global__ void k_vec_scale(double *dst, const double *src, int64_t n, double s)
 void pcmf_solver::setup_problem(const pcmf_problem &pr) {
     n = pr.n_local; n_global = pr.n_global > 0 ? pr.n_global : pr.n_local; row_offset = pr.row_offset; p = pr.p;
     if (n <= 0 || p <= 0) fail(PCMF_EINVAL, "empty count matrix");
-    const int nrep = (pr.dense_f64 != nullptr) + (pr.dense_i32 != nullptr) + (pr.csr_rowptr != nullptr);
-    if (nrep != 1) fail(PCMF_EINVAL, "exactly one of dense_f64, dense_i32, csr_* must be given");
-    if (pr.csr_rowptr) {
+    const int nrep = (pr.dense_f64 != nullptr) + (pr.dense_i32 != nullptr) + (pr.csr_rowptr != nullptr) + (pr.csc_colptr != nullptr);
+    if (nrep != 1) fail(PCMF_EINVAL, "exactly one of dense_f64, dense_i32, csr_*, csc_* must be given");
+    if (pr.csc_colptr) {
+        // Matrix::dgCMatrix (slots p, i, x): compressed columns, int32 indices, double values, host memory.  Turned into
+        // the cell-major CSR on the device by one stable radix sort on the cell index (genes stay ascending inside a cell);
+        // explicit zeros are dropped on the way (they must not count as X != 0, zi_gap_factor_model.cpp:104).
+        if (!pr.csc_rowidx || !pr.csc_val_f64) fail(PCMF_EINVAL, "incomplete CSC input");
+        if (n >= 0x7fffffffLL) fail(PCMF_EINVAL, "CSC input: too many rows for int32 row indices");
+        const int64_t nz_all = pr.csc_colptr[p];
+        if (pr.csc_colptr[0] != 0 || nz_all < 0) fail(PCMF_EINVAL, "CSC input: bad column pointers");
+        const size_t cnt = (size_t)std::max<int64_t>(nz_all, 1);
+        int32_t *cp = dmalloc<int32_t>(p + 1), *ri = dmalloc<int32_t>(cnt); double *xv = dmalloc<double>(cnt);
+        CK(cudaMemcpyAsync(cp, pr.csc_colptr, sizeof(int32_t) * (p + 1), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(ri, pr.csc_rowidx, sizeof(int32_t) * nz_all, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(xv, pr.csc_val_f64, sizeof(double) * nz_all, cudaMemcpyHostToDevice, stream));
+        int end_bit = 1; while ((1ll << end_bit) <= n) ++end_bit;      // keys go up to n inclusive
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (const int64_t *)nullptr,
+                                           (int64_t *)nullptr, nz_all, 0, end_bit, stream));
+        int32_t *keys = dmalloc<int32_t>(cnt), *keys_out = dmalloc<int32_t>(cnt), *colids = dmalloc<int32_t>(cnt);
+        int64_t *perm_in = dmalloc<int64_t>(cnt), *perm_out = dmalloc<int64_t>(cnt);
+        void *tmp = dmalloc<unsigned char>(tmp_bytes);
+        int *d_flag = dmalloc<int>(1);
+        CK(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+        k_csc_keys<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, n, cp, ri, xv, keys, colids, perm_in, d_flag);
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, perm_in, perm_out, nz_all, 0, end_bit, stream));
+        int64_t *drp = dmalloc<int64_t>(n + 1);
+        k_colptr_from_sorted<<<grid_for(n + 1, 256), 256, 0, stream>>>(nz_all, (int32_t)n, keys_out, drp);
+        int h_flag = 0;
+        CK(cudaMemcpyAsync(&nnz, drp + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (h_flag & 2) fail(PCMF_EINVAL, "CSC input: row index out of range");
+        f32 = (h_flag & 1) == 0;
+        int32_t *dci = dmalloc<int32_t>((size_t)std::max<int64_t>(nnz, 1));
+        void *dv = f32 ? (void *)dmalloc<float>((size_t)std::max<int64_t>(nnz, 1)) : (void *)dmalloc<double>((size_t)std::max<int64_t>(nnz, 1));
+        if (f32) k_gather_csr_from_csc<float><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, colids, xv, dci, (float *)dv);
+        else k_gather_csr_from_csc<double><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, colids, xv, dci, (double *)dv);
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        dfree(cp); dfree(ri); dfree(xv); dfree(keys); dfree(keys_out); dfree(colids); dfree(perm_in); dfree(perm_out); dfree(tmp); dfree(d_flag);
+        rowptr = drp; colidx = dci; val_csr = dv; own_csr = true;
+    } else if (pr.csr_rowptr) {
         if (!pr.csr_colidx || (!pr.csr_val_f32 && !pr.csr_val_f64)) fail(PCMF_EINVAL, "incomplete CSR input");
         f32 = pr.csr_val_f32 != nullptr;
         if (pr.csr_on_device) {
@@ -568,8 +717,7 @@ void pcmf_solver::upload_colmajor(const double *host, int64_t rows, double *dst,
 void pcmf_solver::download_colmajor(const double *src, int64_t rows, double *host) {
     double *tmp = dmalloc<double>((size_t)rows * K);
     k_rowpad_to_colmajor<<<grid_for(rows * K, 256), 256, 0, stream>>>(rows, K, KP, src, tmp);
-    CK(cudaMemcpyAsync(host, tmp, sizeof(double) * rows * K, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
+    host_stager().d2h(host, tmp, sizeof(double) * rows * K, stream);
     dfree(tmp);
 }
 
@@ -714,8 +862,14 @@ void pcmf_solver::run_init_stats() {
         // init_zi_param (zi_gap_factor_model.cpp:98-105): prob_D = (X > 0); realised as pass A with c_j = -inf
         ZiPrepArgs zp{p, 1, prior_D, Lg, cz, colw, flag, scal};
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
-        ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
-        launches += 1 + L->zi_cells(za, opt.kernel_variant, stream);
+        if (opt.kernel_variant & 32) {                 // the dense pass with c_j = -inf (kept to cross-check the shortcut below)
+            ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
+            launches += 1 + L->zi_cells(za, opt.kernel_variant, stream);
+        } else {
+            k_zi_init_cells<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, KP, rowptr, colidx, EU[cur], EVS, PV, ar3 + ar3_zsc);
+            k_zi_init_colsum<<<grid_for(p, 256), 256, 0, stream>>>(p, colptr, ar3 + ar3_csP);
+            launches += 3;
+        }
     }
     allreduce(ar1 + ar1_cseu, 64 + 64 + 4);
     if (zi) allreduce(ar3, ar3_total);
@@ -1325,7 +1479,14 @@ int pcmf_get_output(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errle
         CK(cudaMemcpy(h.data(), s->hyp, sizeof(double) * 4 * 64, cudaMemcpyDeviceToHost));
         auto rep = [&](double *dst, int64_t rows, const double *vec) {   // hyper_params are returned replicated (gap...cpp:379-382)
             if (!dst) return;
-            for (int k = 0; k < K; ++k) for (int64_t r = 0; r < rows; ++r) dst[r + (size_t)k * rows] = vec[k];
+            HostStager::par_for(sizeof(double) * (size_t)rows * K, host_stager().nthreads(), [=](size_t lo, size_t hi) {
+                size_t e = lo / sizeof(double); const size_t e1 = hi / sizeof(double);
+                while (e < e1) {                       // column k of the n x K result holds vec[k]
+                    const size_t k = e / (size_t)rows, stop = std::min(e1, (k + 1) * (size_t)rows);
+                    std::fill(dst + e, dst + stop, vec[k]);
+                    e = stop;
+                }
+            });
         };
         rep(res->alpha1, n, h.data()); rep(res->alpha2, n, h.data() + 64); rep(res->beta1, p, h.data() + 128); rep(res->beta2, p, h.data() + 192);
         if (s->sparse) {
@@ -1350,14 +1511,13 @@ int pcmf_get_output(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errle
                 dfree(tmp);
             }
             if (res->prob_D && s->explicitP) {
-                CK(cudaMemcpy(res->prob_D, s->Pexp, sizeof(double) * n * p, cudaMemcpyDeviceToHost));
+                host_stager().d2h(res->prob_D, s->Pexp, sizeof(double) * n * p, s->stream);
             } else if (res->prob_D) {
                 // prob_D is defined by the triple saved at the last ZI update: EU[cur] (the EU of that update), EVS, cz/flag
                 double *tmp = dmalloc<double>((size_t)n * p);
                 ProbDArgs pa{n, p, K, s->KP, s->EU[s->cur], s->EVS, s->cz, s->flag, s->bitT, tmp};
                 k_prob_d_dense<<<s->grid_for(n * (int64_t)p, 256), 256, 0, s->stream>>>(pa);
-                CK(cudaMemcpyAsync(res->prob_D, tmp, sizeof(double) * n * p, cudaMemcpyDeviceToHost, s->stream));
-                CK(cudaStreamSynchronize(s->stream));
+                host_stager().d2h(res->prob_D, tmp, sizeof(double) * n * p, s->stream);
                 dfree(tmp);
             }
         }
@@ -1410,7 +1570,7 @@ int pcmf_fit(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_init 
     return rc;
 }
 
-int pcmf_release_cached_memory(void) { block_cache().release_all(); return PCMF_OK; }
+int pcmf_release_cached_memory(void) { block_cache().release_all(); host_stager().release(); return PCMF_OK; }
 
 int pcmf_device_free(int device, void *ptr) {
     if (cudaSetDevice(device) != cudaSuccess) return PCMF_ECUDA;
