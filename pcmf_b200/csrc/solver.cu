@@ -191,6 +191,8 @@ struct pcmf_solver {
     bool zi = false, sparse = false, f32 = true;
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool zi_at_init = false;            // prob_D still is (X > 0) and the packed records of pass A do not exist yet
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_vals = nullptr;   // value upload of a host CSR, overlapped with the CSC sort
     bool own_stream = false;
     const Launchers *L = nullptr;
     int sms = 148;
@@ -310,6 +312,8 @@ pcmf_solver::~pcmf_solver() {
     for (void *q : ptrs) if (q) dfree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
+    if (ev_vals) cudaEventDestroy(ev_vals);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -529,10 +533,16 @@ void pcmf_solver::setup_problem(const pcmf_problem &pr) {
             void *vv = f32 ? (void *)dmalloc<float>(nnz) : (void *)dmalloc<double>(nnz);
             CK(cudaMemcpyAsync(rp, pr.csr_rowptr, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, stream));
             CK(cudaMemcpyAsync(ci, pr.csr_colidx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, stream));
+            // the values travel on a second stream: the radix sort of build_csc only needs the structure and runs under
+            // their copy (pinned host arrays; a pageable source makes the copy synchronous and nothing is lost)
+            cudaStream_t s2 = nullptr;
+            CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ev_vals, cudaEventDisableTiming));
             CK(cudaMemcpyAsync(vv, f32 ? (const void *)pr.csr_val_f32 : (const void *)pr.csr_val_f64,
-                               (f32 ? sizeof(float) : sizeof(double)) * nnz, cudaMemcpyHostToDevice, stream));
+                               (f32 ? sizeof(float) : sizeof(double)) * nnz, cudaMemcpyHostToDevice, s2));
+            CK(cudaEventRecord(ev_vals, s2));
+            copy_stream = s2;
             rowptr = rp; colidx = ci; val_csr = vv; own_csr = true;
-            StageTimer th(stream); th.t -= 0; th.mark("H2D of the CSR arrays (wait)");
         }
     } else {
         // dense R matrix (wrapper_gap_factor.h:204-211), INTSXP or REALSXP, column-major: uploaded as it is and turned into
@@ -606,6 +616,13 @@ void pcmf_solver::build_csc() {
     colptr = dmalloc<int64_t>(p + 1);
     rowidx = dmalloc<int32_t>(nnz);
     tm.mark("csc: rowidx allocation");
+    if (ev_vals) {                      // the values of a host CSR were uploaded on their own stream
+        CK(cudaStreamWaitEvent(stream, ev_vals, 0));
+        CK(cudaStreamSynchronize(copy_stream));
+        cudaEventDestroy(ev_vals); cudaStreamDestroy(copy_stream);
+        ev_vals = nullptr; copy_stream = nullptr;
+        tm.mark("csc: wait for the value upload");
+    }
     k_colptr_from_sorted<<<grid_for(p + 1, 256), 256, 0, stream>>>(nnz, p, keys_out, colptr);
     if (f32) {
         val_csc = dmalloc<float>(nnz);
@@ -842,6 +859,7 @@ void pcmf_solver::run_init_stats() {
     k_row_extremes<<<grid_for(n, 256), 256, 0, stream>>>(n, K, KP, ElogU, rowext);
     k_row_extremes<<<grid_for(p, 256), 256, 0, stream>>>(p, K, KP, ElogV, colext);
     launches += 4 + (sparse ? 1 : 0);
+    zi_at_init = false;
     if (zi && explicitP) {
         // explicit prob_D: no gene shortcut applies (flag 0, weight 1), the weights of the non-zeros go into the values
         CK(cudaMemsetAsync(flag, 0, p * 4, stream));
@@ -869,6 +887,7 @@ void pcmf_solver::run_init_stats() {
             k_zi_init_cells<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, KP, rowptr, colidx, EU[cur], EVS, PV, ar3 + ar3_zsc);
             k_zi_init_colsum<<<grid_for(p, 256), 256, 0, stream>>>(p, colptr, ar3 + ar3_csP);
             launches += 3;
+            zi_at_init = true;                         // no packed gene records yet; prob_D is exactly (X > 0)
         }
     }
     allreduce(ar1 + ar1_cseu, 64 + 64 + 4);
@@ -990,6 +1009,7 @@ void pcmf_solver::step(bool want_data) {
         k_refresh_weights<<<grid_for(pK, 256), 256, 0, stream>>>(p, K, KP, sparse, prob_S, colw, ev, wS, evw);
         ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
         const int nl = L->zi_cells(za, opt.kernel_variant, stream);
+        zi_at_init = false;
         allreduce(ar3, ar3_total);
         end(PH_ZI_A, 2 + nl);
     }
@@ -1067,7 +1087,7 @@ pcmf_solver::Mon pcmf_solver::monitors_now(bool want_loglik) {
         k_gamma_loglike<<<grid_for(n * KP, 256), 256, 0, stream>>>(n, K, KP, EU[cur], a1, a2, mon + 4);
         k_gamma_loglike<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, EV, b1, b2, mon + 6);
         launches += 2;
-        if (zi) {
+        if (zi && !zi_at_init) {                       // at the initial state prob_D = (X > 0): the zero part is log(1) = 0
             ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
             L->zi_loglik(za, mon + 5, stream);
             launches += 1;
