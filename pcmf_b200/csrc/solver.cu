@@ -509,7 +509,11 @@ void pcmf_solver::setup_problem(const pcmf_problem &pr) {
         CK(cudaMemcpyAsync(&nnz, drp + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
         CK(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        if (h_flag & 2) fail(PCMF_EINVAL, "CSC input: row index out of range");
+        if (h_flag & 2) {
+            for (void *q : {(void *)cp, (void *)ri, (void *)xv, (void *)keys, (void *)keys_out, (void *)colids, (void *)perm_in,
+                            (void *)perm_out, tmp, (void *)d_flag, (void *)drp}) dfree(q);
+            fail(PCMF_EINVAL, "CSC input: row index out of range");
+        }
         f32 = (h_flag & 1) == 0;
         int32_t *dci = dmalloc<int32_t>((size_t)std::max<int64_t>(nnz, 1));
         void *dv = f32 ? (void *)dmalloc<float>((size_t)std::max<int64_t>(nnz, 1)) : (void *)dmalloc<double>((size_t)std::max<int64_t>(nnz, 1));
