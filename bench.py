@@ -188,7 +188,7 @@ def run_reference(args, cfg):
                     "stand-in headers (oracle/_ref, used to pin parity at 1e-10), but that build's linear algebra is not Eigen's "
                     "and runs ~2x slower than this C port of the same loops, so the port is what is timed (the faster, "
                     "conservative baseline); all host cores, dense n x p loops exactly as the reference runs them"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def ncu_traffic(config):
@@ -202,7 +202,30 @@ def ncu_traffic(config):
         return {}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's "NCCL version ..." banner at
+    communicator creation): everything written to fd 1 from now on goes to stderr, the JSON line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -390,7 +413,7 @@ def main():
                 "roofline": roofline, "kernels": kernels, "phases": phases, "cpu_baseline": cb, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clk, "fp64_peak_tflops_measured": fp64_peak, "fp64_dmma_peak_tflops_measured": dmma_peak,
                 "elbo_last": float(elbo[-1]), "conv_crit_last": float(crit[-1])}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
