@@ -55,8 +55,18 @@ __device__ __forceinline__ double fast_exp_neg_tab(double z, const double *__res
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    p *= tab[m & 63];
-    return __hiloint2double(__double2hiint(p) + ((m >> 6) << 20), __double2loint(p));
+    // tab is PRE-BIASED (load_pow2_tab): entry i has (i << 14) taken off its high word, so that adding (m << 14) leaves
+    // exactly ((m - i) << 14) = (m >> 6) << 20 on the exponent field -- one integer multiply-add instead of shift, mask, add
+    const double tb = tab[m & 63];
+    const double sc = __hiloint2double(__double2hiint(tb) + (int)((unsigned)m << 14), __double2loint(tb));
+    return p * sc;
+}
+// the 64-entry table of 2^(i/64) as the dense passes keep it in shared memory (see fast_exp_neg_tab)
+__device__ __forceinline__ void load_pow2_tab(double *s_tab) {
+    if (threadIdx.x < 64) {
+        const double v = kPow2Tab64[threadIdx.x];
+        s_tab[threadIdx.x] = __hiloint2double(__double2hiint(v) - ((int)threadIdx.x << 14), __double2loint(v));
+    }
 }
 // internal::expit (internal.h:151-155): exactly 1 / 0 for z >= 30 / z <= -30.  `ov` is the value the entry takes when
 // `force` is set (X != 0, zi...cpp:359-360).  Also returns y = 1 + exp(-z) (garbage when clamped) and the clamp flag.
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     __shared__ double sh[32];
     __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
+    load_pow2_tab(s_tab);
     for (int t = threadIdx.x; t < 8 * TJ; t += blockDim.x) s_cs[t] = 0.0;
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -177,6 +187,12 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
 #pragma unroll
         for (int s = 0; s < KS; ++s) a1[mt][s] = live[mt] ? __ldg(a.EU + i * KP + 4 * s + q) : 0.0;
     }
+    // rows beyond n (last CTA only) must contribute P = 0 everywhere: their EU fragment is 0 and the accumulator of the first
+    // product starts at 1e305, above every effective logit (|c| <= 1e300), so z = c - lambda is clamped to P = 0 by the
+    // expit itself -- no per-entry select on `live` in the inner loop
+    double dinit[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) dinit[mt] = live[mt] ? 0.0 : 1e305;
     double acc[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -231,7 +247,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             }
             double d[MT][2];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) { d[mt][0] = 0.0; d[mt][1] = 0.0; }
+            for (int mt = 0; mt < MT; ++mt) { d[mt][0] = dinit[mt]; d[mt][1] = dinit[mt]; }
 #pragma unroll
             for (int s = 0; s < KS; ++s) {
                 const double b = rec[s * 32 + lane];
@@ -248,9 +264,9 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
                 const bool nz0 = (bits[mt] >> sh0) & 1u, nz1 = (bits[mt] >> (sh0 + 1)) & 1u;
                 double y0, y1; bool big0, big1;
                 double p0 = fast_expit_tab(z0, s_tab, nz0, n2.x, y0, big0), p1 = fast_expit_tab(z1, s_tab, nz1, n2.y, y1, big1);
-                p0 = live[mt] ? p0 : 0.0; p1 = live[mt] ? p1 : 0.0;
+                // (rows beyond n: lambda starts at 1e305 and their occupancy words are 0, so P is the clamped 0 here)
                 // -bernoulli_loglike(prob_D, prob_D) over 0 < P < 1: sum (1-P)(-z) - log(1 + e^-z)
-                const bool g0 = !big0 && !nz0 && live[mt], g1 = !big1 && !nz1 && live[mt];
+                const bool g0 = !big0 && !nz0, g1 = !big1 && !nz1;
                 ent_lin = fma(g0 ? (p0 - 1.0) : 0.0, z0, ent_lin);
                 ent_lin = fma(g1 ? (p1 - 1.0) : 0.0, z1, ent_lin);
                 prod *= (g0 ? y0 : 1.0) * (g1 ? y1 : 1.0);
@@ -319,7 +335,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? 3 : 2) k_zi_loglik_mma(ZiAAr
     __shared__ double sh[32];
     __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
+    load_pow2_tab(s_tab);
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     const int64_t cell0 = (int64_t)blockIdx.x * (32 * MT) + w * (8 * MT);
@@ -407,7 +423,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     double *s_tab = s_buf + 2 * BUF;                            // 64
     __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
+    load_pow2_tab(s_tab);
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     const int gene0 = blockIdx.x * (32 * MT) + w * (8 * MT);

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(128, MINB) k_core(double *out, int ngroups) {
     const int lane = threadIdx.x & 31, q = lane & 3;
     for (int t = threadIdx.x; t < NG * KS * 32; t += blockDim.x) s_f1[t] = 1e-3 * (t % 17);
     for (int t = threadIdx.x; t < NG * 2 * NT * 32; t += blockDim.x) s_f2[t] = 1e-3 * (t % 13);
-    if (threadIdx.x < 64) s_tab[threadIdx.x] = kPow2Tab64[threadIdx.x];
+    load_pow2_tab(s_tab);
     __syncthreads();
     double a1[MT][KS], c[MT], acc[MT][NT][2];
     for (int mt = 0; mt < MT; ++mt) { c[mt] = 0.5 + mt; for (int s = 0; s < KS; ++s) a1[mt][s] = 1e-2 * (lane + s + mt); }
