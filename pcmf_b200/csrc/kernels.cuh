@@ -52,6 +52,25 @@ __device__ __noinline__ double exact_terms(const double *__restrict__ elu, const
     return T;
 }
 
+// The same guarded terms of ONE entry evaluated by a whole warp, lane k holding factor k (and k + 32 when KP = 64):
+// e_c is the lane's term, the return value the (shifted) sum on every lane.  The non-zero passes hand the entries that
+// cannot take the product formula to this routine one at a time (ballot + shuffle): right after a random initialisation
+// ~1 % of the entries need it, and one lane evaluating K guarded exponentials alone stalled the other 31 for thousands
+// of cycles (C4: first iterations 80 ms instead of 27 ms for the cell pass).
+template <int C>
+__device__ __forceinline__ double exact_terms_warp(const double (&elu)[C], const double (&elv)[C], const double (&sd)[C], int K, int lane,
+                                                   double (&e)[C]) {
+    double m = -1e300;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { e[c] = elu[c] + elv[c]; if (c * 32 + lane < K) m = fmax(m, e[c]); }
+    m = warp_max(m);
+    if (m < 100.0) m = 0.0;
+    double T = 0.0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { e[c] = (c * 32 + lane < K) ? custom_exp(e[c] - m) * sd[c] : 0.0; T += e[c]; }
+    return warp_sum(T);
+}
+
 // One padded K-vector (32-byte aligned, KP a multiple of 4) with 256-bit loads -- LDG.E.256, new on sm_100.  The gather of
 // these rows is what bounds the non-zero passes; measured (scripts/ubench_gather256.cu) the same random 160-byte rows come
 // in at 9.1 TB/s with 256-bit loads against 6.4 TB/s with 128-bit ones from an L2-resident table (6.8-7.6 vs 6.2 TB/s
@@ -144,7 +163,6 @@ struct RowArgs {
 // update_variational_gamma_param, factor U part (gap...cpp:530-532 and variants) + U_stats.
 template <int KP, typename VT>
 __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
-    __shared__ double s_ex[8][KP];   // exact-path contributions of the warp's current cell
     __shared__ double sh[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -155,39 +173,59 @@ __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
     const bool same_w = (a.evw == a.ev);
     UAcc acc[(KP + 31) / 32];
 
+    constexpr int C = (KP + 31) / 32;
     for (int64_t i = warp0; i < a.n; i += nwarps) {
         double u[KP], r[KP];
         load_vec<KP>(a.eu + i * KP, u);
 #pragma unroll
         for (int k = 0; k < KP; ++k) r[k] = 0.0;
-        for (int k = lane; k < KP; k += 32) s_ex[w][k] = 0.0;
-        __syncwarp();
+        double sx[C], elu[C];                      // exact-path contributions / ElogU_i of the factor(s) this lane owns
+#pragma unroll
+        for (int c = 0; c < C; ++c) { sx[c] = 0.0; elu[c] = (c * 32 + lane < KP) ? a.ElogU[i * KP + c * 32 + lane] : 0.0; }
         const double2 ext = a.rowext[i];
         const PathFlags pf = path_flags(ext.x, ext.y, gminV, gmaxV);
         const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
-        for (int64_t e = e0 + lane; e < e1; e += 32) {
-            const int j = __ldg(a.colidx + e);
-            const double x = (double)__ldg(val + e);
-            double v[KP];
-            load_vec<KP>(a.ev + (int64_t)j * KP, v);
-            double T0 = 0.0, T1 = 0.0;
+        for (int64_t eb = e0; eb < e1; eb += 32) {              // warp-uniform trip count: the exact path is cooperative
+            const int64_t e = eb + lane;
+            const bool active = e < e1;
+            int j = 0; double x = 0.0; bool slow = false;
+            if (active) {
+                j = __ldg(a.colidx + e);
+                x = (double)__ldg(val + e);
+                double v[KP];
+                load_vec<KP>(a.ev + (int64_t)j * KP, v);
+                double T0 = 0.0, T1 = 0.0;
 #pragma unroll
-            for (int k = 0; k < KP; k += 2) { T0 = fma(u[k], v[k], T0); T1 = fma(u[k + 1], v[k + 1], T1); }
-            const double T = T0 + T1;
-            if (!pf.force_exact && T >= 1e-26) {
-                const double q = x / T;
-                if (!same_w) load_vec<KP>(a.evw + (int64_t)j * KP, v);
+                for (int k = 0; k < KP; k += 2) { T0 = fma(u[k], v[k], T0); T1 = fma(u[k + 1], v[k + 1], T1); }
+                const double T = T0 + T1;
+                if (!pf.force_exact && T >= 1e-26) {
+                    const double q = x / T;
+                    if (!same_w) load_vec<KP>(a.evw + (int64_t)j * KP, v);
 #pragma unroll
-                for (int k = 0; k < KP; ++k) r[k] = fma(q, v[k], r[k]);
-            } else if (!a.allmasked[j]) {   // all-masked gene: T = 0, r_ijk = 0 (gap...cpp:487), nothing to add
-                atomicAdd(a.dbg, 1ull);
-                double ex[KP];
-                const double Tx = exact_terms<KP>(a.ElogU + i * KP, a.ElogV + (int64_t)j * KP, a.Sd + (int64_t)j * KP, a.K, ex);
-                const double q = x / (Tx > 0.0 ? Tx : 1.0);
-                for (int k = 0; k < a.K; ++k) atomicAdd(&s_ex[w][k], q * ex[k] * a.wS[(int64_t)j * KP + k]);
+                    for (int k = 0; k < KP; ++k) r[k] = fma(q, v[k], r[k]);
+                } else slow = !a.allmasked[j];   // all-masked gene: T = 0, r_ijk = 0 (gap...cpp:487), nothing to add
+            }
+            unsigned need = __ballot_sync(0xffffffffu, slow);
+            if (need && lane == 0) atomicAdd(a.dbg, (unsigned long long)__popc(need));
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const int js = __shfl_sync(0xffffffffu, j, src);
+                const double xs = __shfl_sync(0xffffffffu, x, src);
+                double elv[C], sd[C], ws[C], ex[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int k = c * 32 + lane;
+                    const bool in = k < KP;
+                    elv[c] = in ? a.ElogV[(int64_t)js * KP + k] : 0.0; sd[c] = in ? a.Sd[(int64_t)js * KP + k] : 0.0;
+                    ws[c] = in ? a.wS[(int64_t)js * KP + k] : 0.0;
+                }
+                const double Tx = exact_terms_warp<C>(elu, elv, sd, a.K, lane, ex);
+                const double q = xs / (Tx > 0.0 ? Tx : 1.0);
+#pragma unroll
+                for (int c = 0; c < C; ++c) sx[c] = fma(q * ex[c], ws[c], sx[c]);
             }
         }
-        __syncwarp();
         // reduce over lanes; lane (k & 31) keeps component k
         double mine[(KP + 31) / 32], um[(KP + 31) / 32];
 #pragma unroll
@@ -201,7 +239,7 @@ __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
             const int k = c * 32 + lane;
             if (k < a.K) {
                 const int64_t o = i * KP + k;
-                const double ez = um[c] * mine[c] + s_ex[w][k];
+                const double ez = um[c] * mine[c] + sx[c];
                 const double a1o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a1_old0[o] : a.a1[o]);
                 const double a2o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a2_old0[o] : a.a2[o]);
                 const double a1n = a.alpha1[k] + ez;
@@ -250,7 +288,6 @@ __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
 // Used for the ZI / sparse models (evw != ev); the plain model gathers one vector either way.
 template <int KP, typename VT>
 __global__ void __launch_bounds__(256, 2) k_estep_rows_q(RowArgs a) {
-    __shared__ double s_ex[8][KP];
     __shared__ double sh[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -259,32 +296,51 @@ __global__ void __launch_bounds__(256, 2) k_estep_rows_q(RowArgs a) {
     const VT *__restrict__ val = static_cast<const VT *>(a.val);
     UAcc acc[(KP + 31) / 32];
 
+    constexpr int C = (KP + 31) / 32;
     for (int64_t i = warp0; i < a.n; i += nwarps) {
         double r[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) r[k] = 0.0;
-        for (int k = lane; k < KP; k += 32) s_ex[w][k] = 0.0;
-        __syncwarp();
-        const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
-        for (int64_t e = e0 + lane; e < e1; e += 32) {
-            const int j = __ldg(a.colidx + e);
-            const uint32_t t = __ldg(a.csr2csc + e);
-            double v[KP];
-            load_vec<KP>(a.evw + (int64_t)j * KP, v);      // requested together with q, not after it (latency bound)
-            const double q = __ldg(a.qcsc + t);
-            if (q == q) {
+        double sx[C];
 #pragma unroll
-                for (int k = 0; k < KP; ++k) r[k] = fma(q, v[k], r[k]);
-            } else if (!a.allmasked[j]) {
-                atomicAdd(a.dbg, 1ull);
-                const double x = (double)__ldg(val + e);
-                double ex[KP];
-                const double Tx = exact_terms<KP>(a.ElogU + i * KP, a.ElogV + (int64_t)j * KP, a.Sd + (int64_t)j * KP, a.K, ex);
-                const double qx = x / (Tx > 0.0 ? Tx : 1.0);
-                for (int k = 0; k < a.K; ++k) atomicAdd(&s_ex[w][k], qx * ex[k] * a.wS[(int64_t)j * KP + k]);
+        for (int c = 0; c < C; ++c) sx[c] = 0.0;
+        const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
+        for (int64_t eb = e0; eb < e1; eb += 32) {              // warp-uniform trip count: the exact path is cooperative
+            const int64_t e = eb + lane;
+            int j = 0; bool slow = false;
+            if (e < e1) {
+                j = __ldg(a.colidx + e);
+                const uint32_t t = __ldg(a.csr2csc + e);
+                double v[KP];
+                load_vec<KP>(a.evw + (int64_t)j * KP, v);      // requested together with q, not after it (latency bound)
+                const double q = __ldg(a.qcsc + t);
+                if (q == q) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) r[k] = fma(q, v[k], r[k]);
+                } else slow = !a.allmasked[j];
+            }
+            unsigned need = __ballot_sync(0xffffffffu, slow);
+            if (need && lane == 0) atomicAdd(a.dbg, (unsigned long long)__popc(need));
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const int js = __shfl_sync(0xffffffffu, j, src);
+                const double xs = (double)__ldg(val + eb + src);
+                double elu[C], elv[C], sd[C], ws[C], ex[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int k = c * 32 + lane;
+                    const bool in = k < KP;
+                    elu[c] = in ? a.ElogU[i * KP + k] : 0.0;
+                    elv[c] = in ? a.ElogV[(int64_t)js * KP + k] : 0.0; sd[c] = in ? a.Sd[(int64_t)js * KP + k] : 0.0;
+                    ws[c] = in ? a.wS[(int64_t)js * KP + k] : 0.0;
+                }
+                const double Tx = exact_terms_warp<C>(elu, elv, sd, a.K, lane, ex);
+                const double qx = xs / (Tx > 0.0 ? Tx : 1.0);
+#pragma unroll
+                for (int c = 0; c < C; ++c) sx[c] = fma(qx * ex[c], ws[c], sx[c]);
             }
         }
-        __syncwarp();
         double mine[(KP + 31) / 32];
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
@@ -297,7 +353,7 @@ __global__ void __launch_bounds__(256, 2) k_estep_rows_q(RowArgs a) {
             const int k = c * 32 + lane;
             if (k < a.K) {
                 const int64_t o = i * KP + k;
-                const double ez = a.eu[o] * mine[c] + s_ex[w][k];
+                const double ez = a.eu[o] * mine[c] + sx[c];
                 const double a1o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a1_old0[o] : a.a1[o]);
                 const double a2o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a2_old0[o] : a.a2[o]);
                 const double a1n = a.alpha1[k] + ez;
@@ -416,7 +472,8 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
     __shared__ double sh[4][KP];
     __shared__ double sh2[4][KP];
     __shared__ double shl[4];
-    __shared__ double sx1[KP], sx2[KP];   // exact-path contributions
+    __shared__ double sx1[4][KP], sx2[4][KP];   // exact-path contributions of the four warps
+    constexpr int C = (KP + 31) / 32;
     const VT *__restrict__ val = static_cast<const VT *>(a.val);
     const double gminU = dbl_from_ordered(a.guard[G_MINU]), gmaxU = dbl_from_ordered(a.guard[G_MAXU]);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -432,8 +489,14 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
         }
         double v[KP], b1[KP], b2[WITH_B2 ? KP : 1];
         load_vec<KP>(a.ev + (int64_t)j * KP, v);
-        if (threadIdx.x < KP) { sx1[threadIdx.x] = 0.0; sx2[threadIdx.x] = 0.0; }
-        __syncthreads();
+        // exact-path contributions: lane k of every warp owns factor k (and k + 32 for KP = 64)
+        double x1[C], x2[C], elv[C], sdv[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int k = c * 32 + lane;
+            x1[c] = 0.0; x2[c] = 0.0;
+            elv[c] = k < KP ? a.ElogV[(int64_t)j * KP + k] : 0.0; sdv[c] = k < KP ? a.Sd[(int64_t)j * KP + k] : 0.0;
+        }
         const double2 ext = a.colext[j];
         const PathFlags pf = path_flags(ext.x, ext.y, gminU, gmaxU);
 #pragma unroll
@@ -443,41 +506,59 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
         const int64_t e0 = a.colptr[j], e1 = a.allmasked[j] ? a.colptr[j] : a.colptr[j + 1];
         if (a.qout && a.allmasked[j])
             for (int64_t e = e0 + threadIdx.x; e < a.colptr[j + 1]; e += blockDim.x) a.qout[e] = 0.0;
-        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-            const int64_t i = __ldg(a.rowidx + e);
-            const double x = (double)__ldg(val + e);
-            // both rows of the cell are requested before anything is consumed: the pass is bound by the latency of these
-            // gathers, and a second request issued only once T is known would double it
-            double u[KP], el[WITH_B2 ? KP : 1];
-            load_vec<KP>(a.eu + i * KP, u);
-            if (WITH_B2) load_vec<KP>(a.ElogU + i * KP, reinterpret_cast<double (&)[KP]>(el));
-            double T0 = 0.0, T1 = 0.0;
+        for (int64_t eb = e0 + w * 32; eb < e1; eb += blockDim.x) {    // warp-uniform trip count: the exact path is cooperative
+            const int64_t e = eb + lane;
+            int64_t i = 0; double x = 0.0; bool slow = false;
+            if (e < e1) {
+                i = __ldg(a.rowidx + e);
+                x = (double)__ldg(val + e);
+                // both rows of the cell are requested before anything is consumed: the pass is bound by the latency of these
+                // gathers, and a second request issued only once T is known would double it
+                double u[KP], el[WITH_B2 ? KP : 1];
+                load_vec<KP>(a.eu + i * KP, u);
+                if (WITH_B2) load_vec<KP>(a.ElogU + i * KP, reinterpret_cast<double (&)[KP]>(el));
+                double T0 = 0.0, T1 = 0.0;
 #pragma unroll
-            for (int k = 0; k < KP; k += 2) { T0 = fma(u[k], v[k], T0); T1 = fma(u[k + 1], v[k + 1], T1); }
-            const double T = T0 + T1;
-            if (!pf.force_exact && T >= 1e-26) {
-                const double q = x / T;
-                if (a.qout) a.qout[e] = q;
-                if (WITH_LOGT) lt += x * log(T);
+                for (int k = 0; k < KP; k += 2) { T0 = fma(u[k], v[k], T0); T1 = fma(u[k + 1], v[k + 1], T1); }
+                const double T = T0 + T1;
+                if (!pf.force_exact && T >= 1e-26) {
+                    const double q = x / T;
+                    if (a.qout) a.qout[e] = q;
+                    if (WITH_LOGT) lt += x * log(T);
 #pragma unroll
-                for (int k = 0; k < KP; ++k) b1[k] = fma(q, u[k], b1[k]);
-                if (WITH_B2) {
+                    for (int k = 0; k < KP; ++k) b1[k] = fma(q, u[k], b1[k]);
+                    if (WITH_B2) {
 #pragma unroll
-                    for (int k = 0; k < KP; ++k) b2[k] = fma(q * u[k], el[k], b2[k]);
+                        for (int k = 0; k < KP; ++k) b2[k] = fma(q * u[k], el[k], b2[k]);
+                    }
+                } else {
+                    slow = true;
+                    if (a.qout) a.qout[e] = __longlong_as_double(0x7ff8000000000000LL);   // NaN: the cell pass takes the exact formula too
                 }
-            } else {
-                atomicAdd(a.dbg + 1, 1ull);
-                if (a.qout) a.qout[e] = __longlong_as_double(0x7ff8000000000000LL);   // NaN: the cell pass takes the exact formula too
-                double ex[KP];
-                const double Tx = exact_terms<KP>(a.ElogU + i * KP, a.ElogV + (int64_t)j * KP, a.Sd + (int64_t)j * KP, a.K, ex);
-                const double q = x / (Tx > 0.0 ? Tx : 1.0);
-                if (WITH_LOGT) lt += x * log(Tx);
-                for (int k = 0; k < a.K; ++k) {
-                    atomicAdd(&sx1[k], q * ex[k]);
-                    if (WITH_B2) atomicAdd(&sx2[k], q * ex[k] * a.ElogU[i * KP + k]);
+            }
+            unsigned need = __ballot_sync(0xffffffffu, slow);
+            if (need && lane == 0) atomicAdd(a.dbg + 1, (unsigned long long)__popc(need));
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const int64_t is = __shfl_sync(0xffffffffu, i, src);
+                const double xs = __shfl_sync(0xffffffffu, x, src);
+                double elu[C], ex[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) elu[c] = (c * 32 + lane < KP) ? a.ElogU[is * KP + c * 32 + lane] : 0.0;
+                const double Tx = exact_terms_warp<C>(elu, elv, sdv, a.K, lane, ex);
+                const double q = xs / (Tx > 0.0 ? Tx : 1.0);
+                if (WITH_LOGT && lane == 0) lt += xs * log(Tx);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    x1[c] = fma(q, ex[c], x1[c]);
+                    if (WITH_B2) x2[c] = fma(q * ex[c], elu[c], x2[c]);
                 }
             }
         }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (c * 32 + lane < KP) { sx1[w][c * 32 + lane] = x1[c]; sx2[w][c * 32 + lane] = x2[c]; }
         // block reduction: warp shuffles then 4 partial rows in shared memory
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
@@ -494,8 +575,8 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
             const int k = threadIdx.x;
             // fast path accumulated sum_i q eu_ik; e_ijk = eu_ik ev_jk
             const double evk = __ldg(a.ev + (int64_t)j * KP + k);
-            a.B1[(int64_t)j * KP + k] = (sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k]) * evk + sx1[k];
-            if (WITH_B2) a.B2[(int64_t)j * KP + k] = (sh2[0][k] + sh2[1][k] + sh2[2][k] + sh2[3][k]) * evk + sx2[k];
+            a.B1[(int64_t)j * KP + k] = (sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k]) * evk + ((sx1[0][k] + sx1[1][k]) + (sx1[2][k] + sx1[3][k]));
+            if (WITH_B2) a.B2[(int64_t)j * KP + k] = (sh2[0][k] + sh2[1][k] + sh2[2][k] + sh2[3][k]) * evk + ((sx2[0][k] + sx2[1][k]) + (sx2[2][k] + sx2[3][k]));
         }
         if (WITH_LOGT && threadIdx.x == 0) a.xlogT[j] = shl[0] + shl[1] + shl[2] + shl[3];
         __syncthreads();
