@@ -222,6 +222,9 @@ struct pcmf_solver {
     double *old0[4] = {nullptr, nullptr, nullptr, nullptr};   // multi-init: previous run's last a1, a2, b1, b2
     int first_mode = 1;                 // value of first_iter for the first iteration (1: old = Ones, 2: old = old0)
     std::mt19937 rng;                   // one stream for all random initialisations (wrapper_gap_factor.h:277-284)
+    // raw draws of the first random initialisation, produced by a host thread while the GPU preprocesses X
+    struct DrawAhead { std::thread th; std::vector<uint32_t> u, v; unsigned long long start = 0; bool used = true; } ahead;
+    void start_draw_ahead(const pcmf_init *in, int64_t n_rows, int64_t n_glob, int64_t row_off, int32_t genes);
     unsigned long long rng_consumed = 0;
 
     // U side (n x KP)
@@ -304,6 +307,7 @@ struct pcmf_solver {
 };
 
 pcmf_solver::~pcmf_solver() {
+    if (ahead.th.joinable()) ahead.th.join();
     cudaSetDevice(device);
     if (own_csr) { dfree((void *)rowptr); dfree((void *)colidx); dfree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
@@ -742,6 +746,31 @@ void pcmf_solver::download_colmajor(const double *src, int64_t rows, double *hos
     dfree(tmp);
 }
 
+// The seeded random initialisation walks ONE MT19937 stream over (n_global + p) K draws on the host (~0.1 s at C4).  Nothing
+// it needs depends on the GPU, so the walk starts on a host thread as soon as the arguments are known and is collected
+// by init_state after the preprocessing of X; `start` is the stream position the draws assume (checked there).
+void pcmf_solver::start_draw_ahead(const pcmf_init *in, int64_t n_rows, int64_t n_glob, int64_t row_off, int32_t genes) {
+    static const pcmf_init none{};
+    if (!in) in = &none;
+    const bool random_ab = !in->U && !in->a1;
+    if (!random_ab) return;
+    const bool random_S = sparse && !(in->prob_S && in->prior_S);
+    ahead.start = random_S ? (unsigned long long)genes * K : 0ull;     // init_sparse_param draws p K uniforms first
+    ahead.used = false;
+    const std::mt19937 g0 = rng;
+    const int Kc = K;
+    const unsigned long long start = ahead.start;
+    ahead.th = std::thread([this, g0, Kc, start, n_rows, n_glob, row_off, genes] {
+        std::mt19937 g = g0;
+        g.discard(start + (unsigned long long)row_off * Kc);
+        ahead.u.resize((size_t)n_rows * Kc);
+        for (size_t e = 0; e < ahead.u.size(); ++e) ahead.u[e] = (uint32_t)g();
+        g.discard((unsigned long long)(n_glob - row_off - n_rows) * Kc);
+        ahead.v.resize((size_t)genes * Kc);
+        for (size_t e = 0; e < ahead.v.size(); ++e) ahead.v[e] = (uint32_t)g();
+    });
+}
+
 void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
     const pcmf_init none{};
     if (!in) in = &none;
@@ -815,19 +844,30 @@ void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
         // b1(j,.) ~ Gamma(1, rate sqrt(K / colmean_j)); one MT19937 stream, cells first (in global order) then genes.
         // The raw 32-bit draws come off the single host stream in order; the inversion -log(u) / rate runs on the device,
         // straight into the padded row-major layout (row / column sums of X are already there).
-        auto draw = [&](std::mt19937 g, int64_t rows, const double *sums, double denom, double *dst) {
-            std::vector<uint32_t> raw((size_t)rows * K);
-            for (size_t e = 0; e < raw.size(); ++e) raw[e] = (uint32_t)g();
+        auto invert = [&](const std::vector<uint32_t> &raw, int64_t rows, const double *sums, double denom, double *dst) {
             uint32_t *d_raw = dmalloc<uint32_t>(raw.size());
             CK(cudaMemcpyAsync(d_raw, raw.data(), raw.size() * 4, cudaMemcpyHostToDevice, stream));
             k_init_gamma_rows<<<grid_for(rows * KP, 256), 256, 0, stream>>>(rows, K, KP, d_raw, sums, denom, dst);
             CK(cudaStreamSynchronize(stream));
             dfree(d_raw);
         };
-        std::mt19937 gu = base; gu.discard((unsigned long long)row_offset * K);
-        draw(gu, n, rowsumX, (double)p, a1);
-        std::mt19937 gv = base; gv.discard((unsigned long long)n_global * K);
-        draw(gv, p, colsumX, (double)n_global, b1);
+        if (ahead.th.joinable()) ahead.th.join();
+        if (!ahead.used && ahead.start == rng_consumed) {
+            // the draws were produced while the GPU was busy with the preprocessing of X (pcmf_create)
+            invert(ahead.u, n, rowsumX, (double)p, a1);
+            invert(ahead.v, p, colsumX, (double)n_global, b1);
+        } else {
+            auto draw = [&](std::mt19937 g, int64_t rows, const double *sums, double denom, double *dst) {
+                std::vector<uint32_t> raw((size_t)rows * K);
+                for (size_t e = 0; e < raw.size(); ++e) raw[e] = (uint32_t)g();
+                invert(raw, rows, sums, denom, dst);
+            };
+            std::mt19937 gu = base; gu.discard((unsigned long long)row_offset * K);
+            draw(gu, n, rowsumX, (double)p, a1);
+            std::mt19937 gv = base; gv.discard((unsigned long long)n_global * K);
+            draw(gv, p, colsumX, (double)n_global, b1);
+        }
+        ahead.used = true; ahead.u = std::vector<uint32_t>(); ahead.v = std::vector<uint32_t>();
         rng_consumed += (unsigned long long)(n_global + p) * K;
         k_fill<<<grid_for(n * KP, 256), 256, 0, stream>>>(a2, n * KP, 1.0);
         k_fill<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(b2, (int64_t)p * KP, 1.0);
@@ -1353,12 +1393,14 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
         s->L = get_launchers(s->KP);
         if (!s->L) fail(PCMF_EUNSUPPORTED, "no kernels compiled for padded K = %d", s->KP);
         StageTimer tm(s->stream);
+        s->rng.seed(s->opt.has_seed ? s->opt.seed : (uint32_t)std::chrono::system_clock::now().time_since_epoch().count());
+        if (prob && prob->n_local > 0 && prob->p > 0)
+            s->start_draw_ahead(init, prob->n_local, prob->n_global > 0 ? prob->n_global : prob->n_local, prob->row_offset, prob->p);
         s->setup_problem(*prob);
         tm.mark("setup_problem (total)");
         s->alloc_state();
         tm.mark("alloc_state");
         if (init) s->init_copy = *init;
-        s->rng.seed(s->opt.has_seed ? s->opt.seed : (uint32_t)std::chrono::system_clock::now().time_since_epoch().count());
         s->init_state(init);
         tm.mark("init_state");
     });
