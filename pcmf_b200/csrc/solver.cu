@@ -76,6 +76,7 @@ struct BlockCache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void *> free_blocks;     // (device, bytes) -> pointer
     std::unordered_map<void *, std::pair<int, size_t>> live;        // pointer -> (device, bytes)
+    double miss_seconds = 0; size_t misses = 0, miss_bytes = 0;     // cudaMalloc calls that the cache could not serve (PCMF_TIMING)
     void *get(size_t bytes) {
         int dev = 0;
         CK(cudaGetDevice(&dev));
@@ -90,7 +91,11 @@ struct BlockCache {
             }
         }
         void *p = nullptr;
+        const double t0 = now_s();
         cudaError_t e = cudaMalloc(&p, bytes);
+        miss_seconds += now_s() - t0; ++misses; miss_bytes += bytes;
+        if (now_s() - t0 > 5e-3 && getenv("PCMF_TIMING"))
+            fprintf(stderr, "[pcmf timing] cudaMalloc of %.1f MB took %.1f ms (%zu cached blocks)\n", bytes / 1e6, (now_s() - t0) * 1e3, free_blocks.size());
         if (e != cudaSuccess) {           // out of memory: give the cached blocks back and try once more
             cudaGetLastError();
             release_all();
@@ -366,13 +371,12 @@ __global__ void k_expand_rows(int64_t n, const int64_t *rowptr, int32_t *rowids,
     for (int64_t i = warp; i < n; i += nw)
         for (int64_t e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) { rowids[e] = (int32_t)i; perm[e] = e; }
 }
+__global__ void k_gather_rowidx(int64_t nnz, const int64_t *perm, const int32_t *rowids, int32_t *rowidx) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (int64_t)gridDim.x * blockDim.x) rowidx[t] = rowids[perm[t]];
+}
 template <typename VT>
-__global__ void k_gather_csc(int64_t nnz, const int64_t *perm, const int32_t *rowids, const VT *val, int32_t *rowidx, VT *val_csc) {
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = perm[t];
-        rowidx[t] = rowids[e];
-        val_csc[t] = val[e];
-    }
+__global__ void k_gather_vals(int64_t nnz, const int64_t *perm, const VT *val, VT *val_csc) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (int64_t)gridDim.x * blockDim.x) val_csc[t] = val[perm[t]];
 }
 // dgCMatrix input: sort keys (cell index; explicit zeros get the key n and fall off the end), gene index per entry
 __global__ void k_csc_keys(int32_t p, int64_t n, const int32_t *colptr, const int32_t *rowidx, const double *x, int32_t *keys,
@@ -624,51 +628,46 @@ void pcmf_solver::build_csc() {
     colptr = dmalloc<int64_t>(p + 1);
     rowidx = dmalloc<int32_t>(nnz);
     tm.mark("csc: rowidx allocation");
-    if (ev_vals) {                      // the values of a host CSR were uploaded on their own stream
-        CK(cudaStreamWaitEvent(stream, ev_vals, 0));
-        CK(cudaStreamSynchronize(copy_stream));
-        cudaEventDestroy(ev_vals); cudaStreamDestroy(copy_stream);
-        ev_vals = nullptr; copy_stream = nullptr;
-        tm.mark("csc: wait for the value upload");
-    }
+    // everything that only needs the STRUCTURE first -- it runs under the upload of the values (second stream)
     k_colptr_from_sorted<<<grid_for(p + 1, 256), 256, 0, stream>>>(nnz, p, keys_out, colptr);
-    if (f32) {
-        val_csc = dmalloc<float>(nnz);
-        k_gather_csc<float><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, (const float *)val_csr, rowidx, (float *)val_csc);
-    } else {
-        val_csc = dmalloc<double>(nnz);
-        k_gather_csc<double><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, (const double *)val_csr, rowidx, (double *)val_csc);
-    }
-    tm.mark("csc: value gather (+ alloc)");
+    k_gather_rowidx<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, rowidx);
     // ZI / sparse models: the gene passes leave q_ij in CSC order and the cell pass reads it back through this map
     if ((zi || sparse) && nnz < 0xffffffffLL && !(opt.kernel_variant & 16)) {
         csr2csc = dmalloc<uint32_t>(nnz);
         k_invert_perm<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, csr2csc);
         qcsc = dmalloc<double>(nnz);
     }
-    CK(cudaStreamSynchronize(stream));
-    CK(cudaGetLastError());
-    tm.mark("csc: position map + q allocation");
-    dfree(scratch);
-
-    tm.mark("csc: gather + maps + frees");
-    Lg = dmalloc<double>(p); colsumX = dmalloc<double>(p); colnnz = dmalloc<double>(p); rowsumX = dmalloc<double>(n);
-    xlogx = dmalloc<double>(p);
-    if (f32) {
-        k_gene_constants<float><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz, xlogx);
-        k_row_sums<float><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
-    } else {
-        k_gene_constants<double><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz, xlogx);
-        k_row_sums<double><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
-    }
-    tm.mark("gene/cell constants");
     if (zi) {
         const size_t wT = (size_t)((p + 31) / 32) * n, wB = (size_t)((n + 31) / 32) * p;
         bitT = dmalloc<uint32_t>(wT); bitB = dmalloc<uint32_t>(wB);
         CK(cudaMemsetAsync(bitT, 0, wT * 4, stream)); CK(cudaMemsetAsync(bitB, 0, wB * 4, stream));
         k_build_bitmaps<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, p, rowptr, colidx, bitT, bitB);
     }
-    tm.mark("occupancy bitmaps");
+    Lg = dmalloc<double>(p); colsumX = dmalloc<double>(p); colnnz = dmalloc<double>(p); rowsumX = dmalloc<double>(n);
+    xlogx = dmalloc<double>(p);
+    val_csc = f32 ? (void *)dmalloc<float>(nnz) : (void *)dmalloc<double>(nnz);
+    if (ev_vals) {                      // the values of a host CSR were uploaded on their own stream
+        CK(cudaStreamSynchronize(stream));
+        tm.mark("csc: rowidx, position map, occupancy bitmaps");
+        CK(cudaStreamWaitEvent(stream, ev_vals, 0));
+        CK(cudaStreamSynchronize(copy_stream));
+        cudaEventDestroy(ev_vals); cudaStreamDestroy(copy_stream);
+        ev_vals = nullptr; copy_stream = nullptr;
+        tm.mark("csc: wait for the value upload");
+    }
+    if (f32) {
+        k_gather_vals<float><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, (const float *)val_csr, (float *)val_csc);
+        k_gene_constants<float><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz, xlogx);
+        k_row_sums<float><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
+    } else {
+        k_gather_vals<double><<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, (const double *)val_csr, (double *)val_csc);
+        k_gene_constants<double><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, val_csc, Lg, colsumX, colnnz, xlogx);
+        k_row_sums<double><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, val_csr, rowsumX);
+    }
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    dfree(scratch);
+    tm.mark("csc: value gather, gene / cell constants");
     // gene constants are sums over cells -> all-reduce across the row shards
     allreduce(Lg, p); allreduce(colsumX, p); allreduce(colnnz, p); allreduce(xlogx, p);
     std::vector<double> h(p), hx(p), hs(p);
@@ -1403,6 +1402,9 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
         if (init) s->init_copy = *init;
         s->init_state(init);
         tm.mark("init_state");
+        if (getenv("PCMF_TIMING"))
+            fprintf(stderr, "[pcmf timing] device allocations not served by the block cache so far: %zu (%.1f MB, %.1f ms in cudaMalloc)\n",
+                    block_cache().misses, block_cache().miss_bytes / 1e6, block_cache().miss_seconds * 1e3);
     });
     if (rc != PCMF_OK) { delete s; s = nullptr; }
     if (out) *out = s;
