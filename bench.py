@@ -309,6 +309,8 @@ def main():
 
     # ---- roofline of the E-step kernels, from the per-phase CUDA-event times taken inside the timed region
     hbm_peak, peak_src = measured_peaks()
+    stored_prob_D_bytes = int(ph1.pop("stored_prob_D_bytes", (0.0, 0))[1])
+    ph0.pop("stored_prob_D_bytes", None)
     per = {k: ((ph1[k][0] - ph0[k][0]) / max(1, args.steps), (ph1[k][1] - ph0[k][1]) // max(1, args.steps)) for k in ph1}
     w = 8
     zi, sparse = cfg["zi"], cfg["sparse"]
@@ -345,14 +347,23 @@ def main():
     dmma_peak = api.measure_fp64_mma_tflops(local)
     if zi:
         # dense ZI passes: 2 contractions of length K per entry (4K flop) + expit, on the FP64 tensor pipe (DMMA)
+        # When it fits in HBM the cell pass keeps prob_D (4 bytes per entry) and the gene pass streams it back: that pass is
+        # then the second contraction only (2K flop per entry) over n p 4 bytes of HBM reads.
+        stored_bytes = stored_prob_D_bytes
         for name in ("zi_pass_cells", "zi_pass_genes"):
             t = per[name][0]
-            fl = 4.0 * K * nl * p
-            kernels.append({"kernel": name, "ms": t, "share": t * args.steps / ms, "bound": "tensor", "algorithmic_flops": fl,
-                            "achieved": fl / (t * 1e-3) / 1e12 if t > 0 else None, "peak": dmma_peak, "unit": "TFLOP/s",
-                            "frac": (fl / (t * 1e-3) / 1e12 / dmma_peak) if t > 0 else None, "traffic": traffic.get(name),
-                            "peak_source": "FP64 DMMA m8n8k4 microbenchmark run by this bench (MEASURED_PEAKS.json holds no FP64 "
-                                           "figure; FP64 has no tcgen05 kind)"})
+            stored = stored_bytes > 0 and name == "zi_pass_genes"
+            fl = (2.0 if stored else 4.0) * K * nl * p
+            row = {"kernel": name, "ms": t, "share": t * args.steps / ms, "bound": "tensor", "algorithmic_flops": fl,
+                   "achieved": fl / (t * 1e-3) / 1e12 if t > 0 else None, "peak": dmma_peak, "unit": "TFLOP/s",
+                   "frac": (fl / (t * 1e-3) / 1e12 / dmma_peak) if t > 0 else None, "traffic": traffic.get(name),
+                   "peak_source": "FP64 DMMA m8n8k4 microbenchmark run by this bench (MEASURED_PEAKS.json holds no FP64 "
+                                  "figure; FP64 has no tcgen05 kind)"}
+            if stored_bytes > 0:
+                row["stored_prob_D_bytes"] = stored_bytes
+                row["hbm_stream_gbs"] = stored_bytes / (t * 1e-3) / 1e9 if t > 0 else None   # written by the cell pass, read by the gene pass
+                row["hbm_peak"] = hbm_peak
+            kernels.append(row)
     dom = max(kernels, key=lambda k: k["ms"])
     roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
                 "traffic": dom.get("traffic"), "kernel": dom["kernel"], "ms_per_launch": dom["ms"],

@@ -831,6 +831,8 @@ struct ZiAArgs {
     double *colsumP;             // p (atomic): colsum(prob_D) -> prior_D (zi...cpp:370-372)
     double *zsc;                 // 2 doubles (atomic): sum prob_D o UVt, sum P log P + (1-P) log(1-P)   (all-reduced later)
     double *pack;                // scratch: fragment-ordered gene records for the DMMA kernel (zi_mma.cuh)
+    uint32_t *pstore;            // or null: prob_D kept for the next iteration's gene pass, 32-bit fixed point in 8 x 8 tiles
+                                 //   [ceil(n/8)][ceil(p/8)][gene in tile][cell in tile]  (zi_mma.cuh, k_zi_genes_stored)
 };
 // Pass A: one thread per cell, genes streamed through shared memory in tiles of TJ, two genes per step.
 // Per (cell, gene): lambda = EU_i . EVS_j (K DFMA), P = expit(c_j - lambda) (fast_exp + fast_rcp, ~22 FP64 ops),
@@ -938,6 +940,7 @@ struct ZiBArgs {
     const uint32_t *bitB;        // [ceil(n/32)][p]: bit r of word (ib, j) <-> X(32 ib + r, j) != 0
     double *tmpMat;              // p x KP (atomic): prob_D^T EU_new (zi...cpp:341, zi_sparse...:369)
     double *pack;                // scratch: fragment-ordered cell records for the DMMA kernel (zi_mma.cuh)
+    const uint32_t *pstore;      // or null: prob_D as the last cell pass stored it (ZiAArgs::pstore) -> no recomputation
 };
 // Pass B: one thread per TWO genes (j and j + 128), cells streamed through shared memory in tiles of TI (multiple
 // of 32); every broadcast shared-memory load of a cell's EU feeds four DFMAs.

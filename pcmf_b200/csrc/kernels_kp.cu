@@ -51,7 +51,8 @@ int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
     const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 8 * MMA_TJ + 64);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
     const int64_t groups = (a.p + 7) / 8;
@@ -63,11 +64,28 @@ int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
     if (gx >= 148 * 3 * 8) gy = 1;
     if (gy > 1) cudaMemsetAsync(a.PV, 0, sizeof(double) * (size_t)a.n * KP, st);
     dim3 grid((unsigned)gx, (unsigned)gy);
-    k_zi_cells_mma<KP, MT, MMA_TJ><<<grid, 128, smem, st>>>(a);
+    if (a.pstore) k_zi_cells_mma<KP, MT, MMA_TJ, true><<<grid, 128, smem, st>>>(a);
+    else k_zi_cells_mma<KP, MT, MMA_TJ, false><<<grid, 128, smem, st>>>(a);
+    return 2;
+}
+template <int MT>
+int launch_zi_genes_stored_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
+    using R = ZiRecF2<KP>;
+    const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * R::REC);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_genes_stored<KP, MT, MMA_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    const int64_t groups = (a.n + 7) / 8;
+    k_zi_pack_f2<KP><<<pack_grid(groups * R::REC), 256, 0, st>>>(a.n, a.EUn, a.pack);
+    dim3 grid((a.p + 32 * MT - 1) / (32 * MT), chunks);
+    k_zi_genes_stored<KP, MT, MMA_TI><<<grid, 128, smem, st>>>(a);
     return 2;
 }
 template <int MT>
 int launch_zi_genes_mma_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
+    if (a.pstore) return launch_zi_genes_stored_t<MT>(a, chunks, st);
     using R = ZiRec<KP, false>;
     const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * R::REC + 64);
     static bool attr = false;

@@ -105,6 +105,13 @@ struct BlockCache {
         live[p] = {dev, bytes};
         return p;
     }
+    bool has_block(size_t bytes) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = free_blocks.lower_bound({dev, bytes});
+        return it != free_blocks.end() && it->first.first == dev && it->first.second <= bytes + bytes / 4 + 4096;
+    }
     void put(void *p) {
         if (!p) return;
         cudaDeviceSynchronize();          // like cudaFree: the block is idle on every stream before anyone can reuse it
@@ -196,6 +203,9 @@ struct pcmf_solver {
     bool zi = false, sparse = false, f32 = true;
     int device = 0;
     cudaStream_t stream = nullptr;
+    // prob_D of the last cell pass, 32-bit fixed point in 8 x 8 tiles (zi_mma.cuh): the next gene pass streams it back
+    // instead of recomputing it.  Only when it fits beside everything else; dropped by anything that redefines prob_D.
+    uint32_t *pstore = nullptr; bool pstore_valid = false;
     bool zi_at_init = false;            // prob_D still is (X > 0) and the packed records of pass A do not exist yet
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_vals = nullptr;   // value upload of a host CSR, overlapped with the CSC sort
     bool own_stream = false;
@@ -317,7 +327,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { dfree((void *)rowptr); dfree((void *)colidx); dfree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3]};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3], pstore};
     for (void *q : ptrs) if (q) dfree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -725,6 +735,19 @@ void pcmf_solver::alloc_state() {
     mon = dmalloc<double>(8 + 64 + 64); d_order = dmalloc<int32_t>(64);
     dbg = dmalloc<unsigned long long>(4); CK(cudaMemsetAsync(dbg, 0, 32, stream));
     k_init_guard<<<1, 32, 0, stream>>>(guard[0]); k_init_guard<<<1, 32, 0, stream>>>(guard[1]);
+    // kernel_variant bit 64 forces the stored-prob_D path (small test problems), bit 128 disables it
+    if (zi && !(opt.kernel_variant & (4 | 128)) && ((double)n * (double)p >= 5e7 || (opt.kernel_variant & 64)) &&
+        (double)((n + 127) / 128 * 16) * (double)((p + 7) / 8) < 4.0e9) {
+        // cell groups padded to whole CTAs of the cell pass (128 cells): it stores every tile it computes
+        const size_t need = (size_t)((n + 127) / 128 * 16) * (size_t)((p + 7) / 8) * 64 * sizeof(uint32_t);
+        bool fits = block_cache().has_block(need);
+        if (!fits) {
+            size_t fr = 0, tot = 0;
+            CK(cudaMemGetInfo(&fr, &tot));
+            fits = fr > need + ((size_t)6 << 30);
+        }
+        if (fits) pstore = dmalloc<uint32_t>(need / sizeof(uint32_t));
+    }
     CK(cudaMallocHost(&h_scal, sizeof(double) * S_COUNT));
     for (int i = 0; i < PH_COUNT; ++i) { CK(cudaEventCreate(&ev_a[i])); CK(cudaEventCreate(&ev_b[i])); }
     factor_order.resize(K);
@@ -876,6 +899,7 @@ void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
 
 // U_stats, V_stats, update_poisson_param, update_hyper_param after any initialisation (gap_factor_model.cpp:119-122)
 void pcmf_solver::run_init_stats() {
+    pstore_valid = false;             // prob_D is redefined by the initialisation
     const size_t pK = (size_t)p * KP;
     double *alpha1 = hyp, *alpha2 = hyp + 64, *beta1 = hyp + 128, *beta2 = hyp + 192;
     CK(cudaMemsetAsync(scal, 0, S_COUNT * 8, stream));
@@ -924,7 +948,7 @@ void pcmf_solver::run_init_stats() {
         ZiPrepArgs zp{p, 1, prior_D, Lg, cz, colw, flag, scal};
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
         if (opt.kernel_variant & 32) {                 // the dense pass with c_j = -inf (kept to cross-check the shortcut below)
-            ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
+            ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA, nullptr};
             launches += 1 + L->zi_cells(za, opt.kernel_variant, stream);
         } else {
             k_zi_init_cells<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, KP, rowptr, colidx, EU[cur], EVS, PV, ar3 + ar3_zsc);
@@ -992,7 +1016,7 @@ void pcmf_solver::step(bool want_data) {
         begin(PH_ZI_B);
         ZiBArgs zb{};
         zb.n = n; zb.p = p; zb.K = K; zb.EUz = EU[cur]; zb.EUn = EU[nxt]; zb.EVSz = EVS; zb.cz = cz; zb.flag = flag; zb.bitB = bitB;
-        zb.tmpMat = ar1 + ar1_tmp; zb.pack = zpackB;
+        zb.tmpMat = ar1 + ar1_tmp; zb.pack = zpackB; zb.pstore = pstore_valid ? pstore : nullptr;
         const int gb = L->zi_genes_block(opt.kernel_variant);
         const int gx = (p + gb - 1) / gb;
         // enough (gene block, cell chunk) CTAs for >= 16 full waves at 2 resident CTAs per SM: a 2.1-wave grid measured 29% slower
@@ -1050,9 +1074,10 @@ void pcmf_solver::step(bool want_data) {
         ZiPrepArgs zp{p, 0, prior_D, Lg, cz, colw, flag, scal};
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
         k_refresh_weights<<<grid_for(pK, 256), 256, 0, stream>>>(p, K, KP, sparse, prob_S, colw, ev, wS, evw);
-        ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
+        ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA, pstore};
         const int nl = L->zi_cells(za, opt.kernel_variant, stream);
         zi_at_init = false;
+        pstore_valid = pstore != nullptr;
         allreduce(ar3, ar3_total);
         end(PH_ZI_A, 2 + nl);
     }
@@ -1131,7 +1156,7 @@ pcmf_solver::Mon pcmf_solver::monitors_now(bool want_loglik) {
         k_gamma_loglike<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, EV, b1, b2, mon + 6);
         launches += 2;
         if (zi && !zi_at_init) {                       // at the initial state prob_D = (X > 0): the zero part is log(1) = 0
-            ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA};
+            ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA, nullptr};
             L->zi_loglik(za, mon + 5, stream);
             launches += 1;
         }
@@ -1265,6 +1290,7 @@ void pcmf_solver::restore_state(const Saved &sv) {
     cur = sv.cur; gcur = sv.gcur; first_iter = sv.first_iter; sparse_sums_valid = sv.sparse_sums_valid; have_pending = sv.have_pending;
     last_nodata = sv.last_nodata; std::copy(sv.h.begin(), sv.h.end(), h_scal); iter = sv.iter; first_mode = sv.first_mode;
     sparse_sums_valid = false;   // the stored q of the non-zeros belong to the last run, not to the restored one
+    pstore_valid = false;        // and so does the stored prob_D
     CK(cudaStreamSynchronize(stream));
 }
 
@@ -1614,6 +1640,13 @@ int pcmf_phase_times(pcmf_solver *s, const char **names, double *ms, int64_t *la
         if (names) names[c] = dn[i];
         if (ms) ms[c] = 0.0;
         if (launches) launches[c] = (int64_t)h[i];
+        ++c;
+    }
+    // bytes of prob_D kept between the cell pass and the next gene pass (0: the gene pass recomputes it)
+    if (c < cap) {
+        if (names) names[c] = "stored_prob_D_bytes";
+        if (ms) ms[c] = 0.0;
+        if (launches) launches[c] = s->pstore ? (int64_t)((s->n + 127) / 128 * 16) * (int64_t)((s->p + 7) / 8) * 256 : 0;
         ++c;
     }
     return c;

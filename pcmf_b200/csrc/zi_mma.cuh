@@ -160,7 +160,10 @@ __global__ void k_zi_pack(int64_t rows, const double *__restrict__ M1, const dou
 // Pass A: rows = cells (8 MT per warp, fixed for the CTA), columns = genes streamed through shared memory.
 // Outputs PV = prob_D . EVS (n x KP), colsum(prob_D), sum prob_D o UVt and the Bernoulli self term.
 // ------------------------------------------------------------------------------------------------------------
-template <int KP, int MT, int TJ>
+// prob_D in 32-bit fixed point: q = rint(P (2^32 - 1)), so that 0 and 1 -- the values of every non-zero entry and of every
+// clamped one -- are exact and the others carry an absolute error of 1.2e-10.
+#define PCMF_PSTORE_SCALE 4294967295.0
+template <int KP, int MT, int TJ, bool STORE_P>
 __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_cells_mma(ZiAArgs a) {
     const double *__restrict__ pack = a.pack;
     using R = ZiRec<KP, true>;
@@ -193,6 +196,11 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     double dinit[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) dinit[mt] = live[mt] ? 0.0 : 1e305;
+    // stored prob_D: this lane's two words inside a tile, and the tile index of (cell group of mt = 0, gene group 0)
+    // (tile index = cell group x gene groups + gene group, kept in 32 bits: the host stores prob_D only below 2^32 tiles)
+    const unsigned st_ngg = (unsigned)((a.p + 7) >> 3);
+    const unsigned st_tile0 = (unsigned)(cell0 >> 3) * st_ngg;
+    uint32_t *const st_lane = STORE_P ? a.pstore + (2 * q) * 8 + g : nullptr;
     double acc[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -257,6 +265,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             const double2 c2 = *reinterpret_cast<const double2 *>(rec + R::F1 + R::F2 + 2 * q);
             const double2 n2 = *reinterpret_cast<const double2 *>(rec + R::F1 + R::F2 + 8 + 2 * q);
             const int sh0 = ((grp & 3) << 3) + 2 * q;
+            const unsigned st_tile = st_tile0 + (unsigned)(jg >> 3);
             double cs0 = 0.0, cs1 = 0.0;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -272,6 +281,14 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
                 prod *= (g0 ? y0 : 1.0) * (g1 ? y1 : 1.0);
                 cs0 += p0; cs1 += p1;
                 d[mt][0] = p0; d[mt][1] = p1;
+                if (STORE_P) {   // (the store is padded to whole CTAs of cells: no test on rows beyond n)
+                    // tile (cell group, gene group), element [gene 2q + s][cell g]: the accumulator layout of the gene pass
+                    uint32_t *tp = st_lane + ((size_t)(st_tile + (unsigned)mt * st_ngg) << 6);
+                    // rint(P (2^32 - 1)) read off the low mantissa word of 2^52 + P (2^32 - 1): one FMA per value (an F2I from
+                    // FP64 cost ~20 issue cycles per entry here)
+                    tp[0] = (uint32_t)__double2loint(fma(p0, PCMF_PSTORE_SCALE, 4503599627370496.0));
+                    tp[8] = (uint32_t)__double2loint(fma(p1, PCMF_PSTORE_SCALE, 4503599627370496.0));
+                }
             }
             if (prod > 1e100) { ent_log += log(prod); prod = 1.0; }     // (1 + e^30)^(2 MT) < 1e105 per group
 #pragma unroll
@@ -520,6 +537,124 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             for (int e = 0; e < 2; ++e) {
                 const int k = nt * 8 + 2 * q + e;
                 if (k < a.K) atomicAdd(a.tmpMat + (int64_t)j * KP + k, acc[mt][nt][e]);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Pass B on the STORED prob_D.  The cell pass of the previous iteration evaluated exactly the prob_D this pass needs
+// (same triple); with 180 GB of HBM it can be kept -- 4 bytes per entry, 80 GB at 1M x 20k -- and streamed back here, which
+// leaves this pass with the second product only: no first product, no expit, no occupancy words.
+// A tile is 64 words [gene in tile][cell in tile], i.e. lane (g, q) reads its accumulator pair d0, d1 = P[gene g][cells 2q, 2q+1]
+// as one 8-byte word; the 16 gene groups of a CTA are contiguous (4 KB per cell group).
+// ------------------------------------------------------------------------------------------------------------
+template <int KP>
+struct ZiRecF2 {
+    static constexpr int NT = (KP + 7) / 8, REC = 2 * NT * 32;
+};
+template <int KP>
+__global__ void k_zi_pack_f2(int64_t rows, const double *__restrict__ M2, double *__restrict__ out) {
+    using R = ZiRecF2<KP>;
+    const int64_t ngroups = (rows + 7) >> 3, total = ngroups * R::REC;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t grp = idx / R::REC;
+        const int o2 = (int)(idx - grp * R::REC), lane = o2 & 31, g = lane >> 2, q = lane & 3;
+        const int t = o2 >> 5, sp = t / R::NT, nt = t - sp * R::NT;
+        const int64_t row = grp * 8 + 2 * q + sp;
+        const int k = 8 * nt + g;
+        out[idx] = (row < rows && k < KP) ? M2[row * KP + k] : 0.0;
+    }
+}
+template <int KP, int MT, int TI>
+__global__ void __launch_bounds__(128, 4) k_zi_genes_stored(ZiBArgs a) {
+    const double *__restrict__ pack = a.pack;
+    using R = ZiRecF2<KP>;
+    constexpr int NT = R::NT, NG = TI / 8, BUF = NG * R::REC;
+    static_assert(NG % 2 == 0, "the group loop is unrolled by two");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_buf = reinterpret_cast<double *>(smem_raw);       // 2 x NG records of EU_new second-product fragments
+    __shared__ uint64_t bar[2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    const int gene0 = blockIdx.x * (32 * MT) + w * (8 * MT);
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_chunk;        // multiple of 64
+    const int64_t r1 = min(a.n, r0 + a.rows_per_chunk);
+    const int64_t grp0 = r0 >> 3, grp1 = (r1 + 7) >> 3;
+    const int ntiles = (int)((grp1 - grp0 + NG - 1) / NG);
+    const int64_t ngg = (a.p + 7) >> 3;
+    const uint32_t *__restrict__ pbase = a.pstore + ((int64_t)(gene0 >> 3) << 6) + 2 * lane;
+    bool have[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) have[mt] = gene0 + mt * 8 < a.p;
+    auto fetch = [&](int64_t cg, uint2 (&dst)[MT]) {       // the MT tiles of cell group cg (zeros beyond the chunk)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            dst[mt] = make_uint2(0u, 0u);
+            if (have[mt] && cg < grp1) dst[mt] = __ldg(reinterpret_cast<const uint2 *>(pbase + ((cg * ngg + mt) << 6)));
+        }
+    };
+    auto issue = [&](int tile) {
+        const int64_t g0 = grp0 + (int64_t)tile * NG;
+        const int gn = (int)min((int64_t)NG, grp1 - g0);
+        const unsigned bytes = (unsigned)(gn * R::REC * sizeof(double));
+        mbar_expect_tx(&bar[tile & 1], bytes);
+        bulk_g2s(s_buf + (tile & 1) * BUF, pack + g0 * R::REC, bytes, &bar[tile & 1]);
+    };
+    auto second_product = [&](const uint2 (&pq)[MT], const double *rec) {
+        double d[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) { d[mt][0] = __uint2double_rn(pq[mt].x); d[mt][1] = __uint2double_rn(pq[mt].y); }
+#pragma unroll
+        for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double b = rec[(sp * NT + nt) * 32 + lane];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], d[mt][sp], b);
+            }
+    };
+    uint2 pa[MT], pb[MT];                                   // two cell groups in flight ahead of the one being multiplied
+    fetch(grp0, pa);
+    fetch(grp0 + 1, pb);
+    if (threadIdx.x == 0 && ntiles > 0) issue(0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int64_t cg0 = grp0 + (int64_t)tile * NG;
+        const double *buf = s_buf + (tile & 1) * BUF;
+        if (threadIdx.x == 0 && tile + 1 < ntiles) issue(tile + 1);
+        mbar_wait(&bar[tile & 1], (tile >> 1) & 1);
+#pragma unroll 1
+        for (int grp = 0; grp < NG; grp += 2) {
+            const int64_t cg = cg0 + grp;
+            if (cg >= grp1) break;
+            uint2 cur[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) cur[mt] = pa[mt];
+            fetch(cg + 2, pa);
+            second_product(cur, buf + grp * R::REC);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) cur[mt] = pb[mt];
+            fetch(cg + 3, pb);
+            if (cg + 1 < grp1) second_product(cur, buf + (grp + 1) * R::REC);
+        }
+        __syncthreads();   // every warp is done with this buffer before it is refilled
+    }
+    const double inv = 1.0 / PCMF_PSTORE_SCALE;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int j = gene0 + mt * 8 + g;
+        if (j >= a.p) continue;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = nt * 8 + 2 * q + e;
+                if (k < a.K) atomicAdd(a.tmpMat + (int64_t)j * KP + k, acc[mt][nt][e] * inv);
             }
     }
 }

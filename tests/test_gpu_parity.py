@@ -327,3 +327,31 @@ def test_random_shapes_match_oracle(c, n, p, K, zi, sparse, dens):
         assert abs(s.elbo() - m.elbo()) < RTOL * max(1.0, abs(m.elbo()))
         m.prepare_next_iterate()
     s.close()
+
+
+@pytest.mark.parametrize("sparse", [False, True], ids=["zi", "zi_sparse"])
+@pytest.mark.parametrize("n,p,K", [(300, 190, 3), (65, 33, 20), (129, 95, 12), (2500, 40, 4), (70, 130, 64), (9, 5, 2), (200, 1100, 5)])
+def test_stored_prob_D_path_matches_oracle(sparse, n, p, K):
+    """The gene-side ZI pass on the prob_D that the previous cell pass stored (32-bit fixed point, 8 x 8 tiles) instead of
+    recomputing it -- the default from 5e7 entries on, forced here with kernel_variant bit 64.  Same oracle comparison as
+    the recomputing path at the same tolerance (stored values carry an absolute error of 1.2e-10), and the two paths agree
+    with each other to 1e-9; (2500, 40) splits the cells of a gene block over several CTAs, (200, 1100) the genes of a cell
+    block."""
+    rng = np.random.default_rng(7 + n + p)
+    X = rng.poisson(2.5, (n, p)).astype(float) * (rng.uniform(size=(n, p)) < 0.45)
+    X[X.sum(1) == 0, rng.integers(p)] = 1
+    X[rng.integers(n), X.sum(0) == 0] = 1
+    m, s = make_pair(X, K, True, sparse, kernel_variant=64)
+    _, s0 = make_pair(X, K, True, sparse, kernel_variant=128)
+    for it in range(5):
+        m.update_param()
+        s.iterate(1)
+        s0.iterate(1)
+        compare_state(m, s, True, sparse, "stored prob_D, iter %d" % it)
+        o, o0 = s.get_output(), s0.get_output()
+        for k in ("a1", "a2", "b1", "b2"):
+            assert relerr(o[k], o0[k]) < 1e-9, (it, k)
+        assert abs(s.elbo() - m.elbo()) < RTOL * abs(m.elbo())
+        m.prepare_next_iterate()
+    s.close()
+    s0.close()
