@@ -32,7 +32,7 @@ def main(path, config):
             seen_gene += 1
         elif "k_zi_cells_mma" in name:
             phase = "zi_pass_cells"
-        elif "k_zi_genes_mma" in name:
+        elif "k_zi_genes_mma" in name or "k_zi_genes_stored" in name:
             phase = "zi_pass_genes"
         else:
             continue
