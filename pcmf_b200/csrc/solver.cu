@@ -484,6 +484,26 @@ __global__ void __launch_bounds__(256) k_zi_init_cells(int64_t n, int KP, const 
     spl = block_sum(spl, sh);
     if (threadIdx.x == 0) atomicAdd(zsc, spl);
 }
+// Gene side of the same shortcut: while prob_D still is (X > 0), prob_D^T EU_new is the sum of the EU_new rows of the gene's
+// non-zero cells (zi...cpp:341 with the prob_D of :98-105) -- one gather pass instead of the dense pass B of the first iteration.
+__global__ void __launch_bounds__(256) k_zi_init_genes(int32_t p, int K, int KP, const int64_t *colptr, const int32_t *rowidx, const double *EU,
+                                                       double *tmpMat) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = w0; j < p; j += nw) {
+        const int64_t e0 = colptr[j], e1 = colptr[j + 1];
+        for (int k = lane; k < K; k += 32) {
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            int64_t e = e0;
+            for (; e + 4 <= e1; e += 4) {
+                const int64_t i0 = rowidx[e], i1 = rowidx[e + 1], i2 = rowidx[e + 2], i3 = rowidx[e + 3];
+                a0 += EU[i0 * KP + k]; a1 += EU[i1 * KP + k]; a2 += EU[i2 * KP + k]; a3 += EU[i3 * KP + k];
+            }
+            for (; e < e1; ++e) a0 += EU[(int64_t)rowidx[e] * KP + k];
+            tmpMat[j * KP + k] += (a0 + a1) + (a2 + a3);
+        }
+    }
+}
 __global__ void k_zi_init_colsum(int32_t p, const int64_t *colptr, double *colsumP) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) colsumP[j] = (double)(colptr[j + 1] - colptr[j]);
 }
@@ -741,10 +761,11 @@ void pcmf_solver::alloc_state() {
         // cell groups padded to whole CTAs of the cell pass (128 cells): it stores every tile it computes
         const size_t need = (size_t)((n + 127) / 128 * 16) * (size_t)((p + 7) / 8) * 64 * sizeof(uint32_t);
         bool fits = block_cache().has_block(need);
-        if (!fits) {
+        for (int attempt = 0; attempt < 2 && !fits; ++attempt) {
             size_t fr = 0, tot = 0;
             CK(cudaMemGetInfo(&fr, &tot));
-            fits = fr > need + ((size_t)6 << 30);
+            fits = fr > need + std::max((size_t)8 << 30, tot / 12);     // room for outputs, monitors, saved multi-init states
+            if (!fits && attempt == 0) block_cache().release_all();       // the preprocessing scratch may still sit in the cache
         }
         if (fits) pstore = dmalloc<uint32_t>(need / sizeof(uint32_t));
     }
@@ -1026,6 +1047,9 @@ void pcmf_solver::step(bool want_data) {
         zb.rows_per_chunk = rpc;
         if (explicitP) {
             k_dense_zi_genes<<<(p + 127) / 128, 128, 0, stream>>>(n, p, K, KP, Pexp, EU[nxt], ar1 + ar1_tmp);
+            end(PH_ZI_B, 1);
+        } else if (zi_at_init) {           // prob_D = (X > 0): only the non-zeros contribute
+            k_zi_init_genes<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, K, KP, colptr, rowidx, EU[nxt], ar1 + ar1_tmp);
             end(PH_ZI_B, 1);
         } else {
             end(PH_ZI_B, L->zi_genes(zb, chunks, opt.kernel_variant, stream));
