@@ -463,6 +463,10 @@ struct ColArgs {
     double *B1, *B2;                  // p x KP (plain stores: the block owns the gene)
     double *xlogT;                    // p
     double *qout;                     // nnz or null: q_ij = x_ij / T_ij of every entry visited, CSC order (NaN: exact-formula entry)
+    // Cell blocks (null / 1: the whole gene in one go).  blkptr[b * p + j] = first CSC position of gene j with a cell >= b * rows
+    // per block; blockIdx.y = b walks the blocks one after the other, so that the slice of the cell table a block gathers from
+    // (eu [+ ElogU] of ~1e5 cells) stays in L2 instead of the whole n x K table streaming through it; sums are then added atomically.
+    const int64_t *blkptr; int nblk;
 };
 #ifndef PCMF_GENE_MINB
 #define PCMF_GENE_MINB 2
@@ -477,11 +481,13 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
     const VT *__restrict__ val = static_cast<const VT *>(a.val);
     const double gminU = dbl_from_ordered(a.guard[G_MINU]), gmaxU = dbl_from_ordered(a.guard[G_MAXU]);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool blocked = a.nblk > 1;
+    const int blk = blocked ? (int)blockIdx.y : 0;
     for (int j = blockIdx.x; j < a.p; j += gridDim.x) {
         if (a.reuse && a.reuse[j]) {
             // same statistics, same mask row as the sparse-probability pass of the previous iteration
             // (sparse...cpp:448-451 vs :350-356): the sums are identical, copy them
-            if (threadIdx.x < KP) {
+            if (threadIdx.x < KP && blk == 0) {
                 a.B1[(int64_t)j * KP + threadIdx.x] = a.B1_src[(int64_t)j * KP + threadIdx.x];
                 if (WITH_B2) a.B2[(int64_t)j * KP + threadIdx.x] = a.B2_src[(int64_t)j * KP + threadIdx.x];
             }
@@ -503,9 +509,11 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
         for (int k = 0; k < KP; ++k) { b1[k] = 0.0; if (WITH_B2) b2[k] = 0.0; }
         double lt = 0.0;
         // all-masked gene: every r_ijk is 0 (sparse...cpp:350-356), nothing to accumulate
-        const int64_t e0 = a.colptr[j], e1 = a.allmasked[j] ? a.colptr[j] : a.colptr[j + 1];
+        const int64_t g0 = blocked ? a.blkptr[(int64_t)blk * a.p + j] : a.colptr[j];
+        const int64_t g1 = blocked ? a.blkptr[(int64_t)(blk + 1) * a.p + j] : a.colptr[j + 1];
+        const int64_t e0 = g0, e1 = a.allmasked[j] ? g0 : g1;
         if (a.qout && a.allmasked[j])
-            for (int64_t e = e0 + threadIdx.x; e < a.colptr[j + 1]; e += blockDim.x) a.qout[e] = 0.0;
+            for (int64_t e = e0 + threadIdx.x; e < g1; e += blockDim.x) a.qout[e] = 0.0;
         for (int64_t eb = e0 + w * 32; eb < e1; eb += blockDim.x) {    // warp-uniform trip count: the exact path is cooperative
             const int64_t e = eb + lane;
             int64_t i = 0; double x = 0.0; bool slow = false;
@@ -575,10 +583,17 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
             const int k = threadIdx.x;
             // fast path accumulated sum_i q eu_ik; e_ijk = eu_ik ev_jk
             const double evk = __ldg(a.ev + (int64_t)j * KP + k);
-            a.B1[(int64_t)j * KP + k] = (sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k]) * evk + ((sx1[0][k] + sx1[1][k]) + (sx1[2][k] + sx1[3][k]));
-            if (WITH_B2) a.B2[(int64_t)j * KP + k] = (sh2[0][k] + sh2[1][k] + sh2[2][k] + sh2[3][k]) * evk + ((sx2[0][k] + sx2[1][k]) + (sx2[2][k] + sx2[3][k]));
+            const double s1 = (sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k]) * evk + ((sx1[0][k] + sx1[1][k]) + (sx1[2][k] + sx1[3][k]));
+            if (blocked) atomicAdd(a.B1 + (int64_t)j * KP + k, s1); else a.B1[(int64_t)j * KP + k] = s1;
+            if (WITH_B2) {
+                const double s2 = (sh2[0][k] + sh2[1][k] + sh2[2][k] + sh2[3][k]) * evk + ((sx2[0][k] + sx2[1][k]) + (sx2[2][k] + sx2[3][k]));
+                if (blocked) atomicAdd(a.B2 + (int64_t)j * KP + k, s2); else a.B2[(int64_t)j * KP + k] = s2;
+            }
         }
-        if (WITH_LOGT && threadIdx.x == 0) a.xlogT[j] = shl[0] + shl[1] + shl[2] + shl[3];
+        if (WITH_LOGT && threadIdx.x == 0) {
+            const double sl = shl[0] + shl[1] + shl[2] + shl[3];
+            if (blocked) atomicAdd(a.xlogT + j, sl); else a.xlogT[j] = sl;
+        }
         __syncthreads();
     }
 }

@@ -26,7 +26,8 @@ void launch_estep_rows(bool f32, const RowArgs &a, int grid, int block, cudaStre
 }
 
 template <typename VT>
-void launch_gene_t(int mode, const ColArgs &a, int grid, cudaStream_t st) {
+void launch_gene_t(int mode, const ColArgs &a, int gx, cudaStream_t st) {
+    const dim3 grid(gx, a.nblk > 1 ? a.nblk : 1);
     switch (mode) {
         case GENE_B1: k_gene_pass<KP, VT, false, false><<<grid, 128, 0, st>>>(a); break;
         case GENE_B1_LOGT: k_gene_pass<KP, VT, false, true><<<grid, 128, 0, st>>>(a); break;

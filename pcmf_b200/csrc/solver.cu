@@ -206,6 +206,7 @@ struct pcmf_solver {
     // prob_D of the last cell pass, 32-bit fixed point in 8 x 8 tiles (zi_mma.cuh): the next gene pass streams it back
     // instead of recomputing it.  Only when it fits beside everything else; dropped by anything that redefines prob_D.
     uint32_t *pstore = nullptr; bool pstore_valid = false;
+    int64_t *blkptr = nullptr; int nblk = 1;      // cell blocks of the gene passes (ColArgs::blkptr)
     bool zi_at_init = false;            // prob_D still is (X > 0) and the packed records of pass A do not exist yet
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_vals = nullptr;   // value upload of a host CSR, overlapped with the CSC sort
     bool own_stream = false;
@@ -290,6 +291,7 @@ struct pcmf_solver {
     void build_csc();
     void alloc_state();
     void init_state(const pcmf_init *in, bool reinit = false);
+    void zero_gene_sums(double *B1, double *B2, double *xlogT, int mode);
     void run_init_stats();
     void allreduce(double *ptr, size_t count);
     void step(bool want_data);
@@ -327,7 +329,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { dfree((void *)rowptr); dfree((void *)colidx); dfree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3], pstore};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3], pstore, blkptr};
     for (void *q : ptrs) if (q) dfree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -413,6 +415,19 @@ __global__ void k_gather_csr_from_csc(int64_t nnz, const int64_t *perm, const in
         const int64_t e = perm[t];
         colidx[t] = colids[e];
         val[t] = (VT)x[e];
+    }
+}
+// cell-block boundaries inside every gene's CSC segment (rows ascend within a gene): blkptr[b * p + j] = first position of
+// gene j whose cell index is >= b * rows_blk; b = nblk gives colptr[j + 1]
+__global__ void k_block_ptr(int32_t p, int nblk, int64_t rows_blk, const int64_t *colptr, const int32_t *rowidx, int64_t *blkptr) {
+    const int64_t total = (int64_t)(nblk + 1) * p;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / p); const int j = (int)(t - (int64_t)b * p);
+        int64_t lo = colptr[j], hi = colptr[j + 1];
+        if (b == nblk) lo = hi;
+        const int64_t bound = (int64_t)b * rows_blk;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowidx[mid] < bound) lo = mid + 1; else hi = mid; }
+        blkptr[t] = lo;
     }
 }
 __global__ void k_invert_perm(int64_t nnz, const int64_t *perm, uint32_t *inv) {
@@ -673,6 +688,19 @@ void pcmf_solver::build_csc() {
         CK(cudaMemsetAsync(bitT, 0, wT * 4, stream)); CK(cudaMemsetAsync(bitB, 0, wB * 4, stream));
         k_build_bitmaps<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, p, rowptr, colidx, bitT, bitB);
     }
+    // gene passes walk the cells in blocks whose slice of the cell table (eu and ElogU rows, 16 KP bytes per cell) fits L2
+    // with room to spare: 28 MB measured best at C4 (10 / 14 / 20 / 24 / 30 / 40 / 80 MB: 46.8 / 44.6 / 43.1 / 42.4 / 42.1 / 47.1 /
+    // 50.6 ms for the spike-and-slab pass, 50.8 unblocked); PCMF_BLK_MB overrides, kernel_variant bit 512: one block
+    {
+        // (kernel_variant bit 1024: 64-cell blocks, so that small test problems walk several of them)
+        const int64_t rows_blk = (opt.kernel_variant & 1024) ? 64 : std::max<int64_t>(4096, ((int64_t)(getenv("PCMF_BLK_MB") ? atoi(getenv("PCMF_BLK_MB")) : 28) << 20) / (16 * KP));
+        nblk = (opt.kernel_variant & 512) ? 1 : (int)std::min<int64_t>(256, (n + rows_blk - 1) / rows_blk);
+        if (nblk > 1) {
+            const int64_t rb = ((n + nblk - 1) / nblk + 31) / 32 * 32;
+            blkptr = dmalloc<int64_t>((size_t)(nblk + 1) * p);
+            k_block_ptr<<<grid_for((int64_t)(nblk + 1) * p, 256), 256, 0, stream>>>(p, nblk, rb, colptr, rowidx, blkptr);
+        }
+    }
     Lg = dmalloc<double>(p); colsumX = dmalloc<double>(p); colnnz = dmalloc<double>(p); rowsumX = dmalloc<double>(n);
     xlogx = dmalloc<double>(p);
     val_csc = f32 ? (void *)dmalloc<float>(nnz) : (void *)dmalloc<double>(nnz);
@@ -918,6 +946,15 @@ void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
     run_init_stats();
 }
 
+// the blocked gene pass adds its per-block sums atomically: start from zero
+void pcmf_solver::zero_gene_sums(double *B1, double *B2, double *xlogT, int mode) {
+    if (nblk <= 1) return;
+    const size_t pK = (size_t)p * KP;
+    CK(cudaMemsetAsync(B1, 0, pK * 8, stream));
+    if (mode == GENE_B1_B2) CK(cudaMemsetAsync(B2, 0, pK * 8, stream));
+    if (mode == GENE_B1_LOGT) CK(cudaMemsetAsync(xlogT, 0, (size_t)p * 8, stream));
+}
+
 // U_stats, V_stats, update_poisson_param, update_hyper_param after any initialisation (gap_factor_model.cpp:119-122)
 void pcmf_solver::run_init_stats() {
     pstore_valid = false;             // prob_D is redefined by the initialisation
@@ -1012,8 +1049,9 @@ void pcmf_solver::step(bool want_data) {
         const bool reuse = sparse && sparse_sums_valid;
         const double *src = (opt.world > 1) ? ar2keep : ar2;
         ColArgs ca{p, K, colptr, rowidx, v_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, reuse ? unchanged : nullptr, src + ar2_B1,
-                   src + ar2_B2, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc};
+                   src + ar2_B2, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc, blkptr, nblk};
         const int mode = !want_data ? GENE_B1 : (sparse ? GENE_B1_B2 : GENE_B1_LOGT);
+        zero_gene_sums(ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, mode);
         L->gene_pass(v_f32, mode, ca, std::min<int>(p, sms * 32), stream);
     }
     end(PH_GENE_E, 1);
@@ -1077,7 +1115,8 @@ void pcmf_solver::step(bool want_data) {
     if (sparse) {
         begin(PH_GENE_S);
         ColArgs ca{p, K, colptr, rowidx, v_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, gn, ar2 + ar2_B1,
-                   ar2 + ar2_B2, ar2 + ar2_xlogT, qcsc};
+                   ar2 + ar2_B2, ar2 + ar2_xlogT, qcsc, blkptr, nblk};
+        zero_gene_sums(ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT, GENE_B1_B2);
         L->gene_pass(v_f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
         if (opt.world > 1) CK(cudaMemcpyAsync(ar2keep, ar2, 2 * pK * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         allreduce(ar2, 2 * pK);
@@ -1151,7 +1190,8 @@ double pcmf_solver::data_term_now() {
     const double *src = (opt.world > 1) ? ar2keep : ar2;
     ColArgs ca{p, K, colptr, rowidx, explicitP ? (const void *)valw_csc : val_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked,
                reuse ? unchanged : nullptr, reuse ? src + ar2_B1 : nullptr, reuse ? src + ar2_B2 : nullptr, dbg, guard[gcur],
-               ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc};
+               ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc, blkptr, nblk};
+    zero_gene_sums(ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, sparse ? GENE_B1_B2 : GENE_B1_LOGT);
     L->gene_pass(explicitP ? false : f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
     allreduce(ar1 + ar1_B1, pK);
     allreduce(ar1 + ar1_B2, pK + p);

@@ -355,3 +355,18 @@ def test_stored_prob_D_path_matches_oracle(sparse, n, p, K):
         m.prepare_next_iterate()
     s.close()
     s0.close()
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+def test_cell_blocked_gene_passes_match_oracle(zi, sparse):
+    """The gene passes walk the cells in blocks (so that the slice of the cell table they gather from stays in L2) and add the
+    per-block sums; forced to 64-cell blocks here (kernel_variant bit 1024; one block per ~1e5 cells by default)."""
+    X = problem(61, 300, 190, K_true=5)
+    m, s = make_pair(X, 6, zi, sparse, kernel_variant=1024)
+    for it in range(5):
+        m.update_param()
+        s.iterate(1)
+        compare_state(m, s, zi, sparse, "blocked gene pass, iter %d" % it)
+        assert abs(s.elbo() - m.elbo()) < RTOL * abs(m.elbo())
+        m.prepare_next_iterate()
+    s.close()
