@@ -321,7 +321,11 @@ def main():
     # pass, cell table n x K for the gene passes); that gather, not the HBM stream of X, is what bounds them, so the
     # measured gather bandwidth of this device is reported next to the HBM figure.
     gather_gene_tab = api.measure_gather_gbs(p, local)
-    gather_cell_tab = api.measure_gather_gbs(nl, local)
+    # the gene passes walk the cells in blocks whose slice of the cell table stays in L2 (28 MB of eu + ElogU rows, solver.cu):
+    # their ceiling is the gather rate out of a table of that size, or of the whole table when it is smaller than a block
+    KPAD = next(w for w in (4, 8, 12, 16, 20, 32, 64) if K <= w)
+    blk_rows = max(4096, (28 << 20) // (16 * KPAD))
+    gather_cell_tab = api.measure_gather_gbs(min(nl, 2 * blk_rows), local)
     traffic = ncu_traffic(args.config)
     kernels = []
     # gathered bytes per non-zero: the cell pass of the ZI / sparse models reads one K-vector (evw) plus the stored q of the
