@@ -103,7 +103,11 @@ typedef struct {
     pcmf_progress_fn progress;
     void *progress_ctx;
     int32_t progress_every;    /* default 10 */
-    int32_t kernel_variant;    /* 0 = default; >0 selects experimental kernel variants (bench / tests) */
+    int32_t kernel_variant;    /* 0 = default.  Bit mask for A/B measurements and tests, results are the same within rounding:
+                                *   4 thread-per-row ZI kernels instead of the DMMA tiles, 8 two row tiles per warp,
+                                *   16 no stored q (the cell pass recomputes T), 32 dense first ZI pass instead of the
+                                *   non-zero shortcut, 64 / 128 force / forbid keeping prob_D between the ZI passes,
+                                *   512 gene passes in one cell block, 1024 64-cell blocks */
 } pcmf_options;
 
 /* Optional warm-start values (NULL = absent), column-major, sizes for the LOCAL rows.
