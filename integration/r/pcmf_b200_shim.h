@@ -24,13 +24,17 @@ static int progress_cb(void *, int iter, double crit) {
 inline Rcpp::List fit(SEXP X, int K, bool zi, bool sparse, double sel_bound, bool verbose, bool monitor, int iter_max,
                       int iter_min, double epsilon, int additional_iter, int conv_mode, int ninit, int iter_init,
                       bool reorder_factor, Rcpp::Nullable<uint32_t> seed, const pcmf_init &init) {
-    Rcpp::IntegerVector dim = Rf_getAttrib(X, R_DimSymbol);
+    const bool is_dgC = Rf_isS4(X) && Rf_inherits(X, "dgCMatrix");          // extension: Matrix::dgCMatrix, no dense copy
+    Rcpp::IntegerVector dim = is_dgC ? Rcpp::IntegerVector(Rcpp::S4(X).slot("Dim")) : Rcpp::IntegerVector(Rf_getAttrib(X, R_DimSymbol));
     const int64_t n = dim[0]; const int p = dim[1];
     pcmf_problem prob{};  prob.n_local = prob.n_global = n;  prob.p = p;
-    if (TYPEOF(X) == INTSXP) prob.dense_i32 = INTEGER(X);                    // wrapper_gap_factor.h:204-207
+    if (is_dgC) {                                                             // slots @p, @i, @x as they are
+        Rcpp::S4 Xs(X);
+        prob.csc_colptr = INTEGER(Xs.slot("p")); prob.csc_rowidx = INTEGER(Xs.slot("i")); prob.csc_val_f64 = REAL(Xs.slot("x"));
+    }
+    else if (TYPEOF(X) == INTSXP) prob.dense_i32 = INTEGER(X);               // wrapper_gap_factor.h:204-207
     else if (TYPEOF(X) == REALSXP) prob.dense_f64 = REAL(X);                 // wrapper_gap_factor.h:208-209
     else Rcpp::stop("X parameter should be an integer or real valued matrix");   // wrapper_gap_factor.h:210
-    // (a dgCMatrix would be transposed once to CSR and passed through prob.csr_*; see section 5)
 
     pcmf_options o{};
     o.K = K; o.zero_inflation = zi; o.sparsity = sparse; o.sel_bound = sel_bound;
