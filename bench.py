@@ -373,6 +373,8 @@ def main():
                 "traffic": dom.get("traffic"), "kernel": dom["kernel"], "ms_per_launch": dom["ms"],
                 "peak_source": dom.get("peak_source", peak_src)}
     phases = {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in per.items()}
+    if not args.no_e2e:
+        solver.get_output(want_prob_D=False)     # untimed: creates the process-wide pinned staging buffers of the result download
     solver.close()
 
     # ---- end-to-end leg: the reference-facing call (run_zi_sparse_gap_factor -> pcmf C ABI) with HOST buffers:
