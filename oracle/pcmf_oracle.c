@@ -512,9 +512,9 @@ void orc_init_random(orc_model *m) {
 /* gap_factor_model.cpp:177-192 */
 void orc_perturb_param(orc_model *m, double noise_level) {
     int n = m->n, p = m->p, K = m->K;
-    /* rUnif fills column by column in the reference (random.h:224-237); stream unpinned anyway */
-    for (long e = 0; e < (long)n * K; e++) { m->a1[e] += -noise_level + 2 * noise_level * rng_unif(&m->rng); }
-    for (long e = 0; e < (long)p * K; e++) { m->b1[e] += -noise_level + 2 * noise_level * rng_unif(&m->rng); }
+    /* rUnif fills row by row (rowInd outer, colInd inner, random.h:224-237): noise_a1 first, then noise_b1 */
+    for (int i = 0; i < n; i++) for (int k = 0; k < K; k++) m->a1[i + (long)k * n] += -noise_level + 2 * noise_level * rng_unif(&m->rng);
+    for (int j = 0; j < p; j++) for (int k = 0; k < K; k++) m->b1[j + (long)k * p] += -noise_level + 2 * noise_level * rng_unif(&m->rng);
     for (long e = 0; e < (long)n * K; e++) if (m->a1[e] < 1e-6) m->a1[e] = 1e-6;
     for (long e = 0; e < (long)p * K; e++) if (m->b1[e] < 1e-6) m->b1[e] = 1e-6;
     post_init(m, 1);

@@ -283,13 +283,15 @@ def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True,
     multi-init loop of :296-350 / :328-387), returning a dict shaped like the reference's R list."""
     m = Model(X, K, zero_inflation, sparsity)
 
-    def init(mod):
+    def init(mod, multi=False):
         if sparsity:
             mod.init_sparse_param(sel_bound, prob_S, prior_S)
         if zero_inflation:
             mod.init_zi_param(prob_D, prior_D)       # both given or the default (wrapper_gap_factor.h:352-356)
         if U is not None:
             mod.init_from_factor(U, V)             # wrapper_gap_factor.h:353-354
+            if multi:                              # every multi-init run perturbs the given factors (:312-314)
+                mod.perturb_param(max(np.max(U), np.max(V)) / K)
         elif a1 is not None:
             mod.init_variational_param(a1, a2, b1, b2)
         else:
@@ -302,7 +304,7 @@ def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True,
             tmp.seed(seed)
         best_loss = None
         for nrun in range(ninit):
-            init(tmp)
+            init(tmp, multi=True)
             c = tmp.optimize(iter_init, iter_init, 1e-6, additional_iter, conv_mode, monitor, iter_start=0)
             if nrun == 0 or c["loss"] < best_loss:           # sic: keeps the SMALLEST loss (wrapper_gap_factor.h:342)
                 best_loss, head = c["loss"], c

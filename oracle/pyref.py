@@ -47,6 +47,7 @@ def lib():
         L.ref_init_zi_given.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
         L.ref_init_variational.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int]
         L.ref_init_factor.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int, C.c_int]
+        L.ref_perturb_param.argtypes = [C.c_void_p, C.c_double]
         for nm in ("ref_init_random", "ref_optimize", "ref_order_factor", "ref_output"):
             getattr(L, nm).argtypes = [C.c_void_p]
         L.ref_get.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, dp, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -115,6 +116,9 @@ class RefModel:
 
     def init_random(self):
         self._ck(self.L.ref_init_random(self.h))
+
+    def perturb_param(self, noise_level):
+        self._ck(self.L.ref_perturb_param(self.h, float(noise_level)))
 
     def init_from_factor(self, U, V):
         a, ap = _f(U)

@@ -38,6 +38,7 @@ struct IRunner {
     virtual void init_variational(const MatrixXd &a1, const MatrixXd &a2, const MatrixXd &b1, const MatrixXd &b2) = 0;
     virtual void init_random(myRandom::RNGType &rng) = 0;
     virtual void init_factor(const MatrixXd &U, const MatrixXd &V) = 0;
+    virtual void perturb(myRandom::RNGType &rng, double noise_level) = 0;
     virtual void optimize() = 0;
     virtual void order_factor() = 0;
     virtual void output(Rcpp::List &l) = 0;
@@ -56,6 +57,7 @@ struct Runner : IRunner {
     }
     void init_random(myRandom::RNGType &rng) override { algo.init_random(rng); }
     void init_factor(const MatrixXd &U, const MatrixXd &V) override { algo.init(U, V); }     // wrapper_gap_factor.h:353-354
+    void perturb(myRandom::RNGType &rng, double noise_level) override { algo.perturb_param(rng, noise_level); }   // wrapper_gap_factor.h:314
     void optimize() override { algo.optimize(); }
     void order_factor() override { algo.order_factor(); }
     void output(Rcpp::List &l) override { algo.get_output(l); }
@@ -115,6 +117,7 @@ int ref_init_variational(void *hv, const double *a1, const double *a2, const dou
 }
 int ref_init_random(void *hv) { GUARD(h->r->init_random(h->rng)) }
 int ref_init_factor(void *hv, const double *U, const double *V, int n, int p, int K) { GUARD(h->r->init_factor(mat(U, n, K), mat(V, p, K))) }
+int ref_perturb_param(void *hv, double noise_level) { GUARD(h->r->perturb(h->rng, noise_level)) }
 int ref_optimize(void *hv) { GUARD(h->r->optimize()) }
 int ref_order_factor(void *hv) { GUARD(h->r->order_factor()) }
 int ref_output(void *hv) { GUARD(h->out = Rcpp::List(); h->r->output(h->out)) }

@@ -300,6 +300,7 @@ struct pcmf_solver {
     Mon monitors_now(bool want_loglik);
     void order_factor_now();
     void multi_init(pcmf_result *res);
+    void perturb_now();
     struct Saved { std::vector<std::pair<void *, size_t>> arrays; std::vector<void *> copies; int cur, gcur; bool first_iter, sparse_sums_valid, have_pending;
                    double last_nodata; std::vector<double> h; int iter, first_mode; };
     std::vector<std::pair<void *, size_t>> state_arrays();
@@ -470,6 +471,16 @@ __global__ void k_init_gamma_rows(int64_t rows, int K, int KP, const uint32_t *r
         if (k >= K) { dst[o] = 1.0; continue; }
         const double rate = sqrt((double)K / (sums[r] / denom));
         dst[o] = -log(((double)raw[r * K + k] + 0.5) / 4294967296.0) / rate;
+    }
+}
+// perturb_param (gap_factor_model.cpp:177-192): shape += Uniform(-level, level), floored at 1e-6; raw draws row by row
+__global__ void k_perturb_rows(int64_t rows, int K, int KP, const uint32_t *raw, double level, double *dst) {
+    const int64_t total = rows * K;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / K; const int k = (int)(e - r * K);
+        const double u = ((double)raw[e] + 0.5) / 4294967296.0;
+        const double v = dst[r * KP + k] + (-level + 2.0 * level * u);
+        dst[r * KP + k] = v < 1e-6 ? 1e-6 : v;
     }
 }
 // init_zi_param (zi_gap_factor_model.cpp:98-105) sets prob_D = (X > 0), so the dense cell pass collapses onto the
@@ -1363,9 +1374,9 @@ void pcmf_solver::restore_state(const Saved &sv) {
 // run's state at iteration iter_init so that pcmf_optimize continues from there (my_model = tmp_model, :339-345).
 // Reference details kept: the per-iteration vectors of the kept run stay in `res` for iterations < iter_init; the
 // first iteration of runs after the first measures its gap against the previous run's last iterate (the `old` copies
-// are never reset); with explicit a1..b2 / U,V the reference perturbs by max(U, V)/K, reading U and V even when only
-// a1..b2 were given (undefined behaviour there) -- here explicit initial values are re-used unperturbed unless U, V
-// were given.
+// are never reset); with explicit U, V every run perturbs them by Uniform(+-max(U, V)/K) (perturb_now); with explicit
+// a1..b2 the reference calls the same perturbation with U and V unset (undefined behaviour there) -- here those values
+// are re-used unperturbed.
 void pcmf_solver::multi_init(pcmf_result *res) {
     const pcmf_options saved_opt = opt;
     opt.iter_max = saved_opt.iter_init; opt.iter_min = saved_opt.iter_init; opt.epsilon = 1e-6;   // set_iter(iter_init, iter_init, 1e-6)
@@ -1384,6 +1395,7 @@ void pcmf_solver::multi_init(pcmf_result *res) {
             first_mode = 2;
             init_state(&init_copy, true);   // init_sparse_param / init_zi_param / init_random with the continuing stream
         }
+        if (init_copy.U) perturb_now();  // every run perturbs user-supplied factors (wrapper_gap_factor.h:312-314)
         iter = 0;                        // set_current_iter(0)
         char err[512] = {0};
         const int rc = pcmf_optimize(this, res, err, sizeof err);
@@ -1400,6 +1412,29 @@ void pcmf_solver::multi_init(pcmf_result *res) {
     for (void *q : best.copies) dfree(q);
     opt = saved_opt;                     // set_iter(iter_min, iter_max, epsilon); set_verbosity(verbose)
     first_mode = 1;
+}
+
+// tmp_model.perturb_param(rng, max(U.maxCoeff(), V.maxCoeff()) / K) (wrapper_gap_factor.h:314, gap_factor_model.cpp:177-192)
+void pcmf_solver::perturb_now() {
+    if (opt.world > 1) fail(PCMF_EUNSUPPORTED, "multi-init from user-supplied U, V is not available on cell-sharded runs");
+    double mx = -1e300;
+    for (size_t e = 0; e < (size_t)n * K; ++e) mx = std::max(mx, init_copy.U[e]);
+    for (size_t e = 0; e < (size_t)p * K; ++e) mx = std::max(mx, init_copy.V[e]);
+    const double level = mx / K;
+    std::mt19937 g = rng; g.discard(rng_consumed);
+    auto add = [&](int64_t rows, double *dst) {
+        std::vector<uint32_t> raw((size_t)rows * K);
+        for (size_t e = 0; e < raw.size(); ++e) raw[e] = (uint32_t)g();
+        uint32_t *d_raw = dmalloc<uint32_t>(raw.size());
+        CK(cudaMemcpyAsync(d_raw, raw.data(), raw.size() * 4, cudaMemcpyHostToDevice, stream));
+        k_perturb_rows<<<grid_for(rows * K, 256), 256, 0, stream>>>(rows, K, KP, d_raw, level, dst);
+        CK(cudaStreamSynchronize(stream));
+        dfree(d_raw);
+    };
+    add(n, a1);
+    add(p, b1);
+    rng_consumed += (unsigned long long)(n + p) * K;
+    run_init_stats();
 }
 
 // gap_factor_model::custom_conv_criterion (gap_factor_model.cpp:265-269): 1 - min(RV(EU, EU_old), RV(EV, EV_old))

@@ -180,3 +180,26 @@ def test_init_from_factor_matches_oracle(zi, sparse):
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
     assert relerr(res["monitor"]["optim_criterion"], ref["monitor"]["optim_criterion"]) < 1e-6
+
+
+@pytest.mark.parametrize("zi,sparse", [(False, False), (True, True)], ids=["gap", "zi_sparse"])
+def test_multi_init_from_factors_perturbs_like_oracle(zi, sparse):
+    """ninit = 3 with user-supplied U, V: every run starts from init_from_factor + perturb_param (uniform noise of
+    max(U, V) / K off the one seeded stream, wrapper_gap_factor.h:312-314; pinned against the reference build in
+    tests/test_ref_build.py), smallest loss kept, then optimize continues."""
+    X = problem(28, 70, 40)
+    K = 3
+    rng = np.random.default_rng(11)
+    U, V = rng.exponential(1.0, (70, K)) + 0.05, rng.exponential(1.0, (40, K)) + 0.05
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=16, iter_min=8, epsilon=1e-2, additional_iter=3, seed=91, ninit=3, iter_init=5, U=U, V=V)
+    ref = po.run(X, K, zi, sparse, monitor=True, reorder_factor=False, prob_S=prob_S, prior_S=prior_S, **kw)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    res = RUN[(zi, sparse)](X, K, verbose=False, monitor=True, reorder_factor=False, **kw)
+    assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    assert relerr(res["monitor"]["optim_criterion"], ref["monitor"]["optim_criterion"]) < 1e-6
+    assert abs(res["loss"] - ref["loss"]) < 1e-6 * abs(ref["loss"])
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
+    assert np.abs(res["variational_params"]["a1"] - U).max() > 1e-3

@@ -150,3 +150,33 @@ def test_init_from_factor_matches_reference_build(zi, sparse):
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(orc["variational_params"][k], ref["variational_params"][k]) < TOL, k
     assert relerr(orc["convergence"]["conv_crit"], ref["convergence"]["conv_crit"]) < TOL
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+def test_perturb_param_matches_reference_build(zi, sparse):
+    """perturb_param (gap_factor_model.cpp:177-192), the step every multi-init run applies to user-supplied factors
+    (wrapper_gap_factor.h:312-314): uniform noise on a1 then b1, row by row off the one stream, floor at 1e-6, post-steps."""
+    X, _, _ = datagen.simulate(40, 30, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=44)
+    K = 3
+    rng = np.random.default_rng(9)
+    U, V = rng.exponential(1.0, (40, K)) + 0.05, rng.exponential(1.0, (30, K)) + 0.05
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    noise = max(U.max(), V.max()) / K
+    r = pyref.RefModel(X, K, zi, sparse, True, 6, 6, 1e-2, 10, 1)
+    o = po.Model(X, K, zi, sparse)
+    for m in (r, o):
+        m.seed(777)
+        if sparse:
+            m.init_sparse_param(0.5, prob_S, prior_S)
+        if zi:
+            m.init_zi_param()
+        m.init_from_factor(U, V)
+        m.perturb_param(noise)
+    r.optimize()
+    ref = r.output()
+    for _ in range(6):
+        o.update_param()
+        o.prepare_next_iterate()
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(o.get(k), ref["variational_params"][k]) < TOL, k
+    assert (np.abs(np.asarray(ref["variational_params"]["a1"]) - U).max() > 0)       # the noise did something
