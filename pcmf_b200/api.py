@@ -227,6 +227,9 @@ def _as_problem(X, n_global=None, row_offset=0):
         keep.append(X)
     elif _sp is not None and _sp.issparse(X) and X.format == "csc" and X.nnz < 2 ** 31 and X.shape[0] < 2 ** 31 - 1:
         # compressed columns = Matrix::dgCMatrix (slots p, i, x): handed over as it is, CSR is built on the device
+        if not X.has_canonical_format:           # a dgCMatrix never holds the same entry twice; scipy may
+            X = X.copy()
+            X.sum_duplicates()
         n, p = X.shape
         cp = np.ascontiguousarray(X.indptr, np.int32)
         ri = np.ascontiguousarray(X.indices, np.int32)
@@ -235,8 +238,9 @@ def _as_problem(X, n_global=None, row_offset=0):
         keep += [cp, ri, xv]
     elif _sp is not None and _sp.issparse(X):
         Xc = X.tocsr()
-        if Xc.nnz and (Xc.data == 0).any():      # explicit zeros must not count as X != 0
-            Xc = Xc.copy()
+        if not Xc.has_canonical_format or (Xc.nnz and (Xc.data == 0).any()):   # one entry per (cell, gene); explicit
+            Xc = Xc.copy()                                                      # zeros must not count as X != 0
+            Xc.sum_duplicates()
             Xc.eliminate_zeros()
         n, p = Xc.shape
         rp = np.ascontiguousarray(Xc.indptr, np.int64)
