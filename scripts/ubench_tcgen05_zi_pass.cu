@@ -14,8 +14,26 @@
 
 constexpr int KF = 32;                 // padded factors
 constexpr int TG = 64;                 // genes per tile
-constexpr int COL_S = 0, COL_P = 64, COL_PV = 128, TMEM_COLS = 256;
-constexpr int TILE_B1 = TG * KF * 4, TILE_B2 = KF * TG * 4, TILE_C = TG * 4, TILE_BYTES = TILE_B1 + TILE_B2 + TILE_C;   // 16640
+// -DSPLIT3: 3xTF32 -- every FP32 operand x is split into hi = tf32(x) and lo = x - hi, and a product a.b is taken as
+// a_hi b_hi + a_lo b_hi + a_hi b_lo (the contraction is three times as long; the tensor time stays negligible)
+#ifdef SPLIT3
+constexpr int NS = 3;
+#else
+constexpr int NS = 1;
+#endif
+constexpr int K1 = NS * KF;            // contraction length of the first product
+#ifndef DRAIN
+#define DRAIN 4                        // tiles between two read-outs of the TMEM accumulator
+#endif
+constexpr int COL_S = 0, COL_P = 64, COL_PLO = 128, COL_PV = 192, TMEM_COLS = 256;
+constexpr int TILE_B1 = TG * K1 * 4, TILE_B2 = (NS == 3 ? 2 : 1) * KF * TG * 4, TILE_C = TG * 4, TILE_BYTES = TILE_B1 + TILE_B2 + TILE_C;
+__host__ __device__ inline float tf32_hi(float x) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+#else
+    return x;
+#endif
+}
 
 __host__ __device__ inline uint32_t canon_off(int r, int k, int R) { return (k >> 2) * (R / 8) * 128 + (r >> 3) * 128 + (r & 7) * 16 + (k & 3) * 4; }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -42,8 +60,19 @@ __global__ void k_pack(int p, const float *EVS, const float *c, unsigned char *t
         const int j = t * TG + r;
         const float v = j < p ? EVS[(int64_t)j * KF + k] : 0.f;
         unsigned char *base = tiles + (int64_t)t * TILE_BYTES;
-        *reinterpret_cast<float *>(base + canon_off(r, k, TG)) = v;                       // B1[gene r][factor k]
-        *reinterpret_cast<float *>(base + TILE_B1 + canon_off(k, r, KF)) = v;             // B2[factor k][gene r]
+        if (NS == 1) {
+            *reinterpret_cast<float *>(base + canon_off(r, k, TG)) = v;                       // B1[gene r][factor k]
+            *reinterpret_cast<float *>(base + TILE_B1 + canon_off(k, r, KF)) = v;             // B2[factor k][gene r]
+        } else {
+            const float hi = tf32_hi(v), lo = v - hi;
+            // first product: A' = [a_hi | a_lo | a_hi] against B1' = [b_hi | b_hi | b_lo] along K
+            *reinterpret_cast<float *>(base + canon_off(r, k, TG)) = hi;
+            *reinterpret_cast<float *>(base + canon_off(r, KF + k, TG)) = hi;
+            *reinterpret_cast<float *>(base + canon_off(r, 2 * KF + k, TG)) = lo;
+            // second product: B2_hi and B2_lo as two [factor][gene] operands
+            *reinterpret_cast<float *>(base + TILE_B1 + canon_off(k, r, KF)) = hi;
+            *reinterpret_cast<float *>(base + TILE_B1 + KF * TG * 4 + canon_off(k, r, KF)) = lo;
+        }
         if (k == 0) *reinterpret_cast<float *>(base + TILE_B1 + TILE_B2 + r * 4) = j < p ? c[j] : -1e30f;
     }
 }
@@ -51,7 +80,7 @@ __global__ void k_pack(int p, const float *EVS, const float *c, unsigned char *t
 __global__ void __launch_bounds__(128) k_zi_fp32(int64_t n, int p, const float *EU, const unsigned char *tiles, float *PV) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sA = smem;                                  // 128 x 32 floats, canonical
-    unsigned char *sT = smem + 128 * KF * 4;                   // 2 tiles
+    unsigned char *sT = smem + 128 * K1 * 4;                   // 2 tiles
     __shared__ uint32_t tmem_base;
     __shared__ __align__(8) uint64_t full[2], done_s, done_pv;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -59,7 +88,14 @@ __global__ void __launch_bounds__(128) k_zi_fp32(int64_t n, int p, const float *
     const int ntiles = (p + TG - 1) / TG;
     for (int e = tid; e < 128 * KF; e += 128) {
         const int r = e / KF, k = e % KF;
-        *reinterpret_cast<float *>(sA + canon_off(r, k, 128)) = cell0 + r < n ? EU[(cell0 + r) * KF + k] : 0.f;
+        const float x = cell0 + r < n ? EU[(cell0 + r) * KF + k] : 0.f;
+        if (NS == 1) *reinterpret_cast<float *>(sA + canon_off(r, k, 128)) = x;
+        else {
+            const float hi = tf32_hi(x), lo = x - hi;
+            *reinterpret_cast<float *>(sA + canon_off(r, k, 128)) = hi;
+            *reinterpret_cast<float *>(sA + canon_off(r, KF + k, 128)) = lo;
+            *reinterpret_cast<float *>(sA + canon_off(r, 2 * KF + k, 128)) = hi;
+        }
     }
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&done_s, 1); mbar_init(&done_pv, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -74,12 +110,15 @@ __global__ void __launch_bounds__(128) k_zi_fp32(int64_t n, int p, const float *
     const uint32_t idesc1 = make_idesc(128, TG), idesc2 = make_idesc(128, KF);
     const uint32_t lboA = (128 / 8) * 128, lboB1 = (TG / 8) * 128, lboB2 = (KF / 8) * 128;
     if (tid == 0) { bulk_load(sT, tiles, TILE_BYTES, &full[0]); if (ntiles > 1) bulk_load(sT + TILE_BYTES, tiles + TILE_BYTES, TILE_BYTES, &full[1]); }
+    double pvacc[KF];
+#pragma unroll
+    for (int c = 0; c < KF; ++c) pvacc[c] = 0.0;
     for (int t = 0; t < ntiles; ++t) {
         unsigned char *buf = sT + (t & 1) * TILE_BYTES;
         if (tid == 0) {
             mbar_wait(&full[t & 1], (t >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int s = 0; s < KF / 8; ++s) {
+            for (int s = 0; s < K1 / 8; ++s) {
                 const uint64_t da = make_desc(smem_u32(sA) + 2 * s * lboA, lboA, 128), db = make_desc(smem_u32(buf) + 2 * s * lboB1, lboB1, 128);
                 const uint32_t acc = s > 0;
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -92,7 +131,7 @@ __global__ void __launch_bounds__(128) k_zi_fp32(int64_t n, int p, const float *
         const float *cs = reinterpret_cast<const float *>(buf + TILE_B1 + TILE_B2);
 #pragma unroll
         for (int c0 = 0; c0 < TG; c0 += 16) {
-            uint32_t v[16];
+            uint32_t v[16], w[16];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
                            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(lane_addr + COL_S + c0));
@@ -103,22 +142,31 @@ __global__ void __launch_bounds__(128) k_zi_fp32(int64_t n, int p, const float *
                 float e2, r;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(-1.4426950408889634f * z));
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e2));
-                v[c] = __float_as_uint(r);
+                if (NS == 1) v[c] = __float_as_uint(r);
+                else { const float hi = tf32_hi(r); v[c] = __float_as_uint(hi); w[c] = __float_as_uint(r - hi); }
             }
             asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                          ::"r"(lane_addr + COL_P + c0), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
                            "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+            if (NS == 3)
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                             ::"r"(lane_addr + COL_PLO + c0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
+                               "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int s = 0; s < TG / 8; ++s) {
-                const uint64_t db = make_desc(smem_u32(buf + TILE_B1) + 2 * s * lboB2, lboB2, 128);
-                const uint32_t acc = (t > 0) || (s > 0);
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                             ::"r"(t0 + COL_PV), "r"(t0 + COL_P + 8 * s), "l"(db), "r"(idesc2), "r"(acc));
+            for (int part = 0; part < NS; ++part) {          // P_hi E_hi [+ P_lo E_hi + P_hi E_lo]
+                const uint32_t pcol = part == 1 ? COL_PLO : COL_P;
+                const unsigned char *b2 = buf + TILE_B1 + (part == 2 ? KF * TG * 4 : 0);
+                for (int s = 0; s < TG / 8; ++s) {
+                    const uint64_t db = make_desc(smem_u32(b2) + 2 * s * lboB2, lboB2, 128);
+                    const uint32_t acc = (t % DRAIN != 0) || (s > 0) || (part > 0);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                                 ::"r"(t0 + COL_PV), "r"(t0 + pcol + 8 * s), "l"(db), "r"(idesc2), "r"(acc));
+                }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done_pv)) : "memory");
             // the second product has to be through with this operand buffer (and with P) before either is overwritten
@@ -126,16 +174,25 @@ __global__ void __launch_bounds__(128) k_zi_fp32(int64_t n, int p, const float *
             if (t + 2 < ntiles) bulk_load(buf, tiles + (int64_t)(t + 2) * TILE_BYTES, TILE_BYTES, &full[t & 1]);
         }
         __syncthreads();
+        // The TMEM accumulator adds with truncation: left alone over all 313 tiles it drifts by ~2e-4 relative.  Every DRAIN
+        // tiles it is therefore read out and added to FP64 registers, and the next tile starts a fresh accumulator.
+        if (t % DRAIN == DRAIN - 1 || t == ntiles - 1) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < KF; c0 += 8) {
+                uint32_t v[8];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(lane_addr + COL_PV + c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 8; ++c) pvacc[c0 + c] += (double)__uint_as_float(v[c]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+        }
     }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int64_t row = cell0 + warp * 32 + (tid & 31);
-    for (int c0 = 0; c0 < KF; c0 += 8) {
-        uint32_t v[8];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(lane_addr + COL_PV + c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < n) for (int c = 0; c < 8; ++c) PV[row * KF + c0 + c] = __uint_as_float(v[c]);
-    }
+    if (row < n) for (int c = 0; c < KF; ++c) PV[row * KF + c] = (float)pvacc[c];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(TMEM_COLS));
@@ -155,7 +212,7 @@ int main(int argc, char **argv) {
     cudaMemcpy(dEU, EU.data(), EU.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dEVS, EVS.data(), EVS.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dc, c.data(), c.size() * 4, cudaMemcpyHostToDevice);
     k_pack<<<592, 256>>>(p, dEVS, dc, dT);
-    const size_t smem = 128 * KF * 4 + 2 * TILE_BYTES;
+    const size_t smem = 128 * K1 * 4 + 2 * TILE_BYTES;
     cudaFuncSetAttribute(k_zi_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned grid = (unsigned)((n + 127) / 128);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -179,7 +236,7 @@ int main(int argc, char **argv) {
         for (int k = 0; k < K; ++k) worst = fmax(worst, fabs(PV[i * KF + k] - ref[k]) / fabs(ref[k]));
     }
     const double entries = (double)n * p;
-    printf("FP32 cell-side ZI pass on tcgen05 (TF32 operands, ex2/rcp.approx): n=%lld p=%d K=%d: %.3f ms = %.1f Gentries/s -> %.1f ms for 1M x 20k; "
-           "max rel err of PV on 4 cells %.2e\n", (long long)n, p, K, ms, entries / ms / 1e6, ms * (1e6 * 20000.0) / entries, worst);
+    printf("FP32 cell-side ZI pass on tcgen05 (%s operands, ex2/rcp.approx): n=%lld p=%d K=%d: %.3f ms = %.1f Gentries/s -> %.1f ms for 1M x 20k; "
+           "max rel err of PV on 4 cells %.2e\n", NS == 3 ? "3xTF32" : "TF32", (long long)n, p, K, ms, entries / ms / 1e6, ms * (1e6 * 20000.0) / entries, worst);
     return worst < 5e-3 ? 0 : 2;
 }
