@@ -25,7 +25,12 @@ constexpr int K1 = NS * KF;            // contraction length of the first produc
 #ifndef DRAIN
 #define DRAIN 4                        // tiles between two read-outs of the TMEM accumulator
 #endif
+#ifdef SPLIT3
 constexpr int COL_S = 0, COL_P = 64, COL_PLO = 128, COL_PV = 192, TMEM_COLS = 256;
+#else
+// plain TF32: P overwrites S in place, 96 of 128 allocated columns -> four CTAs share the 512 TMEM columns of an SM
+constexpr int COL_S = 0, COL_P = 0, COL_PLO = 0, COL_PV = 64, TMEM_COLS = 128;
+#endif
 constexpr int TILE_B1 = TG * K1 * 4, TILE_B2 = (NS == 3 ? 2 : 1) * KF * TG * 4, TILE_C = TG * 4, TILE_BYTES = TILE_B1 + TILE_B2 + TILE_C;
 __host__ __device__ inline float tf32_hi(float x) {
 #ifdef __CUDA_ARCH__
