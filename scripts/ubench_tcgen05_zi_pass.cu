@@ -22,11 +22,12 @@ constexpr int NS = 3;
 constexpr int NS = 1;
 #endif
 constexpr int K1 = NS * KF;            // contraction length of the first product
+constexpr int NBUF = NS == 3 ? 1 : 2;  // operand tile buffers (3xTF32: one, so that two CTAs fit an SM)
 #ifndef DRAIN
 #define DRAIN 4                        // tiles between two read-outs of the TMEM accumulator
 #endif
 #ifdef SPLIT3
-constexpr int COL_S = 0, COL_P = 64, COL_PLO = 128, COL_PV = 192, TMEM_COLS = 256;
+constexpr int COL_S = 0, COL_P = 0, COL_PLO = 64, COL_PV = 128, TMEM_COLS = 256;     // P_hi over S in place
 #else
 // plain TF32: P overwrites S in place, 96 of 128 allocated columns -> four CTAs share the 512 TMEM columns of an SM
 constexpr int COL_S = 0, COL_P = 0, COL_PLO = 0, COL_PV = 64, TMEM_COLS = 128;
@@ -114,14 +115,14 @@ __global__ void __launch_bounds__(128) k_zi_fp32(int64_t n, int p, const float *
     const uint32_t t0 = tmem_base, lane_addr = t0 + ((uint32_t)(warp * 32) << 16);
     const uint32_t idesc1 = make_idesc(128, TG), idesc2 = make_idesc(128, KF);
     const uint32_t lboA = (128 / 8) * 128, lboB1 = (TG / 8) * 128, lboB2 = (KF / 8) * 128;
-    if (tid == 0) { bulk_load(sT, tiles, TILE_BYTES, &full[0]); if (ntiles > 1) bulk_load(sT + TILE_BYTES, tiles + TILE_BYTES, TILE_BYTES, &full[1]); }
+    if (tid == 0) { bulk_load(sT, tiles, TILE_BYTES, &full[0]); if (NBUF > 1 && ntiles > 1) bulk_load(sT + TILE_BYTES, tiles + TILE_BYTES, TILE_BYTES, &full[1]); }
     double pvacc[KF];
 #pragma unroll
     for (int c = 0; c < KF; ++c) pvacc[c] = 0.0;
     for (int t = 0; t < ntiles; ++t) {
-        unsigned char *buf = sT + (t & 1) * TILE_BYTES;
+        unsigned char *buf = sT + (t % NBUF) * TILE_BYTES;
         if (tid == 0) {
-            mbar_wait(&full[t & 1], (t >> 1) & 1);
+            mbar_wait(&full[t % NBUF], (t / NBUF) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int s = 0; s < K1 / 8; ++s) {
                 const uint64_t da = make_desc(smem_u32(sA) + 2 * s * lboA, lboA, 128), db = make_desc(smem_u32(buf) + 2 * s * lboB1, lboB1, 128);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(128) k_zi_fp32(int64_t n, int p, const float *
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done_pv)) : "memory");
             // the second product has to be through with this operand buffer (and with P) before either is overwritten
             mbar_wait(&done_pv, t & 1);
-            if (t + 2 < ntiles) bulk_load(buf, tiles + (int64_t)(t + 2) * TILE_BYTES, TILE_BYTES, &full[t & 1]);
+            if (t + NBUF < ntiles) bulk_load(buf, tiles + (int64_t)(t + NBUF) * TILE_BYTES, TILE_BYTES, &full[t % NBUF]);
         }
         __syncthreads();
         // The TMEM accumulator adds with truncation: left alone over all 313 tiles it drifts by ~2e-4 relative.  Every DRAIN
@@ -217,7 +218,7 @@ int main(int argc, char **argv) {
     cudaMemcpy(dEU, EU.data(), EU.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dEVS, EVS.data(), EVS.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dc, c.data(), c.size() * 4, cudaMemcpyHostToDevice);
     k_pack<<<592, 256>>>(p, dEVS, dc, dT);
-    const size_t smem = 128 * K1 * 4 + 2 * TILE_BYTES;
+    const size_t smem = 128 * K1 * 4 + NBUF * TILE_BYTES;
     cudaFuncSetAttribute(k_zi_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned grid = (unsigned)((n + 127) / 128);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
