@@ -266,6 +266,8 @@ typedef struct {
     double *prob_S, *prior_S; int *S; double sel_bound;   /* p x K, p, p x K */
     int *factor_order;
     orc_rng rng;
+    int nz_only;   /* sparse-aware variant of the same loops: entries with X = 0, whose multinomial weights are multiplied by 0, skip the
+                    * K exponentials (orc_set_sparse_aware; bench.py's second CPU figure).  0 = the reference's loops as they are. */
 } orc_model;
 
 static double *dalloc(long len, double v) {
@@ -309,6 +311,7 @@ void orc_destroy(orc_model *m) {
     free(m->S); free(m->factor_order); free(m);
 }
 void orc_seed(orc_model *m, uint32_t seed) { orc_rng_seed(&m->rng, seed); }
+void orc_set_sparse_aware(orc_model *m, int flag) { m->nz_only = flag != 0; }
 /* `my_model = tmp_model` of the multi-init loop (wrapper_gap_factor.h:339-345): deep copy of every member, including
  * the `old` iterates.  Both models must have been created with the same kind and sizes. */
 void orc_copy_state(orc_model *dst, const orc_model *src) {
@@ -553,6 +556,7 @@ static void update_variational_multinomial_param(orc_model *m) {
 #pragma omp for
         for (int j = 0; j < p; j++) {
             for (int i = 0; i < n; i++) {
+                if (m->nz_only && m->X[i + (long)j * n] == 0) continue;   /* every term below carries the factor X_ij */
                 double tv = multinomial_vec(m, i, j, vec);
                 m->T[i + (long)j * n] = tv;
                 tv = tv > 0 ? tv : 1;
@@ -582,7 +586,10 @@ static void intermediate_update_variational_multinomial_param(orc_model *m) {
         double *vec = (double *)malloc(8 * K);
 #pragma omp for
         for (int j = 0; j < p; j++)
-            for (int i = 0; i < n; i++) m->T[i + (long)j * n] = multinomial_vec(m, i, j, vec);
+            for (int i = 0; i < n; i++) {
+                if (m->nz_only && m->X[i + (long)j * n] == 0) continue;   /* T is only read where X != 0 (orc_elbo) */
+                m->T[i + (long)j * n] = multinomial_vec(m, i, j, vec);
+            }
         free(vec);
     }
 }
@@ -646,9 +653,13 @@ static void update_variational_sparse_param(orc_model *m) {
             else {
                 for (int k = 0; k < K; k++) tmp[k] = 0;
                 for (int i = 0; i < n; i++) {
+                    double pd = m->zi ? m->prob_D[i + (long)j * n] : 1.0;
+                    if (m->nz_only && m->X[i + (long)j * n] == 0) {           /* only the rate term is left: no exponentials */
+                        for (int k = 0; k < K; k++) tmp[k] -= pd * m->EU[i + (long)k * n] * m->EV[j + (long)k * p];
+                        continue;
+                    }
                     double tv = multinomial_vec(m, i, j, vec);
                     tv = tv > 0 ? tv : 1;
-                    double pd = m->zi ? m->prob_D[i + (long)j * n] : 1.0;
                     for (int k = 0; k < K; k++) {
                         double r = vec[k] / tv;
                         if (m->zi) {
@@ -765,6 +776,7 @@ double orc_elbo(orc_model *m) {
         for (int j = 0; j < p; j++)
             for (int i = 0; i < n; i++) {
                 long e = i + (long)j * n;
+                if (m->nz_only && m->X[e] == 0) continue;
                 tmp += (m->zi ? m->prob_D[e] : 1.0) * m->X[e] * log(m->T[e]);
             }
     } else {
@@ -775,6 +787,7 @@ double orc_elbo(orc_model *m) {
             for (int j = 0; j < p; j++)
                 for (int i = 0; i < n; i++) {
                     long e = i + (long)j * n;
+                    if (m->nz_only && m->X[e] == 0) continue;
                     double tv = multinomial_vec(m, i, j, vec);
                     tv = tv > 0 ? tv : 1;
                     for (int k = 0; k < K; k++) {

@@ -90,6 +90,7 @@ def lib():
         L.orc_init_from_factor.argtypes = [C.c_void_p, dp, dp]
         L.orc_init_random.argtypes = [C.c_void_p]
         L.orc_perturb_param.argtypes = [C.c_void_p, C.c_double]
+        L.orc_set_sparse_aware.argtypes = [C.c_void_p, C.c_int]
         for name in ("orc_update_param", "orc_phase_estep", "orc_phase_mstep", "orc_phase_sparse", "orc_phase_poisson",
                      "orc_phase_zi", "orc_phase_hyper", "orc_prepare_next_iterate", "orc_order_factor", "orc_estep_only"):
             getattr(L, name).argtypes = [C.c_void_p]
@@ -215,6 +216,11 @@ class Model:
 
     def perturb_param(self, noise_level):
         self.L.orc_perturb_param(self.h, float(noise_level))
+
+    def set_sparse_aware(self, flag=True):
+        """Same loops, but entries with X = 0 skip the K exponentials their zero weight would be multiplied with (the
+        sparse-aware CPU figure of bench.py)."""
+        self.L.orc_set_sparse_aware(self.h, int(bool(flag)))
 
     # ---- iteration ------------------------------------------------------------------
     def update_param(self):

@@ -145,3 +145,36 @@ def test_guard_paths_match_dense_definition():
     assert np.allclose(EZ_i.sum(1), X.sum(0), rtol=1e-12)
     # row 1: every exponent floored -> uniform split 1/K
     assert np.allclose(EZ_j[1], X[1].sum() / K, rtol=1e-12)
+
+
+@pytest.mark.parametrize("zi,sparse", [(False, False), (True, False), (False, True), (True, True)], ids=["gap", "zi", "sparse", "zi_sparse"])
+def test_sparse_aware_cpu_variant_is_the_same_algorithm(zi, sparse):
+    """bench.py's second CPU figure times the oracle with set_sparse_aware(): the same loops, except that an entry with
+    X = 0 -- whose multinomial weights are multiplied by X = 0 everywhere they are used -- skips the K exponentials.  The
+    trajectories must coincide (summation order of the spike-and-slab term aside)."""
+    from pcmf_b200 import datagen
+    X, _, _ = datagen.simulate(60, 45, 4, signal_U=15.0, signal_V=15.0, prob1=0.4, seed=31)
+    K = 3
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=5)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    ms = []
+    for aware in (False, True):
+        m = po.Model(X, K, zi, sparse)
+        m.set_sparse_aware(aware)
+        if sparse:
+            m.init_sparse_param(0.5, prob_S, prior_S)
+        if zi:
+            m.init_zi_param()
+        m.init_variational_param(a1, a2, b1, b2)
+        ms.append(m)
+    for it in range(6):
+        for m in ms:
+            m.update_param()
+        e0, e1 = ms[0].elbo(), ms[1].elbo()
+        assert abs(e0 - e1) < 1e-11 * abs(e0), (it, e0, e1)
+        for k in ("a1", "a2", "b1", "b2"):
+            assert np.max(np.abs(ms[0].get(k) - ms[1].get(k)) / np.abs(ms[0].get(k))) < 1e-11, (it, k)
+        if sparse:
+            assert np.max(np.abs(ms[0].get("prob_S") - ms[1].get("prob_S"))) < 1e-11
+        for m in ms:
+            m.prepare_next_iterate()
