@@ -855,7 +855,7 @@ struct ZiAArgs {
 // a running product of (1+e^-z) and takes one log per ~hundred entries.
 template <int KP, int TJ>
 __global__ void __launch_bounds__(128, 2) k_zi_pass_cells(ZiAArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_evs = reinterpret_cast<double *>(smem_raw);          // TJ x KP
     double *s_c = s_evs + TJ * KP;                                 // TJ
     double *s_cs = s_c + TJ;                                       // 4 x TJ per-warp gene sums
@@ -961,7 +961,7 @@ struct ZiBArgs {
 // of 32); every broadcast shared-memory load of a cell's EU feeds four DFMAs.
 template <int KP, int TI>
 __global__ void __launch_bounds__(128, 2) k_zi_pass_genes(ZiBArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_uz = reinterpret_cast<double *>(smem_raw);   // TI x KP
     double *s_un = s_uz + TI * KP;                         // TI x KP
     const int jA = blockIdx.x * 256 + threadIdx.x, jB = jA + 128;

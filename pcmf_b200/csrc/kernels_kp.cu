@@ -42,7 +42,6 @@ void launch_gene_pass(bool f32, int mode, const ColArgs &a, int grid, cudaStream
 constexpr int MMA_MT = (KP <= 20) ? 4 : 2;          // 8-row tiles per warp in the DMMA ZI passes
 constexpr int MMA_TJ = 64;                           // genes per shared-memory tile, pass A
 constexpr int MMA_TI = 64;                          // cells per shared-memory tile, pass B
-constexpr int MMA_KS = KP / 4, MMA_NT = (KP + 7) / 8;
 
 inline int pack_grid(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 16)); }
 

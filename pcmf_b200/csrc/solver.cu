@@ -448,9 +448,6 @@ __global__ void k_init_guard(long long *g) {
         g[G_MINV] = dbl_ordered(1e300); g[G_MAXV] = dbl_ordered(-1e300);
     }
 }
-__global__ void k_copy_guard_v(long long *dst, const long long *src) {
-    if (threadIdx.x == 0) { dst[G_MINV] = src[G_MINV]; dst[G_MAXV] = src[G_MAXV]; }
-}
 __global__ void k_refresh_weights(int32_t p, int K, int KP, int sparse, const double *prob_S, const double *colw, const double *ev,
                                   double *wS, double *evw) {
     const int64_t total = (int64_t)p * KP;
