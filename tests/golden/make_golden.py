@@ -4,7 +4,7 @@
 -- on small seeded inputs with an explicit initialisation.  The fixtures travel with the repo, /root/reference does
 not; tests/test_golden_vectors.py pins the CPU oracle (and tests/test_gpu_golden.py the CUDA path) against them.
 
-Run from the repo root, only where /root/reference exists:  python tests/golden/make_golden.py"""
+Run from the repo root, only where /root/reference exists:  python tests/golden/make_golden.py  [--extra for the second family]"""
 import os
 import sys
 
@@ -69,5 +69,50 @@ def main():
         print(name, "nb_iter", r["convergence"]["nb_iter"], "loss", r["loss"], "exp_dev", r["exp_dev"])
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--extra" not in sys.argv:
     main()
+
+
+# ---- second family: other entry paths of the same call (seeded random init, RV-coefficient stopping rule, init from
+# factors), again outputs of the reference build.  Only quantities the reference defines for every model are kept
+# (the sparse ELBO of the reference is NaN-prone, see above).
+EXTRA = {"seeded_gap": (False, False), "seeded_zi_sparse": (True, True), "rv_zi": (True, False), "factor_sparse": (False, True)}
+
+
+def extra_inputs(name):
+    zi, sparse = EXTRA[name]
+    seed = {"seeded_gap": 51, "seeded_zi_sparse": 52, "rv_zi": 53, "factor_sparse": 54}[name]
+    X, _, _ = datagen.simulate(44, 32, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=seed)
+    K = 4
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=10, iter_min=10, reorder_factor=False)
+    if name.startswith("seeded"):
+        kw.update(seed=4000 + seed)
+    elif name == "rv_zi":
+        a1, a2, b1, b2 = datagen.random_init(X, K, seed=seed + 100)
+        kw.update(a1=a1, a2=a2, b1=b1, b2=b2, conv_mode=2, iter_max=15, iter_min=3, epsilon=1e-3, additional_iter=2)
+    else:
+        rng = np.random.default_rng(seed)
+        kw.update(U=rng.exponential(1.0, (X.shape[0], K)) + 0.05, V=rng.exponential(1.0, (X.shape[1], K)) + 0.05)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    return X, K, zi, sparse, kw
+
+
+def main_extra():
+    for name in EXTRA:
+        X, K, zi, sparse, kw = extra_inputs(name)
+        r = pyref.run(X, K, zi, sparse, **kw)
+        flat = {"X": X, "K": np.array(K), "nb_iter": np.array(r["convergence"]["nb_iter"]), "converged": np.array(r["convergence"]["converged"]),
+                "conv_crit": np.asarray(r["convergence"]["conv_crit"])}
+        for k, v in kw.items():
+            flat["kw_" + k] = np.asarray(v)
+        for g in ("variational_params", "stats"):
+            for k, v in r[g].items():
+                flat["%s.%s" % (g, k)] = np.asarray(v)
+        np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % name), **flat)
+        print(name, "nb_iter", r["convergence"]["nb_iter"])
+
+
+if __name__ == "__main__" and "--extra" in sys.argv:
+    main_extra()

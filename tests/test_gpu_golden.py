@@ -19,3 +19,14 @@ def test_cuda_path_matches_golden_reference_vectors(name):
     kw = run_kwargs(inp, sparse)
     res = RUN[(zi, sparse)](inp["X"], inp["K"], verbose=False, monitor=True, **kw)
     compare_result(res, ref, sparse, zi, 1e-6, "cuda vs golden " + name)
+
+
+@pytest.mark.parametrize("name", ["seeded_gap", "seeded_zi_sparse", "rv_zi", "factor_sparse"])
+def test_cuda_path_matches_second_family_of_golden_vectors(name):
+    """Seeded random init (one MT19937 stream, cells then genes), the RV-coefficient stopping rule and init_from_factor,
+    each against outputs of the reference build."""
+    from tests.test_golden_vectors import EXTRA, compare_extra, load_extra
+    zi, sparse = EXTRA[name]
+    X, K, kw, ref = load_extra(name)
+    res = RUN[(zi, sparse)](X, K, verbose=False, monitor=True, **kw)
+    compare_extra(res, ref, 1e-6, "cuda vs golden " + name)
