@@ -324,6 +324,8 @@ def main():
     hbm_peak, peak_src = measured_peaks()
     stored_prob_D_bytes = int(ph1.pop("stored_prob_D_bytes", (0.0, 0))[1])
     ph0.pop("stored_prob_D_bytes", None)
+    cell_blocks = int(ph1.pop("gene_pass_cell_blocks", (0.0, 1))[1])
+    ph0.pop("gene_pass_cell_blocks", None)
     per = {k: ((ph1[k][0] - ph0[k][0]) / max(1, args.steps), (ph1[k][1] - ph0[k][1]) // max(1, args.steps)) for k in ph1}
     w = 8
     zi, sparse = cfg["zi"], cfg["sparse"]

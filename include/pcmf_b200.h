@@ -103,11 +103,19 @@ typedef struct {
     pcmf_progress_fn progress;
     void *progress_ctx;
     int32_t progress_every;    /* default 10 */
-    int32_t kernel_variant;    /* 0 = default.  Bit mask for A/B measurements and tests, results are the same within rounding:
-                                *   4 thread-per-row ZI kernels instead of the DMMA tiles, 8 two row tiles per warp,
-                                *   16 no stored q (the cell pass recomputes T), 32 dense first ZI pass instead of the
-                                *   non-zero shortcut, 64 / 128 force / forbid keeping prob_D between the ZI passes,
-                                *   512 gene passes in one cell block, 1024 64-cell blocks */
+    /* precision of the hot kernels.  0 (default): FP64 mode, results within 1e-6 of the reference's C++ path (the parity
+     * tests hold 1e-8).  1: FP32 mode -- the dense zero-inflation passes run on the tcgen05 tensor cores with TF32
+     * operands split three ways and FP32 accumulation in tensor memory, the non-zero passes gather FP32 copies of the
+     * factor statistics; everything that is summed over cells or genes, the M-step and the ELBO stay FP64.  Stated bound
+     * (tests/test_gpu_fp32.py): variational parameters within 1e-4, ELBO within 1e-5 relative of the FP64 path.
+     * The reference is FP64 only (MatrixXd everywhere); there is no reference file for this mode. */
+    int32_t precision;
+    /* > 1: pcmf_fit shards the cells over devices 0 .. ngpus-1 ITSELF (one host thread per device, NCCL communicator
+     * created inside the library, no callback, no launcher): the GPU counterpart of `ncores` -> omp_set_num_threads
+     * (wrapper_gap_factor.h:271-274).  Input and output buffers are the whole matrices, as on one GPU.  0 / 1: one
+     * device (`device`), or an external launcher that sets rank / world / allreduce. */
+    int32_t ngpus;
+    int32_t dev_flags;         /* 0.  Development switches for A/B measurements and tests (include/pcmf_b200_dev.h) */
 } pcmf_options;
 
 /* Optional warm-start values (NULL = absent), column-major, sizes for the LOCAL rows.
@@ -116,11 +124,17 @@ typedef struct {
 typedef struct {
     const double *U, *V;                         /* n_local x K, p x K  -> init_from_factor (gap_factor_model.cpp:135-144) */
     const double *a1, *a2, *b1, *b2;             /* -> init_variational_param (gap_factor_model.cpp:113-123) */
-    const double *alpha1, *alpha2, *beta1, *beta2; /* K-vectors (the reference's n x K / p x K with identical rows) */
+    const double *alpha1, *alpha2, *beta1, *beta2; /* hyper_rows = 0: K-vectors (identical rows, what every state reachable
+                                                    * from Ones has); hyper_rows = 1: the reference's n_local x K / p x K
+                                                    * matrices as given (gap_factor_model.cpp:126-132).  As in the reference's
+                                                    * else-if chain (wrapper_gap_factor.h:352-375) they are only looked at when
+                                                    * neither U, V nor a1..b2 are given: init_hyper_param alone, the variational
+                                                    * state stays at the constructor's Ones, no random draw, no hyper update */
     const double *prob_S, *prior_S;              /* p x K, p -> init_sparse_param (sparse_gap_factor_model.cpp:96-104) */
     const double *prob_D, *prior_D;              /* n_local x p (dense), p -> init_zi_param(prob_D, prior_D)
                                                   * (zi_gap_factor_model.cpp:110-114; both or neither).  The dense matrix is
                                                   * only held until the first zero-inflation update replaces it */
+    int32_t hyper_rows;                          /* layout of alpha1..beta2, see above */
 } pcmf_init;
 
 /* Caller-allocated outputs (NULL = not wanted); column-major; U-side sizes are for the LOCAL rows.
@@ -134,7 +148,8 @@ typedef struct {
     double *prob_D;                                   /* n_local x p  (ZI; dense, only if the caller wants it) */
     double *freq_D, *prior_prob_D;                    /* p, p         (ZI) */
     int32_t *factor_order;                            /* K */
-    /* convergence / monitor vectors: caller allocates iter_max doubles each */
+    /* convergence / monitor vectors: caller allocates iter_max doubles each (multi-init needs iter_init <= iter_max:
+     * the kept run's first iter_init entries are written there, wrapper_gap_factor.h:296-350) */
     double *conv_crit, *norm_gap, *abs_gap, *optim_criterion, *loglikelihood, *deviance;
     /* scalars written by the library */
     int32_t nb_iter;
@@ -184,21 +199,8 @@ int pcmf_get_output(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errle
 /* overwrite the variational state (teacher forcing): same post-steps as init_variational_param */
 int pcmf_set_variational(pcmf_solver *s, const double *a1, const double *a2, const double *b1, const double *b2,
                          char *errbuf, size_t errlen);
-/* per-phase device timings of the last pcmf_iterate/pcmf_optimize call, milliseconds summed over iterations:
- * names[i] points to a static string; returns the number of phases written (<= cap) */
-int pcmf_phase_times(pcmf_solver *s, const char **names, double *ms, int64_t *launches, int cap);
-/* number of kernel launches issued by the solver since creation */
-int64_t pcmf_launch_count(pcmf_solver *s);
 void pcmf_destroy(pcmf_solver *s);
 
-/* Synthetic benchmark input generated ON DEVICE with the package's generative model
- * (pkg/R/data_generation.R:393-463: X = Poisson(U V^T) * Bernoulli(prob1_j)), straight into CSR.
- * U: n_local x K_true, V: p x K_true column-major host arrays; prob1: p host (NULL = no drop-out).
- * Two-pass (count, fill); outputs are device pointers owned by the caller (free with pcmf_device_free). */
-int pcmf_generate_counts_device(int device, int64_t n_local, int32_t p, int32_t K_true, const double *U,
-                                const double *V, const double *prob1, uint64_t seed, int64_t row_offset,
-                                int64_t **rowptr_dev, int32_t **colidx_dev, float **val_dev, int64_t *nnz_out,
-                                char *errbuf, size_t errlen);
 /* Per-gene statistics over the LOCAL cells of a CSR matrix (host or device resident): sum_i x, sum_i x^2, #non-zeros
  * and (colmax, may be NULL) the largest count.  Host outputs of length p.  This is what the R wrapper's prior_S
  * heuristic (pCMF.R:228-229: 1 - exp(-sd_j / mean(X[X != 0]))) and prefilter() (prefiltering.R:127-146: column max,
@@ -206,21 +208,9 @@ int pcmf_generate_counts_device(int device, int64_t n_local, int32_t p, int32_t 
 int pcmf_csr_column_stats(int device, int64_t n_local, int32_t p, const int64_t *rowptr, const int32_t *colidx,
                           const float *val_f32, int32_t on_device, double *colsum, double *colsumsq, double *colnnz,
                           double *colmax, char *errbuf, size_t errlen);
-/* Measured FP64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA microbenchmark, ~50 ms): the
- * roofline denominator of the dense zero-inflation passes, which are FP64-pipe bound, not HBM bound. */
-int pcmf_measure_fp64_tflops(int device, double *tflops_out);
-/* Same for the FP64 tensor pipe (mma.sync m8n8k4 DMMA), which the dense zero-inflation passes run on. */
-int pcmf_measure_fp64_mma_tflops(int device, double *tflops_out);
-/* Measured gather bandwidth (GB/s) of 160-byte K-vector rows out of a `rows`-row FP64 table: the ceiling of the E-step
- * non-zero passes, which read one or two such rows per non-zero through L2. */
-int pcmf_measure_gather_gbs(int device, int64_t rows, double *gbs_out);
-int pcmf_device_free(int device, void *ptr);
 /* The library keeps the device memory a finished fit releases for the next fit of the process;
  * this returns all of it to the driver. */
 int pcmf_release_cached_memory(void);
-/* copy device CSR arrays to host buffers (bench e2e leg) */
-int pcmf_device_to_host(int device, void *dst_host, const void *src_dev, size_t bytes);
-
 #ifdef __cplusplus
 }
 #endif

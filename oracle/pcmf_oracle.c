@@ -284,8 +284,10 @@ orc_model *orc_create(int kind, int n, int p, int K, const double *X) {
     m->sparse = (kind == ORC_SPARSE || kind == ORC_ZI_SPARSE);
     long np = (long)n * p, nK = (long)n * K, pK = (long)p * K;
     m->X = dalloc(np, 0); memcpy(m->X, X, sizeof(double) * np);
-    m->UVt = dalloc(np, 0); m->T = dalloc(np, 0);
-    m->EU = dalloc(nK, 0); m->ElogU = dalloc(nK, 0); m->EV = dalloc(pK, 0); m->ElogV = dalloc(pK, 0);
+    /* constructors' Ones: UVt (model.cpp:86-91), EU, EV, ElogU, ElogV (model.cpp:220-223) -- what init_hyper_param alone
+     * (wrapper_gap_factor.h:362-363) leaves in place */
+    m->UVt = dalloc(np, 1); m->T = dalloc(np, 0);
+    m->EU = dalloc(nK, 1); m->ElogU = dalloc(nK, 1); m->EV = dalloc(pK, 1); m->ElogV = dalloc(pK, 1);
     m->a1 = dalloc(nK, 1); m->a2 = dalloc(nK, 1); m->a1o = dalloc(nK, 1); m->a2o = dalloc(nK, 1);
     m->b1 = dalloc(pK, 1); m->b2 = dalloc(pK, 1); m->b1o = dalloc(pK, 1); m->b2o = dalloc(pK, 1);
     m->alpha1 = dalloc(nK, 1); m->alpha2 = dalloc(nK, 1); m->alpha1o = dalloc(nK, 1); m->alpha2o = dalloc(nK, 1);

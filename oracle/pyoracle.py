@@ -284,7 +284,8 @@ class Model:
 
 def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True, iter_max=1000, iter_min=500,
         epsilon=1e-2, additional_iter=10, conv_mode=1, reorder_factor=True, seed=None,
-        a1=None, a2=None, b1=None, b2=None, prob_S=None, prior_S=None, ninit=1, iter_init=100, prob_D=None, prior_D=None, U=None, V=None):
+        a1=None, a2=None, b1=None, b2=None, prob_S=None, prior_S=None, ninit=1, iter_init=100, prob_D=None, prior_D=None, U=None, V=None,
+        alpha1=None, alpha2=None, beta1=None, beta2=None):
     """Restatement of wrapper_gap_factor.h:164-393 / wrapper_sparse_gap_factor.h:176-435 (init order of :389-417,
     multi-init loop of :296-350 / :328-387), returning a dict shaped like the reference's R list."""
     m = Model(X, K, zero_inflation, sparsity)
@@ -300,6 +301,8 @@ def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True,
                 mod.perturb_param(max(np.max(U), np.max(V)) / K)
         elif a1 is not None:
             mod.init_variational_param(a1, a2, b1, b2)
+        elif alpha1 is not None:                   # wrapper_gap_factor.h:362-363: init_hyper_param alone (else-if chain: only
+            mod.init_hyper_param(alpha1, alpha2, beta1, beta2)   # reached when neither U, V nor a1..b2 are given)
         else:
             mod.init_random()
 

@@ -46,6 +46,7 @@ def lib():
         L.ref_init_zi.argtypes = [C.c_void_p]
         L.ref_init_zi_given.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
         L.ref_init_variational.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int]
+        L.ref_init_hyper.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int]
         L.ref_init_factor.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int, C.c_int]
         L.ref_perturb_param.argtypes = [C.c_void_p, C.c_double]
         for nm in ("ref_init_random", "ref_optimize", "ref_order_factor", "ref_output"):
@@ -117,6 +118,10 @@ class RefModel:
     def init_random(self):
         self._ck(self.L.ref_init_random(self.h))
 
+    def init_hyper_param(self, alpha1, alpha2, beta1, beta2):
+        arrs = [_f(x) for x in (alpha1, alpha2, beta1, beta2)]
+        self._ck(self.L.ref_init_hyper(self.h, *[a[1] for a in arrs], self.n, self.p, self.K))
+
     def perturb_param(self, noise_level):
         self._ck(self.L.ref_perturb_param(self.h, float(noise_level)))
 
@@ -175,7 +180,7 @@ class RefModel:
 
 def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True, iter_max=1000, iter_min=500, epsilon=1e-2,
         additional_iter=10, conv_mode=1, reorder_factor=True, seed=None, a1=None, a2=None, b1=None, b2=None,
-        prob_S=None, prior_S=None, prob_D=None, prior_D=None, U=None, V=None):
+        prob_S=None, prior_S=None, prob_D=None, prior_D=None, U=None, V=None, alpha1=None, alpha2=None, beta1=None, beta2=None):
     m = RefModel(X, K, zero_inflation, sparsity, monitor, iter_max, iter_min, epsilon, additional_iter, conv_mode)
     if seed is not None:
         m.seed(seed)
@@ -187,6 +192,8 @@ def run(X, K, zero_inflation=False, sparsity=False, sel_bound=0.5, monitor=True,
         m.init_from_factor(U, V)
     elif a1 is not None:                           # :402-403
         m.init_variational_param(a1, a2, b1, b2)
+    elif alpha1 is not None:                       # :404-405 -- init_hyper_param alone; the variational state stays at Ones
+        m.init_hyper_param(alpha1, alpha2, beta1, beta2)
     else:                                          # :410-411
         m.init_random()
     m.optimize()                                   # :421

@@ -37,6 +37,7 @@ struct IRunner {
     virtual void init_zi_given(const MatrixXd &prob_D, const VectorXd &prior_D) = 0;
     virtual void init_variational(const MatrixXd &a1, const MatrixXd &a2, const MatrixXd &b1, const MatrixXd &b2) = 0;
     virtual void init_random(myRandom::RNGType &rng) = 0;
+    virtual void init_hyper(const MatrixXd &al1, const MatrixXd &al2, const MatrixXd &be1, const MatrixXd &be2) = 0;
     virtual void init_factor(const MatrixXd &U, const MatrixXd &V) = 0;
     virtual void perturb(myRandom::RNGType &rng, double noise_level) = 0;
     virtual void optimize() = 0;
@@ -56,6 +57,9 @@ struct Runner : IRunner {
         algo.init_variational_param_gap(a1, a2, b1, b2);
     }
     void init_random(myRandom::RNGType &rng) override { algo.init_random(rng); }
+    void init_hyper(const MatrixXd &al1, const MatrixXd &al2, const MatrixXd &be1, const MatrixXd &be2) override {
+        algo.init_hyper_param_gap(al1, al2, be1, be2);                                        // wrapper_gap_factor.h:362-363
+    }
     void init_factor(const MatrixXd &U, const MatrixXd &V) override { algo.init(U, V); }     // wrapper_gap_factor.h:353-354
     void perturb(myRandom::RNGType &rng, double noise_level) override { algo.perturb_param(rng, noise_level); }   // wrapper_gap_factor.h:314
     void optimize() override { algo.optimize(); }
@@ -116,6 +120,9 @@ int ref_init_variational(void *hv, const double *a1, const double *a2, const dou
     GUARD(h->r->init_variational(mat(a1, n, K), mat(a2, n, K), mat(b1, p, K), mat(b2, p, K)))
 }
 int ref_init_random(void *hv) { GUARD(h->r->init_random(h->rng)) }
+int ref_init_hyper(void *hv, const double *al1, const double *al2, const double *be1, const double *be2, int n, int p, int K) {
+    GUARD(h->r->init_hyper(mat(al1, n, K), mat(al2, n, K), mat(be1, p, K), mat(be2, p, K)))
+}
 int ref_init_factor(void *hv, const double *U, const double *V, int n, int p, int K) { GUARD(h->r->init_factor(mat(U, n, K), mat(V, p, K))) }
 int ref_perturb_param(void *hv, double noise_level) { GUARD(h->r->perturb(h->rng, noise_level)) }
 int ref_optimize(void *hv) { GUARD(h->r->optimize()) }

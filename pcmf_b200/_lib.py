@@ -32,12 +32,13 @@ class Options(C.Structure):
                 ("iter_init", C.c_int32), ("has_seed", C.c_int32), ("seed", C.c_uint32), ("verbose", C.c_int32),
                 ("device", C.c_int32), ("stream", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32),
                 ("allreduce", ALLREDUCE_FN), ("allreduce_ctx", C.c_void_p), ("progress", PROGRESS_FN),
-                ("progress_ctx", C.c_void_p), ("progress_every", C.c_int32), ("kernel_variant", C.c_int32)]
+                ("progress_ctx", C.c_void_p), ("progress_every", C.c_int32), ("precision", C.c_int32), ("ngpus", C.c_int32),
+                ("dev_flags", C.c_int32)]
 
 
 class Init(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("U", "V", "a1", "a2", "b1", "b2", "alpha1", "alpha2", "beta1", "beta2",
-                                          "prob_S", "prior_S", "prob_D", "prior_D")]
+                                          "prob_S", "prior_S", "prob_D", "prior_D")] + [("hyper_rows", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -107,9 +108,11 @@ def check(rc, errbuf):
         raise PcmfError(rc, errbuf.value.decode(errors="replace") or ("pcmf error %d" % rc))
 
 
-# every symbol include/pcmf_b200.h declares (tests check the library exports them all)
+# every symbol include/pcmf_b200.h declares (tests check the library exports them all) ...
 HEADER_SYMBOLS = ["pcmf_version", "pcmf_device_count", "pcmf_fit", "pcmf_create", "pcmf_optimize", "pcmf_iterate",
                   "pcmf_elbo", "pcmf_order_factor", "pcmf_multi_init", "pcmf_monitors", "pcmf_get_output", "pcmf_set_variational",
-                  "pcmf_phase_times", "pcmf_launch_count", "pcmf_destroy", "pcmf_generate_counts_device",
-                  "pcmf_device_free", "pcmf_device_to_host", "pcmf_csr_column_stats", "pcmf_measure_fp64_tflops",
-                  "pcmf_measure_fp64_mma_tflops", "pcmf_measure_gather_gbs", "pcmf_release_cached_memory"]
+                  "pcmf_destroy", "pcmf_csr_column_stats", "pcmf_release_cached_memory"]
+# ... and the development / measurement entry points of include/pcmf_b200_dev.h
+DEV_HEADER_SYMBOLS = ["pcmf_phase_times", "pcmf_launch_count", "pcmf_generate_counts_device", "pcmf_device_free",
+                      "pcmf_device_to_host", "pcmf_measure_fp64_tflops", "pcmf_measure_fp64_mma_tflops",
+                      "pcmf_measure_gather_gbs"]

@@ -317,7 +317,7 @@ class Solver:
         o.has_seed, o.seed = (0, 0) if seed is None else (1, int(seed) & 0xFFFFFFFF)
         o.verbose, o.device = int(bool(verbose)), int(device)
         o.stream = stream
-        o.kernel_variant = int(kernel_variant)
+        o.dev_flags = int(kernel_variant)
         self.comm = comm
         if comm is not None:
             o.rank, o.world, o.allreduce = comm.rank, comm.world, comm.cfn
@@ -343,17 +343,16 @@ class Solver:
         put("V", V, (p, Kk), "U and/or V")
         for f, a, r in (("a1", a1, n), ("a2", a2, n), ("b1", b1, p), ("b2", b2, p)):
             put(f, a, (r, Kk), "a1, a2, b1 and/or b2")
-        for f, a, r in (("alpha1", alpha1, n), ("alpha2", alpha2, n), ("beta1", beta1, p), ("beta2", beta2, p)):
-            if a is None:
-                continue
-            a = np.asarray(a, np.float64)
-            if a.ndim == 2:   # the reference's n x K / p x K form: rows must be identical
-                if a.shape != (r, Kk):
+        # hyper-parameters: the reference's n x K / p x K matrices as given (gap_factor_model.cpp:126-132), or K-vectors
+        hyp = [(f, np.asarray(a, np.float64), r) for f, a, r in (("alpha1", alpha1, n), ("alpha2", alpha2, n),
+                                                                  ("beta1", beta1, p), ("beta2", beta2, p)) if a is not None]
+        if hyp:
+            as_rows = hyp[0][1].ndim == 2
+            for f, a, r in hyp:
+                if (a.ndim == 2) != as_rows or (as_rows and a.shape != (r, Kk)):
                     raise PcmfError(_lib.EINVAL, "Wrong dimension for alpha1, alpha2, beta1 and/or beta2 input matrices")
-                if np.ptp(a, axis=0).max() != 0:
-                    raise PcmfError(_lib.EUNSUPPORTED, "hyper-parameter matrices with non-identical rows are not supported")
-                a = a[0]
-            put(f, a, (Kk,), "alpha1, alpha2, beta1 and/or beta2")
+                put(f, a, (r, Kk) if as_rows else (Kk,), "alpha1, alpha2, beta1 and/or beta2")
+            ini.hyper_rows = int(as_rows)
         if self.sparse and prob_S is not None and prior_S is not None:
             put("prob_S", prob_S, (p, Kk), "prob_S and/or prior_S")
             pv = np.ascontiguousarray(np.asarray(prior_S, np.float64).reshape(-1))

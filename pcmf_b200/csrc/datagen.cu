@@ -11,7 +11,7 @@
 #include <cub/cub.cuh>
 #include <curand_kernel.h>
 
-#include "../../include/pcmf_b200.h"
+#include "../../include/pcmf_b200_dev.h"
 
 namespace {
 

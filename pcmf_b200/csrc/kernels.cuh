@@ -142,6 +142,7 @@ struct RowArgs {
     double *a1, *a2, *EU_new, *ElogU, *eu;
     double2 *rowext;                 // n: (min_k, max_k) of ElogU per cell, read then refreshed
     const double *alpha1, *alpha2;   // K-vectors
+    const double *alpha1r, *alpha2r; // or n x KP (hyper-parameter rows that differ, gap_factor_model.cpp:126-132): override the vectors
     const double *rate_vec;          // KP: colsum(EV o prob_S) (non-ZI)   gap...cpp:531 / sparse...cpp:400
     const double *PV;                // n x KP: prob_D * (EV o prob_S) (ZI) zi...cpp:336 / zi_sparse...cpp:363
     int first_iter;                  // 1: old iterate is Ones (gap_factor_model.cpp:72-75; never copied before iter 0)
@@ -242,8 +243,8 @@ __global__ void __launch_bounds__(256) k_estep_rows(RowArgs a) {
                 const double ez = um[c] * mine[c] + sx[c];
                 const double a1o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a1_old0[o] : a.a1[o]);
                 const double a2o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a2_old0[o] : a.a2[o]);
-                const double a1n = a.alpha1[k] + ez;
-                const double a2n = a.alpha2[k] + (a.PV ? a.PV[o] : a.rate_vec[k]);
+                const double a1n = (a.alpha1r ? a.alpha1r[o] : a.alpha1[k]) + ez;
+                const double a2n = (a.alpha2r ? a.alpha2r[o] : a.alpha2[k]) + (a.PV ? a.PV[o] : a.rate_vec[k]);
                 a.a1[o] = a1n;
                 a.a2[o] = a2n;
                 double el;
@@ -356,8 +357,8 @@ __global__ void __launch_bounds__(256, 2) k_estep_rows_q(RowArgs a) {
                 const double ez = a.eu[o] * mine[c] + sx[c];
                 const double a1o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a1_old0[o] : a.a1[o]);
                 const double a2o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.a2_old0[o] : a.a2[o]);
-                const double a1n = a.alpha1[k] + ez;
-                const double a2n = a.alpha2[k] + (a.PV ? a.PV[o] : a.rate_vec[k]);
+                const double a1n = (a.alpha1r ? a.alpha1r[o] : a.alpha1[k]) + ez;
+                const double a2n = (a.alpha2r ? a.alpha2r[o] : a.alpha2[k]) + (a.PV ? a.PV[o] : a.rate_vec[k]);
                 a.a1[o] = a1n;
                 a.a2[o] = a2n;
                 double el;
@@ -401,6 +402,8 @@ struct UInitArgs {
     double *EU, *ElogU, *eu;
     long long *guard_next;
     double *cs_eu, *cs_elog, *usc;
+    int ones;      // 1: the statistics keep the constructor's Ones (model.cpp:220-223) whatever a1, a2 say -- the state
+                   // init_hyper_param alone leaves behind (wrapper_gap_factor.h:366-367); the entropy still comes from (a1, a2)
 };
 #ifdef PCMF_COMMON_KERNELS
 __global__ void k_stats_u(UInitArgs a) {
@@ -415,6 +418,7 @@ __global__ void k_stats_u(UInitArgs a) {
         if (k < a.K) {
             UAcc one;
             u_element(a.a1[o], a.a2[o], 1.0, 1.0, a.EU + o, a.ElogU + o, a.eu + o, one);
+            if (a.ones) { a.EU[o] = 1.0; a.ElogU[o] = 1.0; a.eu[o] = exp(1.0); one.cs_eu = 1.0; one.cs_elog = 1.0; one.mn = 1.0; one.mx = 1.0; }
             atomicAdd(&scs[0][k], one.cs_eu);
             atomicAdd(&scs[1][k], one.cs_elog);
             acc.ent += one.ent;
@@ -614,6 +618,8 @@ struct VArgs {
     const double *tmpMat;                 // p x KP: prob_D^T EU_new (ZI, all-reduced)
     const double *cs_eu;                  // KP: colsum(EU_new) (all-reduced)
     const double *beta1, *beta2;          // K-vectors
+    const double *beta1r, *beta2r;        // or p x KP rows (see RowArgs::alpha1r)
+    int ones;                             // stats_only: statistics are the constructor's Ones (see UInitArgs::ones)
     double *b1, *b2, *EV, *ElogV;
     const double *prob_S, *Sd, *colw;     // old sparse state / nnz weight of the gene
     double *ev, *evw, *EVS, *wS;          // refreshed here for the non-sparse models; ev (old mask) for the sparse pass
@@ -648,8 +654,8 @@ __global__ void __launch_bounds__(256) k_mstep_genes(VArgs a) {
             }
             b1o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.b1_old0[o] : a.b1[o]);
             b2o = a.first_iter == 1 ? 1.0 : (a.first_iter == 2 ? a.b2_old0[o] : a.b2[o]);
-            b1n = a.beta1[k] + ps * cw * a.B1[o];
-            b2n = a.beta2[k] + ps * (a.zi ? a.tmpMat[o] : a.cs_eu[k]);
+            b1n = (a.beta1r ? a.beta1r[o] : a.beta1[k]) + ps * cw * a.B1[o];
+            b2n = (a.beta2r ? a.beta2r[o] : a.beta2[k]) + ps * (a.zi ? a.tmpMat[o] : a.cs_eu[k]);
             a.b1[o] = b1n;
             a.b2[o] = b2n;
             const double d1 = b1n - b1o, d2 = b2n - b2o;
@@ -660,8 +666,8 @@ __global__ void __launch_bounds__(256) k_mstep_genes(VArgs a) {
             b2n = a.b2[o];
         }
         const double psi = digamma_pos(b1n);
-        const double el = psi - log(b2n);
-        const double EVn = b1n / b2n;
+        const double el = (a.stats_only && a.ones) ? 1.0 : psi - log(b2n);
+        const double EVn = (a.stats_only && a.ones) ? 1.0 : b1n / b2n;
         a.EV[o] = EVn;
         a.ElogV[o] = el;
         en += gamma_entropy1(b1n, b2n, psi);
@@ -1023,6 +1029,31 @@ __global__ void __launch_bounds__(128, 2) k_zi_pass_genes(ZiBArgs a) {
     }
 }
 
+// update_prior_gamma_param (gap...cpp:541-548) when the rows of alpha / beta DIFFER (only reachable from user-supplied
+// matrices, gap...cpp:126-132): alpha1(i,k) = digammaInv(log alpha2_old(i,k) + colmean(ElogU)_k), alpha2 = alpha1 / colmean(EU)_k,
+// one thread per element, plus the Gamma term of the ELBO (likelihood.h:108-113), which has no closed form then.
+#ifdef PCMF_COMMON_KERNELS
+__global__ void k_hyper_rows(int64_t rows, int K, int KP, double count, int update, double *h1, double *h2, const double *cs_e,
+                             const double *cs_elog, const double *E, const double *Elog, double *gout) {
+    __shared__ double sh[32];
+    double g = 0;
+    const int64_t total = rows * KP;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(o % KP);
+        if (k >= K) continue;
+        double al1 = h1[o], al2 = h2[o];
+        if (update) {
+            al1 = digamma_inv(log(al2) + cs_elog[k] / count, 6);
+            al2 = al1 / (cs_e[k] / count);
+            h1[o] = al1; h2[o] = al2;
+        }
+        g += al1 * log(al2) - lgamma(al1) + (al1 - 1.0) * Elog[o] - al2 * E[o];
+    }
+    g = block_sum(g, sh);
+    if (threadIdx.x == 0) atomicAdd(gout, g);
+}
+#endif  // PCMF_COMMON_KERNELS
+
 // ------------------------------------------------------------------------------------------------------------
 // Hyper-parameter update + iteration scalars, one block:
 //   update_prior_gamma_param (gap...cpp:541-548) with internal::digammaInv(., 6); update_prior_zi_param
@@ -1038,6 +1069,9 @@ struct HyperArgs {
     const double *zsc;     // sum prob_D o UVt, Bernoulli self term (all-reduced; ZI only)
     double lgx_const;      // sum_ij lgamma(X_ij + 1) for the non-ZI models
     double *scal;
+    int update;            // 0: keep alpha / beta as they are (init_hyper_param alone runs no update_hyper_param)
+    const double *rows_g;  // or null.  Hyper-parameter ROWS that differ (k_hyper_rows did the update): [0] Gamma term of U
+                           //   (all-reduced), [1] of V; the K-vectors are not used then
 };
 #ifdef PCMF_COMMON_KERNELS
 __global__ void __launch_bounds__(256) k_hyper(HyperArgs a) {
@@ -1046,11 +1080,12 @@ __global__ void __launch_bounds__(256) k_hyper(HyperArgs a) {
     if (threadIdx.x < a.K) {
         const int k = threadIdx.x;
         const double n = (double)a.n_global, p = (double)a.p;
-        const double al1 = digamma_inv(log(a.alpha2[k]) + a.cs_elog[k] / n, 6);
-        const double al2 = al1 / (a.cs_eu[k] / n);
+        const bool upd = a.update && !a.rows_g;
+        const double al1 = upd ? digamma_inv(log(a.alpha2[k]) + a.cs_elog[k] / n, 6) : a.alpha1[k];
+        const double al2 = upd ? al1 / (a.cs_eu[k] / n) : a.alpha2[k];
         a.alpha1[k] = al1; a.alpha2[k] = al2;
-        const double be1 = digamma_inv(log(a.beta2[k]) + a.cs_elogv[k] / p, 6);
-        const double be2 = be1 / (a.cs_ev[k] / p);
+        const double be1 = upd ? digamma_inv(log(a.beta2[k]) + a.cs_elogv[k] / p, 6) : a.beta1[k];
+        const double be2 = upd ? be1 / (a.cs_ev[k] / p) : a.beta2[k];
         a.beta1[k] = be1; a.beta2[k] = be2;
         gU = n * (al1 * log(al2) - lgamma(al1)) + (al1 - 1.0) * a.cs_elog[k] - al2 * a.cs_eu[k];
         gV = p * (be1 * log(be2) - lgamma(be1)) + (be1 - 1.0) * a.cs_elogv[k] - be2 * a.cs_ev[k];
@@ -1068,6 +1103,7 @@ __global__ void __launch_bounds__(256) k_hyper(HyperArgs a) {
     }
     gU = block_sum(gU, sh); gV = block_sum(gV, sh); closed = block_sum(closed, sh); bd = block_sum(bd, sh);
     if (threadIdx.x == 0) {
+        if (a.rows_g) { gU = a.rows_g[0]; gV = a.rows_g[1]; }
         double *s = a.scal;
         s[S_GAMMAU] = gU; s[S_GAMMAV] = gV; s[S_SUMUVT_CLOSED] = closed; s[S_BERND_PRIOR] = bd;
         s[S_GAPU_D] = a.usc[0]; s[S_GAPU_O] = a.usc[1]; s[S_ENTU] = a.usc[2];
@@ -1331,6 +1367,44 @@ __global__ void k_dense_zi_cells(int64_t n, int32_t p, int K, int KP, const doub
     if (live) for (int k = 0; k < KP; ++k) PV[i * KP + k] = k < K ? pv[k] : 0.0;
     spl = block_sum(spl, sh); ent = block_sum(ent, sh);
     if (threadIdx.x == 0) { atomicAdd(zsc + 0, spl); atomicAdd(zsc + 1, ent); }
+}
+// Monitors while prob_D still is the explicit matrix of a warm start (zi...cpp:160-167, :218-245; likelihood.h:149-155,
+// :197-212), thread per cell, lambda = EU_i . EVS_j:
+//   out[0] += sum_nnz x clog(P lambda)           deviance / exp_deviance, rate prob_D o UVt
+//   out[1] += sum_nnz x clog(lambda)             zi_poisson_loglike, non-zero entries
+//   out[2] += sum_nnz lambda
+//   out[3] += #non-zeros with P = 0              log(prob_D) = -inf
+//   out[5] += sum_zeros log(1 - P + P e^-lambda)
+//   out[7] += sum_nnz log P                      (over P > 0)
+template <typename VT>
+__global__ void k_dense_zi_monitor(int64_t n, int32_t p, int K, int KP, const double *P, const double *EU, const double *EVS,
+                                   const int64_t *rowptr, const int32_t *colidx, const void *val_, const uint32_t *bitT, double *out) {
+    const VT *val = static_cast<const VT *>(val_);
+    __shared__ double sh[32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t5 = 0, t7 = 0;
+    if (live) {
+        for (int j = 0; j < p; ++j) {
+            if ((bitT[(int64_t)(j >> 5) * n + i] >> (j & 31)) & 1u) continue;
+            double lam = 0;
+            for (int k = 0; k < K; ++k) lam = fma(EU[i * KP + k], EVS[(int64_t)j * KP + k], lam);
+            const double pj = P[i + (int64_t)j * n];
+            t5 += log(1.0 - pj + pj * exp(-lam));
+        }
+        for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+            const int j = colidx[e];
+            const double x = (double)val[e], pj = P[i + (int64_t)j * n];
+            double lam = 0;
+            for (int k = 0; k < K; ++k) lam = fma(EU[i * KP + k], EVS[(int64_t)j * KP + k], lam);
+            t0 += x * custom_log(pj * lam); t1 += x * custom_log(lam); t2 += lam;
+            if (pj > 0.0) t7 += log(pj); else t3 += 1.0;
+        }
+    }
+    t0 = block_sum(t0, sh); t1 = block_sum(t1, sh); t2 = block_sum(t2, sh); t3 = block_sum(t3, sh); t5 = block_sum(t5, sh); t7 = block_sum(t7, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(out + 0, t0); atomicAdd(out + 1, t1); atomicAdd(out + 2, t2); atomicAdd(out + 3, t3); atomicAdd(out + 5, t5); atomicAdd(out + 7, t7);
+    }
 }
 // "pass B" on an explicit P: tmpMat += P^T EU_new; thread per gene
 __global__ void k_dense_zi_genes(int64_t n, int32_t p, int K, int KP, const double *P, const double *EUn, double *tmpMat) {

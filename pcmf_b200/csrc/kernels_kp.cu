@@ -48,7 +48,7 @@ inline int pack_grid(int64_t total) { return (int)std::max<int64_t>(1, std::min<
 template <int MT>
 int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
     using R = ZiRec<KP, true>;
-    const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 8 * MMA_TJ + 64);
+    const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 8 * MMA_TJ + kTabDoubles);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -87,7 +87,7 @@ template <int MT>
 int launch_zi_genes_mma_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
     if (a.pstore) return launch_zi_genes_stored_t<MT>(a, chunks, st);
     using R = ZiRec<KP, false>;
-    const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * R::REC + 64);
+    const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * R::REC + kTabDoubles);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_genes_mma<KP, MT, MMA_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -109,7 +109,7 @@ int launch_zi_genes_mma(const ZiBArgs &a, int chunks, int variant, cudaStream_t 
 }
 void launch_zi_loglik(const ZiAArgs &a, double *out, cudaStream_t st) {
     using R = ZiRec<KP, true>;
-    const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 2 * MMA_TJ + 64);
+    const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 2 * MMA_TJ + kTabDoubles);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_zi_loglik_mma<KP, MMA_MT, MMA_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

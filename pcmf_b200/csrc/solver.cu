@@ -22,7 +22,7 @@
 
 #include <cub/cub.cuh>
 
-#include "../../include/pcmf_b200.h"
+#include "../../include/pcmf_b200_dev.h"
 #define PCMF_COMMON_KERNELS 1
 #include "launch.cuh"
 
@@ -252,6 +252,11 @@ struct pcmf_solver {
     int32_t *S = nullptr, *flag = nullptr;
     double *prior_S = nullptr, *prior_D = nullptr, *cz = nullptr, *colw = nullptr;
     double *hyp = nullptr;   // alpha1, alpha2, beta1, beta2, colsum(EV o prob_S) kept for the next a2 update: 5 x 64
+    // hyper-parameter matrices whose rows differ (only reachable from user-supplied alpha / beta, gap_factor_model.cpp:126-132):
+    // alpha1, alpha2 (n x KP), beta1, beta2 (p x KP) and the two Gamma ELBO terms k_hyper_rows accumulates
+    double *hrow[4] = {nullptr, nullptr, nullptr, nullptr}, *rowsg = nullptr;
+    bool rows_mode = false;
+    void hyper_update(bool update, const double *EU_now);
     double *csv = nullptr;   // cs_ev, cs_elogv, cs_evs: 3 x 64
     // reduction buffers
     double *ar1 = nullptr; size_t ar1_B1 = 0, ar1_tmp = 0, ar1_cseu = 0, ar1_cselog = 0, ar1_usc = 0, ar1_core = 0, ar1_B2 = 0,
@@ -292,7 +297,7 @@ struct pcmf_solver {
     void alloc_state();
     void init_state(const pcmf_init *in, bool reinit = false);
     void zero_gene_sums(double *B1, double *B2, double *xlogT, int mode);
-    void run_init_stats();
+    void run_init_stats(bool ones_stats = false, bool update_hyper = true);
     void allreduce(double *ptr, size_t count);
     void step(bool want_data);
     double data_term_now();
@@ -330,7 +335,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { dfree((void *)rowptr); dfree((void *)colidx); dfree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3], pstore, blkptr};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3], pstore, blkptr, hrow[0], hrow[1], hrow[2], hrow[3], rowsg};
     for (void *q : ptrs) if (q) dfree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -685,7 +690,7 @@ void pcmf_solver::build_csc() {
     k_colptr_from_sorted<<<grid_for(p + 1, 256), 256, 0, stream>>>(nnz, p, keys_out, colptr);
     k_gather_rowidx<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, rowidx);
     // ZI / sparse models: the gene passes leave q_ij in CSC order and the cell pass reads it back through this map
-    if ((zi || sparse) && nnz < 0xffffffffLL && !(opt.kernel_variant & 16)) {
+    if ((zi || sparse) && nnz < 0xffffffffLL && !(opt.dev_flags & 16)) {
         csr2csc = dmalloc<uint32_t>(nnz);
         k_invert_perm<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, csr2csc);
         qcsc = dmalloc<double>(nnz);
@@ -701,8 +706,8 @@ void pcmf_solver::build_csc() {
     // 50.6 ms for the spike-and-slab pass, 50.8 unblocked); PCMF_BLK_MB overrides, kernel_variant bit 512: one block
     {
         // (kernel_variant bit 1024: 64-cell blocks, so that small test problems walk several of them)
-        const int64_t rows_blk = (opt.kernel_variant & 1024) ? 64 : std::max<int64_t>(4096, ((int64_t)(getenv("PCMF_BLK_MB") ? atoi(getenv("PCMF_BLK_MB")) : 28) << 20) / (16 * KP));
-        nblk = (opt.kernel_variant & 512) ? 1 : (int)std::min<int64_t>(256, (n + rows_blk - 1) / rows_blk);
+        const int64_t rows_blk = (opt.dev_flags & 1024) ? 64 : std::max<int64_t>(4096, ((int64_t)(getenv("PCMF_BLK_MB") ? atoi(getenv("PCMF_BLK_MB")) : 28) << 20) / (16 * KP));
+        nblk = (opt.dev_flags & 512) ? 1 : (int)std::min<int64_t>(256, (n + rows_blk - 1) / rows_blk);
         if (nblk > 1) {
             const int64_t rb = ((n + nblk - 1) / nblk + 31) / 32 * 32;
             blkptr = dmalloc<int64_t>((size_t)(nblk + 1) * p);
@@ -792,7 +797,7 @@ void pcmf_solver::alloc_state() {
     dbg = dmalloc<unsigned long long>(4); CK(cudaMemsetAsync(dbg, 0, 32, stream));
     k_init_guard<<<1, 32, 0, stream>>>(guard[0]); k_init_guard<<<1, 32, 0, stream>>>(guard[1]);
     // kernel_variant bit 64 forces the stored-prob_D path (small test problems), bit 128 disables it
-    if (zi && !(opt.kernel_variant & (4 | 128)) && ((double)n * (double)p >= 5e7 || (opt.kernel_variant & 64)) &&
+    if (zi && !(opt.dev_flags & (4 | 128)) && ((double)n * (double)p >= 5e7 || (opt.dev_flags & 64)) &&
         (double)((n + 127) / 128 * 16) * (double)((p + 7) / 8) < 4.0e9) {
         // cell groups padded to whole CTAs of the cell pass (128 cells): it stores every tile it computes
         const size_t need = (size_t)((n + 127) / 128 * 16) * (size_t)((p + 7) / 8) * 64 * sizeof(uint32_t);
@@ -831,7 +836,7 @@ void pcmf_solver::download_colmajor(const double *src, int64_t rows, double *hos
 void pcmf_solver::start_draw_ahead(const pcmf_init *in, int64_t n_rows, int64_t n_glob, int64_t row_off, int32_t genes) {
     static const pcmf_init none{};
     if (!in) in = &none;
-    const bool random_ab = !in->U && !in->a1;
+    const bool random_ab = !in->U && !in->a1 && !in->alpha1;
     if (!random_ab) return;
     const bool random_S = sparse && !(in->prob_S && in->prior_S);
     ahead.start = random_S ? (unsigned long long)genes * K : 0ull;     // init_sparse_param draws p K uniforms first
@@ -876,12 +881,33 @@ void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
     } else {
         explicitP = false;
     }
+    // The reference's else-if chain (wrapper_gap_factor.h:352-375, wrapper_sparse_gap_factor.h:399-417): U, V > a1..b2 >
+    // alpha / beta > random.  alpha / beta are therefore only looked at when nothing else is given, and then
+    // init_hyper_param (gap_factor_model.cpp:126-132) is ALL that runs: the variational parameters and the statistics keep
+    // the constructors' Ones (gap...cpp:67-70, model.cpp:220-223), nothing is drawn, no update_hyper_param.
+    const bool hyper_only = nhy == 4 && !in->U && nab != 4;
     // a later multi-init run starts from the hyper-parameters the previous run ended with (the reference re-uses one
     // model object, wrapper_gap_factor.h:299-301: update_prior_gamma_param then reads log(alpha2) of that run)
-    if (!reinit || nhy == 4) {
+    if (!reinit || hyper_only) {
         std::vector<double> h(4 * 64, 1.0);
-        if (nhy == 4) {
-            for (int k = 0; k < K; ++k) { h[k] = in->alpha1[k]; h[64 + k] = in->alpha2[k]; h[128 + k] = in->beta1[k]; h[192 + k] = in->beta2[k]; }
+        rows_mode = false;
+        if (hyper_only) {
+            const double *src[4] = {in->alpha1, in->alpha2, in->beta1, in->beta2};
+            const int64_t rows[4] = {n, n, p, p};
+            if (in->hyper_rows)       // n x K / p x K column-major as the reference takes them: do the rows differ?
+                for (int v = 0; v < 4 && !rows_mode; ++v)
+                    for (int k = 0; k < K && !rows_mode; ++k)
+                        for (int64_t r = 1; r < rows[v]; ++r)
+                            if (src[v][r + (int64_t)k * rows[v]] != src[v][(int64_t)k * rows[v]]) { rows_mode = true; break; }
+            for (int v = 0; v < 4; ++v)
+                for (int k = 0; k < K; ++k) h[64 * v + k] = in->hyper_rows ? src[v][(int64_t)k * rows[v]] : src[v][k];
+            if (rows_mode) {
+                for (int v = 0; v < 4; ++v) {
+                    if (!hrow[v]) hrow[v] = dmalloc<double>((size_t)rows[v] * KP);
+                    upload_colmajor(src[v], rows[v], hrow[v], 1.0);
+                }
+                if (!rowsg) rowsg = dmalloc<double>(2);
+            }
         }
         CK(cudaMemcpyAsync(hyp, h.data(), sizeof(double) * 4 * 64, cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));
@@ -911,6 +937,14 @@ void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
         }
     }
     // variational parameters (wrapper_gap_factor.h:352-375)
+    if (hyper_only) {
+        for (double *A : {a1, a2}) k_fill<<<grid_for(n * KP, 256), 256, 0, stream>>>(A, n * KP, 1.0);
+        for (double *A : {b1, b2}) k_fill<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(A, (int64_t)p * KP, 1.0);
+        if (ahead.th.joinable()) ahead.th.join();
+        ahead.used = true;
+        run_init_stats(true, false);
+        return;
+    }
     if (in->U) {
         upload_colmajor(in->U, n, a1, 1.0); upload_colmajor(in->V, p, b1, 1.0);
         k_fill<<<grid_for(n * KP, 256), 256, 0, stream>>>(a2, n * KP, 1.0);
@@ -964,19 +998,20 @@ void pcmf_solver::zero_gene_sums(double *B1, double *B2, double *xlogT, int mode
 }
 
 // U_stats, V_stats, update_poisson_param, update_hyper_param after any initialisation (gap_factor_model.cpp:119-122)
-void pcmf_solver::run_init_stats() {
+void pcmf_solver::run_init_stats(bool ones_stats, bool update_hyper) {
     pstore_valid = false;             // prob_D is redefined by the initialisation
     const size_t pK = (size_t)p * KP;
-    double *alpha1 = hyp, *alpha2 = hyp + 64, *beta1 = hyp + 128, *beta2 = hyp + 192;
+    double *beta1 = hyp + 128, *beta2 = hyp + 192;
     CK(cudaMemsetAsync(scal, 0, S_COUNT * 8, stream));
     CK(cudaMemsetAsync(csv, 0, 3 * 64 * 8, stream));
     CK(cudaMemsetAsync(ar1 + ar1_cseu, 0, (64 + 64 + 4) * 8, stream));
     CK(cudaMemsetAsync(ar3, 0, ar3_total * 8, stream));
     k_init_guard<<<1, 32, 0, stream>>>(guard[gcur]);
-    UInitArgs ua{n, K, KP, a1, a2, EU[cur], ElogU, eu, guard[gcur], ar1 + ar1_cseu, ar1 + ar1_cselog, ar1 + ar1_usc};
+    UInitArgs ua{n, K, KP, a1, a2, EU[cur], ElogU, eu, guard[gcur], ar1 + ar1_cseu, ar1 + ar1_cselog, ar1 + ar1_usc, ones_stats ? 1 : 0};
     k_stats_u<<<grid_for(n * KP, 256), 256, 0, stream>>>(ua);
     VArgs va{};
     va.p = p; va.K = K; va.KP = KP; va.sparse = sparse; va.zi = zi; va.first_iter = 1; va.want_data = 0; va.stats_only = 1;
+    va.ones = ones_stats ? 1 : 0;
     va.beta1 = beta1; va.beta2 = beta2; va.b1 = b1; va.b2 = b2; va.EV = EV; va.ElogV = ElogV; va.prob_S = prob_S; va.Sd = Sd;
     va.colw = colw; va.ev = ev; va.evw = evw; va.EVS = EVS; va.wS = wS; va.guard_next = guard[gcur];
     va.cs_ev = csv; va.cs_elogv = csv + 64; va.cs_evs = csv + 128; va.scal = scal;
@@ -1013,9 +1048,9 @@ void pcmf_solver::run_init_stats() {
         // init_zi_param (zi_gap_factor_model.cpp:98-105): prob_D = (X > 0); realised as pass A with c_j = -inf
         ZiPrepArgs zp{p, 1, prior_D, Lg, cz, colw, flag, scal};
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
-        if (opt.kernel_variant & 32) {                 // the dense pass with c_j = -inf (kept to cross-check the shortcut below)
+        if (opt.dev_flags & 32) {                 // the dense pass with c_j = -inf (kept to cross-check the shortcut below)
             ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA, nullptr};
-            launches += 1 + L->zi_cells(za, opt.kernel_variant, stream);
+            launches += 1 + L->zi_cells(za, opt.dev_flags, stream);
         } else {
             k_zi_init_cells<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, KP, rowptr, colidx, EU[cur], EVS, PV, ar3 + ar3_zsc);
             k_zi_init_colsum<<<grid_for(p, 256), 256, 0, stream>>>(p, colptr, ar3 + ar3_csP);
@@ -1025,15 +1060,33 @@ void pcmf_solver::run_init_stats() {
     }
     allreduce(ar1 + ar1_cseu, 64 + 64 + 4);
     if (zi) allreduce(ar3, ar3_total);
-    HyperArgs ha{n_global, p, K, zi, sparse, alpha1, alpha2, beta1, beta2, ar1 + ar1_cseu, ar1 + ar1_cselog, csv, csv + 64, csv + 128,
-                 ar3 + ar3_csP, prior_D, ar1 + ar1_usc, ar3 + ar3_zsc, lgx_const, scal};
-    k_hyper<<<1, 256, 0, stream>>>(ha);
+    hyper_update(update_hyper, EU[cur]);
     k_vec_scale<<<1, 64, 0, stream>>>(hyp + 256, csv + 128, 64, 1.0);
     launches += 2;
     read_scal();
     CK(cudaGetLastError());
     last_nodata = h_scal[S_ELBO_NODATA];
     first_iter = true; have_pending = false; sparse_sums_valid = false;
+}
+
+// update_hyper_param (gap...cpp:541-548, zi...cpp:370-372) + the scalars of the iteration (k_hyper); when the rows of the
+// hyper-parameter matrices differ the Gamma part runs element-wise first (k_hyper_rows)
+void pcmf_solver::hyper_update(bool update, const double *EU_now) {
+    double *alpha1 = hyp, *alpha2 = hyp + 64, *beta1 = hyp + 128, *beta2 = hyp + 192;
+    HyperArgs ha{n_global, p, K, zi, sparse, alpha1, alpha2, beta1, beta2, ar1 + ar1_cseu, ar1 + ar1_cselog, csv, csv + 64, csv + 128,
+                 ar3 + ar3_csP, prior_D, ar1 + ar1_usc, ar3 + ar3_zsc, lgx_const, scal};
+    ha.update = update ? 1 : 0;
+    if (rows_mode) {
+        CK(cudaMemsetAsync(rowsg, 0, 2 * sizeof(double), stream));
+        k_hyper_rows<<<grid_for(n * KP, 256), 256, 0, stream>>>(n, K, KP, (double)n_global, ha.update, hrow[0], hrow[1], ar1 + ar1_cseu,
+                                                                 ar1 + ar1_cselog, EU_now, ElogU, rowsg);
+        k_hyper_rows<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, (double)p, ha.update, hrow[2], hrow[3], csv, csv + 64, EV, ElogV,
+                                                                          rowsg + 1);
+        allreduce(rowsg, 1);
+        launches += 2;
+        ha.rows_g = rowsg;
+    }
+    k_hyper<<<1, 256, 0, stream>>>(ha);
 }
 
 // One VEM iteration: model.update_param() (model.cpp:243-246) + the quantities check_convergence needs.
@@ -1073,6 +1126,7 @@ void pcmf_solver::step(bool want_data) {
         ra.guard_next = gn; ra.csr2csc = csr2csc; ra.qcsc = qcsc; ra.cs_eu = ar1 + ar1_cseu; ra.cs_elog = ar1 + ar1_cselog; ra.usc = ar1 + ar1_usc;
         // colsum(EV o prob_S) of the OLD state: csv+128 is re-accumulated during this iteration, hyp+256 keeps the copy
         ra.rate_vec = hyp + 256;
+        if (rows_mode) { ra.alpha1r = hrow[0]; ra.alpha2r = hrow[1]; }
         const int block = 256;
         const int64_t warps = std::min<int64_t>(n, (int64_t)sms * 8 * 8);
         L->estep_rows(v_f32, ra, (int)((warps + 7) / 8), block, stream);
@@ -1084,7 +1138,7 @@ void pcmf_solver::step(bool want_data) {
         ZiBArgs zb{};
         zb.n = n; zb.p = p; zb.K = K; zb.EUz = EU[cur]; zb.EUn = EU[nxt]; zb.EVSz = EVS; zb.cz = cz; zb.flag = flag; zb.bitB = bitB;
         zb.tmpMat = ar1 + ar1_tmp; zb.pack = zpackB; zb.pstore = pstore_valid ? pstore : nullptr;
-        const int gb = L->zi_genes_block(opt.kernel_variant);
+        const int gb = L->zi_genes_block(opt.dev_flags);
         const int gx = (p + gb - 1) / gb;
         // enough (gene block, cell chunk) CTAs for >= 16 full waves at 2 resident CTAs per SM: a 2.1-wave grid measured 29% slower
         int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, (int64_t)(sms * 2 * 16 + gx - 1) / gx));
@@ -1098,7 +1152,7 @@ void pcmf_solver::step(bool want_data) {
             k_zi_init_genes<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, K, KP, colptr, rowidx, EU[nxt], ar1 + ar1_tmp);
             end(PH_ZI_B, 1);
         } else {
-            end(PH_ZI_B, L->zi_genes(zb, chunks, opt.kernel_variant, stream));
+            end(PH_ZI_B, L->zi_genes(zb, chunks, opt.dev_flags, stream));
         }
     }
     // 4. all-reduce of the gene-side sums + U partials over the row shards
@@ -1115,6 +1169,7 @@ void pcmf_solver::step(bool want_data) {
         va.cs_eu = ar1 + ar1_cseu; va.beta1 = beta1; va.beta2 = beta2; va.b1 = b1; va.b2 = b2; va.EV = EV; va.ElogV = ElogV;
         va.prob_S = prob_S; va.Sd = Sd; va.colw = colw; va.ev = ev; va.evw = evw; va.EVS = EVS; va.wS = wS; va.guard_next = gn;
         va.cs_ev = csv; va.cs_elogv = csv + 64; va.cs_evs = csv + 128; va.scal = scal;
+        if (rows_mode) { va.beta1r = hrow[2]; va.beta2r = hrow[3]; }
         k_mstep_genes<<<grid_for(pK, 256), 256, 0, stream>>>(va);
         k_row_extremes<<<grid_for(p, 256), 256, 0, stream>>>(p, K, KP, ElogV, colext);
     }
@@ -1146,7 +1201,7 @@ void pcmf_solver::step(bool want_data) {
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
         k_refresh_weights<<<grid_for(pK, 256), 256, 0, stream>>>(p, K, KP, sparse, prob_S, colw, ev, wS, evw);
         ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA, pstore};
-        const int nl = L->zi_cells(za, opt.kernel_variant, stream);
+        const int nl = L->zi_cells(za, opt.dev_flags, stream);
         zi_at_init = false;
         pstore_valid = pstore != nullptr;
         allreduce(ar3, ar3_total);
@@ -1155,9 +1210,7 @@ void pcmf_solver::step(bool want_data) {
     // 8. hyper-parameters + scalars
     begin(PH_HYPER);
     k_vec_scale<<<1, 64, 0, stream>>>(hyp + 256, csv + 128, 64, 1.0);   // keep colsum(EV o prob_S) for the next a2 update
-    HyperArgs ha{n_global, p, K, zi, sparse, alpha1, alpha2, beta1, beta2, ar1 + ar1_cseu, ar1 + ar1_cselog, csv, csv + 64, csv + 128,
-                 ar3 + ar3_csP, prior_D, ar1 + ar1_usc, ar3 + ar3_zsc, lgx_const, scal};
-    k_hyper<<<1, 256, 0, stream>>>(ha);
+    hyper_update(true, EU[nxt]);
     end(PH_HYPER, 2);
     if (keep_old) {
         if (first_iter) {
@@ -1218,22 +1271,29 @@ double pcmf_solver::data_term_now() {
 // pl(X, rate) = sum_nnz x clog(rate) - sum_ij rate - sum lgamma(x + 1): one non-zero pass + the total rate, which is
 // the closed form of gap...cpp:298 or, for ZI, sum prob_D o UVt of the last dense pass.
 pcmf_solver::Mon pcmf_solver::monitors_now(bool want_loglik) {
-    if (explicitP) fail(PCMF_EUNSUPPORTED, "monitors are not available before the first iteration of a run warm-started from a dense prob_D");
     CK(cudaMemsetAsync(mon, 0, 8 * sizeof(double), stream));
-    LamArgs la{p, K, colptr, rowidx, val_csc, EU[cur], EVS, zi ? flag : nullptr, mon};
-    L->gene_loglam(f32, la, std::min<int>(p, sms * 32), stream);
+    if (explicitP) {
+        // prob_D still is the dense matrix of a warm start (it lives until the first zero-inflation update): one plain dense
+        // kernel evaluates what the closed-form passes below cannot (zi_gap_factor_model.cpp:160-167 on init_zi_param(prob_D, prior_D))
+        if (f32) k_dense_zi_monitor<float><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, p, K, KP, Pexp, EU[cur], EVS, rowptr, colidx, val_csr, bitT, mon);
+        else k_dense_zi_monitor<double><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, p, K, KP, Pexp, EU[cur], EVS, rowptr, colidx, val_csr, bitT, mon);
+    } else {
+        LamArgs la{p, K, colptr, rowidx, val_csc, EU[cur], EVS, zi ? flag : nullptr, mon};
+        L->gene_loglam(f32, la, std::min<int>(p, sms * 32), stream);
+    }
     launches += 1;
     if (want_loglik) {
         k_gamma_loglike<<<grid_for(n * KP, 256), 256, 0, stream>>>(n, K, KP, EU[cur], a1, a2, mon + 4);
         k_gamma_loglike<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, EV, b1, b2, mon + 6);
         launches += 2;
-        if (zi && !zi_at_init) {                       // at the initial state prob_D = (X > 0): the zero part is log(1) = 0
+        if (zi && !zi_at_init && !explicitP) {         // at the initial state prob_D = (X > 0): the zero part is log(1) = 0
             ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA, nullptr};
             L->zi_loglik(za, mon + 5, stream);
             launches += 1;
         }
     }
     allreduce(mon, 6);    // [0..3] non-zero sums, [4] Gamma term of U, [5] zero part: sums over the local cells; [6] is replicated
+    if (explicitP) allreduce(mon + 7, 1);
     double h[8];
     CK(cudaMemcpyAsync(h, mon, sizeof h, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -1248,7 +1308,7 @@ pcmf_solver::Mon pcmf_solver::monitors_now(bool want_loglik) {
         if (!zi) ll = h[1] - h_scal[S_SUMUVT_CLOSED] - lgx_const;
         else {
             // zi_poisson_loglike (likelihood.h:197-212): non-zeros log(prob_D) + pl1(x, lambda), zeros log(1 - P + P e^-lambda)
-            ll = h[1] - h[2] - lgx_const + h[5];
+            ll = h[1] - h[2] - lgx_const + h[5] + h[7];   // h[7]: sum log(prob_D) over the non-zeros (0 unless prob_D is explicit)
             if (h[3] > 0) ll = -INFINITY;    // log(prob_D) with prob_D = 0 on a non-zero entry (prior_D == 0 shortcut)
             ll += h_scal[S_BERND_SELF];
         }
@@ -1318,6 +1378,7 @@ void pcmf_solver::order_factor_now() {
     };
     for (double *A : {a1, a2, EU[0], EU[1], ElogU, eu, PV}) perm_d(A, n, KP);
     for (double *A : {b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd}) perm_d(A, p, KP);
+    perm_d(hrow[0], n, KP); perm_d(hrow[1], n, KP); perm_d(hrow[2], p, KP); perm_d(hrow[3], p, KP);
     for (int v = 0; v < 5; ++v) perm_d(hyp + 64 * v, 1, 64);
     for (int v = 0; v < 3; ++v) perm_d(csv + 64 * v, 1, 64);
     perm_d(ar1 + ar1_cseu, 1, 64); perm_d(ar1 + ar1_cselog, 1, 64);
@@ -1338,6 +1399,7 @@ std::vector<std::pair<void *, size_t>> pcmf_solver::state_arrays() {
     v.push_back({S, (size_t)p * KP * 4}); v.push_back({flag, (size_t)p * 4});
     for (double *A : {prior_S, prior_D, cz, colw}) v.push_back({A, (size_t)p * 8});
     v.push_back({hyp, 5 * 64 * 8}); v.push_back({csv, 3 * 64 * 8});
+    if (rows_mode) { v.push_back({hrow[0], nK}); v.push_back({hrow[1], nK}); v.push_back({hrow[2], pK}); v.push_back({hrow[3], pK}); }
     v.push_back({ar1, ar1_total * 8}); v.push_back({ar2, ar2_total * 8}); v.push_back({ar3, ar3_total * 8});
     if (ar2keep) v.push_back({ar2keep, 2 * pK});
     v.push_back({scal, S_COUNT * 8}); v.push_back({guard[0], G_COUNT * 8}); v.push_back({guard[1], G_COUNT * 8});
@@ -1475,8 +1537,26 @@ void check_options(const pcmf_problem *prob, const pcmf_options *opt) {
     // wrapper_sparse_gap_factor.h:236
     if (opt->sparsity && (opt->sel_bound < 0 || opt->sel_bound > 1))
         fail(PCMF_EINVAL, "Input parameter sel_bound should be a real value between 0 and 1");
+    // multi-init writes the kept run's first iter_init per-iteration entries into the caller's iter_max-long vectors
+    // (wrapper_gap_factor.h:296-350: the reference indexes past the end of its own vectors in that case)
+    if (opt->ninit > 1 && opt->iter_init > opt->iter_max)
+        fail(PCMF_EINVAL, "with ninit > 1, iter_init (%d) must not exceed iter_max (%d)", opt->iter_init, opt->iter_max);
+    if (opt->precision < 0 || opt->precision > 1) fail(PCMF_EINVAL, "precision must be 0 (FP64) or 1 (FP32)");
     // algorithm.h:427
     if (opt->conv_mode < 0 || opt->conv_mode > 2) fail(PCMF_EINVAL, "`conv_mode` parameter should take value in {0,1,2}");
+}
+// argument consistency of the warm-start values, with the reference's messages (wrapper_gap_factor.h:215-258); host only
+void check_init(const pcmf_init *in) {
+    if (!in) return;
+    if ((in->U != nullptr) != (in->V != nullptr))
+        fail(PCMF_EINVAL, "You should supply initial values for both U and V or for neither of them");
+    const int nab = (in->a1 != nullptr) + (in->a2 != nullptr) + (in->b1 != nullptr) + (in->b2 != nullptr);
+    if (nab != 0 && nab != 4) fail(PCMF_EINVAL, "You should supply initial values for all a1, a2, b1, b2 or for none of them");
+    const int nhy = (in->alpha1 != nullptr) + (in->alpha2 != nullptr) + (in->beta1 != nullptr) + (in->beta2 != nullptr);
+    if (nhy != 0 && nhy != 4)
+        fail(PCMF_EINVAL, "You should supply initial values for all alpha1, alpha2, beta1, beta2 or for none of them");
+    if ((in->prob_D != nullptr) != (in->prior_D != nullptr))
+        fail(PCMF_EINVAL, "You should supply initial values for both prob_D and prior_D or for neither of them");
 }
 }  // namespace
 
@@ -1496,6 +1576,7 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
     int rc = guarded(errbuf, errlen, [&] {
         if (!out) fail(PCMF_EINVAL, "null output handle");
         check_options(prob, opt);
+        check_init(init);
         int cnt = 0;
         if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0)
             fail(PCMF_ECUDA, "no CUDA device available: libpcmf_b200 has no CPU fallback");
@@ -1678,7 +1759,14 @@ int pcmf_get_output(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errle
                 }
             });
         };
-        rep(res->alpha1, n, h.data()); rep(res->alpha2, n, h.data() + 64); rep(res->beta1, p, h.data() + 128); rep(res->beta2, p, h.data() + 192);
+        if (s->rows_mode) {
+            if (res->alpha1) s->download_colmajor(s->hrow[0], n, res->alpha1);
+            if (res->alpha2) s->download_colmajor(s->hrow[1], n, res->alpha2);
+            if (res->beta1) s->download_colmajor(s->hrow[2], p, res->beta1);
+            if (res->beta2) s->download_colmajor(s->hrow[3], p, res->beta2);
+        } else {
+            rep(res->alpha1, n, h.data()); rep(res->alpha2, n, h.data() + 64); rep(res->beta1, p, h.data() + 128); rep(res->beta2, p, h.data() + 192);
+        }
         if (s->sparse) {
             if (res->prob_S) s->download_colmajor(s->prob_S, p, res->prob_S);
             if (res->prior_prob_S) CK(cudaMemcpy(res->prior_prob_S, s->prior_S, sizeof(double) * p, cudaMemcpyDeviceToHost));
@@ -1743,6 +1831,13 @@ int pcmf_phase_times(pcmf_solver *s, const char **names, double *ms, int64_t *la
         if (names) names[c] = "stored_prob_D_bytes";
         if (ms) ms[c] = 0.0;
         if (launches) launches[c] = s->pstore ? (int64_t)((s->n + 127) / 128 * 16) * (int64_t)((s->p + 7) / 8) * 256 : 0;
+        ++c;
+    }
+    // cell blocks the gene passes walk (1: whole genes in one go)
+    if (c < cap) {
+        if (names) names[c] = "gene_pass_cell_blocks";
+        if (ms) ms[c] = 0.0;
+        if (launches) launches[c] = s->nblk;
         ++c;
     }
     return c;

@@ -38,46 +38,72 @@ __device__ const double kPow2Tab64[64] = {
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
 
 // exp(-z) for |z| < 30 with a 64-entry table of 2^(i/64) (shared memory): m = rint(-64 z / ln 2), r = -z - m ln2/64
-// (two-term Cody-Waite, |r| <= ln2/128 = 0.0054), degree-5 Taylor (truncation 3.5e-17), scaled through the exponent
-// field.  10 FP64 instructions (fast_exp: 20).  Arguments outside the range give garbage that the caller discards.
+// (|r| <= ln2/128 = 0.0054), degree-4 Taylor (truncation r^5/120 <= 3.9e-14 relative), scaled through the exponent field.
+// 8 FP64 instructions (fast_exp: 20).  Arguments outside the range give garbage that the caller discards.
 // On this part the SM sub-partition's dispatch port is what the dense passes saturate (a DFMA holds it for 2 cycles, a
-// DMMA for 16, nothing else issues meanwhile -- scripts/ubench_zi_core.cu), so every instruction removed here counts.
-__device__ __forceinline__ double fast_exp_neg_tab(double z, const double *__restrict__ tab) {
+// DMMA for 16, nothing else issues meanwhile -- scripts/ubench_zi_core.cu), so every instruction removed here counts:
+// round 1 ran a degree-5 polynomial with a two-term Cody-Waite reduction (1e-16); the second reduction term moves r by
+// |m| 3.6e-19 <= 1e-15 and the fifth-order term by 3.9e-14, both far below the 1.2e-10 of the stored prob_D (PCMF_PSTORE_SCALE)
+// and the 1e-8 the parity tests ask for, so they are gone (-DPCMF_EXPIT_FULL restores them).
+//
+// The table is REPLICATED 16 times, entry i of copy c at tab[16 i + c], and lane l reads copy l & 15: a 64-bit shared load is
+// served per half-warp, and the 16 lanes of a half-warp then always touch 16 different bank pairs whatever their i -- the
+// single 512-byte copy of round 1 cost ~3 wavefronts per lookup (ncu: 29 % of all shared wavefronts were bank conflicts).
+constexpr int kTabRep = 16, kTabDoubles = 64 * kTabRep;
+__device__ __forceinline__ double fast_exp_neg_tab(double z, const double *__restrict__ tab_lane) {
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
     double t = fma(z, -92.33248261689366, MAGIC);
     const int m = __double2loint(t);
     t -= MAGIC;
     double r = fma(t, -0.010830424696249145, -z);
+#ifdef PCMF_EXPIT_FULL
     r = fma(t, -3.623510646634843e-19, r);
     double p = 8.33333333333333333333e-03;                  // 1/5!
     p = fma(p, r, 4.16666666666666666667e-02);              // 1/4!
+#else
+    double p = 4.16666666666666666667e-02;                  // 1/4!
+#endif
     p = fma(p, r, 1.66666666666666666667e-01);              // 1/3!
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     // tab is PRE-BIASED (load_pow2_tab): entry i has (i << 14) taken off its high word, so that adding (m << 14) leaves
     // exactly ((m - i) << 14) = (m >> 6) << 20 on the exponent field -- one integer multiply-add instead of shift, mask, add
-    const double tb = tab[m & 63];
+    const double tb = tab_lane[(m & 63) * kTabRep];
     const double sc = __hiloint2double(__double2hiint(tb) + (int)((unsigned)m << 14), __double2loint(tb));
     return p * sc;
 }
-// the 64-entry table of 2^(i/64) as the dense passes keep it in shared memory (see fast_exp_neg_tab)
+// the replicated table of 2^(i/64) as the dense passes keep it in shared memory (see fast_exp_neg_tab); a thread passes
+// pow2_tab_lane(s_tab) to the evaluation
 __device__ __forceinline__ void load_pow2_tab(double *s_tab) {
-    if (threadIdx.x < 64) {
-        const double v = kPow2Tab64[threadIdx.x];
-        s_tab[threadIdx.x] = __hiloint2double(__double2hiint(v) - ((int)threadIdx.x << 14), __double2loint(v));
+    for (int t = threadIdx.x; t < kTabDoubles; t += blockDim.x) {
+        const int i = t / kTabRep;
+        const double v = kPow2Tab64[i];
+        s_tab[t] = __hiloint2double(__double2hiint(v) - (i << 14), __double2loint(v));
     }
 }
-// internal::expit (internal.h:151-155): exactly 1 / 0 for z >= 30 / z <= -30.  `ov` is the value the entry takes when
-// `force` is set (X != 0, zi...cpp:359-360).  Also returns y = 1 + exp(-z) (garbage when clamped) and the clamp flag.
-__device__ __forceinline__ double fast_expit_tab(double z, const double *__restrict__ tab, bool force, double ov, double &y,
-                                                 bool &big) {
+__device__ __forceinline__ const double *pow2_tab_lane(const double *s_tab) { return s_tab + (threadIdx.x & (kTabRep - 1)); }
+// 1/y for normal y in the dense passes: MUFU.RCP64H seed (relative error e <= 2^-23) + one Newton step (error e^2 <= 1.4e-14)
+__device__ __forceinline__ double fast_rcp2(double y) {
+#ifdef PCMF_EXPIT_FULL
+    return fast_rcp(y);
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    return fma(r, fma(-y, r, 1.0), r);
+#endif
+}
+// internal::expit (internal.h:151-155): exactly 1 / 0 for z >= 30 / z <= -30.  Also returns y = 1 + exp(-z) (garbage when
+// clamped) and the clamp flag.  Entries with X != 0 (zi...cpp:359-360) do not get a select of their own: the caller hands
+// them z = +-1e300 (the value the packed record carries for the gene: +1e300, or -1e300 under the prior_D == 0 shortcut),
+// which the clamp turns into exactly 1 / 0 and which takes them out of the entropy sums like every other clamped entry.
+__device__ __forceinline__ double fast_expit_tab(double z, const double *__restrict__ tab_lane, double &y, bool &big) {
     const int hi = __double2hiint(z);
     big = (hi & 0x7fffffff) >= 0x403E0000;                 // |z| >= 30, also NaN / inf
-    y = 1.0 + fast_exp_neg_tab(z, tab);
-    const double pr = fast_rcp(y);
+    y = 1.0 + fast_exp_neg_tab(z, tab_lane);
+    const double pr = fast_rcp2(y);
     const double sat = __hiloint2double((hi < 0) ? 0 : 0x3FF00000, 0);
-    return force ? ov : (big ? sat : pr);
+    return big ? sat : pr;
 }
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
@@ -116,11 +142,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 
 // Fragment-ordered copy of a row-major [rows][KP] matrix, one record per group of 8 rows, so that a tile of the dense
 // passes is ONE contiguous bulk copy and every fragment load is a conflict-free 256-byte shared-memory read:
-//   record = [ f1: KS x 32 | f2: 2 x NT x 32 | (WITH_C) c: 8 | nzv: 8 ]
+//   record = [ f1: KS x 32 | f2: 2 x NT x 32 | (WITH_C) c: 8 | zf: 8 ]
 //   f1[s][lane]      = M1[8 grp + g][4 s + q]               first product, contraction over the K factors
 //   f2[s'][nt][lane] = M2[8 grp + 2 q + s'][8 nt + g]       second product, contraction over the 8 rows (0 beyond KP)
-//   c / nzv: effective logit of the gene (+-1e300 for the whole-gene shortcuts, zi...cpp:353-356) and the value prob_D
-//   takes on its non-zero entries (zi...cpp:359-360).  Rows beyond `rows` are zero (c = -1e300 -> P = 0).
+//   c / zf: effective logit of the gene (+-1e300 for the whole-gene shortcuts, zi...cpp:353-356) and the z that stands for
+//   its non-zero entries (+1e300 -> prob_D = 1, zi...cpp:359-360; -1e300 under the prior_D == 0 shortcut).  Rows beyond
+//   `rows` are zero (c = zf = -1e300 -> P = 0).
 template <int KP, bool WITH_C>
 struct ZiRec {
     static constexpr int KS = KP / 4, NT = (KP + 7) / 8;
@@ -150,7 +177,7 @@ __global__ void k_zi_pack(int64_t rows, const double *__restrict__ M1, const dou
             const int64_t row = grp * 8 + e;
             const int f = row < rows ? flag[row] : 2;
             if (o3 < 8) v = (row < rows && f == 0) ? cz[row] : ((f == 1) ? 1e300 : -1e300);
-            else v = (f == 2) ? 0.0 : 1.0;
+            else v = (f == 2) ? -1e300 : 1e300;
         }
         out[idx] = v;
     }
@@ -172,11 +199,12 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     double *s_buf = reinterpret_cast<double *>(smem_raw);       // 2 x NG records, double buffered
     double *s_cs = s_buf + 2 * BUF;                             // 2 x 4 x TJ: per-warp column sums, double buffered (plain stores:
                                                                 //   a shared-memory FP64 atomicAdd is a CAS spin loop)
-    double *s_tab = s_cs + 8 * TJ;                              // 64
+    double *s_tab = s_cs + 8 * TJ;                              // kTabDoubles
     __shared__ double sh[32];
     __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     load_pow2_tab(s_tab);
+    const double *tabl = pow2_tab_lane(s_tab);
     for (int t = threadIdx.x; t < 8 * TJ; t += blockDim.x) s_cs[t] = 0.0;
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -269,13 +297,13 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             double cs0 = 0.0, cs1 = 0.0;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const double z0 = c2.x - d[mt][0], z1 = c2.y - d[mt][1];
                 const bool nz0 = (bits[mt] >> sh0) & 1u, nz1 = (bits[mt] >> (sh0 + 1)) & 1u;
+                const double z0 = nz0 ? n2.x : c2.x - d[mt][0], z1 = nz1 ? n2.y : c2.y - d[mt][1];
                 double y0, y1; bool big0, big1;
-                double p0 = fast_expit_tab(z0, s_tab, nz0, n2.x, y0, big0), p1 = fast_expit_tab(z1, s_tab, nz1, n2.y, y1, big1);
+                const double p0 = fast_expit_tab(z0, tabl, y0, big0), p1 = fast_expit_tab(z1, tabl, y1, big1);
                 // (rows beyond n: lambda starts at 1e305 and their occupancy words are 0, so P is the clamped 0 here)
                 // -bernoulli_loglike(prob_D, prob_D) over 0 < P < 1: sum (1-P)(-z) - log(1 + e^-z)
-                const bool g0 = !big0 && !nz0, g1 = !big1 && !nz1;
+                const bool g0 = !big0, g1 = !big1;
                 ent_lin = fma(g0 ? (p0 - 1.0) : 0.0, z0, ent_lin);
                 ent_lin = fma(g1 ? (p1 - 1.0) : 0.0, z1, ent_lin);
                 prod *= (g0 ? y0 : 1.0) * (g1 ? y1 : 1.0);
@@ -353,6 +381,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? 3 : 2) k_zi_loglik_mma(ZiAAr
     __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     load_pow2_tab(s_tab);
+    const double *tabl = pow2_tab_lane(s_tab);
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     const int64_t cell0 = (int64_t)blockIdx.x * (32 * MT) + w * (8 * MT);
@@ -409,8 +438,8 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? 3 : 2) k_zi_loglik_mma(ZiAAr
                     const bool zero = !((bits[mt] >> (sh0 + e)) & 1u);      // dead rows carry all-ones words
                     const int hi = __double2hiint(z);
                     const bool big = (hi & 0x7fffffff) >= 0x403E0000;
-                    const double em = fast_exp_neg_tab(z, s_tab);               // y - 1
-                    const double el = fast_exp_neg_tab(fmin(lam, 690.0), s_tab);
+                    const double em = fast_exp_neg_tab(z, tabl);               // y - 1
+                    const double el = fast_exp_neg_tab(fmin(lam, 690.0), tabl);
                     const bool in_ = zero && !big;
                     pn *= in_ ? (em + el) : 1.0;
                     pd *= in_ ? (1.0 + em) : 1.0;
@@ -437,24 +466,25 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
     constexpr int KS = R::KS, NT = R::NT, NG = TI / 8, BUF = NG * R::REC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_buf = reinterpret_cast<double *>(smem_raw);       // 2 x NG records [EUz first-product | EUn second-product]
-    double *s_tab = s_buf + 2 * BUF;                            // 64
+    double *s_tab = s_buf + 2 * BUF;                            // kTabDoubles
     __shared__ uint64_t bar[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     load_pow2_tab(s_tab);
+    const double *tabl = pow2_tab_lane(s_tab);
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     const int gene0 = blockIdx.x * (32 * MT) + w * (8 * MT);
-    double a1[MT][KS], c[MT], nzv[MT];
+    double a1[MT][KS], c[MT], zf[MT];
     bool live[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int j = gene0 + mt * 8 + g;
         live[mt] = j < a.p;
-        c[mt] = -1e300; nzv[mt] = 0.0;
+        c[mt] = -1e300; zf[mt] = -1e300;
         if (live[mt]) {
             const int f = a.flag[j];
             c[mt] = (f == 0) ? a.cz[j] : ((f == 1) ? 1e300 : -1e300);
-            nzv[mt] = (f == 2) ? 0.0 : 1.0;
+            zf[mt] = (f == 2) ? -1e300 : 1e300;
         }
 #pragma unroll
         for (int s = 0; s < KS; ++s) a1[mt][s] = live[mt] ? __ldg(a.EVSz + (int64_t)j * KP + 4 * s + q) : 0.0;
@@ -512,8 +542,8 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 double y; bool big;
-                const double p0 = fast_expit_tab(c[mt] - d[mt][0], s_tab, (bits[mt] >> sh0) & 1u, nzv[mt], y, big);
-                const double p1 = fast_expit_tab(c[mt] - d[mt][1], s_tab, (bits[mt] >> (sh0 + 1)) & 1u, nzv[mt], y, big);
+                const double p0 = fast_expit_tab(((bits[mt] >> sh0) & 1u) ? zf[mt] : c[mt] - d[mt][0], tabl, y, big);
+                const double p1 = fast_expit_tab(((bits[mt] >> (sh0 + 1)) & 1u) ? zf[mt] : c[mt] - d[mt][1], tabl, y, big);
                 d[mt][0] = p0; d[mt][1] = p1;      // cells beyond n have EU_new = 0 in the packed records
             }
 #pragma unroll

@@ -2,7 +2,9 @@
  * shim or any other host language sees.  Used by tests/test_cabi_client.py.
  *
  *   cabi_client sizes                       print sizeof / offsetof of the four boundary structs
- *   cabi_client fit <in.bin> <out.bin>      one pcmf_fit call (= one run_*_gap_factor call of the reference)
+ *   cabi_client fit <in.bin> <out.bin>      one pcmf_fit call (= one run_*_gap_factor call of the reference);
+ *                                           environment: PCMF_CABI_NGPUS -> pcmf_options.ngpus (the library shards the cells
+ *                                           over that many devices itself), PCMF_CABI_PRECISION -> pcmf_options.precision
  *
  * in.bin : int32 n, p, K, zi, sparse, iter_max, reorder | double X[n*p] (column-major) | a1[n*K] a2[n*K] b1[p*K] b2[p*K]
  *          | prob_S[p*K] prior_S[p]
@@ -26,9 +28,10 @@ int main(int argc, char **argv) {
     if (argc >= 2 && strcmp(argv[1], "sizes") == 0) {
         printf("pcmf_problem %zu csr_on_device %zu csc_val_f64 %zu\n", sizeof(pcmf_problem), offsetof(pcmf_problem, csr_on_device),
                offsetof(pcmf_problem, csc_val_f64));
-        printf("pcmf_options %zu sel_bound %zu seed %zu stream %zu kernel_variant %zu\n", sizeof(pcmf_options), offsetof(pcmf_options, sel_bound),
-               offsetof(pcmf_options, seed), offsetof(pcmf_options, stream), offsetof(pcmf_options, kernel_variant));
-        printf("pcmf_init %zu prior_D %zu\n", sizeof(pcmf_init), offsetof(pcmf_init, prior_D));
+        printf("pcmf_options %zu sel_bound %zu seed %zu stream %zu precision %zu ngpus %zu dev_flags %zu\n", sizeof(pcmf_options), offsetof(pcmf_options, sel_bound),
+               offsetof(pcmf_options, seed), offsetof(pcmf_options, stream), offsetof(pcmf_options, precision), offsetof(pcmf_options, ngpus),
+               offsetof(pcmf_options, dev_flags));
+        printf("pcmf_init %zu prior_D %zu hyper_rows %zu\n", sizeof(pcmf_init), offsetof(pcmf_init, prior_D), offsetof(pcmf_init, hyper_rows));
         printf("pcmf_result %zu S %zu nb_iter %zu loss %zu seconds_total %zu\n", sizeof(pcmf_result), offsetof(pcmf_result, S),
                offsetof(pcmf_result, nb_iter), offsetof(pcmf_result, loss), offsetof(pcmf_result, seconds_total));
         printf("version %s\n", pcmf_version());
@@ -51,6 +54,8 @@ int main(int argc, char **argv) {
     opt.K = K;  opt.zero_inflation = zi;  opt.sparsity = sparse;  opt.sel_bound = 0.5;
     opt.iter_max = iter_max;  opt.iter_min = iter_max / 2;  opt.epsilon = 1e-2;  opt.additional_iter = 10;  opt.conv_mode = 1;
     opt.monitor = 1;  opt.reorder_factor = reorder;  opt.ninit = 1;  opt.iter_init = 100;  opt.world = 1;  opt.progress_every = 10;
+    if (getenv("PCMF_CABI_NGPUS")) opt.ngpus = atoi(getenv("PCMF_CABI_NGPUS"));
+    if (getenv("PCMF_CABI_PRECISION")) opt.precision = atoi(getenv("PCMF_CABI_PRECISION"));
     pcmf_init init;  memset(&init, 0, sizeof init);
     init.a1 = a1;  init.a2 = a2;  init.b1 = b1;  init.b2 = b2;
     if (sparse) { init.prob_S = prob_S;  init.prior_S = prior_S; }

@@ -13,8 +13,8 @@ from pcmf_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "pcmf_b200.h")).read()
+def header_functions(name="pcmf_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b(pcmf_[a-z_0-9]+)\s*\(", src)
     return sorted(set(n for n in names if not n.endswith("_fn")))
@@ -24,9 +24,19 @@ def test_library_exports_every_header_symbol():
     L = _lib.lib()
     declared = header_functions()
     assert set(declared) == set(_lib.HEADER_SYMBOLS), (declared, _lib.HEADER_SYMBOLS)
-    for name in declared:
+    dev = header_functions("pcmf_b200_dev.h")
+    assert set(dev) == set(_lib.DEV_HEADER_SYMBOLS), (dev, _lib.DEV_HEADER_SYMBOLS)
+    for name in declared + dev:
         assert hasattr(L, name), name
     assert b"sm_100a" in L.pcmf_version()
+
+
+def test_public_header_carries_no_bench_or_test_plumbing():
+    # the header a pCMF maintainer links against declares the boundary only: measurement hooks, the input
+    # generator and the A/B switches live in pcmf_b200_dev.h
+    pub = open(os.path.join(ROOT, "include", "pcmf_b200.h")).read()
+    for word in ("pcmf_measure", "pcmf_generate", "kernel_variant", "pcmf_phase_times"):
+        assert word not in pub, word
 
 
 def test_struct_layouts_match_header_field_order():
@@ -84,3 +94,20 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pyoracle" not in txt and "pcmf_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_multi_init_longer_than_iter_max_is_rejected():
+    # ninit > 1 with iter_init > iter_max would write iter_init entries into iter_max-long caller vectors
+    X = np.random.default_rng(0).poisson(2.0, (20, 15))
+    with pytest.raises(pcmf_b200.PcmfError, match="iter_init") as e:
+        pcmf_b200.run_gap_factor(X, 2, verbose=False, iter_max=50, ninit=2, iter_init=100)
+    assert e.value.code == _lib.EINVAL
+
+
+def test_hyper_parameter_forms_are_checked():
+    X = np.random.default_rng(0).poisson(2.0, (20, 15))
+    ones_n, ones_p = np.ones((20, 2)), np.ones((15, 2))
+    with pytest.raises(pcmf_b200.PcmfError, match="alpha1, alpha2, beta1 and/or beta2"):
+        pcmf_b200.run_gap_factor(X, 2, alpha1=ones_n, alpha2=ones_n, beta1=ones_p, beta2=np.ones((14, 2)), verbose=False)
+    with pytest.raises(pcmf_b200.PcmfError, match="all alpha1, alpha2, beta1, beta2 or for none"):
+        pcmf_b200.run_gap_factor(X, 2, alpha1=ones_n, verbose=False)

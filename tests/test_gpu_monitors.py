@@ -141,6 +141,11 @@ def test_warm_start_from_dense_prob_D_matches_oracle(sparse):
     o = s.get_output()
     assert np.abs(o["prob_D"] - PD).max() == 0.0
     assert relerr(o["prior_prob_D"], m.get("prior_D")) < 1e-12
+    # monitors on the explicit matrix, before any iteration (zi_gap_factor_model.cpp:160-167, :218-245)
+    mon = s.monitors()
+    assert abs(mon["loglikelihood"] - m.loglikelihood()) < 1e-8 * abs(m.loglikelihood())
+    assert abs(mon["deviance"] - m.deviance()) < 1e-8 * abs(m.deviance())
+    assert abs(mon["exp_dev"] - m.exp_deviance()) < 1e-8 * max(1.0, abs(m.exp_deviance()))
     s.close()
 
 
@@ -203,3 +208,56 @@ def test_multi_init_from_factors_perturbs_like_oracle(zi, sparse):
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
     assert np.abs(res["variational_params"]["a1"] - U).max() > 1e-3
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+@pytest.mark.parametrize("form", ["vectors", "same_rows", "rows_differ"])
+def test_hyper_only_warm_start_matches_oracle(zi, sparse, form):
+    """run_*(X, K, alpha1 =, alpha2 =, beta1 =, beta2 =) and nothing else: init_hyper_param alone (wrapper_gap_factor.h:362-363,
+    gap_factor_model.cpp:126-132) -- Ones everywhere else, no draw, no hyper update; matrices whose rows differ are taken as
+    given and stay row-dependent through update_prior_gamma_param (gap...cpp:541-548).  Pinned against the reference build
+    in tests/test_ref_build.py."""
+    X = problem(27, 70, 52)
+    n, p, K = 70, 52, 4
+    rng = np.random.default_rng(10)
+    if form == "rows_differ":
+        hy = dict(alpha1=rng.uniform(0.5, 2.0, (n, K)), alpha2=rng.uniform(0.5, 2.0, (n, K)),
+                  beta1=rng.uniform(0.5, 2.0, (p, K)), beta2=rng.uniform(0.5, 2.0, (p, K)))
+        gpu_hy = hy
+    else:
+        vec = {k: rng.uniform(0.5, 2.0, K) for k in ("alpha1", "alpha2", "beta1", "beta2")}
+        hy = {k: np.tile(v, (n if k.startswith("alpha") else p, 1)) for k, v in vec.items()}
+        gpu_hy = vec if form == "vectors" else hy
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=12, iter_min=4, epsilon=1e-2, additional_iter=2)
+    ref = po.run(X, K, zi, sparse, monitor=True, reorder_factor=True, prob_S=prob_S, prior_S=prior_S, **kw, **hy)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    res = RUN[(zi, sparse)](X, K, verbose=False, monitor=True, reorder_factor=True, **kw, **gpu_hy)
+    assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    assert relerr(res["convergence"]["conv_crit"], ref["convergence"]["conv_crit"]) < 1e-6
+    for k in ("optim_criterion", "loglikelihood", "deviance"):
+        assert relerr(res["monitor"][k], ref["monitor"][k]) < 1e-6, k
+    assert list(res["factor_order"]) == list(ref["factor_order"])
+    for grp in ("variational_params", "hyper_params"):
+        for k in res[grp]:
+            assert relerr(res[grp][k], ref[grp][k]) < 1e-6, (grp, k)
+    assert abs(res["loss"] - ref["loss"]) < 1e-6 * abs(ref["loss"])
+
+
+@pytest.mark.parametrize("zi,sparse", [(False, False), (True, True)], ids=["gap", "zi_sparse"])
+def test_hyper_parameters_are_ignored_next_to_variational_parameters(zi, sparse):
+    """The reference's else-if chain never reaches init_all_param (wrapper_gap_factor.h:364-367 is dead code): with a1..b2
+    (or U, V) given, alpha / beta arguments change nothing."""
+    X = problem(28, 50, 40)
+    K = 3
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=13)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(verbose=False, iter_max=6, iter_min=6, reorder_factor=False, a1=a1, a2=a2, b1=b1, b2=b2)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    plain = RUN[(zi, sparse)](X, K, **kw)
+    hy = dict(alpha1=np.full(K, 3.0), alpha2=np.full(K, 0.5), beta1=np.full(K, 2.0), beta2=np.full(K, 4.0))
+    with_hy = RUN[(zi, sparse)](X, K, **kw, **hy)
+    for k in ("a1", "a2", "b1", "b2"):
+        assert np.array_equal(plain["variational_params"][k], with_hy["variational_params"][k]), k

@@ -180,3 +180,34 @@ def test_perturb_param_matches_reference_build(zi, sparse):
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(o.get(k), ref["variational_params"][k]) < TOL, k
     assert (np.abs(np.asarray(ref["variational_params"]["a1"]) - U).max() > 0)       # the noise did something
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+@pytest.mark.parametrize("rows_differ", [False, True], ids=["same_rows", "rows_differ"])
+def test_hyper_only_warm_start_matches_reference_build(zi, sparse, rows_differ):
+    """alpha / beta given and nothing else: the reference's else-if chain (wrapper_gap_factor.h:352-375) calls
+    init_hyper_param ALONE (gap_factor_model.cpp:126-132) -- variational parameters and statistics stay at the constructors'
+    Ones, nothing is drawn, no update_hyper_param -- and copies the matrices as given, rows that differ included."""
+    X, _, _ = datagen.simulate(40, 30, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=43)
+    n, p, K = 40, 30, 3
+    rng = np.random.default_rng(9)
+    if rows_differ:
+        hy = dict(alpha1=rng.uniform(0.5, 2.0, (n, K)), alpha2=rng.uniform(0.5, 2.0, (n, K)),
+                  beta1=rng.uniform(0.5, 2.0, (p, K)), beta2=rng.uniform(0.5, 2.0, (p, K)))
+    else:
+        hy = dict(alpha1=np.tile(rng.uniform(0.5, 2.0, K), (n, 1)), alpha2=np.tile(rng.uniform(0.5, 2.0, K), (n, 1)),
+                  beta1=np.tile(rng.uniform(0.5, 2.0, K), (p, 1)), beta2=np.tile(rng.uniform(0.5, 2.0, K), (p, 1)))
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=8, iter_min=8, reorder_factor=False, **hy)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    ref = pyref.run(X, K, zi, sparse, **kw)
+    orc = po.run(X, K, zi, sparse, **kw)
+    for grp in ("variational_params", "hyper_params"):
+        for k in orc[grp]:
+            assert relerr(orc[grp][k], ref[grp][k]) < TOL, (grp, k)
+    assert relerr(orc["convergence"]["conv_crit"], ref["convergence"]["conv_crit"]) < TOL
+    for k in ("loglikelihood", "deviance"):
+        assert relerr(orc["monitor"][k], ref["monitor"][k]) < TOL, k
+    if not sparse and not zi:
+        assert relerr(orc["monitor"]["optim_criterion"], ref["monitor"]["optim_criterion"]) < TOL
