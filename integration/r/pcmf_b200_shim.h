@@ -8,12 +8,28 @@ namespace pcmf_shim {
 inline const double *opt_mat(const Rcpp::Nullable<Rcpp::NumericMatrix> &m) {
     return m.isNotNull() ? REAL(Rcpp::NumericMatrix(m)) : nullptr;
 }
-// hyper-parameters: the reference takes n x K / p x K matrices with identical rows (gap_factor_model.cpp:56-59);
-// the C ABI takes the K-vector, i.e. row 0
-inline std::vector<double> first_row(const Rcpp::NumericMatrix &m) {
-    std::vector<double> v(m.ncol());
-    for (int k = 0; k < m.ncol(); ++k) v[k] = m(0, k);
-    return v;
+typedef Rcpp::Nullable<Rcpp::NumericMatrix> OptMat;
+typedef Rcpp::Nullable<Rcpp::NumericVector> OptVec;
+inline const double *opt_vec(const OptVec &v) { return v.isNotNull() ? REAL(Rcpp::NumericVector(v)) : nullptr; }
+// the warm-start arguments of run_* as the C ABI takes them.  Hyper-parameters travel as the reference's n x K / p x K
+// matrices (hyper_rows = 1, gap_factor_model.cpp:126-132): the library collapses identical rows and keeps rows that differ.
+inline pcmf_init make_init(const OptMat &U, const OptMat &V, const OptMat &a1, const OptMat &a2, const OptMat &b1, const OptMat &b2,
+                           const OptMat &alpha1, const OptMat &alpha2, const OptMat &beta1, const OptMat &beta2,
+                           const OptMat &prob_S = R_NilValue, const OptVec &prior_S = R_NilValue,
+                           const OptMat &prob_D = R_NilValue, const OptVec &prior_D = R_NilValue) {
+    pcmf_init init{};
+    init.U = opt_mat(U);   init.V = opt_mat(V);
+    init.a1 = opt_mat(a1); init.a2 = opt_mat(a2); init.b1 = opt_mat(b1); init.b2 = opt_mat(b2);
+    init.alpha1 = opt_mat(alpha1); init.alpha2 = opt_mat(alpha2); init.beta1 = opt_mat(beta1); init.beta2 = opt_mat(beta2);
+    init.hyper_rows = 1;
+    init.prob_S = opt_mat(prob_S); init.prior_S = opt_vec(prior_S);
+    init.prob_D = opt_mat(prob_D); init.prior_D = opt_vec(prior_D);
+    return init;
+}
+inline void check_init_mode(const Rcpp::CharacterVector &init_mode) {
+    const std::string m = Rcpp::as<std::string>(init_mode[0]);
+    if (m == "nmf") Rcpp::stop("FixMe not implemented yet");                                      // wrapper_gap_factor.h:370
+    if (m != "random") Rcpp::stop("`init_mode` input parameter should be 'random' or 'nmf'");     // wrapper_gap_factor.h:372
 }
 static int progress_cb(void *, int iter, double crit) {
     Rcpp::Rcout << "iter " << iter << "  criterion " << crit << std::endl;   // algorithm.h:170-173
@@ -42,7 +58,12 @@ inline Rcpp::List fit(SEXP X, int K, bool zi, bool sparse, double sel_bound, boo
     o.conv_mode = conv_mode; o.monitor = monitor; o.reorder_factor = reorder_factor;
     o.ninit = ninit; o.iter_init = iter_init; o.verbose = verbose;
     o.has_seed = seed.isNotNull(); if (o.has_seed) o.seed = Rcpp::as<uint32_t>(seed);
-    o.device = Rcpp::as<int>(Rcpp::Function("getOption")("pCMF.device", 0));
+    Rcpp::Function getOption("getOption");
+    o.device = Rcpp::as<int>(getOption("pCMF.device", 0));
+    // the GPU counterpart of `ncores` (wrapper_gap_factor.h:271-274): options(pCMF.ngpus = 8) shards the cells over 8 devices
+    // inside the library (NCCL communicator and per-device threads are its own); options(pCMF.precision = 1) selects FP32 mode
+    o.ngpus = Rcpp::as<int>(getOption("pCMF.ngpus", 1));
+    o.precision = Rcpp::as<int>(getOption("pCMF.precision", 0));
     o.world = 1;
     if (verbose) { o.progress = progress_cb; o.progress_every = 10; }
 

@@ -206,6 +206,14 @@ class _Comm:
 
         self.cfn = _lib.ALLREDUCE_FN(cb)
 
+    def allreduce_host(self, arr):
+        """Sum of a small host array over the ranks (set-up statistics, e.g. the per-gene sums behind pCMF()'s prior_S)."""
+        torch = self.torch
+        dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.as_tensor(np.ascontiguousarray(arr, np.float64)).to(dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
     def _wrap(self, devptr, count):
         torch = self.torch
 
@@ -570,6 +578,31 @@ def run_zi_sparse_gap_factor(X, K, sel_bound=0.5, U=None, V=None, verbose=True, 
                 beta1, beta2, prob_S=prob_S, prior_S=prior_S, prob_D=prob_D, prior_D=prior_D, **gpu)
 
 
+def sparse_prior(X, K, comm=None, device=0, n_global=None):
+    """prior_S <- 1-exp(-apply(X,2,sd)/mean(X[X!=0])); prob_S <- matrix(rep(prior_S, K), ncol=K)   (pCMF.R:228-229)"""
+    from .datagen import prior_S_heuristic
+    sparse_in = isinstance(X, (DeviceCSR, tuple)) or (_sp is not None and _sp.issparse(X))
+    if sparse_in or comm is not None:
+        # X never exists as a dense matrix, or this process only holds a shard of the cells: the same heuristic from
+        # per-gene sums (one GPU pass over the non-zeros), summed over the ranks so that every rank starts from the
+        # SAME prob_S / prior_S -- gene-side state is replicated, a per-shard heuristic would silently fork the model
+        if sparse_in:
+            s1, s2, cn = csr_column_stats(X, device=device)
+            n_loc = X.n if isinstance(X, DeviceCSR) else (len(X[0]) - 1 if isinstance(X, tuple) else X.shape[0])
+        else:
+            A = np.asarray(X, np.float64)
+            s1, s2, cn, n_loc = A.sum(0), (A * A).sum(0), (A != 0).sum(0).astype(np.float64), A.shape[0]
+        n_tot = n_loc
+        if comm is not None:
+            red = comm.allreduce_host(np.concatenate([s1, s2, cn, [float(n_loc)]]))
+            p_ = len(s1)
+            s1, s2, cn, n_tot = red[:p_], red[p_:2 * p_], red[2 * p_:3 * p_], int(round(red[-1]))
+            if n_global not in (None, n_tot):
+                raise PcmfError(_lib.EINVAL, "n_global does not equal the number of cells summed over the ranks")
+        return prior_S_from_stats(s1, s2, cn, n_tot, K)
+    return prior_S_heuristic(np.asarray(X), K)
+
+
 def pCMF(X, K, zero_inflation=True, sparsity=True, sel_bound=0.5, verbose=True, monitor=True, iter_max=1000,
          iter_min=None, ninit=1, iter_init=100, ncores=1, reorder_factor=True, seed=None, **gpu):
     """pkg/R/pCMF.R:197-259, argument for argument.  Extra keyword arguments (device=, comm=, return_prob_D=, ...) are
@@ -584,14 +617,7 @@ def pCMF(X, K, zero_inflation=True, sparsity=True, sel_bound=0.5, verbose=True, 
         return run_gap_factor(X, K, **common)
     if zero_inflation and not sparsity:
         return run_zi_gap_factor(X, K, **common)
-    # prior_S <- 1-exp(-apply(X,2,sd)/mean(X[X!=0])); prob_S <- matrix(rep(prior_S, K), ncol=K)   (pCMF.R:228-229)
-    from .datagen import prior_S_heuristic
-    if isinstance(X, DeviceCSR) or (_sp is not None and _sp.issparse(X)):
-        # X never exists as a dense matrix: the same heuristic from per-gene sums taken in one GPU pass over the non-zeros
-        s1, s2, cn = csr_column_stats(X, device=gpu.get("device", 0))
-        prob_S, prior_S = prior_S_from_stats(s1, s2, cn, X.n if isinstance(X, DeviceCSR) else X.shape[0], K)
-    else:
-        prob_S, prior_S = prior_S_heuristic(np.asarray(X), K)
+    prob_S, prior_S = sparse_prior(X, K, comm=gpu.get("comm"), device=gpu.get("device", 0), n_global=gpu.get("n_global"))
     if not zero_inflation:
         return run_sparse_gap_factor(X, K, sel_bound=sel_bound, prob_S=prob_S, prior_S=prior_S, **common)
     return run_zi_sparse_gap_factor(X, K, sel_bound=sel_bound, prob_S=prob_S, prior_S=prior_S, **common)

@@ -93,7 +93,7 @@ struct BlockCache {
         void *p = nullptr;
         const double t0 = now_s();
         cudaError_t e = cudaMalloc(&p, bytes);
-        miss_seconds += now_s() - t0; ++misses; miss_bytes += bytes;
+        { std::lock_guard<std::mutex> lk(mu); miss_seconds += now_s() - t0; ++misses; miss_bytes += bytes; }
         if (now_s() - t0 > 5e-3 && getenv("PCMF_TIMING"))
             fprintf(stderr, "[pcmf timing] cudaMalloc of %.1f MB took %.1f ms (%zu cached blocks)\n", bytes / 1e6, (now_s() - t0) * 1e3, free_blocks.size());
         if (e != cudaSuccess) {           // out of memory: give the cached blocks back and try once more
@@ -114,12 +114,23 @@ struct BlockCache {
     }
     void put(void *p) {
         if (!p) return;
-        cudaDeviceSynchronize();          // like cudaFree: the block is idle on every stream before anyone can reuse it
+        std::pair<int, size_t> key{-1, 0};
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = live.find(p);
+            if (it != live.end()) key = it->second;
+        }
+        // like cudaFree: the block is idle on every stream of ITS device before anyone can reuse it
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (key.first >= 0 && key.first != cur) cudaSetDevice(key.first);
+        cudaDeviceSynchronize();
+        if (key.first < 0) cudaFree(p);
+        if (key.first >= 0 && key.first != cur) cudaSetDevice(cur);
+        if (key.first < 0) return;
         std::lock_guard<std::mutex> lk(mu);
-        auto it = live.find(p);
-        if (it == live.end()) { cudaFree(p); return; }
-        free_blocks.insert({it->second, p});
-        live.erase(it);
+        free_blocks.insert({key, p});
+        live.erase(p);
     }
     void release_all() {
         std::lock_guard<std::mutex> lk(mu);
@@ -137,9 +148,11 @@ BlockCache &block_cache() { static BlockCache c; return c; }
 // threads.  Measured need: at C4 the result is ~1 GB and a plain cudaMemcpy into pageable memory ran at ~4 GB/s.
 struct HostStager {
     static constexpr size_t CH = (size_t)32 << 20;
-    std::mutex mu;
-    void *buf[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2];
+    // staging buffers and events belong to the device that was current when they were created: one set per device
+    // (a multi-device process -- pcmf_options.ngpus, or an R session that changes options(pCMF.device) -- uses several)
+    struct PerDev { std::mutex mu; void *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2]; };
+    std::mutex map_mu;
+    std::map<int, PerDev> per;
     int nthreads() const { return (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency())); }
     static void par_for(size_t bytes, int T, const std::function<void(size_t, size_t)> &f) {
         size_t per = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
@@ -157,9 +170,14 @@ struct HostStager {
             CK(cudaStreamSynchronize(st));
             return;
         }
-        std::lock_guard<std::mutex> lk(mu);
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        PerDev *pd;
+        { std::lock_guard<std::mutex> lk(map_mu); pd = &per[dev]; }
+        std::lock_guard<std::mutex> lk(pd->mu);
+        void **buf = pd->buf; cudaEvent_t *ev = pd->ev;
         if (!buf[0]) {
-            for (int i = 0; i < 2; ++i) { CK(cudaHostAlloc(&buf[i], CH, cudaHostAllocDefault)); CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+            for (int i = 0; i < 2; ++i) { CK(cudaHostAlloc(&buf[i], CH, cudaHostAllocPortable)); CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
         }
         const int T = nthreads();
         const size_t nch = (bytes + CH - 1) / CH;
@@ -178,8 +196,15 @@ struct HostStager {
         drain(nch - 1);
     }
     void release() {
-        std::lock_guard<std::mutex> lk(mu);
-        for (int i = 0; i < 2; ++i) if (buf[i]) { cudaFreeHost(buf[i]); cudaEventDestroy(ev[i]); buf[i] = nullptr; }
+        std::lock_guard<std::mutex> lk(map_mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto &kv : per) {
+            std::lock_guard<std::mutex> l2(kv.second.mu);
+            cudaSetDevice(kv.first);
+            for (int i = 0; i < 2; ++i) if (kv.second.buf[i]) { cudaFreeHost(kv.second.buf[i]); cudaEventDestroy(kv.second.ev[i]); kv.second.buf[i] = nullptr; }
+        }
+        cudaSetDevice(cur);
     }
 };
 HostStager &host_stager() { static HostStager h; return h; }
@@ -381,6 +406,24 @@ __global__ void k_dense_fill(int64_t n, int64_t nb, int32_t j0, const T *X, int6
         }
         pos[i] = e;
     }
+}
+// CSR input is taken as it is (no copy for a device-resident matrix): check what every later kernel relies on.
+// flag bit 1: row pointers not ascending / not starting at 0, 2: gene index outside [0, p), 4: an explicit zero (it would
+// count as X != 0 in the zero-inflation occupancy, zi_gap_factor_model.cpp:104, and in the per-gene non-zero counts)
+template <typename VT>
+__global__ void k_validate_csr(int64_t n, int32_t p, int64_t nnz, const int64_t *rowptr, const int32_t *colidx, const VT *val, int *flag) {
+    int bad = 0;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = gid; i < n; i += gsz) {
+        const int64_t a = rowptr[i], b = rowptr[i + 1];
+        if (a > b || a < 0 || b > nnz || (i == 0 && a != 0)) bad |= 1;
+    }
+    for (int64_t e = gid; e < nnz; e += gsz) {
+        const int32_t j = colidx[e];
+        if (j < 0 || j >= p) bad |= 2;
+        if (val && val[e] == (VT)0) bad |= 4;
+    }
+    if (bad) atomicOr(flag, bad);
 }
 __global__ void k_expand_rows(int64_t n, const int64_t *rowptr, int32_t *rowids, int64_t *perm) {
     const int lane = threadIdx.x & 31;
@@ -614,6 +657,22 @@ void pcmf_solver::setup_problem(const pcmf_problem &pr) {
             copy_stream = s2;
             rowptr = rp; colidx = ci; val_csr = vv; own_csr = true;
         }
+        {
+            int *d_flag = dmalloc<int>(1);
+            CK(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+            if (nnz < 0) fail(PCMF_EINVAL, "CSR input: negative number of non-zeros");
+            // (the values of a host CSR are still travelling on their own stream: they are checked in build_csc)
+            const void *vchk = copy_stream ? nullptr : val_csr;
+            if (f32) k_validate_csr<float><<<grid_for(std::max<int64_t>(n, nnz), 256), 256, 0, stream>>>(n, p, nnz, rowptr, colidx, (const float *)vchk, d_flag);
+            else k_validate_csr<double><<<grid_for(std::max<int64_t>(n, nnz), 256), 256, 0, stream>>>(n, p, nnz, rowptr, colidx, (const double *)vchk, d_flag);
+            int h_flag = 0;
+            CK(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            dfree(d_flag);
+            if (h_flag & 1) fail(PCMF_EINVAL, "CSR input: row pointers must start at 0 and ascend");
+            if (h_flag & 2) fail(PCMF_EINVAL, "CSR input: gene index out of range");
+            if (h_flag & 4) fail(PCMF_EINVAL, "CSR input: explicit zeros are not allowed (drop them: they would count as X != 0)");
+        }
     } else {
         // dense R matrix (wrapper_gap_factor.h:204-211), INTSXP or REALSXP, column-major: uploaded as it is and turned into
         // CSR on the device (count per cell, scan, fill in ascending gene order); column blocks bound the staging buffer
@@ -747,6 +806,13 @@ void pcmf_solver::build_csc() {
     CK(cudaMemcpyAsync(hs.data(), colsumX, sizeof(double) * p, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     lgx_const = 0; for (double x : h) lgx_const += x;
+    {   // explicit zeros among the stored entries (values of a host CSR arrive after the structure was checked)
+        std::vector<double> hn(p);
+        CK(cudaMemcpy(hn.data(), colnnz, sizeof(double) * p, cudaMemcpyDeviceToHost));
+        double tot = 0; for (double x : hn) tot += x;
+        if (opt.world <= 1 && tot != (double)nnz)
+            fail(PCMF_EINVAL, "CSR input: explicit zeros are not allowed (drop them: they would count as X != 0)");
+    }
     // constants of deviance / exp_deviance (gap...cpp:329-341): poisson_loglike(X, X) and poisson_loglike_vec(X, colmean X)
     ll_XX = -lgx_const; ll_Xmean = -lgx_const;
     for (int j = 0; j < p; ++j) {

@@ -121,3 +121,18 @@ def test_zi_init_shortcut_matches_dense_pass(sparse, K):
             assert relerr(o0[k], o1[k]) < 1e-11, (it, k)
     s0.close()
     s1.close()
+
+
+def test_malformed_csr_input_is_rejected():
+    """host / device CSR is taken as it is, so what the kernels rely on is checked on the device first."""
+    rp = np.array([0, 2, 3, 5], np.int64)
+    ci = np.array([0, 3, 1, 2, 4], np.int32)
+    vv = np.array([1, 2, 3, 4, 5], np.float32)
+    ok = pcmf_b200.Solver((rp, ci, vv, 5), 2, False, False, seed=1)
+    ok.close()
+    for bad, msg in (((rp, np.array([0, 3, 1, 2, 7], np.int32), vv, 5), "gene index out of range"),
+                     ((np.array([0, 3, 2, 5], np.int64), ci, vv, 5), "row pointers"),
+                     ((rp, ci, np.array([1, 0, 3, 4, 5], np.float32), 5), "explicit zeros")):
+        with pytest.raises(pcmf_b200.PcmfError, match=msg) as e:
+            pcmf_b200.Solver(bad, 2, False, False, seed=1)
+        assert e.value.code == 1

@@ -180,3 +180,39 @@ def test_world2_gloo_sharding_matches_unsharded_oracle(zi, sparse):
         pr.join(120)
     assert errors.empty(), errors.get()
     assert all(pr.exitcode == 0 for pr in procs)
+
+
+def _prior_worker(rank, world, port, X, K, expect, errors):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from pcmf_b200 import api
+        r0, r1 = sharding.equal_row_partition(X.shape[0], world)[rank]
+        prob_S, prior_S = api.sparse_prior(X[r0:r1], K, comm=api._Comm(), n_global=X.shape[0])
+        assert np.max(np.abs(prior_S - expect)) < 1e-12, np.max(np.abs(prior_S - expect))
+        assert prob_S.shape == (X.shape[1], K) and np.array_equal(prob_S[:, 0], prior_S)
+        dist.destroy_process_group()
+    except Exception as e:   # pragma: no cover
+        errors.put((rank, repr(e)))
+        raise
+
+
+def test_world2_pcmf_prior_S_heuristic_is_global():
+    """pCMF(X_shard, comm=...) must derive prob_S / prior_S (pCMF.R:228-229) from the statistics of ALL cells --
+    gene-side state is replicated, a per-shard heuristic would give every rank a different model."""
+    X, _, _ = datagen.simulate(60, 25, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=8)
+    X = X.astype(float)
+    _, expect = datagen.prior_S_heuristic(X, 3)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    errors = ctx.Queue()
+    procs = [ctx.Process(target=_prior_worker, args=(r, 2, port, X, 3, expect, errors)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(120)
+    assert errors.empty(), errors.get()
+    assert all(pr.exitcode == 0 for pr in procs)
