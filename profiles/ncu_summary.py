@@ -18,7 +18,15 @@ def main(path):
              "l1tex__t_sector_hit_rate.pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
              "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
              "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum"]
+             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum",
+             # the FP64 / DMMA dispatch model of DESIGN.md section 4.1 as counters (round 2): a DFMA-class instruction keeps the
+             # shared FP64 pipe 2 cycles, a DMMA 16; "shared" = fp64 + tensor
+             "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active",
+             "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+             "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+             "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_tensor_subpipe_dmma.sum", "sm__inst_executed.sum",
+             "sm__issue_active.avg.pct_of_peak_sustained_active",
+             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum"]
     stall = [h for h in hdr if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued")]
     for r in rows[2:]:
         print("==== %s" % r[idx["Kernel Name"]][:90])

@@ -259,5 +259,5 @@ def test_hyper_parameters_are_ignored_next_to_variational_parameters(zi, sparse)
     plain = RUN[(zi, sparse)](X, K, **kw)
     hy = dict(alpha1=np.full(K, 3.0), alpha2=np.full(K, 0.5), beta1=np.full(K, 2.0), beta2=np.full(K, 4.0))
     with_hy = RUN[(zi, sparse)](X, K, **kw, **hy)
-    for k in ("a1", "a2", "b1", "b2"):
-        assert np.array_equal(plain["variational_params"][k], with_hy["variational_params"][k]), k
+    for k in ("a1", "a2", "b1", "b2"):     # (atomic accumulation order: equal up to rounding, not bit for bit)
+        assert relerr(plain["variational_params"][k], with_hy["variational_params"][k]) < 1e-12, k
