@@ -250,6 +250,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
     ap.add_argument("--variant", type=int, default=0, help="experimental kernel variant bits")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="fp64 (default, the headline: results within 1e-6 of the reference) or the optional FP32 mode")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -294,7 +296,7 @@ def main():
     stream = torch.cuda.current_stream()
     solver = pcmf_b200.Solver(csr, K, cfg["zi"], cfg["sparse"], seed=args.seed + 1000, prob_S=prob_S, prior_S=prior_S,
                               device=local, stream=stream.cuda_stream, comm=comm, n_global=n, row_offset=r0,
-                              iter_max=10 ** 6, kernel_variant=args.variant)
+                              iter_max=10 ** 6, kernel_variant=args.variant, precision=args.precision)
     # ---- warm-up, then exactly `steps` timed iterations (ELBO evaluated every iteration, as monitor=TRUE does)
     solver.iterate(args.warmup, with_elbo=True)
     ph0, l0 = solver.phase_times(), solver.launch_count()
@@ -406,7 +408,8 @@ def main():
         fn = {(False, False): pcmf_b200.run_gap_factor, (True, False): pcmf_b200.run_zi_gap_factor,
               (False, True): pcmf_b200.run_sparse_gap_factor, (True, True): pcmf_b200.run_zi_sparse_gap_factor}[(zi, sparse)]
         kw = dict(verbose=False, monitor=2, iter_max=args.steps, iter_min=args.steps, epsilon=0.0, reorder_factor=False,
-                  seed=args.seed + 1000, device=local, comm=comm, n_global=n, row_offset=r0, return_prob_D=False)
+                  seed=args.seed + 1000, device=local, comm=comm, n_global=n, row_offset=r0, return_prob_D=False,
+                  precision=args.precision)
         if sparse:
             kw.update(prob_S=prob_S, prior_S=prior_S)
         torch.cuda.synchronize()
@@ -436,8 +439,8 @@ def main():
     if rank == 0:
         line = {"metric": "VEM iterations/sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": cfg["label"], "n": n, "p": p, "K": K, "nnz": nnz, "density": nnz / (n * p),
+                "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
+                "config": {"workload": cfg["label"], "precision": args.precision, "n": n, "p": p, "K": K, "nnz": nnz, "density": nnz / (n * p),
                            "model": ("zi_" if zi else "") + ("sparse_" if sparse else "") + "gap",
                            "parallelism": "cells sharded over %d GPU(s), all-reduce of p x K gene statistics" % world,
                            "l2": "inputs larger than L2 (CSR+CSC %.1f GB per rank); no explicit flush" % (16e-9 * nnz_local),

@@ -311,7 +311,7 @@ class Solver:
                  epsilon=1e-2, additional_iter=10, conv_mode=1, monitor=True, reorder_factor=False, ninit=1, iter_init=100,
                  seed=None, verbose=False, U=None, V=None, a1=None, a2=None, b1=None, b2=None, alpha1=None, alpha2=None,
                  beta1=None, beta2=None, prob_S=None, prior_S=None, prob_D=None, prior_D=None, device=0, stream=None,
-                 comm=None, n_global=None, row_offset=0, progress=None, kernel_variant=0):
+                 comm=None, n_global=None, row_offset=0, progress=None, kernel_variant=0, precision=0, ngpus=0):
         self.L = _lib.lib()
         self.h = None
         pr, self._keep, n, p = _as_problem(X, n_global, row_offset)
@@ -326,6 +326,8 @@ class Solver:
         o.verbose, o.device = int(bool(verbose)), int(device)
         o.stream = stream
         o.dev_flags = int(kernel_variant)
+        o.precision = {0: 0, 1: 1, "fp64": 0, "fp32": 1}[precision]
+        o.ngpus = int(ngpus)
         self.comm = comm
         if comm is not None:
             o.rank, o.world, o.allreduce = comm.rank, comm.world, comm.cfn

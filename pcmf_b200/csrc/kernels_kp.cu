@@ -116,6 +116,8 @@ void launch_zi_loglik(const ZiAArgs &a, double *out, cudaStream_t st) {
         attr = true;
     }
     const int64_t grid = (a.n + 32 * MMA_MT - 1) / (32 * MMA_MT);
+    // (the gene records are packed here as well: in FP32 mode the cell pass does not leave them behind)
+    k_zi_pack<KP, true><<<pack_grid(((a.p + 7) / 8) * R::REC), 256, 0, st>>>(a.p, a.EVS, a.EVS, a.cz, a.flag, a.pack);
     k_zi_loglik_mma<KP, MMA_MT, MMA_TJ><<<(unsigned)grid, 128, smem, st>>>(a, out);
 }
 void launch_gene_loglam(bool f32, const LamArgs &a, int grid, cudaStream_t st) {
@@ -159,8 +161,50 @@ int launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) 
 
 int zi_genes_block(int variant) { return !(variant & 4) ? (((variant & 8) && MMA_MT == 4) ? 64 : 32 * MMA_MT) : 256; }
 
+// ---- FP32 mode: tcgen05 dense passes ---------------------------------------------------------------------------
+constexpr int TC_KF1 = (KP + 7) / 8 * 8;            // factors of the first product (tf32 MMA: K in steps of 8)
+constexpr int TC_KF2 = (KP + 15) / 16 * 16;         // accumulator columns of the second product (N in steps of 16 at M = 128)
+using TcC = TcCfg<TC_KF1, TC_KF2>;
+
+size_t tc_pack_bytes(int64_t records) { return (size_t)((records + TC_TG - 1) / TC_TG) * TcC::TILE_BYTES; }
+
+template <bool CELLS>
+void tc_attr() {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_tc<TC_KF1, TC_KF2, CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcC::SMEM);
+        attr = true;
+    }
+}
+int launch_zi_cells_tc(ZiTcArgs a, const double *M1, const double *M2, unsigned char *pack, int sms, cudaStream_t st) {
+    (void)sms;
+    tc_attr<true>();
+    const int64_t ntiles = (a.streamed + TC_TG - 1) / TC_TG;
+    k_tc_pack<TC_KF1, TC_KF2><<<pack_grid(ntiles * TC_TG * TC_KF2), 256, 0, st>>>(a.streamed, KP, M1, M2, a.cz, a.flag, pack);
+    a.tiles = pack;
+    a.tiles_per_chunk = ntiles;
+    k_zi_tc<TC_KF1, TC_KF2, true><<<(unsigned)((a.rows + 127) / 128), 128, TcC::SMEM, st>>>(a);
+    return 2;
+}
+int launch_zi_genes_tc(ZiTcArgs a, const double *M1, const double *M2, unsigned char *pack, int sms, cudaStream_t st) {
+    tc_attr<false>();
+    const int64_t ntiles = (a.streamed + TC_TG - 1) / TC_TG;
+    k_tc_pack<TC_KF1, TC_KF2><<<pack_grid(ntiles * TC_TG * TC_KF2), 256, 0, st>>>(a.streamed, KP, M1, M2, nullptr, nullptr, pack);
+    a.tiles = pack;
+    // (gene block, cell chunk) CTAs for ~8 waves at the resident CTA count; the gene blocks of one chunk are adjacent in the
+    // grid, so the cell tiles they all stream are read from HBM once and from L2 afterwards
+    const int64_t gx = (a.rows + 127) / 128;
+    const int resident = (TcC::SMEM <= 110 * 1024) ? 2 : 1;
+    int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(ntiles, ((int64_t)sms * resident * 8 + gx - 1) / gx));
+    a.tiles_per_chunk = (ntiles + chunks - 1) / chunks;
+    chunks = (ntiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+    dim3 grid((unsigned)gx, (unsigned)chunks);
+    k_zi_tc<TC_KF1, TC_KF2, false><<<grid, 128, TcC::SMEM, st>>>(a);
+    return 2;
+}
+
 const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes, zi_genes_block, zi_pack_doubles,
-                         launch_zi_loglik, launch_gene_loglam, launch_gene_order};
+                         launch_zi_loglik, launch_gene_loglam, launch_gene_order, tc_pack_bytes, launch_zi_cells_tc, launch_zi_genes_tc};
 
 }  // namespace
 

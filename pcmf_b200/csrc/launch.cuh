@@ -2,6 +2,7 @@
 // (kernels_kp.cu with -DPCMF_KP=<n>) so the build parallelises; the solver picks a table at run time.
 #pragma once
 #include "kernels.cuh"
+#include "zi_tc.cuh"
 
 namespace pcmf {
 
@@ -18,6 +19,11 @@ struct Launchers {
     void (*zi_loglik)(const ZiAArgs &, double *out, cudaStream_t);            // zero part of zi_poisson_loglike (monitor)
     void (*gene_loglam)(bool f32, const LamArgs &, int grid, cudaStream_t);   // deviance / log-likelihood non-zero pass
     void (*gene_order)(bool f32, const OrderArgs &, int grid, cudaStream_t);  // one round of the greedy factor ordering   // scratch size of ZiAArgs::pack (0) / ZiBArgs::pack (1)
+    // FP32 mode: the dense passes on tcgen05 (zi_tc.cuh).  M1 / M2: row-major FP64 matrices of the streamed side for the first /
+    // second product; the launcher packs them into ZiTcArgs::tiles (tc_pack_bytes(records) bytes) and runs the pass
+    size_t (*tc_pack_bytes)(int64_t records);
+    int (*zi_cells_tc)(ZiTcArgs, const double *M1, const double *M2, unsigned char *pack, int sms, cudaStream_t);
+    int (*zi_genes_tc)(ZiTcArgs, const double *M1, const double *M2, unsigned char *pack, int sms, cudaStream_t);
 };
 
 const Launchers *get_launchers_4();

@@ -244,6 +244,8 @@ struct pcmf_solver {
     int64_t *colptr = nullptr; int32_t *rowidx = nullptr; void *val_csc = nullptr;
     uint32_t *bitT = nullptr, *bitB = nullptr;
     double *zpackA = nullptr, *zpackB = nullptr;   // fragment-ordered scratch of the DMMA ZI passes
+    bool fp32_mode = false;                        // pcmf_options.precision = 1: dense ZI passes on tcgen05 (zi_tc.cuh), FP32 gathers
+    unsigned char *tcpackA = nullptr, *tcpackB = nullptr;   // their tile records (genes / cells)
     // explicit dense prob_D of a warm start: held until the first zero-inflation update (init_zi_param(prob_D, prior_D))
     double *Pexp = nullptr, *valw_csr = nullptr, *valw_csc = nullptr;
     bool explicitP = false, freq_ones = false;
@@ -360,7 +362,7 @@ pcmf_solver::~pcmf_solver() {
     if (own_csr) { dfree((void *)rowptr); dfree((void *)colidx); dfree((void *)val_csr); }
     void *ptrs[] = {colptr, rowidx, val_csc, bitT, bitB, Lg, colsumX, colnnz, rowsumX, a1, a2, EU[0], EU[1], ElogU, eu, PV,
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
-                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3], pstore, blkptr, hrow[0], hrow[1], hrow[2], hrow[3], rowsg};
+                    ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3], pstore, blkptr, hrow[0], hrow[1], hrow[2], hrow[3], rowsg, tcpackA, tcpackB};
     for (void *q : ptrs) if (q) dfree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
@@ -831,7 +833,9 @@ void pcmf_solver::alloc_state() {
     if (keep_old && !zi) { EU[1] = dmalloc<double>(nK); CK(cudaMemsetAsync(EU[1], 0, nK * 8, stream)); }
     if (zi) {
         EU[1] = dmalloc<double>(nK); PV = dmalloc<double>(nK); CK(cudaMemsetAsync(EU[1], 0, nK * 8, stream));
-        zpackA = dmalloc<double>(L->zi_pack_doubles(p, 0)); zpackB = dmalloc<double>(L->zi_pack_doubles(n, 1));
+        zpackA = dmalloc<double>(L->zi_pack_doubles(p, 0));
+        if (fp32_mode) { tcpackA = dmalloc<unsigned char>(L->tc_pack_bytes(p)); tcpackB = dmalloc<unsigned char>(L->tc_pack_bytes(n)); }
+        else zpackB = dmalloc<double>(L->zi_pack_doubles(n, 1));
     }
     b1 = dmalloc<double>(pK); b2 = dmalloc<double>(pK); EV = dmalloc<double>(pK); ElogV = dmalloc<double>(pK);
     ev = dmalloc<double>(pK); evw = dmalloc<double>(pK); EVS = dmalloc<double>(pK); wS = dmalloc<double>(pK);
@@ -863,7 +867,7 @@ void pcmf_solver::alloc_state() {
     dbg = dmalloc<unsigned long long>(4); CK(cudaMemsetAsync(dbg, 0, 32, stream));
     k_init_guard<<<1, 32, 0, stream>>>(guard[0]); k_init_guard<<<1, 32, 0, stream>>>(guard[1]);
     // kernel_variant bit 64 forces the stored-prob_D path (small test problems), bit 128 disables it
-    if (zi && !(opt.dev_flags & (4 | 128)) && ((double)n * (double)p >= 5e7 || (opt.dev_flags & 64)) &&
+    if (zi && !fp32_mode && !(opt.dev_flags & (4 | 128)) && ((double)n * (double)p >= 5e7 || (opt.dev_flags & 64)) &&
         (double)((n + 127) / 128 * 16) * (double)((p + 7) / 8) < 4.0e9) {
         // cell groups padded to whole CTAs of the cell pass (128 cells): it stores every tile it computes
         const size_t need = (size_t)((n + 127) / 128 * 16) * (size_t)((p + 7) / 8) * 64 * sizeof(uint32_t);
@@ -1217,6 +1221,11 @@ void pcmf_solver::step(bool want_data) {
         } else if (zi_at_init) {           // prob_D = (X > 0): only the non-zeros contribute
             k_zi_init_genes<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, K, KP, colptr, rowidx, EU[nxt], ar1 + ar1_tmp);
             end(PH_ZI_B, 1);
+        } else if (fp32_mode) {
+            ZiTcArgs ta{};
+            ta.n = n; ta.p = p; ta.K = K; ta.KP = KP; ta.A1 = EVS; ta.rows = p; ta.streamed = n; ta.bits = bitB; ta.cz = cz; ta.flag = flag;
+            ta.tmpMat = ar1 + ar1_tmp;
+            end(PH_ZI_B, L->zi_genes_tc(ta, EU[cur], EU[nxt], tcpackB, sms, stream));
         } else {
             end(PH_ZI_B, L->zi_genes(zb, chunks, opt.dev_flags, stream));
         }
@@ -1267,7 +1276,13 @@ void pcmf_solver::step(bool want_data) {
         k_zi_prepare<<<grid_for(p, 256), 256, 0, stream>>>(zp);
         k_refresh_weights<<<grid_for(pK, 256), 256, 0, stream>>>(p, K, KP, sparse, prob_S, colw, ev, wS, evw);
         ZiAArgs za{n, p, K, EU[nxt], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA, pstore};
-        const int nl = L->zi_cells(za, opt.dev_flags, stream);
+        int nl;
+        if (fp32_mode) {
+            ZiTcArgs ta{};
+            ta.n = n; ta.p = p; ta.K = K; ta.KP = KP; ta.A1 = EU[nxt]; ta.rows = n; ta.streamed = p; ta.bits = bitT; ta.EU = EU[nxt];
+            ta.PV = PV; ta.colsumP = ar3 + ar3_csP; ta.zsc = ar3 + ar3_zsc; ta.cz = cz; ta.flag = flag;
+            nl = L->zi_cells_tc(ta, EVS, EVS, tcpackA, sms, stream);
+        } else nl = L->zi_cells(za, opt.dev_flags, stream);
         zi_at_init = false;
         pstore_valid = pstore != nullptr;
         allreduce(ar3, ar3_total);
@@ -1628,7 +1643,7 @@ void check_init(const pcmf_init *in) {
 
 extern "C" {
 
-const char *pcmf_version(void) { return "pcmf_b200 0.1.0 (sm_100a, fp64)"; }
+const char *pcmf_version(void) { return "pcmf_b200 0.2.0 (sm_100a; fp64 mode, fp32 mode on tcgen05)"; }
 
 int pcmf_device_count(void) {
     int c = 0;
@@ -1658,6 +1673,7 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
         if (opt->stream) { s->stream = (cudaStream_t)opt->stream; s->own_stream = false; }
         else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
         s->K = opt->K; s->KP = padded_K(opt->K); s->zi = opt->zero_inflation != 0; s->sparse = opt->sparsity != 0;
+        s->fp32_mode = opt->precision == 1;
         s->L = get_launchers(s->KP);
         if (!s->L) fail(PCMF_EUNSUPPORTED, "no kernels compiled for padded K = %d", s->KP);
         StageTimer tm(s->stream);

@@ -155,6 +155,21 @@ __device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lan
     return v[0];
 }
 
+// FP32 flavour (FP32-mode dense pass, zi_tc.cuh)
+__device__ __forceinline__ float warp_reduce_scatter32f(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
 // double atomic min/max through the ordered-integer trick (values are finite)
 __device__ __forceinline__ long long dbl_ordered(double d) {
     long long i = __double_as_longlong(d);
