@@ -46,7 +46,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         src = os.path.join(CSRC, "kernels_kp.cu")
         if force or _newer(o, [src] + headers):
             jobs.append([NVCC] + FLAGS + extra + ["-DPCMF_KP=%d" % kp, "-c", src, "-o", o])
-    for name in ("solver", "datagen"):
+    for name in ("solver", "datagen", "multi"):
         o = os.path.join(OBJ, name + ".o")
         objs.append(o)
         src = os.path.join(CSRC, name + ".cu")
@@ -60,7 +60,7 @@ def build(force=False, verbose=False, ptxas_info=False):
                 if verbose and out.strip():
                     print(out)
     if jobs or not os.path.exists(SO):
-        _run([NVCC, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++"])
+        _run([NVCC, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-ldl"])
     return SO, logs
 
 

@@ -43,13 +43,15 @@ constexpr int MMA_MT = (KP <= 20) ? 4 : 2;          // 8-row tiles per warp in t
 constexpr int MMA_TJ = 64;                           // genes per shared-memory tile, pass A
 constexpr int MMA_TI = 64;                          // cells per shared-memory tile, pass B
 
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d & 63; }
 inline int pack_grid(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 16)); }
 
 template <int MT>
 int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
     using R = ZiRec<KP, true>;
     const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 8 * MMA_TJ + kTabDoubles);
-    static bool attr = false;
+    static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
+    bool &attr = attr_dev[current_device()];
     if (!attr) {
         cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -72,7 +74,8 @@ template <int MT>
 int launch_zi_genes_stored_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
     using R = ZiRecF2<KP>;
     const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * R::REC);
-    static bool attr = false;
+    static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
+    bool &attr = attr_dev[current_device()];
     if (!attr) {
         cudaFuncSetAttribute(k_zi_genes_stored<KP, MT, MMA_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
@@ -88,7 +91,8 @@ int launch_zi_genes_mma_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
     if (a.pstore) return launch_zi_genes_stored_t<MT>(a, chunks, st);
     using R = ZiRec<KP, false>;
     const size_t smem = sizeof(double) * (2 * (MMA_TI / 8) * R::REC + kTabDoubles);
-    static bool attr = false;
+    static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
+    bool &attr = attr_dev[current_device()];
     if (!attr) {
         cudaFuncSetAttribute(k_zi_genes_mma<KP, MT, MMA_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
@@ -110,7 +114,8 @@ int launch_zi_genes_mma(const ZiBArgs &a, int chunks, int variant, cudaStream_t 
 void launch_zi_loglik(const ZiAArgs &a, double *out, cudaStream_t st) {
     using R = ZiRec<KP, true>;
     const size_t smem = sizeof(double) * (2 * (MMA_TJ / 8) * R::REC + 2 * MMA_TJ + kTabDoubles);
-    static bool attr = false;
+    static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
+    bool &attr = attr_dev[current_device()];
     if (!attr) {
         cudaFuncSetAttribute(k_zi_loglik_mma<KP, MMA_MT, MMA_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
@@ -136,7 +141,8 @@ size_t zi_pack_doubles(int64_t rows, int cells_side) {
 int launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
     if (!(variant & 4)) return launch_zi_cells_mma(a, variant, st);
     const size_t smem = sizeof(double) * (ZI_TJ * KP + ZI_TJ + 4 * ZI_TJ + 4 * 32 * 33) + sizeof(int) * ZI_TJ;
-    static bool attr = false;
+    static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
+    bool &attr = attr_dev[current_device()];
     if (!attr) {
         cudaFuncSetAttribute(k_zi_pass_cells<KP, ZI_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
@@ -149,7 +155,8 @@ int launch_zi_cells(const ZiAArgs &a, int variant, cudaStream_t st) {
 int launch_zi_genes(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
     if (!(variant & 4)) return launch_zi_genes_mma(a, chunks, variant, st);
     const size_t smem = sizeof(double) * 2 * ZI_TI * KP;
-    static bool attr = false;
+    static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
+    bool &attr = attr_dev[current_device()];
     if (!attr) {
         cudaFuncSetAttribute(k_zi_pass_genes<KP, ZI_TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
@@ -170,7 +177,8 @@ size_t tc_pack_bytes(int64_t records) { return (size_t)((records + TC_TG - 1) / 
 
 template <bool CELLS>
 void tc_attr() {
-    static bool attr = false;
+    static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
+    bool &attr = attr_dev[current_device()];
     if (!attr) {
         cudaFuncSetAttribute(k_zi_tc<TC_KF1, TC_KF2, CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcC::SMEM);
         attr = true;

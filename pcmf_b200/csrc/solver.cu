@@ -1641,6 +1641,9 @@ void check_init(const pcmf_init *in) {
 }
 }  // namespace
 
+extern "C" int pcmf_fit_multi(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_init *init, pcmf_result *res,
+                              char *errbuf, size_t errlen);     // multi.cu
+
 extern "C" {
 
 const char *pcmf_version(void) { return "pcmf_b200 0.2.0 (sm_100a; fp64 mode, fp32 mode on tcgen05)"; }
@@ -1658,6 +1661,7 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
         if (!out) fail(PCMF_EINVAL, "null output handle");
         check_options(prob, opt);
         check_init(init);
+        if (opt->ngpus > 1) fail(PCMF_EUNSUPPORTED, "ngpus > 1 is driven by pcmf_fit (one call, whole matrices); the step-wise API is one device per solver");
         int cnt = 0;
         if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0)
             fail(PCMF_ECUDA, "no CUDA device available: libpcmf_b200 has no CPU fallback");
@@ -1929,6 +1933,10 @@ int64_t pcmf_launch_count(pcmf_solver *s) { return s ? s->launches : 0; }
 
 int pcmf_fit(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_init *init, pcmf_result *res, char *errbuf, size_t errlen) {
     if (!res) { if (errbuf && errlen) snprintf(errbuf, errlen, "null result"); return PCMF_EINVAL; }
+    if (prob && opt && opt->ngpus > 1) {              // the library shards the cells over the devices itself (multi.cu)
+        int rc0 = guarded(errbuf, errlen, [&] { check_options(prob, opt); check_init(init); });
+        return rc0 != PCMF_OK ? rc0 : pcmf_fit_multi(prob, opt, init, res, errbuf, errlen);
+    }
     const double t0 = now_s();
     pcmf_solver *s = nullptr;
     int rc = pcmf_create(prob, opt, init, &s, errbuf, errlen);

@@ -9,12 +9,22 @@
 // lo = x - hi and a product a.b taken as a_hi b_hi + a_lo b_hi + a_hi b_lo ("3xTF32": relative error 2^-22 per term instead of
 // the 2^-11 of plain TF32 operands).  One CTA = 128 rows = the 128 lanes of tensor memory; the other side streams through
 // shared memory in tiles of 64 records prepared once per pass by k_tc_pack (one cp.async.bulk per tile, mbarrier):
-//      S (128 x 64)   = A' (128 x 3 KF1) . B1'^T                    A' = [a_hi | a_lo | a_hi], B1' = [b_hi | b_hi | b_lo]
-//      tcgen05.ld -> P = 1 / (1 + 2^(-z log2 e)) with ex2.approx / rcp.approx -> tcgen05.st (P_hi over S in place, P_lo beside it)
-//      D (128 x KF2) += P_hi . E_hi + P_lo . E_hi + P_hi . E_lo      with P as the A operand STRAIGHT FROM TENSOR MEMORY
-// The tensor-memory accumulator adds with truncation (measured in round 1: 2e-4 relative drift over 313 tiles), so it is
-// read out into FP64 registers every TC_DRAIN tiles and restarted.  Everything that is summed over cells or genes leaves the
-// kernel in FP64.  Stated accuracy of the mode: tests/test_gpu_fp32.py.
+//      S (128 x 64)   = A' (128 x 3 KF1) . B1'^T                    A' = [a_lo | a_hi | a_hi], B1' = [b_hi | b_lo | b_hi]
+//      tcgen05.ld -> P = expit(z) with ex2.approx / rcp.approx -> tcgen05.st (P_hi over S in place, P_lo beside it)
+//      D (128 x KF2)  = P_lo . E_hi + P_hi . E_lo + P_hi . E_hi      with P as the A operand STRAIGHT FROM TENSOR MEMORY
+// The tensor-memory accumulator adds with TRUNCATION, once per MMA instruction (measured in round 1: 2e-4 relative drift of an
+// accumulator left alone over 313 tiles; first cut of this kernel: 1e-4 on b2 at K = 64).  Hence (i) the small cross terms
+// come FIRST in both products, so that the running sum is small while they are added and only the KF1 / 8 resp. 8 steps of
+// the hi.hi part truncate at the size of the result, and (ii) the accumulator of the second product is read out into FP64
+// registers after EVERY tile and restarted.  Everything that is summed over cells or genes leaves the kernel in FP64.
+// Stated accuracy of the mode: tests/test_gpu_fp32.py.
+//
+// The expit is evaluated on x = -z log2(e) without a clamp and without a select on the entry kind:
+//      t = 2^-|x|, r = 1 / (1 + t), P = z > 0 ? r : t r      -- exactly 1 / 0 once |x| is large (ex2 underflows to 0)
+//      entries with X != 0 take lambda = -1e29, whole-gene shortcuts c = +-1e30, rows / records beyond the matrix an offset of
+//      1e30: all of them land on P = 1 or P = 0 through the same arithmetic (zi...cpp:353-360, internal.h:151-155)
+//      -[P log P + (1-P) log(1-P)] = log(1 + t) + |z| t r   -- no cancellation, 0 for the saturated entries, so no mask either;
+//      log(1 + t) through the running product of (1 + t) <= 2, one lg2 per 16 entries.
 //
 // Shared-memory operand layout: K-major, no swizzle -- core matrices of 8 rows x 16 bytes, SBO = 128 B between 8-row
 // groups, LBO = (rows / 8) x 128 B between 16-byte K chunks (descriptor version 1); one MMA consumes K = 8 (two chunks).
@@ -24,7 +34,6 @@
 namespace pcmf {
 
 constexpr int TC_TG = 64;          // streamed records per tile
-constexpr int TC_DRAIN = 4;        // tiles between two read-outs of the tensor-memory accumulator
 
 template <int KF1, int KF2>
 struct TcCfg {
@@ -33,7 +42,7 @@ struct TcCfg {
     static constexpr int A_BYTES = 128 * K1 * 4;                          // the CTA's own 128 rows, split three ways
     static constexpr int TILE_B1 = TC_TG * K1 * 4;                        // [64 records][K1]
     static constexpr int TILE_B2 = 2 * KF2 * TC_TG * 4;                   // hi and lo: [KF2 factors][64 records]
-    static constexpr int TILE_C = 2 * TC_TG * 4;                          // per record: c | zf (pass A), offset | unused (pass B)
+    static constexpr int TILE_C = TC_TG * 4;                              // per record: c2 = -c log2(e)
     static constexpr int TILE_BYTES = TILE_B1 + TILE_B2 + TILE_C;
     static constexpr int COL_P = 0, COL_PLO = 64, COL_ACC = 128, TMEM_COLS = 256;
     static_assert(COL_ACC + KF2 <= TMEM_COLS, "accumulator does not fit the allocation");
@@ -92,11 +101,10 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
 
 // Tile records of the streamed side, written once per pass: record t holds 64 consecutive rows of the row-major FP64
 // matrices M1 (first product) and M2 (second product), converted to FP32 and split:
-//   [ B1: 64 x 3 KF1, K-major canonical: b_hi | b_hi | b_lo ][ B2 hi: KF2 x 64 ][ B2 lo: KF2 x 64 ][ c: 64 ][ zf: 64 ]
-// Pass A (rows = genes): c = effective logit of the gene (+-1e30 for the whole-gene shortcuts, zi...cpp:353-356), zf = the z
-// that stands for its non-zero entries (+1e30 -> prob_D = 1, zi...cpp:359-360; -1e30 under the prior_D == 0 shortcut); rows
-// beyond `rows` get c = zf = -1e30 (P = 0).  Pass B (rows = cells, cz == null): c = 0 for a real cell, 1e30 beyond `rows`
-// (subtracted from z: P = 0), zf unused.
+//   [ B1: 64 x 3 KF1, K-major canonical: b_hi | b_lo | b_hi ][ B2 hi: KF2 x 64 ][ B2 lo: KF2 x 64 ][ c2: 64 ]
+// c2 = -c log2(e), the record's additive part of x = -z log2(e).  Pass A (records = genes): c = effective logit of the gene,
+// +-1e30 for the whole-gene shortcuts (zi...cpp:353-356), -1e30 beyond `rows` (P = 0).  Pass B (records = cells, cz == null):
+// c = 0 for a real cell, -1e30 beyond `rows` (P = 0 there: the row sums and the second product must not see them).
 template <int KF1, int KF2>
 __global__ void k_tc_pack(int64_t rows, int KP, const double *__restrict__ M1, const double *__restrict__ M2,
                           const double *__restrict__ cz, const int32_t *__restrict__ flag, unsigned char *__restrict__ out) {
@@ -112,9 +120,9 @@ __global__ void k_tc_pack(int64_t rows, int KP, const double *__restrict__ M1, c
         if (k < KF1) {
             const float v = (in && k < KP) ? (float)M1[row * KP + k] : 0.f;
             const float hi = tc_tf32_hi(v), lo = v - hi;
-            *reinterpret_cast<float *>(base + tc_canon_off(r, k, TC_TG)) = hi;
-            *reinterpret_cast<float *>(base + tc_canon_off(r, KF1 + k, TC_TG)) = hi;
-            *reinterpret_cast<float *>(base + tc_canon_off(r, 2 * KF1 + k, TC_TG)) = lo;
+            *reinterpret_cast<float *>(base + tc_canon_off(r, k, TC_TG)) = hi;                 // x a_lo
+            *reinterpret_cast<float *>(base + tc_canon_off(r, KF1 + k, TC_TG)) = lo;           // x a_hi
+            *reinterpret_cast<float *>(base + tc_canon_off(r, 2 * KF1 + k, TC_TG)) = hi;       // x a_hi
         }
         {
             const float v = (in && k < KP) ? (float)M2[row * KP + k] : 0.f;
@@ -123,14 +131,12 @@ __global__ void k_tc_pack(int64_t rows, int KP, const double *__restrict__ M1, c
             *reinterpret_cast<float *>(base + C::TILE_B1 + KF2 * TC_TG * 4 + tc_canon_off(k, r, KF2)) = lo;
         }
         if (k == 0) {
-            float c, zf;
+            float c;
             if (cz) {
                 const int f = in ? flag[row] : 2;
                 c = (f == 0) ? (float)cz[row] : ((f == 1) ? 1e30f : -1e30f);
-                zf = (f == 2) ? -1e30f : 1e30f;
-            } else { c = in ? 0.f : 1e30f; zf = 0.f; }
-            *reinterpret_cast<float *>(base + C::TILE_B1 + C::TILE_B2 + r * 4) = c;
-            *reinterpret_cast<float *>(base + C::TILE_B1 + C::TILE_B2 + (TC_TG + r) * 4) = zf;
+            } else c = in ? 0.f : -1e30f;
+            *reinterpret_cast<float *>(base + C::TILE_B1 + C::TILE_B2 + r * 4) = -1.4426950408889634f * c;
         }
     }
 }
@@ -169,8 +175,8 @@ __global__ void __launch_bounds__(128, (TcCfg<KF1, KF2>::SMEM <= 110 * 1024) ? 2
         const int r = e / KF1, k = e - r * KF1;
         const float x = (row0 + r < a.rows && k < a.KP) ? (float)a.A1[(row0 + r) * a.KP + k] : 0.f;
         const float hi = tc_tf32_hi(x), lo = x - hi;
-        *reinterpret_cast<float *>(sA + tc_canon_off(r, k, 128)) = hi;
-        *reinterpret_cast<float *>(sA + tc_canon_off(r, KF1 + k, 128)) = lo;
+        *reinterpret_cast<float *>(sA + tc_canon_off(r, k, 128)) = lo;
+        *reinterpret_cast<float *>(sA + tc_canon_off(r, KF1 + k, 128)) = hi;
         *reinterpret_cast<float *>(sA + tc_canon_off(r, 2 * KF1 + k, 128)) = hi;
     }
     if (tid == 0) {
@@ -192,17 +198,19 @@ __global__ void __launch_bounds__(128, (TcCfg<KF1, KF2>::SMEM <= 110 * 1024) ? 2
     const int64_t ntiles_all = (a.streamed + TC_TG - 1) / TC_TG;
     const int64_t tile_first = CELLS ? 0 : (int64_t)blockIdx.y * a.tiles_per_chunk;
     const int ntiles = (int)max((int64_t)0, min(ntiles_all, tile_first + (CELLS ? ntiles_all : a.tiles_per_chunk)) - tile_first);
-    // pass B: the row's own gene constants
-    float crow = 0.f, zfrow = 0.f;
-    if (!CELLS) {
-        crow = -1e30f; zfrow = -1e30f;
+    // x = -z log2(e) = lambda log2(e) + c2(record) + xrow: the row's own part.  Pass A: 0, or 1e30 log2(e) for rows beyond n
+    // (P = 0 everywhere).  Pass B: -c_j log2(e) of the row's gene (+-1e30 under the whole-gene shortcuts, zi...cpp:353-356).
+    constexpr float L2E = 1.4426950408889634f;
+    float xrow = 0.f;
+    if (CELLS) xrow = live ? 0.f : 1e30f * L2E;
+    else {
+        float crow = -1e30f;
         if (live) {
             const int f = a.flag[row];
             crow = (f == 0) ? (float)a.cz[row] : ((f == 1) ? 1e30f : -1e30f);
-            zfrow = (f == 2) ? -1e30f : 1e30f;
         }
+        xrow = -L2E * crow;
     }
-    const float rowoff = (CELLS && !live) ? 1e30f : 0.f;     // rows beyond n: P = 0 everywhere
     if (tid == 0 && ntiles > 0) tc_bulk_load(sT, a.tiles + tile_first * C::TILE_BYTES, C::TILE_BYTES, &bar_full);
     double acc[KF2];
 #pragma unroll
@@ -228,8 +236,8 @@ __global__ void __launch_bounds__(128, (TcCfg<KF1, KF2>::SMEM <= 110 * 1024) ? 2
         }
         tc_mbar_wait(&bar_s, t & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float *cs = reinterpret_cast<const float *>(sT + C::TILE_B1 + C::TILE_B2);
-        float ent_lin = 0.f, ent_log = 0.f, rsum = 0.f;
+        const float4 *cs4 = reinterpret_cast<const float4 *>(sT + C::TILE_B1 + C::TILE_B2);
+        float h_lin = 0.f, h_log = 0.f, rsum = 0.f;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float pk[32];                                        // this row's P for 32 streamed records (column sums, pass A)
@@ -240,28 +248,37 @@ __global__ void __launch_bounds__(128, (TcCfg<KF1, KF2>::SMEM <= 110 * 1024) ? 2
                 uint32_t v[16], w[16];
                 TC_LD16(v, lane_addr + C::COL_P + c0);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float prod = 1.0f;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const bool nz = (bw >> (q * 16 + c)) & 1u;
-                    const float lam = __uint_as_float(v[c]);
-                    const float z = CELLS ? (nz ? cs[TC_TG + c0 + c] : (cs[c0 + c] - rowoff) - lam)
-                                          : (nz ? zfrow : (crow - cs[c0 + c]) - lam);
-                    float e2, pr;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(-1.4426950408889634f * z));
-                    const float y = 1.0f + e2;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pr) : "f"(y));
-                    if (CELLS) {
-                        // -bernoulli_loglike(prob_D, prob_D) over 0 < P < 1 (|z| < 30, internal.h:151-155): (1 - P)(-z) - log(1 + e^-z)
-                        const bool g = fabsf(z) < 30.0f;
-                        ent_lin = fmaf(g ? (pr - 1.0f) : 0.0f, z, ent_lin);
-                        float l2;
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(g ? y : 1.0f));
-                        ent_log += l2;
-                        pk[q * 16 + c] = pr;
-                    } else rsum += pr;
-                    const float hi = tc_tf32_hi(pr);
-                    v[c] = __float_as_uint(hi);
-                    w[c] = __float_as_uint(pr - hi);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 cc = cs4[(c0 >> 2) + c4];
+                    const float c2v[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = c4 * 4 + e;
+                        const bool nz = (bw >> (q * 16 + c)) & 1u;
+                        const float lam = nz ? -1e29f : __uint_as_float(v[c]);      // X != 0: z = +huge (or stays -huge under the gene shortcut)
+                        const float x = fmaf(lam, L2E, c2v[e]) + xrow;
+                        float t, r;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(x)));
+                        const float y = 1.0f + t;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+                        const float tr = t * r;
+                        const float pr = x < 0.f ? r : tr;
+                        if (CELLS) {
+                            h_lin = fmaf(fabsf(x), tr, h_lin);
+                            prod *= y;
+                            pk[q * 16 + c] = pr;
+                        } else rsum += pr;
+                        const float hi = tc_tf32_hi(pr);
+                        v[c] = __float_as_uint(hi);
+                        w[c] = __float_as_uint(pr - hi);
+                    }
+                }
+                if (CELLS) {
+                    float l2;
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(prod));    // (1 + t)^16 <= 65536
+                    h_log += l2;
                 }
                 TC_ST16(lane_addr + C::COL_P + c0, v);
                 TC_ST16(lane_addr + C::COL_PLO + c0, w);
@@ -271,7 +288,8 @@ __global__ void __launch_bounds__(128, (TcCfg<KF1, KF2>::SMEM <= 110 * 1024) ? 2
                 s_cs[warp][half * 32 + lane] = tot;
             }
         }
-        if (CELLS) ent += (double)ent_lin - 0.6931471805599453 * (double)ent_log;
+        // sum P log P + (1-P) log(1-P) = -ln 2 (sum log2(1 + t) + sum |x| t r)
+        if (CELLS) ent -= 0.6931471805599453 * ((double)h_lin + (double)h_log);
         (void)rsum;
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -279,13 +297,13 @@ __global__ void __launch_bounds__(128, (TcCfg<KF1, KF2>::SMEM <= 110 * 1024) ? 2
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int part = 0; part < 3; ++part) {               // P_hi E_hi + P_lo E_hi + P_hi E_lo
-                const uint32_t pcol = part == 1 ? C::COL_PLO : C::COL_P;
-                const unsigned char *b2 = sT + C::TILE_B1 + (part == 2 ? KF2 * TC_TG * 4 : 0);
+            for (int part = 0; part < 3; ++part) {               // P_lo E_hi + P_hi E_lo + P_hi E_hi: small terms first
+                const uint32_t pcol = part == 0 ? C::COL_PLO : C::COL_P;
+                const unsigned char *b2 = sT + C::TILE_B1 + (part == 1 ? KF2 * TC_TG * 4 : 0);
 #pragma unroll
                 for (int s = 0; s < TC_TG / 8; ++s)
                     tc_mma_ta(t0 + C::COL_ACC, t0 + pcol + 8 * s, tc_desc(tc_smem_u32(b2) + 2 * s * lboB2, lboB2, 128), idesc2,
-                              (t % TC_DRAIN != 0) || (s > 0) || (part > 0));
+                              (s > 0) || (part > 0));
             }
             tc_commit(&bar_acc);
         }
@@ -300,7 +318,7 @@ __global__ void __launch_bounds__(128, (TcCfg<KF1, KF2>::SMEM <= 110 * 1024) ? 2
             if (t + 1 < ntiles) tc_bulk_load(sT, a.tiles + (tile_first + t + 1) * C::TILE_BYTES, C::TILE_BYTES, &bar_full);
         }
         __syncthreads();
-        if (t % TC_DRAIN == TC_DRAIN - 1 || t == ntiles - 1) {
+        {   // read the tile's product out into FP64 (the accumulator truncates: it is not left to grow)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int c0 = 0; c0 < KF2; c0 += 16) {
