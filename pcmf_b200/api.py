@@ -377,11 +377,22 @@ class Solver:
                 raise PcmfError(_lib.EINVAL, "Wrong dimension for prob_D and/or prior_D input matrix/vector")
             k.append(pd)
             ini.prior_D = pd.ctypes.data_as(C.c_void_p)
+        self._pr, self._ini = pr, ini
+        if o.ngpus > 1:
+            return                      # pcmf_fit drives several devices in one call (Solver.fit); no step-wise handle
         h = C.c_void_p()
         err = C.create_string_buffer(512)
         rc = self.L.pcmf_create(C.byref(pr), C.byref(o), C.byref(ini), C.byref(h), err, 512)
         _lib.check(rc, err)
         self.h = h
+
+    def fit(self, want_prob_D=True):
+        """One pcmf_fit call: wrapper_*gap_factor end to end (init -> [multi-init] -> optimize -> order_factor -> output).
+        -> (convergence dict, exp_dev, output arrays)"""
+        r, bufs = self._result_buffers(want_prob_D, vectors=True)
+        err = C.create_string_buffer(512)
+        _lib.check(self.L.pcmf_fit(C.byref(self._pr), C.byref(self.opt), C.byref(self._ini), C.byref(r), err, 512), err)
+        return self._conv_dict(r, bufs), r.exp_dev, bufs
 
     def close(self):
         if self.h:
@@ -512,11 +523,15 @@ def _run(X, K, zero_inflation, sparsity, sel_bound=0.5, U=None, V=None, verbose=
                alpha1=alpha1, alpha2=alpha2, beta1=beta1, beta2=beta2, prob_S=prob_S, prior_S=prior_S, prob_D=prob_D,
                prior_D=prior_D, progress=progress, **gpu)
     try:
-        conv = s.optimize(multi_init=bool(ninit and ninit > 1))     # wrapper_gap_factor.h:296-350, :379
-        if reorder_factor:
-            s.order_factor()                                        # :382-385
-        exp_dev = s.monitors(loglikelihood=False)["exp_dev"]        # algorithm.h:367
-        o = s.get_output(want_prob_D=return_prob_D)
+        if s.opt.ngpus > 1:
+            # the library shards the cells over the devices itself: ONE pcmf_fit call, whole matrices in and out (multi.cu)
+            conv, exp_dev, o = s.fit(want_prob_D=return_prob_D)
+        else:
+            conv = s.optimize(multi_init=bool(ninit and ninit > 1))     # wrapper_gap_factor.h:296-350, :379
+            if reorder_factor:
+                s.order_factor()                                        # :382-385
+            exp_dev = s.monitors(loglikelihood=False)["exp_dev"]        # algorithm.h:367
+            o = s.get_output(want_prob_D=return_prob_D)
     finally:
         s.close()
     res = PcmfResult()

@@ -104,3 +104,50 @@ def test_c_client_fit_matches_python_host(client, tmp_path, zi, sparse):
     assert abs(got["exp_dev"] - ref["exp_dev"]) < 1e-10
     nb = got["nb_iter"]
     assert np.max(np.abs(got["optim_criterion"][:nb] - ref["monitor"]["optim_criterion"]) / np.abs(ref["monitor"]["optim_criterion"])) < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("zi,sparse", [(False, False), (True, True)], ids=["gap", "zi_sparse"])
+def test_c_client_two_gpus_inside_the_library(client, tmp_path, zi, sparse):
+    """pcmf_options.ngpus = 2 from plain C: the library shards the cells over two devices itself (host threads + NCCL
+    communicator of its own, multi.cu) -- no launcher, no callback.  Must equal the one-device fit (VERDICT r1 item 5;
+    replaces wrapper_gap_factor.h:271-274 + the OpenMP reduction of gap_factor_model.cpp:474-478)."""
+    if _lib.lib().pcmf_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    X, _, _ = datagen.simulate(150, 70, 4, signal_U=20.0, signal_V=20.0, prob1=0.6, seed=6)
+    n, p, K, iter_max = 150, 70, 3, 12
+    write_case(str(tmp_path / "in.bin"), X, K, zi, sparse, iter_max, True, 7)
+    out = {}
+    for ng in (1, 2):
+        env = dict(os.environ, PCMF_CABI_NGPUS=str(ng))
+        r = subprocess.run([client, "fit", str(tmp_path / "in.bin"), str(tmp_path / ("out%d.bin" % ng))], stderr=subprocess.PIPE,
+                           text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr
+        out[ng] = read_result(str(tmp_path / ("out%d.bin" % ng)), n, p, K, iter_max)
+    a, b = out[1], out[2]
+    assert a["nb_iter"] == b["nb_iter"] and list(a["factor_order"]) == list(b["factor_order"])
+    for k in ("a1", "a2", "b1", "b2", "EU", "EV"):
+        assert np.max(np.abs(a[k] - b[k]) / np.abs(a[k])) < 1e-10, k
+    assert abs(a["loss"] - b["loss"]) < 1e-10 * abs(a["loss"])
+    nb = a["nb_iter"]
+    assert np.max(np.abs(a["optim_criterion"][:nb] - b["optim_criterion"][:nb]) / np.abs(a["optim_criterion"][:nb])) < 1e-10
+
+
+@pytest.mark.gpu
+def test_python_host_ngpus_matches_single_device():
+    """run_zi_sparse_gap_factor(..., ngpus = 2): scipy CSR input (nnz-balanced row ranges), seeded random init, monitors."""
+    if _lib.lib().pcmf_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import scipy.sparse as sp
+    X, _, _ = datagen.simulate(400, 120, 4, signal_U=20.0, signal_V=20.0, prob1=0.5, seed=9)
+    Xs = sp.csr_matrix(X)
+    kw = dict(verbose=False, monitor=True, iter_max=10, iter_min=10, reorder_factor=True, seed=77,
+              prob_S=np.full((120, 3), 0.5), prior_S=np.full(120, 0.5))
+    one = pcmf_b200.run_zi_sparse_gap_factor(Xs, 3, **kw)
+    two = pcmf_b200.run_zi_sparse_gap_factor(Xs, 3, ngpus=2, **kw)
+    for k in ("a1", "a2", "b1", "b2"):
+        assert np.max(np.abs(one["variational_params"][k] - two["variational_params"][k]) / np.abs(one["variational_params"][k])) < 1e-10, k
+    for k in ("optim_criterion", "loglikelihood", "deviance"):
+        assert np.max(np.abs(one["monitor"][k] - two["monitor"][k]) / np.abs(one["monitor"][k])) < 1e-10, k
+    assert np.abs(one["ZI_param"]["prob_D"] - two["ZI_param"]["prob_D"]).max() < 1e-10
+    assert (one["sparse_param"]["S"] == two["sparse_param"]["S"]).all()
