@@ -2,6 +2,9 @@
 #include <algorithm>
 #include "launch.cuh"
 #include "zi_mma.cuh"
+#if PCMF_KP <= 20
+#include "xtile_kernels.cuh"
+#endif
 
 #ifndef PCMF_KP
 #error "compile with -DPCMF_KP=<padded K>"
@@ -211,8 +214,50 @@ int launch_zi_genes_tc(ZiTcArgs a, const double *M1, const double *M2, unsigned 
     return 2;
 }
 
+// ---- non-zero passes on the tiled copy of X --------------------------------------------------------------------
+#if PCMF_KP <= 20
+template <bool B2, bool LOGT>
+void launch_tile_genes_t(TileGeneArgs a, int sms, cudaStream_t st) {
+    using C = TileGeneCfg<KP, B2, LOGT>;
+    static bool attr_dev[64] = {false};
+    bool &attr = attr_dev[current_device()];
+    if (!attr) {
+        cudaFuncSetAttribute(k_tile_genes<KP, B2, LOGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        attr = true;
+    }
+    // (gene block, range of cell blocks) CTAs for ~32 waves of one CTA per SM; the gene blocks of one range are adjacent in
+    // the grid, so the cell rows they all stream come from HBM once and from L2 afterwards
+    const int nI = a.x.nI, nJ = a.x.nJ;
+    int chunks = std::max(1, std::min(nI, (sms * 32 + nJ - 1) / nJ));
+    a.blocks_per_chunk = (nI + chunks - 1) / chunks;
+    chunks = (nI + a.blocks_per_chunk - 1) / a.blocks_per_chunk;
+    k_tile_genes<KP, B2, LOGT><<<dim3((unsigned)nJ, (unsigned)chunks), 512, C::SMEM, st>>>(a);
+}
+void launch_tile_genes(int mode, TileGeneArgs a, int sms, cudaStream_t st) {
+    switch (mode) {
+        case GENE_B1: launch_tile_genes_t<false, false>(a, sms, st); break;
+        case GENE_B1_LOGT: launch_tile_genes_t<false, true>(a, sms, st); break;
+        default: launch_tile_genes_t<true, false>(a, sms, st); break;
+    }
+}
+void launch_tile_cells(const TileCellArgs &a, cudaStream_t st) {
+    using C = TileCellCfg<KP>;
+    static bool attr_dev[64] = {false};
+    bool &attr = attr_dev[current_device()];
+    if (!attr) {
+        cudaFuncSetAttribute(k_tile_cells<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        attr = true;
+    }
+    k_tile_cells<KP><<<(unsigned)((a.x.nI + C::RB - 1) / C::RB), 512, C::SMEM, st>>>(a);
+}
+#define PCMF_TILE_LAUNCHERS launch_tile_genes, launch_tile_cells
+#else
+#define PCMF_TILE_LAUNCHERS nullptr, nullptr
+#endif
+
 const Launchers table = {KP, launch_estep_rows, launch_gene_pass, launch_zi_cells, launch_zi_genes, zi_genes_block, zi_pack_doubles,
-                         launch_zi_loglik, launch_gene_loglam, launch_gene_order, tc_pack_bytes, launch_zi_cells_tc, launch_zi_genes_tc};
+                         launch_zi_loglik, launch_gene_loglam, launch_gene_order, tc_pack_bytes, launch_zi_cells_tc, launch_zi_genes_tc,
+                         PCMF_TILE_LAUNCHERS};
 
 }  // namespace
 

@@ -3,6 +3,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "zi_tc.cuh"
+#include "xtile.cuh"
 
 namespace pcmf {
 
@@ -24,6 +25,9 @@ struct Launchers {
     size_t (*tc_pack_bytes)(int64_t records);
     int (*zi_cells_tc)(ZiTcArgs, const double *M1, const double *M2, unsigned char *pack, int sms, cudaStream_t);
     int (*zi_genes_tc)(ZiTcArgs, const double *M1, const double *M2, unsigned char *pack, int sms, cudaStream_t);
+    // non-zero passes on the 2-D tiled copy of X (xtile.cuh); null for factor widths that do not fit (KP > XT_MAXKP)
+    void (*tile_genes)(int mode, TileGeneArgs, int sms, cudaStream_t);
+    void (*tile_cells)(const TileCellArgs &, cudaStream_t);
 };
 
 const Launchers *get_launchers_4();

@@ -254,6 +254,12 @@ struct pcmf_solver {
     double *EVold = nullptr, *rvbuf = nullptr;
     double rv_crit = 0;
     double rv_criterion();
+    // 2-D tiled copy of X for the non-zero passes (xtile.cuh); when it exists the CSR / CSC passes only serve the iteration
+    // that starts from an explicit prob_D, the monitors and the factor ordering
+    bool tiled = false;
+    XTile xt{};
+    void *xt_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void build_tiles(const int64_t *perm_out);
     uint32_t *csr2csc = nullptr;                   // nnz: CSC position of every CSR entry (stored-q cell pass)
     double *qcsc = nullptr;                        // nnz: q_ij = x_ij / T_ij left by the gene passes, CSC order
     double *Lg = nullptr, *colsumX = nullptr, *colnnz = nullptr, *rowsumX = nullptr;
@@ -364,6 +370,7 @@ pcmf_solver::~pcmf_solver() {
                     b1, b2, EV, ElogV, ev, evw, EVS, wS, prob_S, Sd, S, flag, prior_S, prior_D, cz, colw, hyp, csv, ar1, ar2,
                     ar3, scal, guard[0], guard[1], rowext, colext, allmasked, dbg, unchanged, ar2keep, zpackA, zpackB, EVold, rvbuf, Pexp, valw_csr, valw_csc, csr2csc, qcsc, xlogx, mon, d_order, old0[0], old0[1], old0[2], old0[3], pstore, blkptr, hrow[0], hrow[1], hrow[2], hrow[3], rowsg, tcpackA, tcpackB};
     for (void *q : ptrs) if (q) dfree(q);
+    for (void *q : xt_buf) if (q) dfree(q);
     if (h_scal) cudaFreeHost(h_scal);
     for (int i = 0; i < PH_COUNT; ++i) { if (ev_a[i]) cudaEventDestroy(ev_a[i]); if (ev_b[i]) cudaEventDestroy(ev_b[i]); }
     if (ev_vals) cudaEventDestroy(ev_vals);
@@ -750,8 +757,13 @@ void pcmf_solver::build_csc() {
     // everything that only needs the STRUCTURE first -- it runs under the upload of the values (second stream)
     k_colptr_from_sorted<<<grid_for(p + 1, 256), 256, 0, stream>>>(nnz, p, keys_out, colptr);
     k_gather_rowidx<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, rowidx);
+    // The non-zero passes run on a 2-D tiled copy of X (xtile.cuh) when the cell pass has enough CTAs to fill the machine
+    // (one per 256 cells) and the factor block fits shared memory twice over; kernel_variant bit 2048 forces the tiles
+    // (small test problems), bit 4096 keeps the CSR / CSC passes.
+    tiled = f32 && KP <= XT_MAXKP && L->tile_genes && nnz > 0 && nnz < 0xffffffffLL && !(opt.dev_flags & 4096) &&
+            (n >= 65536 || (opt.dev_flags & 2048));
     // ZI / sparse models: the gene passes leave q_ij in CSC order and the cell pass reads it back through this map
-    if ((zi || sparse) && nnz < 0xffffffffLL && !(opt.dev_flags & 16)) {
+    if (!tiled && (zi || sparse) && nnz < 0xffffffffLL && !(opt.dev_flags & 16)) {
         csr2csc = dmalloc<uint32_t>(nnz);
         k_invert_perm<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, csr2csc);
         qcsc = dmalloc<double>(nnz);
@@ -798,8 +810,9 @@ void pcmf_solver::build_csc() {
     }
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
-    dfree(scratch);
     tm.mark("csc: value gather, gene / cell constants");
+    if (tiled) { build_tiles(perm_out); tm.mark("tiled copy of X"); }
+    dfree(scratch);
     // gene constants are sums over cells -> all-reduce across the row shards
     allreduce(Lg, p); allreduce(colsumX, p); allreduce(colnnz, p); allreduce(xlogx, p);
     std::vector<double> h(p), hx(p), hs(p);
@@ -823,6 +836,53 @@ void pcmf_solver::build_csc() {
         ll_Xmean += hs[j] * (m > 0 ? std::log(m) : 0.0) - (double)n_global * m;
     }
     CK(cudaGetLastError());
+}
+
+// The tiled copy of X (xtile.cuh) from the CSR and CSC copies: no further sort -- inside a cell's CSR segment the genes
+// ascend, so the entries of a (cell, gene block) pair are a run whose length and start give the cell-order position, and
+// likewise for a gene's CSC segment; the CSR -> CSC map links the two orders.
+void pcmf_solver::build_tiles(const int64_t *perm_out) {
+    const int nI = (int)((n + XT_TI - 1) / XT_TI), nJ = (p + XT_TJ - 1) / XT_TJ;
+    const int64_t nT = (int64_t)nI * nJ;
+    int64_t *tptr = dmalloc<int64_t>(nT + 1);
+    uint2 *grec = dmalloc<uint2>(nnz);
+    uint16_t *gofs = dmalloc<uint16_t>((size_t)nT * (XT_TJ + 1));
+    uint8_t *gperm = dmalloc<uint8_t>((size_t)nT * XT_TJ);
+    uint8_t *ccol = dmalloc<uint8_t>(nnz);
+    double *tq = dmalloc<double>(nnz);
+    uint16_t *cofs = dmalloc<uint16_t>((size_t)nT * (XT_TI + 1));
+    uint8_t *cperm = dmalloc<uint8_t>((size_t)nT * XT_TI);
+    void *bufs[8] = {tptr, grec, gofs, gperm, ccol, tq, cofs, cperm};
+    for (int i = 0; i < 8; ++i) xt_buf[i] = bufs[i];
+    uint32_t *map = csr2csc;
+    if (!map) { map = dmalloc<uint32_t>(nnz); k_invert_perm<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, map); }
+    uint16_t *postmp = dmalloc<uint16_t>(nnz);
+    int64_t *tcnt = dmalloc<int64_t>(nT + 1);
+    CK(cudaMemsetAsync(gofs, 0, (size_t)nT * (XT_TJ + 1) * 2, stream));
+    CK(cudaMemsetAsync(cofs, 0, (size_t)nT * (XT_TI + 1) * 2, stream));
+    CK(cudaMemsetAsync(tcnt, 0, (nT + 1) * 8, stream));
+    k_xt_count<true><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, nJ, cofs);
+    k_xt_count<false><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, nJ, gofs);
+    k_xt_scan<XT_TI><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, cofs, tcnt);
+    k_xt_scan<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, nullptr);
+    {
+        size_t tb = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, tcnt, tptr, nT + 1, stream));
+        void *tmp = dmalloc<unsigned char>(tb);
+        CK(cub::DeviceScan::ExclusiveSum(tmp, tb, tcnt, tptr, nT + 1, stream));
+        CK(cudaStreamSynchronize(stream));
+        dfree(tmp);
+    }
+    k_xt_perm<XT_TI><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, cofs, cperm);
+    k_xt_perm<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, gperm);
+    k_xt_scatter_rows<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, map, nJ, tptr, cofs, ccol, postmp);
+    k_xt_scatter_cols<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, (const float *)val_csc, postmp, nJ, tptr, gofs, grec);
+    CK(cudaMemsetAsync(tq, 0, (size_t)nnz * 8, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    dfree(postmp); dfree(tcnt);
+    if (map != csr2csc) dfree(map);
+    xt.nI = nI; xt.nJ = nJ; xt.tptr = tptr; xt.grec = grec; xt.gofs = gofs; xt.gperm = gperm; xt.ccol = ccol; xt.q = tq; xt.cofs = cofs; xt.cperm = cperm;
 }
 
 void pcmf_solver::alloc_state() {
@@ -1060,7 +1120,7 @@ void pcmf_solver::init_state(const pcmf_init *in, bool reinit) {
 
 // the blocked gene pass adds its per-block sums atomically: start from zero
 void pcmf_solver::zero_gene_sums(double *B1, double *B2, double *xlogT, int mode) {
-    if (nblk <= 1) return;
+    if (nblk <= 1 && !tiled) return;
     const size_t pK = (size_t)p * KP;
     CK(cudaMemsetAsync(B1, 0, pK * 8, stream));
     if (mode == GENE_B1_B2) CK(cudaMemsetAsync(B2, 0, pK * 8, stream));
@@ -1183,7 +1243,8 @@ void pcmf_solver::step(bool want_data) {
                    src + ar2_B2, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc, blkptr, nblk};
         const int mode = !want_data ? GENE_B1 : (sparse ? GENE_B1_B2 : GENE_B1_LOGT);
         zero_gene_sums(ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, mode);
-        L->gene_pass(v_f32, mode, ca, std::min<int>(p, sms * 32), stream);
+        if (tiled && !explicitP) L->tile_genes(mode, TileGeneArgs{ca, xt, n, 0}, sms, stream);
+        else L->gene_pass(v_f32, mode, ca, std::min<int>(p, sms * 32), stream);
     }
     end(PH_GENE_E, 1);
     // 2. E-step, cell side + U-side M-step (in place)
@@ -1199,7 +1260,8 @@ void pcmf_solver::step(bool want_data) {
         if (rows_mode) { ra.alpha1r = hrow[0]; ra.alpha2r = hrow[1]; }
         const int block = 256;
         const int64_t warps = std::min<int64_t>(n, (int64_t)sms * 8 * 8);
-        L->estep_rows(v_f32, ra, (int)((warps + 7) / 8), block, stream);
+        if (tiled && !explicitP) L->tile_cells(TileCellArgs{ra, xt, p}, stream);
+        else L->estep_rows(v_f32, ra, (int)((warps + 7) / 8), block, stream);
     }
     end(PH_ROWS, 1);
     // 3. ZI: prob_D^T EU_new with prob_D recomputed from the triple saved when it was defined
@@ -1255,7 +1317,8 @@ void pcmf_solver::step(bool want_data) {
         ColArgs ca{p, K, colptr, rowidx, v_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, gn, ar2 + ar2_B1,
                    ar2 + ar2_B2, ar2 + ar2_xlogT, qcsc, blkptr, nblk};
         zero_gene_sums(ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT, GENE_B1_B2);
-        L->gene_pass(v_f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
+        if (tiled && !explicitP) L->tile_genes(GENE_B1_B2, TileGeneArgs{ca, xt, n, 0}, sms, stream);
+        else L->gene_pass(v_f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
         if (opt.world > 1) CK(cudaMemcpyAsync(ar2keep, ar2, 2 * pK * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         allreduce(ar2, 2 * pK);
         sparse_sums_valid = true;
@@ -1334,7 +1397,8 @@ double pcmf_solver::data_term_now() {
                reuse ? unchanged : nullptr, reuse ? src + ar2_B1 : nullptr, reuse ? src + ar2_B2 : nullptr, dbg, guard[gcur],
                ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc, blkptr, nblk};
     zero_gene_sums(ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, sparse ? GENE_B1_B2 : GENE_B1_LOGT);
-    L->gene_pass(explicitP ? false : f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
+    if (tiled && !explicitP) L->tile_genes(sparse ? GENE_B1_B2 : GENE_B1_LOGT, TileGeneArgs{ca, xt, n, 0}, sms, stream);
+    else L->gene_pass(explicitP ? false : f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
     allreduce(ar1 + ar1_B1, pK);
     allreduce(ar1 + ar1_B2, pK + p);
     CK(cudaMemsetAsync(scal + S_DATA, 0, 8, stream));

@@ -3,12 +3,21 @@
 The reference is FP64 only, so the oracle stays the checker: the FP32-mode CUDA path (dense zero-inflation passes on
 tcgen05 with 3xTF32 operands and FP32 accumulation in tensor memory, zi_tc.cuh) must stay within
 
-    variational parameters a1, a2, b1, b2 and E[U], E[V]:   1e-4 relative
-    prob_S: 1e-4 absolute, prior_D: 1e-4 relative, ELBO and convergence criterion: 1e-5 relative
+    zero-inflated model:              a1, a2, b1, b2, E[U], E[V], hyper-parameters, prior_D: 1e-5 relative (observed 3e-7:
+                                      scripts/fp32_accuracy.py), prob_D 1e-5 absolute
+    zero-inflated + sparse-V model:   the same quantities 1e-3 relative, prob_S 1e-3 absolute
+    ELBO, convergence criterion:      1e-5 relative (1e-3 over a whole run of the sparse model)
 
-of the oracle after free-running iterations from the same explicit initial values, for all four models (the two
-models without zero-inflation have no dense pass; they run the same code in both modes and must match at the FP64
-tolerance).  The selection mask S may differ where prob_S sits within the bound of sel_bound; such entries are counted.
+of the oracle after free-running iterations from the same explicit initial values (the two models without zero-inflation
+have no dense pass; they run the same code in both modes and must match at the FP64 tolerance).
+
+Why the sparse model gets the looser figure: the dense products carry ~2e-7 (FP32 operands, ex2.approx, truncating
+tensor-memory accumulator -- the latter a one-sided bias, PV is always a little low), and the spike-and-slab update
+amplifies it: tmp_jk = -EV_jk (prob_D^T EU)_jk + ... is a difference of terms of size 1e3..1e4, and prob_S = expit(logit
+prior + tmp) moves by up to tmp_err / 4 while a loading is being switched on or off.  Measured: everything stays at 3e-7
+except single entries of b1 / b2 that spike to ~1e-4 for the one or two iterations in which their prob_S crosses (0, 1), then
+fall back.  The selection mask S = (prob_S >= sel_bound) is discontinuous: it may differ where prob_S sits within the bound of
+sel_bound (such entries are excluded from the S comparison), and a run in which that happens follows a neighbouring trajectory.
 """
 import numpy as np
 import pytest
@@ -20,7 +29,7 @@ from tests.test_gpu_parity import IDS, MODELS, problem, relerr
 
 pytestmark = pytest.mark.gpu
 
-PAR_TOL, ELBO_TOL = 1e-4, 1e-5
+TOL_ZI, TOL_SPARSE, ELBO_TOL = 1e-5, 1e-3, 1e-5
 
 
 def pair(X, K, zi, sparse, seed=11, **kw):
@@ -38,6 +47,7 @@ def pair(X, K, zi, sparse, seed=11, **kw):
 
 def check(m, s, zi, sparse, tag):
     o = s.get_output(want_prob_D=zi)
+    PAR_TOL = TOL_SPARSE if sparse else TOL_ZI
     for name in ("a1", "a2", "b1", "b2", "EU", "EV", "alpha1", "alpha2", "beta1", "beta2"):
         assert relerr(o[name], m.get(name)) < PAR_TOL, (tag, name, relerr(o[name], m.get(name)))
     if sparse:
@@ -94,7 +104,23 @@ def test_fp32_mode_run_driver_and_monitors():
     assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
     assert list(res["factor_order"]) == list(ref["factor_order"])
     for k in ("optim_criterion", "loglikelihood", "deviance"):
-        assert relerr(res["monitor"][k], ref["monitor"][k]) < 1e-4, k
+        assert relerr(res["monitor"][k], ref["monitor"][k]) < TOL_SPARSE, k
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-3, k     # 40 iterations of drift
     assert abs(res["exp_dev"] - ref["exp_dev"]) < 1e-4
+
+
+def test_fp32_mode_run_driver_zi_model_tight_bound():
+    """Same driver on the zero-inflated model without the discontinuous selection step: the whole trajectory stays at 1e-5."""
+    X = problem(5, 120, 90)
+    K = 4
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=7)
+    kw = dict(iter_max=40, iter_min=10, epsilon=1e-2, additional_iter=3, a1=a1, a2=a2, b1=b1, b2=b2)
+    ref = po.run(X, K, True, False, monitor=True, reorder_factor=True, **kw)
+    res = pcmf_b200.run_zi_gap_factor(X, K, verbose=False, monitor=True, reorder_factor=True, precision=1, **kw)
+    assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
+    assert list(res["factor_order"]) == list(ref["factor_order"])
+    for k in ("optim_criterion", "loglikelihood", "deviance"):
+        assert relerr(res["monitor"][k], ref["monitor"][k]) < TOL_ZI, k
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(res["variational_params"][k], ref["variational_params"][k]) < TOL_ZI, k
