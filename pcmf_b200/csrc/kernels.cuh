@@ -471,6 +471,9 @@ struct ColArgs {
     // per block; blockIdx.y = b walks the blocks one after the other, so that the slice of the cell table a block gathers from
     // (eu [+ ElogU] of ~1e5 cells) stays in L2 instead of the whole n x K table streaming through it; sums are then added atomically.
     const int64_t *blkptr; int nblk;
+    // tiled copy of X (xtile.cuh): q goes to qout[qmap[e]] (the cell-order position of CSC entry e) and an entry that needs
+    // the guarded formula is marked -x instead of NaN
+    const uint32_t *qmap;
 };
 #ifndef PCMF_GENE_MINB
 #define PCMF_GENE_MINB 2
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
         const int64_t g1 = blocked ? a.blkptr[(int64_t)(blk + 1) * a.p + j] : a.colptr[j + 1];
         const int64_t e0 = g0, e1 = a.allmasked[j] ? g0 : g1;
         if (a.qout && a.allmasked[j])
-            for (int64_t e = e0 + threadIdx.x; e < g1; e += blockDim.x) a.qout[e] = 0.0;
+            for (int64_t e = e0 + threadIdx.x; e < g1; e += blockDim.x) a.qout[a.qmap ? (int64_t)a.qmap[e] : e] = 0.0;
         for (int64_t eb = e0 + w * 32; eb < e1; eb += blockDim.x) {    // warp-uniform trip count: the exact path is cooperative
             const int64_t e = eb + lane;
             int64_t i = 0; double x = 0.0; bool slow = false;
@@ -535,7 +538,7 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
                 const double T = T0 + T1;
                 if (!pf.force_exact && T >= 1e-26) {
                     const double q = x / T;
-                    if (a.qout) a.qout[e] = q;
+                    if (a.qout) a.qout[a.qmap ? (int64_t)a.qmap[e] : e] = q;
                     if (WITH_LOGT) lt += x * log(T);
 #pragma unroll
                     for (int k = 0; k < KP; ++k) b1[k] = fma(q, u[k], b1[k]);
@@ -545,7 +548,8 @@ __global__ void __launch_bounds__(128, PCMF_GENE_MINB) k_gene_pass(ColArgs a) {
                     }
                 } else {
                     slow = true;
-                    if (a.qout) a.qout[e] = __longlong_as_double(0x7ff8000000000000LL);   // NaN: the cell pass takes the exact formula too
+                    // NaN (or -x for the tiled cell pass): the cell pass takes the exact formula too
+                    if (a.qout) { if (a.qmap) a.qout[a.qmap[e]] = -x; else a.qout[e] = __longlong_as_double(0x7ff8000000000000LL); }
                 }
             }
             unsigned need = __ballot_sync(0xffffffffu, slow);

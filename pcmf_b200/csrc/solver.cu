@@ -258,7 +258,10 @@ struct pcmf_solver {
     // that starts from an explicit prob_D, the monitors and the factor ordering
     bool tiled = false;
     XTile xt{};
-    void *xt_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *xt_buf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t *qmap = nullptr;                      // CSC entry -> position of its q in the tiled copy
+    double2 *eupairs = nullptr;                    // (eu, eu o ElogU) rows for the B2 gene pass on the tiles (sparse models)
+    void tile_gene_pass(int mode, ColArgs &ca, bool v_f32_csc);
     void build_tiles(const int64_t *perm_out);
     uint32_t *csr2csc = nullptr;                   // nnz: CSC position of every CSR entry (stored-q cell pass)
     double *qcsc = nullptr;                        // nnz: q_ij = x_ij / T_ij left by the gene passes, CSC order
@@ -852,8 +855,10 @@ void pcmf_solver::build_tiles(const int64_t *perm_out) {
     double *tq = dmalloc<double>(nnz);
     uint16_t *cofs = dmalloc<uint16_t>((size_t)nT * (XT_TI + 1));
     uint8_t *cperm = dmalloc<uint8_t>((size_t)nT * XT_TI);
-    void *bufs[8] = {tptr, grec, gofs, gperm, ccol, tq, cofs, cperm};
-    for (int i = 0; i < 8; ++i) xt_buf[i] = bufs[i];
+    qmap = dmalloc<uint32_t>(nnz);
+    if (sparse) eupairs = dmalloc<double2>((size_t)n * KP);
+    void *bufs[10] = {tptr, grec, gofs, gperm, ccol, tq, cofs, cperm, qmap, eupairs};
+    for (int i = 0; i < 10; ++i) xt_buf[i] = bufs[i];
     uint32_t *map = csr2csc;
     if (!map) { map = dmalloc<uint32_t>(nnz); k_invert_perm<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, map); }
     uint16_t *postmp = dmalloc<uint16_t>(nnz);
@@ -876,7 +881,7 @@ void pcmf_solver::build_tiles(const int64_t *perm_out) {
     k_xt_perm<XT_TI><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, cofs, cperm);
     k_xt_perm<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, gperm);
     k_xt_scatter_rows<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, map, nJ, tptr, cofs, ccol, postmp);
-    k_xt_scatter_cols<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, (const float *)val_csc, postmp, nJ, tptr, gofs, grec);
+    k_xt_scatter_cols<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, (const float *)val_csc, postmp, nJ, tptr, gofs, grec, qmap);
     CK(cudaMemsetAsync(tq, 0, (size_t)nnz * 8, stream));
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
@@ -1243,7 +1248,7 @@ void pcmf_solver::step(bool want_data) {
                    src + ar2_B2, dbg, gc, ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc, blkptr, nblk};
         const int mode = !want_data ? GENE_B1 : (sparse ? GENE_B1_B2 : GENE_B1_LOGT);
         zero_gene_sums(ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, mode);
-        if (tiled && !explicitP) L->tile_genes(mode, TileGeneArgs{ca, xt, n, 0}, sms, stream);
+        if (tiled && !explicitP) tile_gene_pass(mode, ca, v_f32);
         else L->gene_pass(v_f32, mode, ca, std::min<int>(p, sms * 32), stream);
     }
     end(PH_GENE_E, 1);
@@ -1317,7 +1322,7 @@ void pcmf_solver::step(bool want_data) {
         ColArgs ca{p, K, colptr, rowidx, v_csc, eu, ElogU, ev, ElogV, Sd, colext, allmasked, nullptr, nullptr, nullptr, dbg, gn, ar2 + ar2_B1,
                    ar2 + ar2_B2, ar2 + ar2_xlogT, qcsc, blkptr, nblk};
         zero_gene_sums(ar2 + ar2_B1, ar2 + ar2_B2, ar2 + ar2_xlogT, GENE_B1_B2);
-        if (tiled && !explicitP) L->tile_genes(GENE_B1_B2, TileGeneArgs{ca, xt, n, 0}, sms, stream);
+        if (tiled && !explicitP) tile_gene_pass(GENE_B1_B2, ca, v_f32);
         else L->gene_pass(v_f32, GENE_B1_B2, ca, std::min<int>(p, sms * 32), stream);
         if (opt.world > 1) CK(cudaMemcpyAsync(ar2keep, ar2, 2 * pK * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         allreduce(ar2, 2 * pK);
@@ -1384,6 +1389,20 @@ void pcmf_solver::step(bool want_data) {
     }
 }
 
+// Gene pass when X has its tiled copy.  A full pass streams the tiles; a pass in which most genes copy the sums of the last
+// spike-and-slab pass (ColArgs::reuse) walks the CSC segments of the genes that changed instead -- its cost is proportional
+// to their number, a tiled CTA would stream every cell block for a single gene -- and leaves their q where the cell pass
+// reads it (ColArgs::qmap).
+void pcmf_solver::tile_gene_pass(int mode, ColArgs &ca, bool v_f32_csc) {
+    if (ca.reuse) {
+        ca.qout = xt.q; ca.qmap = qmap;
+        L->gene_pass(v_f32_csc, mode, ca, std::min<int>(p, sms * 32), stream);
+        return;
+    }
+    if (mode == GENE_B1_B2) { k_eu_pairs<<<grid_for(n * KP, 256), 256, 0, stream>>>(n * KP, eu, ElogU, eupairs); ++launches; }
+    L->tile_genes(mode, TileGeneArgs{ca, xt, n, 0, eupairs}, sms, stream);
+}
+
 // ELBO data term of the current state (gap...cpp:301-313, sparse...cpp:194-212): one gene pass, nothing updated.
 double pcmf_solver::data_term_now() {
     const size_t pK = (size_t)p * KP;
@@ -1397,7 +1416,7 @@ double pcmf_solver::data_term_now() {
                reuse ? unchanged : nullptr, reuse ? src + ar2_B1 : nullptr, reuse ? src + ar2_B2 : nullptr, dbg, guard[gcur],
                ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, qcsc, blkptr, nblk};
     zero_gene_sums(ar1 + ar1_B1, ar1 + ar1_B2, ar1 + ar1_xlogT, sparse ? GENE_B1_B2 : GENE_B1_LOGT);
-    if (tiled && !explicitP) L->tile_genes(sparse ? GENE_B1_B2 : GENE_B1_LOGT, TileGeneArgs{ca, xt, n, 0}, sms, stream);
+    if (tiled && !explicitP) tile_gene_pass(sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, f32);
     else L->gene_pass(explicitP ? false : f32, sparse ? GENE_B1_B2 : GENE_B1_LOGT, ca, std::min<int>(p, sms * 32), stream);
     allreduce(ar1 + ar1_B1, pK);
     allreduce(ar1 + ar1_B2, pK + p);

@@ -37,7 +37,7 @@ struct XTile {
     const uint8_t *cperm;             // nT x XT_TI
 };
 
-struct TileGeneArgs { ColArgs c; XTile x; int64_t n; int blocks_per_chunk; };
+struct TileGeneArgs { ColArgs c; XTile x; int64_t n; int blocks_per_chunk; const double2 *pairs; };   // pairs: (eu, eu o ElogU), n x KP (B2 mode)
 struct TileCellArgs { RowArgs r; XTile x; int32_t p; };
 
 #ifdef PCMF_COMMON_KERNELS
@@ -141,10 +141,18 @@ __global__ void k_xt_scatter_rows(int64_t n, const int64_t *__restrict__ rowptr,
         }
     }
 }
+// (eu, eu o ElogU) pairs of every cell: the rows the spike-and-slab gene pass streams (one 16-byte read per factor)
+__global__ void k_eu_pairs(int64_t total, const double *__restrict__ eu, const double *__restrict__ ElogU, double2 *__restrict__ out) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const double u = eu[o];
+        out[o] = make_double2(u, u * ElogU[o]);
+    }
+}
 // gene order: the record of every CSC entry
 __global__ void k_xt_scatter_cols(int32_t p, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                                   const float *__restrict__ val_csc, const uint16_t *__restrict__ postmp, int nJ,
-                                  const int64_t *__restrict__ tptr, const uint16_t *__restrict__ gofs, uint2 *__restrict__ grec) {
+                                  const int64_t *__restrict__ tptr, const uint16_t *__restrict__ gofs, uint2 *__restrict__ grec,
+                                  uint32_t *__restrict__ qmap) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t j = warp; j < p; j += nw) {
@@ -163,7 +171,10 @@ __global__ void k_xt_scatter_cols(int32_t p, const int64_t *__restrict__ colptr,
             if (valid) {
                 const int64_t t = (int64_t)B * nJ + (j >> 8);
                 const int pos = gofs[t * (XT_TJ + 1) + c] + rank;
-                grec[tptr[t] + pos] = make_uint2((unsigned)(i & 127) | ((unsigned)postmp[e] << 8), __float_as_uint(val_csc[e]));
+                const int64_t tb = tptr[t];
+                const unsigned pc = postmp[e];
+                grec[tb + pos] = make_uint2((unsigned)(i & 127) | (pc << 8), __float_as_uint(val_csc[e]));
+                qmap[e] = (uint32_t)(tb + pc);        // where the cell pass reads the q of this CSC entry
             }
             const int lastB = __shfl_sync(0xffffffffu, B, 31), lastTot = __shfl_sync(0xffffffffu, __popc(mask) + before, 31);
             if (lastB == nextB) { carryB = lastB; carryCnt = lastTot; } else { carryB = -1; carryCnt = 0; }

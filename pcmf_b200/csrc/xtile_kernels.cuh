@@ -18,17 +18,40 @@ __device__ __forceinline__ int warp_max_int_groups(int v) {      // value is uni
     v = max(v, __shfl_xor_sync(0xffffffffu, v, 16));
     return v;
 }
-// The reference's guarded multinomial terms of ONE entry (gap_factor_model.cpp:481-487) by a group of 4 lanes, lane l
-// holding factors l, l + 4, ...: e[i] = S_jk cexp(ElogU_ik + ElogV_jk - m), returns the (shifted) sum on the 4 lanes.
+// Which factors a lane of a 4-lane group holds.  VEC: rows of doubles read 16 bytes at a time -- slot i < 2A of lane l is
+// factor 8 (i / 2) + 2 l + (i & 1), the tail slot (KP = 8 A + 4) factor 8 A + l.  PAIR: rows of (eu, eu ElogU) pairs, one
+// pair = 16 bytes per slot -- slot i is factor l + 4 i.  Either way a group reads 64 contiguous bytes per instruction
+// (LDS.128): a quarter-warp phase then serves two groups instead of the four 32-byte pieces of 8-byte reads.
+template <int KP, bool PAIR>
+struct FMap {
+    static constexpr int A = KP / 8, B = (KP % 8) / 4, F = KP / 4;
+    __device__ __forceinline__ static int k(int i, int l) {
+        if (PAIR) return l + 4 * i;
+        return i < 2 * A ? 8 * (i >> 1) + 2 * l + (i & 1) : 8 * A + l;
+    }
+};
+template <int KP>
+__device__ __forceinline__ void load_row_vec(const double *__restrict__ row, int l, double (&u)[KP / 4]) {
+    using M = FMap<KP, false>;
+#pragma unroll
+    for (int s = 0; s < M::A; ++s) {
+        const double2 t = *reinterpret_cast<const double2 *>(row + 8 * s + 2 * l);
+        u[2 * s] = t.x; u[2 * s + 1] = t.y;
+    }
+    if (M::B) u[2 * M::A] = row[8 * M::A + l];
+}
+// The reference's guarded multinomial terms of ONE entry (gap_factor_model.cpp:481-487) by a group of 4 lanes:
+// e[i] = S_jk cexp(ElogU_ik + ElogV_jk - m), returns the (shifted) sum on the 4 lanes.
 // Called by the whole group together (the condition that leads here is uniform in the group).
-template <int F>
+template <int KP, bool PAIR>
 __device__ __noinline__ double exact_terms_group(const double *__restrict__ elu_row, const double *__restrict__ elv_row,
                                                  const double *__restrict__ sd_row, int K, int l, unsigned gmask,
-                                                 double (&e)[F], double (&elu)[F]) {
+                                                 double (&e)[KP / 4], double (&elu)[KP / 4]) {
+    using M = FMap<KP, PAIR>;
     double m = -1e300;
 #pragma unroll
-    for (int i = 0; i < F; ++i) {
-        const int k = l + 4 * i;
+    for (int i = 0; i < M::F; ++i) {
+        const int k = M::k(i, l);
         elu[i] = elu_row[k];
         e[i] = elu[i] + elv_row[k];
         if (k < K) m = fmax(m, e[i]);
@@ -38,8 +61,8 @@ __device__ __noinline__ double exact_terms_group(const double *__restrict__ elu_
     if (m < 100.0) m = 0.0;
     double T = 0.0;
 #pragma unroll
-    for (int i = 0; i < F; ++i) {
-        const int k = l + 4 * i;
+    for (int i = 0; i < M::F; ++i) {
+        const int k = M::k(i, l);
         e[i] = (k < K) ? custom_exp(e[i] - m) * sd_row[k] : 0.0;
         T += e[i];
     }
@@ -50,8 +73,9 @@ __device__ __noinline__ double exact_terms_group(const double *__restrict__ elu_
 
 // ------------------------------------------------------------------------------------------------------------
 // Gene side: B1(j,k) = sum_i q_ij e_ijk [, B2(j,k) = sum_i q_ij e_ijk ElogU_ik | xlogT(j) = sum_i x_ij log T_ij], q left in
-// cell order for the cell pass.  CTA = one block of 256 genes x a range of cell blocks; the cell rows (eu [, ElogU]) of
+// cell order for the cell pass.  CTA = one block of 256 genes x a range of cell blocks; the cell rows (eu, or the pairs) of
 // a tile arrive by bulk copy, double buffered; gene rows and the gene sums stay in shared memory for the whole CTA.
+// The 32 rounds of a tile (8 segments each, longest first) are dealt to the 16 warps as (w, 31 - w): a long and a short one.
 // ------------------------------------------------------------------------------------------------------------
 template <int KP, bool WITH_B2, bool WITH_LOGT>
 struct TileGeneCfg {
@@ -62,7 +86,9 @@ struct TileGeneCfg {
 template <int KP, bool WITH_B2, bool WITH_LOGT>
 __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
     using C = TileGeneCfg<KP, WITH_B2, WITH_LOGT>;
+    using M = FMap<KP, WITH_B2>;
     constexpr int TI = XT_TI, TJ = XT_TJ, F = KP / 4, ROUNDS = TJ / 8, STAGE = C::STAGE;
+    static_assert(ROUNDS == 32, "two rounds per warp");
     extern __shared__ __align__(128) unsigned char xt_smem[];
     double *ev_s = reinterpret_cast<double *>(xt_smem);
     double *acc1 = ev_s + TJ * KP;
@@ -70,14 +96,13 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
     double *ltacc = acc1 + C::NB * TJ * KP;                          // WITH_LOGT only
     double *stage = ltacc + (WITH_LOGT ? TJ : 0);
     __shared__ uint64_t full[2];
-    __shared__ int ctr[2];
     __shared__ uint8_t gflag[TJ];        // 0: product formula, 1: skip (sums copied / beyond p), 2: guarded formula, 3: every factor masked
     __shared__ uint16_t s_ofs[2][TJ + 2];   // segment tables of the current / next tile
     __shared__ uint8_t s_perm[2][TJ];
     __shared__ int64_t s_tb[2];
     const ColArgs &a = A.c;
     const XTile &x = A.x;
-    const int tid = threadIdx.x, lane = tid & 31, l = lane & 3, grp = lane >> 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l = lane & 3, grp = lane >> 2;
     const unsigned gmask = 0xFu << (lane & ~3);
     const int J = blockIdx.x, j0 = J * TJ;
     const int ib0 = (int)blockIdx.y * A.blocks_per_chunk, ib1 = min(x.nI, ib0 + A.blocks_per_chunk);
@@ -88,6 +113,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
         acc1[e] = 0.0;
         if (WITH_B2) acc2[e] = 0.0;
     }
+    int work = 0;
     for (int c = tid; c < TJ; c += blockDim.x) {
         const int j = j0 + c;
         uint8_t f = 1;
@@ -99,8 +125,11 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
             }
         }
         gflag[c] = f;
+        work |= (f != 1);
         if (WITH_LOGT) ltacc[c] = 0.0;
     }
+    // no gene of the block needs anything (all copied): nothing to stream
+    const bool idle = !__syncthreads_or(work);
     // same statistics, same mask row as the spike-and-slab pass of the previous iteration (sparse...cpp:448-451 vs :350-356):
     // the sums are identical, copy them (first chunk only; nobody adds to these genes)
     if (a.reuse && blockIdx.y == 0)
@@ -111,16 +140,16 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
                 if (WITH_B2) a.B2[(int64_t)j0 * KP + e] = a.B2_src[(int64_t)j0 * KP + e];
             }
         }
+    if (idle) return;
+    const double *cellrows = WITH_B2 ? reinterpret_cast<const double *>(A.pairs) : a.eu;
     auto issue = [&](int ib, int s) {
         const int rows = (int)min((int64_t)TI, A.n - (int64_t)ib * TI);
-        const unsigned bytes = (unsigned)(rows * KP * sizeof(double));
-        mbar_expect_tx(&full[s], C::NB * bytes);
-        bulk_g2s(stage + s * STAGE, a.eu + (int64_t)ib * TI * KP, bytes, &full[s]);
-        if (WITH_B2) bulk_g2s(stage + s * STAGE + TI * KP, a.ElogU + (int64_t)ib * TI * KP, bytes, &full[s]);
+        const unsigned bytes = (unsigned)(rows * KP * sizeof(double) * C::NB);
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(stage + s * STAGE, cellrows + (int64_t)ib * TI * KP * C::NB, bytes, &full[s]);
     };
     if (tid == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init();
-        ctr[0] = 0; ctr[1] = 0;
         if (ib0 < ib1) issue(ib0, 0);
     }
     if (ib0 < ib1) {
@@ -132,7 +161,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
     __syncthreads();
     for (int ib = ib0; ib < ib1; ++ib) {
         const int it = ib - ib0, s = it & 1;
-        if (tid == 0) { ctr[s ^ 1] = 0; if (ib + 1 < ib1) issue(ib + 1, s ^ 1); }
+        if (tid == 0 && ib + 1 < ib1) issue(ib + 1, s ^ 1);
         // the next tile's segment tables travel through registers under this tile's work; its records are pulled into L2
         uint16_t nofs = 0; uint8_t nperm = 0; int64_t ntb = 0;
         if (ib + 1 < ib1) {
@@ -151,31 +180,24 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
         }
         mbar_wait(&full[s], (it >> 1) & 1);
         const double *su = stage + s * STAGE;
-        double *sl = stage + s * STAGE + TI * KP;
-        if (WITH_B2) {      // E[log U] -> eu o E[log U], in place
-            const int rows = (int)min((int64_t)TI, A.n - (int64_t)ib * TI);
-            for (int e = tid; e < rows * KP; e += blockDim.x) sl[e] *= su[e];
-            __syncthreads();
-        }
         const int64_t tbase = s_tb[s];
         const uint16_t *ofs = s_ofs[s];
         const uint8_t *perm = s_perm[s];
         const uint2 *rec = x.grec + tbase;
         double *qout = x.q + tbase;
-        for (;;) {
-            int r = 0;
-            if (lane == 0) r = atomicAdd(&ctr[s], 1);
-            r = __shfl_sync(0xffffffffu, r, 0);
-            if (r >= ROUNDS) break;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int r = half ? (ROUNDS - 1 - warp) : warp;
             const int c = perm[r * 8 + grp];
             const int beg = ofs[c];
             const int flag = gflag[c];
             const int len = (flag == 1) ? 0 : (int)ofs[c + 1] - beg;
             const int maxlen = warp_max_int_groups(len);
             if (maxlen == 0) continue;
+            const bool normal = flag == 0;
             double v[F], b1[F], b2[WITH_B2 ? F : 1];
 #pragma unroll
-            for (int i = 0; i < F; ++i) { v[i] = ev_s[c * KP + l + 4 * i]; b1[i] = 0.0; if (WITH_B2) b2[i] = 0.0; }
+            for (int i = 0; i < F; ++i) { v[i] = ev_s[c * KP + M::k(i, l)]; b1[i] = 0.0; if (WITH_B2) b2[i] = 0.0; }
             double lt = 0.0;
             // a group reads its segment 4 records at a time (one per lane), two such loads ahead of the one being consumed
             uint2 nx = (l < len) ? __ldg(rec + beg + l) : make_uint2(0u, 0u);
@@ -191,37 +213,37 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
                     const int rr = (int)(w0 & 127u), pos = (int)(w0 >> 8);
                     const double xv = (double)__uint_as_float(w1);
                     double uu[F], ul[WITH_B2 ? F : 1];
+                    if (WITH_B2) {
+#pragma unroll
+                        for (int i = 0; i < F; ++i) {
+                            const double2 t2 = *reinterpret_cast<const double2 *>(su + 2 * (rr * KP + l + 4 * i));
+                            uu[i] = t2.x; ul[i] = t2.y;
+                        }
+                    } else load_row_vec<KP>(su + rr * KP, l, reinterpret_cast<double (&)[KP / 4]>(uu));
                     double T = 0.0;
 #pragma unroll
-                    for (int i = 0; i < F; ++i) {
-                        uu[i] = su[rr * KP + l + 4 * i];
-                        if (WITH_B2) ul[i] = sl[rr * KP + l + 4 * i];
-                        T = fma(uu[i], v[i], T);
-                    }
+                    for (int i = 0; i < F; ++i) T = fma(uu[i], v[i], T);
                     T = grp_sum(T);
-                    if (base + u4 < len) {
-                        if (flag == 3) {                                      // every factor masked: r_ijk = 0 (gap...cpp:487)
-                            if (l == 0) qout[pos] = 0.0;
-                        } else if (flag == 0 && T >= 1e-26) {
-                            const double q = xv / T;
-                            if (l == 0) { qout[pos] = q; if (WITH_LOGT) lt += xv * log(T); }
+                    const bool act = base + u4 < len;
+                    const bool ok = act && normal && T >= 1e-26;
+                    const double q = ok ? xv * fast_rcp(T) : 0.0;
+                    if (act && l == 0) qout[pos] = ok ? q : (flag == 3 ? 0.0 : -xv);   // 0: masked gene; -x: guarded formula
 #pragma unroll
-                            for (int i = 0; i < F; ++i) { b1[i] = fma(q, uu[i], b1[i]); if (WITH_B2) b2[i] = fma(q, ul[i], b2[i]); }
-                        } else {
-                            double e[F], elu[F];
-                            const int64_t ig = (int64_t)ib * TI + rr, jg = j0 + c;
-                            const double Tx = exact_terms_group<F>(a.ElogU + ig * KP, a.ElogV + jg * KP, a.Sd + jg * KP, a.K, l, gmask, e, elu);
-                            const double q = xv / (Tx > 0.0 ? Tx : 1.0);
+                    for (int i = 0; i < F; ++i) { b1[i] = fma(q, uu[i], b1[i]); if (WITH_B2) b2[i] = fma(q, ul[i], b2[i]); }
+                    if (WITH_LOGT && ok && l == 0) lt += xv * log(T);
+                    if (act && !ok && flag != 3) {
+                        double e[F], elu[F];
+                        const int64_t ig = (int64_t)ib * TI + rr, jg = j0 + c;
+                        const double Tx = exact_terms_group<KP, WITH_B2>(a.ElogU + ig * KP, a.ElogV + jg * KP, a.Sd + jg * KP, a.K, l, gmask, e, elu);
+                        const double qx = xv / (Tx > 0.0 ? Tx : 1.0);
 #pragma unroll
-                            for (int i = 0; i < F; ++i) {
-                                acc1[c * KP + l + 4 * i] += q * e[i];
-                                if (WITH_B2) acc2[c * KP + l + 4 * i] += q * e[i] * elu[i];
-                            }
-                            if (l == 0) {
-                                qout[pos] = -xv;                              // the cell pass takes the guarded formula too
-                                if (WITH_LOGT) lt += xv * log(Tx);
-                                atomicAdd(a.dbg + 1, 1ull);
-                            }
+                        for (int i = 0; i < F; ++i) {
+                            acc1[c * KP + M::k(i, l)] += qx * e[i];
+                            if (WITH_B2) acc2[c * KP + M::k(i, l)] += qx * e[i] * elu[i];
+                        }
+                        if (l == 0) {
+                            if (WITH_LOGT) lt += xv * log(Tx);
+                            atomicAdd(a.dbg + 1, 1ull);
                         }
                     }
                 }
@@ -229,8 +251,8 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
             if (len > 0 && flag != 3) {
 #pragma unroll
                 for (int i = 0; i < F; ++i) {
-                    acc1[c * KP + l + 4 * i] += b1[i] * v[i];                 // e_ijk = eu_ik ev_jk
-                    if (WITH_B2) acc2[c * KP + l + 4 * i] += b2[i] * v[i];
+                    acc1[c * KP + M::k(i, l)] += b1[i] * v[i];                 // e_ijk = eu_ik ev_jk
+                    if (WITH_B2) acc2[c * KP + M::k(i, l)] += b2[i] * v[i];
                 }
                 if (WITH_LOGT && l == 0) ltacc[c] += lt;
             }
@@ -240,7 +262,6 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
             if (tid < TJ) s_perm[s ^ 1][tid] = nperm;
             if (tid == 32) s_tb[s ^ 1] = ntb;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();      // the tile's buffer may be refilled, its genes taken by other groups
     }
     for (int e = tid; e < TJ * KP; e += blockDim.x) {
@@ -258,7 +279,8 @@ __global__ void __launch_bounds__(512, 1) k_tile_genes(TileGeneArgs A) {
 // ------------------------------------------------------------------------------------------------------------
 // Cell side + fused U-side M-step: EZ_j(i,.) = eu_i o sum_j q_ij evw_j from the q the gene pass left, then exactly the
 // epilogue of k_estep_rows_q.  CTA = 256 cells (two cell blocks); the evw rows of a gene block arrive by bulk copy,
-// three buffers; the cells' sums stay in shared memory.
+// three buffers; the cells' sums stay in shared memory.  Warp w takes round w of the first cell block and round
+// 15 - w of the second (rounds are sorted by length).
 // ------------------------------------------------------------------------------------------------------------
 template <int KP>
 struct TileCellCfg {
@@ -268,13 +290,14 @@ struct TileCellCfg {
 template <int KP>
 __global__ void __launch_bounds__(512, 1) k_tile_cells(TileCellArgs A) {
     using C = TileCellCfg<KP>;
-    constexpr int TI = XT_TI, TJ = XT_TJ, RB = C::RB, ROWS = C::ROWS, F = KP / 4, RPT = TI / 8, ROUNDS = RB * RPT, NS = C::NS, STAGE = C::STAGE;
+    using M = FMap<KP, false>;
+    constexpr int TI = XT_TI, TJ = XT_TJ, RB = C::RB, ROWS = C::ROWS, F = KP / 4, RPT = TI / 8, NS = C::NS, STAGE = C::STAGE;
+    static_assert(RPT == 16 && RB == 2, "one round per warp and cell block");
     extern __shared__ __align__(128) unsigned char xt_smem[];
     double *acc = reinterpret_cast<double *>(xt_smem);
     double *eu_s = acc + ROWS * KP;
     double *stage = eu_s + ROWS * KP;
     __shared__ uint64_t full[NS];
-    __shared__ int ctr[2];
     __shared__ double sh[32];
     __shared__ double scs[2][64];
     __shared__ uint16_t s_ofs[2][RB][TI + 2];   // segment tables of the current / next gene block, per cell block
@@ -282,7 +305,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_cells(TileCellArgs A) {
     __shared__ int64_t s_tb[2][RB];
     const RowArgs &a = A.r;
     const XTile &x = A.x;
-    const int tid = threadIdx.x, lane = tid & 31, l = lane & 3, grp = lane >> 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l = lane & 3, grp = lane >> 2;
     const unsigned gmask = 0xFu << (lane & ~3);
     const int64_t i0 = (int64_t)blockIdx.x * ROWS;
     const int rows_here = (int)min((int64_t)ROWS, a.n - i0);
@@ -301,7 +324,6 @@ __global__ void __launch_bounds__(512, 1) k_tile_cells(TileCellArgs A) {
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
-        ctr[0] = 0; ctr[1] = 0;
         issue(0, 0);
         if (nJ > 1) issue(1, 1);
     }
@@ -318,7 +340,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_cells(TileCellArgs A) {
     __syncthreads();
     for (int Jt = 0; Jt < nJ; ++Jt) {
         const int s = Jt % NS;
-        if (tid == 0) { ctr[(Jt + 1) & 1] = 0; if (Jt + 2 < nJ) issue(Jt + 2, (Jt + 2) % NS); }
+        if (tid == 0 && Jt + 2 < nJ) issue(Jt + 2, (Jt + 2) % NS);
         uint16_t nofs = 0; uint8_t nperm = 0; int64_t ntb = 0;
         if (tlive && Jt + 1 < nJ) {
             const int64_t tn = tib * nJ + Jt + 1;
@@ -339,14 +361,10 @@ __global__ void __launch_bounds__(512, 1) k_tile_cells(TileCellArgs A) {
         }
         mbar_wait(&full[s], (Jt / NS) & 1);
         const double *st = stage + s * STAGE;
-        for (;;) {
-            int r = 0;
-            if (lane == 0) r = atomicAdd(&ctr[Jt & 1], 1);
-            r = __shfl_sync(0xffffffffu, r, 0);
-            if (r >= ROUNDS) break;
-            const int rb = r / RPT, rr = r - rb * RPT;
-            const int64_t ibk = (int64_t)blockIdx.x * RB + rb;
-            if (ibk >= x.nI) continue;
+#pragma unroll 1
+        for (int rb = 0; rb < RB; ++rb) {
+            if ((int64_t)blockIdx.x * RB + rb >= x.nI) break;
+            const int rr = rb ? (RPT - 1 - warp) : warp;
             const int64_t tbase = s_tb[Jt & 1][rb];
             const int lr = s_perm[Jt & 1][rb][rr * 8 + grp];
             const int beg = s_ofs[Jt & 1][rb][lr];
@@ -376,23 +394,28 @@ __global__ void __launch_bounds__(512, 1) k_tile_cells(TileCellArgs A) {
                     if (base + u4 >= maxlen) break;                          // warp-uniform
                     const double q = __shfl_sync(0xffffffffu, qc, u4, 4);
                     const int col = __shfl_sync(0xffffffffu, ccur, u4, 4);
-                    if (q > 0.0) {
+                    double w[F];
+                    load_row_vec<KP>(st + col * KP, l, w);
+                    const double qf = q > 0.0 ? q : 0.0;
 #pragma unroll
-                        for (int i = 0; i < F; ++i) racc[i] = fma(q, st[col * KP + l + 4 * i], racc[i]);
-                    } else if (q < 0.0) {                                     // -x: the guarded formula (gap...cpp:481-487)
+                    for (int i = 0; i < F; ++i) racc[i] = fma(qf, w[i], racc[i]);
+                    if (q < 0.0) {                                            // -x: the guarded formula (gap...cpp:481-487)
                         double e[F], elu[F];
                         const int64_t ig = i0 + row, jg = (int64_t)Jt * TJ + col;
-                        const double Tx = exact_terms_group<F>(a.ElogU + ig * KP, a.ElogV + jg * KP, a.Sd + jg * KP, a.K, l, gmask, e, elu);
+                        const double Tx = exact_terms_group<KP, false>(a.ElogU + ig * KP, a.ElogV + jg * KP, a.Sd + jg * KP, a.K, l, gmask, e, elu);
                         const double qx = -q / (Tx > 0.0 ? Tx : 1.0);
 #pragma unroll
-                        for (int i = 0; i < F; ++i) acc[row * KP + l + 4 * i] += qx * e[i] * a.wS[jg * KP + l + 4 * i];
+                        for (int i = 0; i < F; ++i) acc[row * KP + M::k(i, l)] += qx * e[i] * a.wS[jg * KP + M::k(i, l)];
                         if (l == 0) atomicAdd(a.dbg, 1ull);
                     }
                 }
             }
             if (len > 0) {
+                double eur[F], cur[F];
+                load_row_vec<KP>(eu_s + row * KP, l, eur);
+                load_row_vec<KP>(acc + row * KP, l, cur);
 #pragma unroll
-                for (int i = 0; i < F; ++i) acc[row * KP + l + 4 * i] += eu_s[row * KP + l + 4 * i] * racc[i];
+                for (int i = 0; i < F; ++i) acc[row * KP + M::k(i, l)] = fma(eur[i], racc[i], cur[i]);
             }
         }
         if (tlive && Jt + 1 < nJ) {
