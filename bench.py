@@ -121,9 +121,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None, warmup=0, sparse_aware=False):
-    """The oracle (dense OpenMP restatement of the reference) on the first `max_rows` cells of the same workload."""
-    from oracle import pyoracle as po
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple a CPU baseline)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_sample(cfg, U, V, seed, max_rows):
+    """First `max_rows` cells of the workload as a dense host matrix (the reference's input format), plus the same seeded
+    initial values the GPU arm uses."""
     from pcmf_b200 import datagen
     n, p, K = cfg["n"], cfg["p"], cfg["K"]
     ns = min(max_rows, n)
@@ -134,15 +142,17 @@ def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None, warmup=0, spars
         X *= rng.uniform(size=X.shape) < cfg["prob1"]
     X[X.sum(1) == 0, 0] = 1
     X[0, X.sum(0) == 0] = 1
-    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the baseline)
-    if not threads:
-        try:
-            threads = len(os.sched_getaffinity(0))
-        except Exception:
-            threads = os.cpu_count() or 1
-    po.lib().orc_set_num_threads(int(threads))
+    return X, datagen.random_init(X, K, seed=seed + 1000)
+
+
+def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None, warmup=0, sparse_aware=False, sample=None):
+    """The oracle (dense OpenMP restatement of the reference) on the first `max_rows` cells of the same workload."""
+    from oracle import pyoracle as po
+    n, p, K = cfg["n"], cfg["p"], cfg["K"]
+    X, (a1, a2, b1, b2) = sample if sample is not None else cpu_sample(cfg, U, V, seed, max_rows)
+    ns = X.shape[0]
+    po.lib().orc_set_num_threads(int(threads or host_threads()))
     cores = po.lib().orc_num_threads()
-    a1, a2, b1, b2 = datagen.random_init(X, K, seed=seed + 1000)
     m = po.Model(X, K, cfg["zi"], cfg["sparse"])
     if cfg["sparse"]:
         m.init_sparse_param(0.5, np.full((p, K), 0.5), np.full(p, 0.5))
@@ -163,11 +173,13 @@ def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None, warmup=0, spars
 
     t_iter = timed(m)
     full = (1.0 / t_iter) * (ns / n)
+    measured = ns == n
     out = {"value": full, "unit": "iter/s", "cores": int(cores), "kind": "port",
            "sample": "oracle (dense OpenMP restatement of the reference C++) on %d of %d cells, same p=%d K=%d, %d timed "
-                     "iterations of update_param+elbo+gap, %.3f s/iter on the sample; extrapolated linearly in n (x %d/%d)"
-                     % (ns, n, p, K, iters, t_iter, ns, n),
-           "sample_seconds_per_iter": t_iter}
+                     "iterations of update_param+elbo+gap, %.3f s/iter on the sample%s"
+                     % (ns, n, p, K, iters, t_iter, "; the whole matrix, nothing extrapolated" if measured else
+                        "; extrapolated linearly in n (x %d/%d)" % (ns, n)),
+           "sample_rows": int(ns), "extrapolated": not measured, "sample_seconds_per_iter": t_iter}
     # Second figure, for a fairer comparison: the same loops made sparse-aware -- an entry with X = 0, whose
     # multinomial weights are multiplied by 0 wherever they are used, skips the K exponentials (orc_set_sparse_aware; the
     # dense zero-inflation products stay).  Continues from the state the first model reached.
@@ -180,39 +192,73 @@ def cpu_baseline(cfg, U, V, seed, max_rows, iters, threads=None, warmup=0, spars
     return out
 
 
+def ref_build_baseline(cfg, sample, iters):
+    """The reference's OWN model and algorithm sources (oracle/_ref: compiled unmodified against stand-in Rcpp / Eigen / Boost
+    headers, oracle/README_ref.md) on the same sample: algorithm::optimize for `iters` iterations with monitor = FALSE, i.e.
+    update_param + check_convergence per iteration -- no ELBO, a lighter iteration than the one the other arms time."""
+    from oracle import pyref
+    if not pyref.available():
+        return None
+    n, p, K = cfg["n"], cfg["p"], cfg["K"]
+    X, (a1, a2, b1, b2) = sample
+    ns = X.shape[0]
+    m = pyref.RefModel(X, K, cfg["zi"], cfg["sparse"], monitor=False, iter_max=iters, iter_min=iters, epsilon=1e-12)
+    if cfg["sparse"]:
+        m.init_sparse_param(0.5, np.full((p, K), 0.5), np.full(p, 0.5))
+    if cfg["zi"]:
+        m.init_zi_param()
+    m.init_variational_param(a1, a2, b1, b2)
+    t0 = time.perf_counter()
+    m.optimize()
+    t_iter = (time.perf_counter() - t0) / iters
+    return {"value": (1.0 / t_iter) * (ns / n), "unit": "iter/s", "cores": int(os.environ.get("OMP_NUM_THREADS", "1")),
+            "kind": "reference", "sample_rows": int(ns), "extrapolated": ns != n, "sample_seconds_per_iter": t_iter,
+            "sample": "the reference's own gap_factor_model / algorithm sources (oracle/_ref build, stand-in Eigen underneath) on "
+                      "%d of %d cells, %d iterations of optimize() with monitor = FALSE (no ELBO), %.3f s/iter" % (ns, n, iters, t_iter)}
+
+
+def workload_config(cfg, precision="fp64", nnz=None):
+    """The `config` object both arms print: same keys, so that `same_config` is decidable."""
+    c = {"workload": cfg["label"], "precision": precision, "n": cfg["n"], "p": cfg["p"], "K": cfg["K"],
+         "model": ("zi_" if cfg["zi"] else "") + ("sparse_" if cfg["sparse"] else "") + "gap"}
+    if nnz is not None:
+        c["nnz"] = nnz
+        c["density"] = nnz / (cfg["n"] * cfg["p"])
+    return c
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())      # before any OpenMP runtime is loaded (torchrun sets it to 1)
     U, V = factor_matrices(cfg, args.seed)
     # K timed + W warm-up steps, each on the bounded cell sample; rows are reduced if the run would exceed a few minutes
     iters, warm = max(1, args.steps), max(0, args.warmup)
-    rows = args.cpu_rows
+    rows = args.cpu_rows if args.cpu_rows > 0 else cfg["n"]
     if (iters + warm) > 20:
         rows = max(200, int(rows * 20 / (iters + warm)))
-    cb = cpu_baseline(cfg, U, V, args.seed, rows, iters, warmup=warm)
+    sample = cpu_sample(cfg, U, V, args.seed, rows)
+    cb = cpu_baseline(cfg, U, V, args.seed, rows, iters, warmup=warm, sample=sample)
+    try:
+        rb = ref_build_baseline(cfg, sample, max(2, min(iters, 3)))
+    except Exception as e:   # the checker's build is optional on a box without oracle/_ref
+        rb = {"unavailable": repr(e)}
+    config = workload_config(cfg)
+    config.update({"sample_rows": cb["sample_rows"], "extrapolated": cb["extrapolated"]})
     line = {"impl": "reference", "metric": "VEM iterations/sec", "value": cb["value"], "unit": "iter/s", "n_gpus": args.gpus,
             "steps": iters, "warmup": warm, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["label"], "model": "zi_sparse_gap" if cfg["zi"] and cfg["sparse"] else "gap"},
+            "config": config,
             "cpu_baseline": cb,
+            "reference_build": rb,
             "e2e": {"value": cb["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference's R package cannot be built here (no R/Rcpp/Eigen/Boost). Its own sources do compile against "
-                    "stand-in headers (oracle/_ref, used to pin parity at 1e-10), but that build's linear algebra is not Eigen's "
-                    "and runs ~2x slower than this C port of the same loops, so the port is what is timed (the faster, "
-                    "conservative baseline); all host cores, dense n x p loops exactly as the reference runs them"}
+                    "stand-in headers (oracle/_ref, used to pin parity at 1e-10); that build is timed beside the port "
+                    "(`reference_build`), but its linear algebra is not Eigen's, so the C port of the same loops -- the faster "
+                    "of the two -- is the line's value (the conservative baseline); all host cores, dense n x p loops exactly "
+                    "as the reference runs them"}
     emit(line)
-
-
-def ncu_traffic(config):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-    workload (profiles/r01_ncu_traffic.json, written by profiles/ncu_traffic.py); {} when there is none."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f).get(config, {})
-    except Exception:
-        return {}
 
 
 _JSON_FD = None
@@ -246,7 +292,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--cpu-rows", type=int, default=1500)
+    ap.add_argument("--cpu-rows", type=int, default=1500, help="cells of the CPU sample (0: the whole matrix -- c2 / c3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
     ap.add_argument("--variant", type=int, default=0, help="experimental kernel variant bits")
@@ -328,6 +374,8 @@ def main():
     ph0.pop("stored_prob_D_bytes", None)
     cell_blocks = int(ph1.pop("gene_pass_cell_blocks", (0.0, 1))[1])
     ph0.pop("gene_pass_cell_blocks", None)
+    tiled = bool(int(ph1.pop("tiled_nonzero_passes", (0.0, 0))[1]))
+    ph0.pop("tiled_nonzero_passes", None)
     per = {k: ((ph1[k][0] - ph0[k][0]) / max(1, args.steps), (ph1[k][1] - ph0[k][1]) // max(1, args.steps)) for k in ph1}
     w = 8
     zi, sparse = cfg["zi"], cfg["sparse"]
@@ -344,6 +392,8 @@ def main():
     blk_rows = max(4096, (28 << 20) // (16 * KPAD))
     gather_cell_tab = api.measure_gather_gbs(min(nl, 2 * blk_rows), local)
     traffic = ncu_traffic(args.config)
+    n_sms = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_mhz_max = float((clk or {}).get("sm_max_mhz") or 1965.0)
     kernels = []
     # gathered bytes per non-zero: the cell pass of the ZI / sparse models reads one K-vector (evw) plus the stored q of the
     # entry (a 32-byte sector) and its 4-byte CSR->CSC position; the plain model reads ev and recomputes T; the gene passes
@@ -355,15 +405,26 @@ def main():
         nz_rows["sparse_gene_pass"] = (b_genes, 16.0 * K, gather_cell_tab)
     for name, (byts, per_nnz, gpk) in nz_rows.items():
         t = per[name][0]
-        gb = per_nnz * nnz_local if per_nnz else None
-        kernels.append({"kernel": name, "ms": t, "share": t * args.steps / ms if ms else None, "bound": "hbm",
-                        "algorithmic_bytes": byts, "achieved": byts / (t * 1e-3) / 1e9 if t > 0 else None,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": (byts / (t * 1e-3) / 1e9 / hbm_peak) if t > 0 else None,
-                        "traffic": traffic.get(name),
-                        "gathered_bytes": gb, "gather_achieved": gb / (t * 1e-3) / 1e9 if (gb and t > 0) else None,
-                        "gather_peak_measured": gpk, "gather_frac": (gb / (t * 1e-3) / 1e9 / gpk) if (gb and t > 0) else None,
-                        "note": "steady state: genes whose mask row did not change copy the sums of the previous spike-and-slab "
-                                "pass, so only a few genes are gathered for" if name == "estep_genes" and sparse else None})
+        row = {"kernel": name, "ms": t, "share": t * args.steps / ms if ms else None, "bound": "hbm",
+               "algorithmic_bytes": byts, "achieved": byts / (t * 1e-3) / 1e9 if t > 0 else None,
+               "peak": hbm_peak, "unit": "GB/s", "frac": (byts / (t * 1e-3) / 1e9 / hbm_peak) if t > 0 else None,
+               "traffic": traffic.get(name),
+               "note": "steady state: genes whose mask row did not change copy the sums of the previous spike-and-slab "
+                       "pass; the CSC segments of the others are walked" if name == "estep_genes" and sparse else None}
+        if tiled and not (name == "estep_genes" and sparse):
+            # 2-D tiled copy of X (xtile.cuh): the factor rows of both sides of a tile sit in shared memory, so what bounds
+            # the pass is the shared-memory pipe -- one 8K-byte row per non-zero (two in the spike-and-slab pass: eu and
+            # eu o ElogU), read as 64-byte pieces by groups of 4 lanes.  Peak: 128 B / clk / SM.
+            rows_per_nnz = 2 if name == "sparse_gene_pass" else 1
+            sb = 8.0 * KPAD * rows_per_nnz * nnz_local
+            speak = 128.0 * n_sms * sm_mhz_max * 1e6 / 1e9
+            row.update({"layout": "tiled", "shared_bytes": sb, "shared_achieved": sb / (t * 1e-3) / 1e9 if t > 0 else None,
+                        "shared_peak": speak, "shared_frac": (sb / (t * 1e-3) / 1e9 / speak) if t > 0 else None})
+        else:
+            gb = per_nnz * nnz_local if per_nnz else None
+            row.update({"layout": "csr/csc", "gathered_bytes": gb, "gather_achieved": gb / (t * 1e-3) / 1e9 if (gb and t > 0) else None,
+                        "gather_peak_measured": gpk, "gather_frac": (gb / (t * 1e-3) / 1e9 / gpk) if (gb and t > 0) else None})
+        kernels.append(row)
     fp64_peak = api.measure_fp64_tflops(local)
     dmma_peak = api.measure_fp64_mma_tflops(local)
     if zi:
@@ -396,56 +457,64 @@ def main():
 
     # ---- end-to-end leg: the reference-facing call (run_zi_sparse_gap_factor -> pcmf C ABI) with HOST buffers:
     # H2D of the CSR matrix, preprocessing, `steps` iterations with the ELBO, D2H of the factors, all inside the timed region
-    e2e = None
+    e2e = e2e_defaults = None
     if not args.no_e2e:
         rp, ci, vv = csr.to_host()
         csr.free()
         hrp = torch.from_numpy(rp).pin_memory()
         hci = torch.from_numpy(ci).pin_memory()
         hvv = torch.from_numpy(vv).pin_memory()
-        del rp, ci, vv
-        Xh = (hrp.numpy(), hci.numpy(), hvv.numpy(), p)
         fn = {(False, False): pcmf_b200.run_gap_factor, (True, False): pcmf_b200.run_zi_gap_factor,
               (False, True): pcmf_b200.run_sparse_gap_factor, (True, True): pcmf_b200.run_zi_sparse_gap_factor}[(zi, sparse)]
-        kw = dict(verbose=False, monitor=2, iter_max=args.steps, iter_min=args.steps, epsilon=0.0, reorder_factor=False,
-                  seed=args.seed + 1000, device=local, comm=comm, n_global=n, row_offset=r0, return_prob_D=False,
-                  precision=args.precision)
-        if sparse:
-            kw.update(prob_S=prob_S, prior_S=prior_S)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        res = fn(Xh, K, **kw)
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
-        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item())
         h2d = hrp.numel() * 8 + hci.numel() * 4 + hvv.numel() * 4 + (p * K + p) * 8 * (1 if sparse else 0)
         d2h = 8 * (6 * nl * K + 6 * p * K) + (8 * (p * K + p) + 4 * p * K if sparse else 0) + (16 * p if zi else 0)
+
+        def whole_call(Xh, monitor, reorder):
+            kw = dict(verbose=False, monitor=monitor, iter_max=args.steps, iter_min=args.steps, epsilon=0.0, reorder_factor=reorder,
+                      seed=args.seed + 1000, device=local, comm=comm, n_global=n, row_offset=r0, return_prob_D=False,
+                      precision=args.precision)
+            if sparse:
+                kw.update(prob_S=prob_S, prior_S=prior_S)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            res = fn(Xh, K, **kw)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()), res
+
+        t_e2e, res = whole_call((hrp.numpy(), hci.numpy(), hvv.numpy(), p), 2, False)
         e2e = {"value": args.steps / t_e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps, "seconds_total": t_e2e, "nb_iter": res["convergence"]["nb_iter"],
-               "note": "whole run_* call from pinned host CSR: H2D + CSC/bitmap preprocessing + init + %d iterations with ELBO "
+               "note": "whole run_* call from pinned host CSR: H2D + CSC/bitmap/tile preprocessing + init + %d iterations with ELBO "
                        "+ D2H of the return object; copies and preprocessing are amortised over the %d steps" % (args.steps, args.steps)}
+        # the same call with the arguments pCMF() passes by default -- monitor = TRUE (ELBO, log-likelihood and deviance
+        # every iteration), reorder_factor = TRUE -- from ordinary (pageable) host arrays
+        del hrp, hci, hvv
+        t_def, res = whole_call((rp, ci, vv, p), 1, True)
+        e2e_defaults = {"value": args.steps / t_def, "unit": "iter/s", "seconds_total": t_def, "nb_iter": res["convergence"]["nb_iter"],
+                        "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": (d2h + 8 * 3 * args.steps) / args.steps,
+                        "note": "monitor = TRUE, reorder_factor = TRUE (the defaults of pCMF(), pCMF.R:197-201), pageable host CSR"}
+        del rp, ci, vv
     else:
         csr.free()
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:      # the CPU baseline is reported at N = 1 only
-        cb = cpu_baseline(cfg, U, V, args.seed, args.cpu_rows, 2, sparse_aware=True)
+        cb = cpu_baseline(cfg, U, V, args.seed, args.cpu_rows if args.cpu_rows > 0 else n, 2, sparse_aware=True)
 
     if rank == 0:
         line = {"metric": "VEM iterations/sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
-                "config": {"workload": cfg["label"], "precision": args.precision, "n": n, "p": p, "K": K, "nnz": nnz, "density": nnz / (n * p),
-                           "model": ("zi_" if zi else "") + ("sparse_" if sparse else "") + "gap",
+                "config": {**workload_config(cfg, args.precision, nnz),
                            "parallelism": "cells sharded over %d GPU(s), all-reduce of p x K gene statistics" % world,
                            "l2": "inputs larger than L2 (CSR+CSC %.1f GB per rank); no explicit flush" % (16e-9 * nnz_local),
                            "generator_seconds": t_gen},
-                "roofline": roofline, "kernels": kernels, "phases": phases, "cpu_baseline": cb, "e2e": e2e,
+                "roofline": roofline, "kernels": kernels, "phases": phases, "cpu_baseline": cb, "e2e": e2e, "e2e_defaults": e2e_defaults,
                 "gpu_launches": int(launches), "clocks": clk, "fp64_peak_tflops_measured": fp64_peak, "fp64_dmma_peak_tflops_measured": dmma_peak,
                 "elbo_last": float(elbo[-1]), "conv_crit_last": float(crit[-1])}
         emit(line)

@@ -2009,6 +2009,13 @@ int pcmf_phase_times(pcmf_solver *s, const char **names, double *ms, int64_t *la
         if (launches) launches[c] = s->nblk;
         ++c;
     }
+    // 1: the non-zero passes run on the 2-D tiled copy of X (xtile.cuh), 0: on CSR / CSC
+    if (c < cap) {
+        if (names) names[c] = "tiled_nonzero_passes";
+        if (ms) ms[c] = 0.0;
+        if (launches) launches[c] = s->tiled ? 1 : 0;
+        ++c;
+    }
     return c;
 }
 

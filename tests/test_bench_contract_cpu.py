@@ -21,3 +21,8 @@ def test_reference_arm_prints_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the reference's own sources (oracle/_ref) are timed beside the port; both arms print the same config keys
+    rb = d["reference_build"]
+    assert rb is None or "unavailable" in rb or (rb["kind"] == "reference" and rb["value"] > 0)
+    for key in ("workload", "precision", "n", "p", "K", "model", "sample_rows", "extrapolated"):
+        assert key in d["config"], key
