@@ -261,6 +261,17 @@ def run_reference(args, cfg):
     emit(line)
 
 
+def ncu_traffic(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
+    workload (profiles/r02_ncu_traffic.json, written by profiles/ncu_traffic.py); {} when there is none."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(config, {})
+    except Exception:
+        return {}
+
+
 _JSON_FD = None
 
 

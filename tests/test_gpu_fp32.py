@@ -6,7 +6,8 @@ tcgen05 with 3xTF32 operands and FP32 accumulation in tensor memory, zi_tc.cuh) 
     zero-inflated model:              a1, a2, b1, b2, E[U], E[V], hyper-parameters, prior_D: 1e-5 relative (observed 3e-7:
                                       scripts/fp32_accuracy.py), prob_D 1e-5 absolute
     zero-inflated + sparse-V model:   the same quantities 1e-3 relative, prob_S 1e-3 absolute
-    ELBO, convergence criterion:      1e-5 relative (1e-3 over a whole run of the sparse model)
+    ELBO, log-likelihood, convergence criterion: 1e-5 relative (1e-3 over a whole run of the sparse model);
+    deviance (a difference of log-likelihoods): 1e-4
 
 of the oracle after free-running iterations from the same explicit initial values (the two models without zero-inflation
 have no dense pass; they run the same code in both modes and must match at the FP64 tolerance).
@@ -120,7 +121,9 @@ def test_fp32_mode_run_driver_zi_model_tight_bound():
     res = pcmf_b200.run_zi_gap_factor(X, K, verbose=False, monitor=True, reorder_factor=True, precision=1, **kw)
     assert res["convergence"]["nb_iter"] == ref["convergence"]["nb_iter"]
     assert list(res["factor_order"]) == list(ref["factor_order"])
-    for k in ("optim_criterion", "loglikelihood", "deviance"):
+    for k in ("optim_criterion", "loglikelihood"):
         assert relerr(res["monitor"][k], ref["monitor"][k]) < TOL_ZI, k
+    # the deviance is a difference of two log-likelihoods of similar size (-2 (pl(X, rate) - pl(X, X)), gap...cpp:329-333)
+    assert relerr(res["monitor"]["deviance"], ref["monitor"]["deviance"]) < 10 * TOL_ZI
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(res["variational_params"][k], ref["variational_params"][k]) < TOL_ZI, k
