@@ -19,7 +19,7 @@ namespace pcmf {
 enum Scal : int {
     S_GAPU_D = 0, S_GAPU_O, S_ENTU, S_GAPV_D, S_GAPV_O, S_ENTV,
     S_BERNS_PRIOR, S_BERNS_SELF, S_BERND_PRIOR, S_BERND_SELF, S_SUM_PUVT, S_DATA, S_LGX,
-    S_GAMMAU, S_GAMMAV, S_SUMUVT_CLOSED, S_ABS_GAP, S_NORM_GAP, S_ELBO_NODATA,
+    S_GAMMAU, S_GAMMAV, S_SUMUVT_CLOSED, S_ABS_GAP, S_NORM_GAP, S_ELBO_NODATA, S_LL_ZERO,
     S_COUNT = 32
 };
 // guard block: min/max of ElogU / ElogV stored as ordered long long
@@ -854,10 +854,12 @@ struct ZiAArgs {
     const uint32_t *bitT;        // [ceil(p/32)][n]: bit c of word (jb, i) <-> X(i, 32 jb + c) != 0
     double *PV;                  // n x KP out: prob_D * EVS  (next iteration's a2, zi...cpp:336)
     double *colsumP;             // p (atomic): colsum(prob_D) -> prior_D (zi...cpp:370-372)
-    double *zsc;                 // 2 doubles (atomic): sum prob_D o UVt, sum P log P + (1-P) log(1-P)   (all-reduced later)
+    double *zsc;                 // 3 doubles (atomic): sum prob_D o UVt, sum P log P + (1-P) log(1-P), [want_ll] zero part of the
+                                 //   log-likelihood monitor   (all-reduced later)
     double *pack;                // scratch: fragment-ordered gene records for the DMMA kernel (zi_mma.cuh)
     uint32_t *pstore;            // or null: prob_D kept for the next iteration's gene pass, 32-bit fixed point in 8 x 8 tiles
                                  //   [ceil(n/8)][ceil(p/8)][gene in tile][cell in tile]  (zi_mma.cuh, k_zi_genes_stored)
+    int want_ll;                 // the pass also evaluates the zero part of the log-likelihood monitor (zsc[2])
 };
 // Pass A: one thread per cell, genes streamed through shared memory in tiles of TJ, two genes per step.
 // Per (cell, gene): lambda = EU_i . EVS_j (K DFMA), P = expit(c_j - lambda) (fast_exp + fast_rcp, ~22 FP64 ops),
@@ -1111,7 +1113,7 @@ __global__ void __launch_bounds__(256) k_hyper(HyperArgs a) {
         double *s = a.scal;
         s[S_GAMMAU] = gU; s[S_GAMMAV] = gV; s[S_SUMUVT_CLOSED] = closed; s[S_BERND_PRIOR] = bd;
         s[S_GAPU_D] = a.usc[0]; s[S_GAPU_O] = a.usc[1]; s[S_ENTU] = a.usc[2];
-        if (a.zi) { s[S_SUM_PUVT] = a.zsc[0]; s[S_BERND_SELF] = a.zsc[1]; }
+        if (a.zi) { s[S_SUM_PUVT] = a.zsc[0]; s[S_BERND_SELF] = a.zsc[1]; s[S_LL_ZERO] = a.zsc[2]; }
         else s[S_LGX] = a.lgx_const;
         const double diff = sqrt(s[S_GAPU_D] + s[S_GAPV_D]);
         const double nrm = sqrt(s[S_GAPU_O] + s[S_GAPV_O]);

@@ -56,8 +56,10 @@ int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
     static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
     bool &attr = attr_dev[current_device()];
     if (!attr) {
-        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_zi_cells_mma<KP, MT, MMA_TJ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
     const int64_t groups = (a.p + 7) / 8;
@@ -69,8 +71,13 @@ int launch_zi_cells_mma_t(const ZiAArgs &a, cudaStream_t st) {
     if (gx >= 148 * 3 * 8) gy = 1;
     if (gy > 1) cudaMemsetAsync(a.PV, 0, sizeof(double) * (size_t)a.n * KP, st);
     dim3 grid((unsigned)gx, (unsigned)gy);
-    if (a.pstore) k_zi_cells_mma<KP, MT, MMA_TJ, true><<<grid, 128, smem, st>>>(a);
-    else k_zi_cells_mma<KP, MT, MMA_TJ, false><<<grid, 128, smem, st>>>(a);
+    if (a.want_ll) {
+        if (a.pstore) k_zi_cells_mma<KP, MT, MMA_TJ, true, true><<<grid, 128, smem, st>>>(a);
+        else k_zi_cells_mma<KP, MT, MMA_TJ, false, true><<<grid, 128, smem, st>>>(a);
+    } else {
+        if (a.pstore) k_zi_cells_mma<KP, MT, MMA_TJ, true, false><<<grid, 128, smem, st>>>(a);
+        else k_zi_cells_mma<KP, MT, MMA_TJ, false, false><<<grid, 128, smem, st>>>(a);
+    }
     return 2;
 }
 template <int MT>

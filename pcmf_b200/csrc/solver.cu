@@ -256,6 +256,9 @@ struct pcmf_solver {
     double rv_criterion();
     // 2-D tiled copy of X for the non-zero passes (xtile.cuh); when it exists the CSR / CSC passes only serve the iteration
     // that starts from an explicit prob_D, the monitors and the factor ordering
+    // zero part of the log-likelihood monitor evaluated by the cell-side ZI pass on the way (k_zi_cells_mma<.., WITH_LL>):
+    // requested by pcmf_optimize when monitor = 1; valid for the state of the step that produced it
+    bool want_ll_zero = false; uint64_t state_ver = 0, ll_zero_ver = ~0ull; double ll_zero = 0;
     bool tiled = false;
     XTile xt{};
     void *xt_buf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -920,7 +923,7 @@ void pcmf_solver::alloc_state() {
     ar1 = dmalloc<double>(ar1_total); CK(cudaMemsetAsync(ar1, 0, ar1_total * 8, stream));
     ar2_B1 = 0; ar2_B2 = pK; ar2_xlogT = 2 * pK; ar2_total = 2 * pK + p;
     ar2 = dmalloc<double>(ar2_total); CK(cudaMemsetAsync(ar2, 0, ar2_total * 8, stream));
-    ar3_csP = 0; ar3_zsc = p; ar3_total = p + 2;
+    ar3_csP = 0; ar3_zsc = p; ar3_total = p + 3;
     ar3 = dmalloc<double>(ar3_total); CK(cudaMemsetAsync(ar3, 0, ar3_total * 8, stream));
     scal = dmalloc<double>(S_COUNT); CK(cudaMemsetAsync(scal, 0, S_COUNT * 8, stream));
     guard[0] = dmalloc<long long>(G_COUNT); guard[1] = dmalloc<long long>(G_COUNT);
@@ -1202,6 +1205,7 @@ void pcmf_solver::run_init_stats(bool ones_stats, bool update_hyper) {
     CK(cudaGetLastError());
     last_nodata = h_scal[S_ELBO_NODATA];
     first_iter = true; have_pending = false; sparse_sums_valid = false;
+    ++state_ver;
 }
 
 // update_hyper_param (gap...cpp:541-548, zi...cpp:370-372) + the scalars of the iteration (k_hyper); when the rows of the
@@ -1350,7 +1354,10 @@ void pcmf_solver::step(bool want_data) {
             ta.n = n; ta.p = p; ta.K = K; ta.KP = KP; ta.A1 = EU[nxt]; ta.rows = n; ta.streamed = p; ta.bits = bitT; ta.EU = EU[nxt];
             ta.PV = PV; ta.colsumP = ar3 + ar3_csP; ta.zsc = ar3 + ar3_zsc; ta.cz = cz; ta.flag = flag;
             nl = L->zi_cells_tc(ta, EVS, EVS, tcpackA, sms, stream);
-        } else nl = L->zi_cells(za, opt.dev_flags, stream);
+        } else {
+            za.want_ll = (want_ll_zero && !(opt.dev_flags & 4)) ? 1 : 0;
+            nl = L->zi_cells(za, opt.dev_flags, stream);
+        }
         zi_at_init = false;
         pstore_valid = pstore != nullptr;
         allreduce(ar3, ar3_total);
@@ -1378,6 +1385,8 @@ void pcmf_solver::step(bool want_data) {
         launches += 2;
     }
     read_scal();
+    ++state_ver;
+    if (zi && want_ll_zero && !fp32_mode && !(opt.dev_flags & 4)) { ll_zero = h_scal[S_LL_ZERO]; ll_zero_ver = state_ver; }
     if (keep_old) rv_crit = rv_criterion();
     collect_phase_times();
     cur = nxt; gcur = 1 - gcur; first_iter = false;
@@ -1450,7 +1459,7 @@ pcmf_solver::Mon pcmf_solver::monitors_now(bool want_loglik) {
         k_gamma_loglike<<<grid_for(n * KP, 256), 256, 0, stream>>>(n, K, KP, EU[cur], a1, a2, mon + 4);
         k_gamma_loglike<<<grid_for((int64_t)p * KP, 256), 256, 0, stream>>>(p, K, KP, EV, b1, b2, mon + 6);
         launches += 2;
-        if (zi && !zi_at_init && !explicitP) {         // at the initial state prob_D = (X > 0): the zero part is log(1) = 0
+        if (zi && !zi_at_init && !explicitP && ll_zero_ver != state_ver) {   // at the initial state prob_D = (X > 0): the zero part is log(1) = 0
             ZiAArgs za{n, p, K, EU[cur], EVS, cz, flag, bitT, PV, ar3 + ar3_csP, ar3 + ar3_zsc, zpackA, nullptr};
             L->zi_loglik(za, mon + 5, stream);
             launches += 1;
@@ -1472,6 +1481,8 @@ pcmf_solver::Mon pcmf_solver::monitors_now(bool want_loglik) {
         if (!zi) ll = h[1] - h_scal[S_SUMUVT_CLOSED] - lgx_const;
         else {
             // zi_poisson_loglike (likelihood.h:197-212): non-zeros log(prob_D) + pl1(x, lambda), zeros log(1 - P + P e^-lambda)
+            // (the zero part comes from the cell-side ZI pass of the step when that evaluated it on the way: already all-reduced)
+            if (!zi_at_init && !explicitP && ll_zero_ver == state_ver) h[5] = ll_zero;
             ll = h[1] - h[2] - lgx_const + h[5] + h[7];   // h[7]: sum log(prob_D) over the non-zeros (0 unless prob_D is explicit)
             if (h[3] > 0) ll = -INFINITY;    // log(prob_D) with prob_D = 0 on a non-zero entry (prior_D == 0 shortcut)
             ll += h_scal[S_BERND_SELF];
@@ -1587,6 +1598,7 @@ void pcmf_solver::restore_state(const Saved &sv) {
         CK(cudaMemcpyAsync(sv.arrays[i].first, sv.copies[i], sv.arrays[i].second, cudaMemcpyDeviceToDevice, stream));
     cur = sv.cur; gcur = sv.gcur; first_iter = sv.first_iter; sparse_sums_valid = sv.sparse_sums_valid; have_pending = sv.have_pending;
     last_nodata = sv.last_nodata; std::copy(sv.h.begin(), sv.h.end(), h_scal); iter = sv.iter; first_mode = sv.first_mode;
+    ++state_ver;
     sparse_sums_valid = false;   // the stored q of the non-zeros belong to the last run, not to the restored one
     pstore_valid = false;        // and so does the stored prob_D
     CK(cudaStreamSynchronize(stream));
@@ -1811,6 +1823,7 @@ int pcmf_optimize(pcmf_solver *s, pcmf_result *res, char *errbuf, size_t errlen)
         const double t0 = now_s();
         s->converged = false;
         s->nb_iter_stab = 0;     // local to optimize() in the reference (algorithm.h:161)
+        s->want_ll_zero = o.monitor == 1 && res->loglikelihood != nullptr;
         // algorithm.h:158-210
         int pending = -1;   // iteration whose ELBO still lacks its data term
         while (s->iter < o.iter_max && !s->converged) {

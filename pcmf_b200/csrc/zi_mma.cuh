@@ -97,13 +97,19 @@ __device__ __forceinline__ double fast_rcp2(double y) {
 // clamped) and the clamp flag.  Entries with X != 0 (zi...cpp:359-360) do not get a select of their own: the caller hands
 // them z = +-1e300 (the value the packed record carries for the gene: +1e300, or -1e300 under the prior_D == 0 shortcut),
 // which the clamp turns into exactly 1 / 0 and which takes them out of the entropy sums like every other clamped entry.
-__device__ __forceinline__ double fast_expit_tab(double z, const double *__restrict__ tab_lane, double &y, bool &big) {
+__device__ __forceinline__ double fast_expit_tab(double z, const double *__restrict__ tab_lane, double &y, bool &big, double &em) {
     const int hi = __double2hiint(z);
     big = (hi & 0x7fffffff) >= 0x403E0000;                 // |z| >= 30, also NaN / inf
-    y = 1.0 + fast_exp_neg_tab(z, tab_lane);
+    em = fast_exp_neg_tab(z, tab_lane);                    // e^-z (garbage when clamped)
+    y = 1.0 + em;
     const double pr = fast_rcp2(y);
     const double sat = __hiloint2double((hi < 0) ? 0 : 0x3FF00000, 0);
     return big ? sat : pr;
+}
+
+__device__ __forceinline__ double fast_expit_tab(double z, const double *__restrict__ tab_lane, double &y, bool &big) {
+    double em;
+    return fast_expit_tab(z, tab_lane, y, big, em);
 }
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
@@ -142,16 +148,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 
 // Fragment-ordered copy of a row-major [rows][KP] matrix, one record per group of 8 rows, so that a tile of the dense
 // passes is ONE contiguous bulk copy and every fragment load is a conflict-free 256-byte shared-memory read:
-//   record = [ f1: KS x 32 | f2: 2 x NT x 32 | (WITH_C) c: 8 | zf: 8 ]
+//   record = [ f1: KS x 32 | f2: 2 x NT x 32 | (WITH_C) c: 8 | zf: 8 | e^-c: 8 ]
 //   f1[s][lane]      = M1[8 grp + g][4 s + q]               first product, contraction over the K factors
 //   f2[s'][nt][lane] = M2[8 grp + 2 q + s'][8 nt + g]       second product, contraction over the 8 rows (0 beyond KP)
 //   c / zf: effective logit of the gene (+-1e300 for the whole-gene shortcuts, zi...cpp:353-356) and the z that stands for
 //   its non-zero entries (+1e300 -> prob_D = 1, zi...cpp:359-360; -1e300 under the prior_D == 0 shortcut).  Rows beyond
-//   `rows` are zero (c = zf = -1e300 -> P = 0).
+//   `rows` are zero (c = zf = -1e300 -> P = 0).  e^-c feeds the zero part of the log-likelihood monitor when pass A
+//   evaluates it on the way (k_zi_cells_mma<.., WITH_LL>).
 template <int KP, bool WITH_C>
 struct ZiRec {
     static constexpr int KS = KP / 4, NT = (KP + 7) / 8;
-    static constexpr int F1 = KS * 32, F2 = 2 * NT * 32, REC = F1 + F2 + (WITH_C ? 16 : 0);
+    static constexpr int F1 = KS * 32, F2 = 2 * NT * 32, REC = F1 + F2 + (WITH_C ? 24 : 0);
 };
 template <int KP, bool WITH_C>
 __global__ void k_zi_pack(int64_t rows, const double *__restrict__ M1, const double *__restrict__ M2,
@@ -177,7 +184,8 @@ __global__ void k_zi_pack(int64_t rows, const double *__restrict__ M1, const dou
             const int64_t row = grp * 8 + e;
             const int f = row < rows ? flag[row] : 2;
             if (o3 < 8) v = (row < rows && f == 0) ? cz[row] : ((f == 1) ? 1e300 : -1e300);
-            else v = (f == 2) ? -1e300 : 1e300;
+            else if (o3 < 16) v = (f == 2) ? -1e300 : 1e300;
+            else v = (row < rows && f == 0) ? exp(-cz[row]) : 1.0;
         }
         out[idx] = v;
     }
@@ -190,7 +198,11 @@ __global__ void k_zi_pack(int64_t rows, const double *__restrict__ M1, const dou
 // prob_D in 32-bit fixed point: q = rint(P (2^32 - 1)), so that 0 and 1 -- the values of every non-zero entry and of every
 // clamped one -- are exact and the others carry an absolute error of 1.2e-10.
 #define PCMF_PSTORE_SCALE 4294967295.0
-template <int KP, int MT, int TJ, bool STORE_P>
+// WITH_LL: also the zero part of likelihood::zi_poisson_loglike (likelihood.h:197-212) of the state this pass defines -- the
+// log-likelihood monitor of the iteration (zi_gap_factor_model.cpp:160-167) -- from what is in registers anyway: with
+// e = e^-z and lambda = c - z,  log(1 - P + P e^-lambda) = log(e + e^-c / e) - log(1 + e) = log(e^2 + e^-c) + z - log(1 + e),
+// and sum log(1 + e) is the entropy's running product.  ~4 FP64 instructions per entry instead of a second dense pass.
+template <int KP, int MT, int TJ, bool STORE_P, bool WITH_LL>
 __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_cells_mma(ZiAArgs a) {
     const double *__restrict__ pack = a.pack;
     using R = ZiRec<KP, true>;
@@ -235,6 +247,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
     double ent_lin = 0, ent_log = 0, prod = 1.0;
+    double ll_lin = 0, ll_log = 0, ll_prod = 1.0;
     uint32_t bits[MT], bits_nx[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) { bits[mt] = 0u; bits_nx[mt] = 0u; }
@@ -292,6 +305,8 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             }
             const double2 c2 = *reinterpret_cast<const double2 *>(rec + R::F1 + R::F2 + 2 * q);
             const double2 n2 = *reinterpret_cast<const double2 *>(rec + R::F1 + R::F2 + 8 + 2 * q);
+            double2 ec2 = make_double2(1.0, 1.0);
+            if (WITH_LL) ec2 = *reinterpret_cast<const double2 *>(rec + R::F1 + R::F2 + 16 + 2 * q);
             const int sh0 = ((grp & 3) << 3) + 2 * q;
             const unsigned st_tile = st_tile0 + (unsigned)(jg >> 3);
             double cs0 = 0.0, cs1 = 0.0;
@@ -299,8 +314,14 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             for (int mt = 0; mt < MT; ++mt) {
                 const bool nz0 = (bits[mt] >> sh0) & 1u, nz1 = (bits[mt] >> (sh0 + 1)) & 1u;
                 const double z0 = nz0 ? n2.x : c2.x - d[mt][0], z1 = nz1 ? n2.y : c2.y - d[mt][1];
-                double y0, y1; bool big0, big1;
-                const double p0 = fast_expit_tab(z0, tabl, y0, big0), p1 = fast_expit_tab(z1, tabl, y1, big1);
+                double y0, y1, em0, em1; bool big0, big1;
+                const double p0 = fast_expit_tab(z0, tabl, y0, big0, em0), p1 = fast_expit_tab(z1, tabl, y1, big1, em1);
+                if (WITH_LL) {
+                    // interior entries (all of them zeros of X): log(e^2 + e^-c) + z; a zero entry with P = 1: -lambda
+                    ll_prod *= (big0 ? 1.0 : fma(em0, em0, ec2.x)) * (big1 ? 1.0 : fma(em1, em1, ec2.y));
+                    ll_lin += (big0 ? 0.0 : z0) + (big1 ? 0.0 : z1);
+                    ll_lin -= ((big0 && !nz0 && z0 > 0.0) ? d[mt][0] : 0.0) + ((big1 && !nz1 && z1 > 0.0) ? d[mt][1] : 0.0);
+                }
                 // (rows beyond n: lambda starts at 1e305 and their occupancy words are 0, so P is the clamped 0 here)
                 // -bernoulli_loglike(prob_D, prob_D) over 0 < P < 1: sum (1-P)(-z) - log(1 + e^-z)
                 const bool g0 = !big0, g1 = !big1;
@@ -319,6 +340,7 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
                 }
             }
             if (prod > 1e100) { ent_log += log(prod); prod = 1.0; }     // (1 + e^30)^(2 MT) < 1e105 per group
+            if (WITH_LL && (ll_prod > 1e60 || ll_prod < 1e-60)) { ll_log += log(ll_prod); ll_prod = 1.0; }   // (e^60 + e^28)^(2 MT) < 1e209
 #pragma unroll
             for (int sp = 0; sp < 2; ++sp)
 #pragma unroll
@@ -358,9 +380,15 @@ __global__ void __launch_bounds__(128, (KP <= 20) ? (MT <= 2 ? 4 : 3) : 2) k_zi_
             }
         }
     }
-    double ent = ent_lin - (ent_log + log(prod));
+    const double sum_log_y = ent_log + log(prod);
+    double ent = ent_lin - sum_log_y;
     sum_pl = block_sum(sum_pl, sh); ent = block_sum(ent, sh);
     if (threadIdx.x == 0) { atomicAdd(a.zsc + 0, sum_pl); atomicAdd(a.zsc + 1, ent); }
+    if (WITH_LL) {
+        double ll = ll_lin + ll_log + log(ll_prod) - sum_log_y;
+        ll = block_sum(ll, sh);
+        if (threadIdx.x == 0) atomicAdd(a.zsc + 2, ll);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -261,3 +261,29 @@ def test_hyper_parameters_are_ignored_next_to_variational_parameters(zi, sparse)
     with_hy = RUN[(zi, sparse)](X, K, **kw, **hy)
     for k in ("a1", "a2", "b1", "b2"):     # (atomic accumulation order: equal up to rounding, not bit for bit)
         assert relerr(plain["variational_params"][k], with_hy["variational_params"][k]) < 1e-12, k
+
+
+@pytest.mark.parametrize("sparse", [False, True], ids=["zi", "zi_sparse"])
+def test_loglikelihood_fused_into_the_cell_pass(sparse):
+    """monitor = TRUE: the zero part of zi_poisson_loglike (likelihood.h:197-212, zi_gap_factor_model.cpp:160-167) comes out of
+    the cell-side zero-inflation pass of the iteration (k_zi_cells_mma<.., WITH_LL>) instead of a second dense pass.  The
+    per-iteration vector of run_* (fused) must equal the oracle's, and the last entry the stand-alone monitor pass."""
+    X = problem(31, 333, 217, prob1=0.4)
+    X[:, 5] = 0; X[0, 5] = 3                      # a gene that is almost never expressed
+    X[:, 9] = np.maximum(X[:, 9], 1)              # a gene without zeros: prior_D == 1 shortcut (zi...cpp:353-356)
+    K = 20
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=3)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    kw = dict(iter_max=6, iter_min=6, epsilon=1e-9, additional_iter=3, a1=a1, a2=a2, b1=b1, b2=b2)
+    ref = po.run(X, K, True, sparse, monitor=True, reorder_factor=False, prob_S=prob_S, prior_S=prior_S, **kw)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    res = RUN[(True, sparse)](X, K, verbose=False, monitor=True, reorder_factor=False, **kw)
+    assert relerr(res["monitor"]["loglikelihood"], ref["monitor"]["loglikelihood"]) < 1e-9
+    # the same state, iterated step-wise: pcmf_monitors takes the stand-alone pass
+    kw2 = {k: v for k, v in kw.items() if k in ("a1", "a2", "b1", "b2", "prob_S", "prior_S")}
+    s = pcmf_b200.Solver(X, K, True, sparse, **kw2)
+    s.iterate(6)
+    alone = s.monitors()["loglikelihood"]
+    s.close()
+    assert abs(alone - res["monitor"]["loglikelihood"][-1]) < 1e-11 * abs(alone)
