@@ -2,7 +2,7 @@
 #include <algorithm>
 #include "launch.cuh"
 #include "zi_mma.cuh"
-#if PCMF_KP <= 20
+#if PCMF_KP >= 16 && PCMF_KP <= 20
 #include "xtile_kernels.cuh"
 #endif
 
@@ -222,7 +222,10 @@ int launch_zi_genes_tc(ZiTcArgs a, const double *M1, const double *M2, unsigned 
 }
 
 // ---- non-zero passes on the tiled copy of X --------------------------------------------------------------------
-#if PCMF_KP <= 20
+// Factor widths 16 and 20 only.  Narrower blocks: the tiled kernels' per-entry work does not shrink with K (C5, 200k x 10k at
+// K = 2 / 10: gene pass 3.7 / 4.0 ms on the tiles against 1.3 / 2.1 ms on CSC; with only the cell pass tiled the scatter of
+// q into tile order ate the gain), so they keep the CSR / CSC passes.  Wider blocks do not fit shared memory twice over.
+#if PCMF_KP >= 16 && PCMF_KP <= 20
 template <bool B2, bool LOGT>
 void launch_tile_genes_t(TileGeneArgs a, int sms, cudaStream_t st) {
     using C = TileGeneCfg<KP, B2, LOGT>;

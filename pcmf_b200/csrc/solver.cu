@@ -766,7 +766,7 @@ void pcmf_solver::build_csc() {
     // The non-zero passes run on a 2-D tiled copy of X (xtile.cuh) when the cell pass has enough CTAs to fill the machine
     // (one per 256 cells) and the factor block fits shared memory twice over; kernel_variant bit 2048 forces the tiles
     // (small test problems), bit 4096 keeps the CSR / CSC passes.
-    tiled = f32 && KP <= XT_MAXKP && L->tile_genes && nnz > 0 && nnz < 0xffffffffLL && !(opt.dev_flags & 4096) &&
+    tiled = f32 && KP >= XT_MINKP && KP <= XT_MAXKP && L->tile_cells && nnz > 0 && nnz < 0xffffffffLL && !(opt.dev_flags & 4096) &&
             (n >= 65536 || (opt.dev_flags & 2048));
     // ZI / sparse models: the gene passes leave q_ij in CSC order and the cell pass reads it back through this map
     if (!tiled && (zi || sparse) && nnz < 0xffffffffLL && !(opt.dev_flags & 16)) {
@@ -848,31 +848,34 @@ void pcmf_solver::build_csc() {
 // ascend, so the entries of a (cell, gene block) pair are a run whose length and start give the cell-order position, and
 // likewise for a gene's CSC segment; the CSR -> CSC map links the two orders.
 void pcmf_solver::build_tiles(const int64_t *perm_out) {
+    StageTimer tm(stream);
     const int nI = (int)((n + XT_TI - 1) / XT_TI), nJ = (p + XT_TJ - 1) / XT_TJ;
     const int64_t nT = (int64_t)nI * nJ;
+    const bool gene_side = L->tile_genes != nullptr;       // (else the gene passes stay on CSC and only the cell order is built)
     int64_t *tptr = dmalloc<int64_t>(nT + 1);
-    uint2 *grec = dmalloc<uint2>(nnz);
-    uint16_t *gofs = dmalloc<uint16_t>((size_t)nT * (XT_TJ + 1));
-    uint8_t *gperm = dmalloc<uint8_t>((size_t)nT * XT_TJ);
+    uint2 *grec = gene_side ? dmalloc<uint2>(nnz) : nullptr;
+    uint16_t *gofs = gene_side ? dmalloc<uint16_t>((size_t)nT * (XT_TJ + 1)) : nullptr;
+    uint8_t *gperm = gene_side ? dmalloc<uint8_t>((size_t)nT * XT_TJ) : nullptr;
     uint8_t *ccol = dmalloc<uint8_t>(nnz);
     double *tq = dmalloc<double>(nnz);
     uint16_t *cofs = dmalloc<uint16_t>((size_t)nT * (XT_TI + 1));
     uint8_t *cperm = dmalloc<uint8_t>((size_t)nT * XT_TI);
     qmap = dmalloc<uint32_t>(nnz);
-    if (sparse) eupairs = dmalloc<double2>((size_t)n * KP);
+    if (sparse && L->tile_genes) eupairs = dmalloc<double2>((size_t)n * KP);
     void *bufs[10] = {tptr, grec, gofs, gperm, ccol, tq, cofs, cperm, qmap, eupairs};
     for (int i = 0; i < 10; ++i) xt_buf[i] = bufs[i];
     uint32_t *map = csr2csc;
     if (!map) { map = dmalloc<uint32_t>(nnz); k_invert_perm<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, map); }
     uint16_t *postmp = dmalloc<uint16_t>(nnz);
     int64_t *tcnt = dmalloc<int64_t>(nT + 1);
-    CK(cudaMemsetAsync(gofs, 0, (size_t)nT * (XT_TJ + 1) * 2, stream));
+    if (gene_side) CK(cudaMemsetAsync(gofs, 0, (size_t)nT * (XT_TJ + 1) * 2, stream));
     CK(cudaMemsetAsync(cofs, 0, (size_t)nT * (XT_TI + 1) * 2, stream));
     CK(cudaMemsetAsync(tcnt, 0, (nT + 1) * 8, stream));
+    tm.mark("tiles: allocation, map");
     k_xt_count<true><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, nJ, cofs);
-    k_xt_count<false><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, nJ, gofs);
+    if (gene_side) k_xt_count<false><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, nJ, gofs);
     k_xt_scan<XT_TI><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, cofs, tcnt);
-    k_xt_scan<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, nullptr);
+    if (gene_side) k_xt_scan<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, nullptr);
     {
         size_t tb = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, tcnt, tptr, nT + 1, stream));
@@ -881,10 +884,14 @@ void pcmf_solver::build_tiles(const int64_t *perm_out) {
         CK(cudaStreamSynchronize(stream));
         dfree(tmp);
     }
+    tm.mark("tiles: counts, offsets");
     k_xt_perm<XT_TI><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, cofs, cperm);
-    k_xt_perm<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, gperm);
+    if (gene_side) k_xt_perm<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, gperm);
+    tm.mark("tiles: segment ranking");
     k_xt_scatter_rows<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, map, nJ, tptr, cofs, ccol, postmp);
+    tm.mark("tiles: cell-order scatter");
     k_xt_scatter_cols<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, (const float *)val_csc, postmp, nJ, tptr, gofs, grec, qmap);
+    tm.mark("tiles: gene-order scatter");
     CK(cudaMemsetAsync(tq, 0, (size_t)nnz * 8, stream));
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
@@ -1401,9 +1408,9 @@ void pcmf_solver::step(bool want_data) {
 // Gene pass when X has its tiled copy.  A full pass streams the tiles; a pass in which most genes copy the sums of the last
 // spike-and-slab pass (ColArgs::reuse) walks the CSC segments of the genes that changed instead -- its cost is proportional
 // to their number, a tiled CTA would stream every cell block for a single gene -- and leaves their q where the cell pass
-// reads it (ColArgs::qmap).
+// reads it (ColArgs::qmap).  So do the factor widths below 16, where the tiled gene kernel does not pay (kernels_kp.cu).
 void pcmf_solver::tile_gene_pass(int mode, ColArgs &ca, bool v_f32_csc) {
-    if (ca.reuse) {
+    if (ca.reuse || !L->tile_genes) {
         ca.qout = xt.q; ca.qmap = qmap;
         L->gene_pass(v_f32_csc, mode, ca, std::min<int>(p, sms * 32), stream);
         return;
@@ -1795,7 +1802,11 @@ int pcmf_create(const pcmf_problem *prob, const pcmf_options *opt, const pcmf_in
     return rc;
 }
 
-void pcmf_destroy(pcmf_solver *s) { delete s; }
+void pcmf_destroy(pcmf_solver *s) {
+    const double t0 = now_s();
+    delete s;
+    if (getenv("PCMF_TIMING")) fprintf(stderr, "[pcmf timing] %-28s %8.1f ms\n", "destroy", (now_s() - t0) * 1e3);
+}
 
 int pcmf_iterate(pcmf_solver *s, int niter, double *conv_crit_out, double *elbo_out, char *errbuf, size_t errlen) {
     return guarded(errbuf, errlen, [&] {

@@ -23,7 +23,7 @@
 namespace pcmf {
 
 constexpr int XT_TI = 128, XT_TJ = 256;
-constexpr int XT_MAXKP = 20;          // wider factor blocks do not fit two sides + accumulators in shared memory: CSR / CSC passes
+constexpr int XT_MINKP = 16, XT_MAXKP = 20;   // narrower factor blocks: no gain (kernels_kp.cu); wider: do not fit shared memory
 
 struct XTile {
     int32_t nI, nJ;
@@ -170,10 +170,12 @@ __global__ void k_xt_scatter_cols(int32_t p, const int64_t *__restrict__ colptr,
             const int rank = __popc(mask & ((1u << lane) - 1u)) + before;
             if (valid) {
                 const int64_t t = (int64_t)B * nJ + (j >> 8);
-                const int pos = gofs[t * (XT_TJ + 1) + c] + rank;
                 const int64_t tb = tptr[t];
                 const unsigned pc = postmp[e];
-                grec[tb + pos] = make_uint2((unsigned)(i & 127) | (pc << 8), __float_as_uint(val_csc[e]));
+                if (grec) {       // (null: this factor width keeps the CSC gene pass, only the map is needed)
+                    const int pos = gofs[t * (XT_TJ + 1) + c] + rank;
+                    grec[tb + pos] = make_uint2((unsigned)(i & 127) | (pc << 8), __float_as_uint(val_csc[e]));
+                }
                 qmap[e] = (uint32_t)(tb + pc);        // where the cell pass reads the q of this CSC entry
             }
             const int lastB = __shfl_sync(0xffffffffu, B, 31), lastTot = __shfl_sync(0xffffffffu, __popc(mask) + before, 31);

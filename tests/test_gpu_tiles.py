@@ -16,8 +16,8 @@ TILES = 2048
 
 
 @pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
-# several cell blocks (128) and gene blocks (256), partial last blocks, every factor width the tiles are compiled for
-@pytest.mark.parametrize("n,p,K", [(60, 45, 3), (300, 530, 20), (517, 260, 5), (130, 257, 10), (260, 300, 14), (1000, 700, 20)])
+# several cell blocks (128) and gene blocks (256), partial last blocks, both factor widths the tiles are compiled for (16, 20)
+@pytest.mark.parametrize("n,p,K", [(60, 45, 13), (300, 530, 20), (517, 260, 16), (130, 257, 17), (260, 300, 14), (1000, 700, 20)])
 def test_tiled_passes_match_oracle(zi, sparse, n, p, K):
     X = problem(3, n, p)
     m, s = make_pair(X, K, zi, sparse, kernel_variant=TILES)
@@ -63,13 +63,14 @@ def test_tiled_passes_equal_csr_csc_passes(zi, sparse):
 def test_tiled_guard_path_matches_oracle(zi, sparse):
     """The +-100 guards (gap...cpp:483, internal.h:121-127) inside the tiled kernels: entries that need the reference's
     per-entry formula are evaluated by their group of 4 lanes and marked for the cell pass (q = -x)."""
-    n, p, K = 200, 300, 3
+    n, p, K = 200, 300, 14
     X = problem(9, n, p)
     a1, a2, b1, b2 = datagen.random_init(X, K, seed=2)
     a1[0, 0] = 1e60
     a1[1, :] = 1e-3
     a1[2, 1] = 5e-3
     b1[3, 2] = 2e-3
+    a1[7, 13] = 1e55
     a1[150, :] = 1e-3
     b1[270, :] = 3e-3
     prob_S, prior_S = datagen.prior_S_heuristic(X, K)
@@ -92,7 +93,7 @@ def test_tiled_guard_path_matches_oracle(zi, sparse):
 
 def test_tiled_run_driver_with_monitors_and_reorder():
     X = problem(5, 300, 280)
-    K = 4
+    K = 14
     a1, a2, b1, b2 = datagen.random_init(X, K, seed=7)
     prob_S, prior_S = datagen.prior_S_heuristic(X, K)
     kw = dict(iter_max=40, iter_min=10, epsilon=1e-2, additional_iter=3, a1=a1, a2=a2, b1=b1, b2=b2, prob_S=prob_S, prior_S=prior_S)
