@@ -100,7 +100,22 @@ def test_many_cells_blocked_gene_passes_default():
     ph = s.phase_times()
     assert ph["gene_pass_cell_blocks"][1] > 1, "the default heuristics did not block the gene passes at this size"
     assert ph["stored_prob_D_bytes"][1] > 0
+    assert ph["tiled_nonzero_passes"][1] == 1, "the non-zero passes did not take the 2-D tiled copy of X at this size"
     check_state(m, s, True, True)
+    s.close()
+
+
+@pytest.mark.parametrize("zi,sparse,K", [(False, False, 14), (True, False, 20), (False, True, 16)], ids=["gap", "zi", "sparse"])
+def test_tiled_nonzero_passes_are_the_default_from_65536_cells(zi, sparse, K):
+    """70k cells x 330 genes: above the threshold (solver.cu build_csc) the E-step non-zero passes run on the tiled copy of X
+    (xtile.cuh) without any kernel_variant bit -- 547 cell blocks x 2 gene blocks, last blocks partial; all three gene-pass
+    variants (B1, B1 + x log T for the ELBO, B1 + B2) against the oracle (gap_factor_model.cpp:458-499, sparse...:327-368)."""
+    X, _, _ = datagen.simulate(70_000, 330, 20, signal_U=20.0, signal_V=20.0, prob1=0.3, seed=8)
+    X[X.sum(1) == 0, 0] = 1
+    X[0, X.sum(0) == 0] = 1
+    m, s = run_pair(X, K, zi, sparse)
+    assert s.phase_times()["tiled_nonzero_passes"][1] == 1
+    check_state(m, s, zi, sparse)
     s.close()
 
 
