@@ -105,3 +105,36 @@ def test_tiled_run_driver_with_monitors_and_reorder():
         assert relerr(res["monitor"][k], ref["monitor"][k]) < 1e-6, k
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
+
+
+@pytest.mark.parametrize("sparse", [False, True], ids=["zi", "zi_sparse"])
+def test_tiled_warm_start_from_dense_prob_D_and_multi_init(sparse):
+    """States the tiles must hand over to / take back from the CSR / CSC passes: the first iteration after a warm start from
+    an explicit dense prob_D runs on the weighted non-zeros (wrapper_sparse_gap_factor.h:394-398), the closed form and the
+    tiles from then on; a multi-init (wrapper_gap_factor.h:296-350) restores a saved state, after which the stored q is stale."""
+    X = problem(25, 300, 280)
+    K = 14
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=12)
+    prob_S, prior_S = datagen.prior_S_heuristic(X, K)
+    rng = np.random.default_rng(3)
+    PD, prD = rng.uniform(0.05, 0.95, X.shape), np.full(X.shape[1], 0.5)
+    kw = dict(iter_max=8, iter_min=8, epsilon=1e-9, additional_iter=2, a1=a1, a2=a2, b1=b1, b2=b2, prob_D=PD, prior_D=prD)
+    ref = po.run(X, K, True, sparse, monitor=True, reorder_factor=False, prob_S=prob_S, prior_S=prior_S, **kw)
+    if sparse:
+        kw.update(prob_S=prob_S, prior_S=prior_S)
+    fn = pcmf_b200.run_zi_sparse_gap_factor if sparse else pcmf_b200.run_zi_gap_factor
+    res = fn(X, K, verbose=False, monitor=True, reorder_factor=False, kernel_variant=TILES, **kw)
+    for k in ("optim_criterion", "loglikelihood", "deviance"):
+        assert relerr(res["monitor"][k], ref["monitor"][k]) < 1e-6, k
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
+    # multi-init from seeded random initialisations
+    kw2 = dict(iter_max=10, iter_min=10, epsilon=1e-9, additional_iter=2, ninit=3, iter_init=4, seed=5)
+    ref = po.run(X, K, True, sparse, monitor=True, reorder_factor=True, prob_S=prob_S, prior_S=prior_S, **kw2)
+    if sparse:
+        kw2.update(prob_S=prob_S, prior_S=prior_S)
+    res = fn(X, K, verbose=False, monitor=True, reorder_factor=True, kernel_variant=TILES, **kw2)
+    assert list(res["factor_order"]) == list(ref["factor_order"])
+    for k in ("a1", "a2", "b1", "b2"):
+        assert relerr(res["variational_params"][k], ref["variational_params"][k]) < 1e-6, k
+    assert abs(res["loss"] - ref["loss"]) < 1e-6 * abs(ref["loss"])
