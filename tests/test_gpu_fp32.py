@@ -127,3 +127,22 @@ def test_fp32_mode_run_driver_zi_model_tight_bound():
     assert relerr(res["monitor"]["deviance"], ref["monitor"]["deviance"]) < 10 * TOL_ZI
     for k in ("a1", "a2", "b1", "b2"):
         assert relerr(res["variational_params"][k], ref["variational_params"][k]) < TOL_ZI, k
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+@pytest.mark.parametrize("n,p,K", [(300, 530, 20), (517, 260, 14)])
+def test_fp32_mode_with_tiled_nonzero_passes(zi, sparse, n, p, K):
+    """FP32 mode next to the non-zero passes on the 2-D tiled copy of X (forced here, the default from 65 536 cells -- the
+    combination the FP32-mode bench line runs): the tiled passes stay FP64, the dense passes run on tcgen05; same bound."""
+    X = problem(3, n, p)
+    m, s = pair(X, K, zi, sparse, kernel_variant=2048)
+    for it in range(5):
+        m.update_param()
+        crit = s.iterate(1)[0]
+        _, ng = m.gap_between_iterates()
+        assert abs(crit - ng) < 1e-4 * ng, (it, crit, ng)
+        check(m, s, zi, sparse, "iter %d" % it)
+        e_gpu, e_cpu = s.elbo(), m.elbo()
+        assert abs(e_gpu - e_cpu) < ELBO_TOL * abs(e_cpu), (it, e_gpu, e_cpu)
+        m.prepare_next_iterate()
+    s.close()
