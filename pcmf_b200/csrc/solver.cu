@@ -864,16 +864,14 @@ void pcmf_solver::build_tiles(const int64_t *perm_out) {
     if (sparse && L->tile_genes) eupairs = dmalloc<double2>((size_t)n * KP);
     void *bufs[10] = {tptr, grec, gofs, gperm, ccol, tq, cofs, cperm, qmap, eupairs};
     for (int i = 0; i < 10; ++i) xt_buf[i] = bufs[i];
-    uint32_t *map = csr2csc;
-    if (!map) { map = dmalloc<uint32_t>(nnz); k_invert_perm<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, map); }
-    uint16_t *postmp = dmalloc<uint16_t>(nnz);
+    uint32_t *runofs = dmalloc<uint32_t>((size_t)nJ * n);
     int64_t *tcnt = dmalloc<int64_t>(nT + 1);
     if (gene_side) CK(cudaMemsetAsync(gofs, 0, (size_t)nT * (XT_TJ + 1) * 2, stream));
     CK(cudaMemsetAsync(cofs, 0, (size_t)nT * (XT_TI + 1) * 2, stream));
     CK(cudaMemsetAsync(tcnt, 0, (nT + 1) * 8, stream));
-    tm.mark("tiles: allocation, map");
-    k_xt_count<true><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, nJ, cofs);
-    if (gene_side) k_xt_count<false><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, nJ, gofs);
+    tm.mark("tiles: allocation");
+    k_xt_count<true><<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, nJ, cofs, runofs);
+    if (gene_side) k_xt_count<false><<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, nJ, gofs, nullptr);
     k_xt_scan<XT_TI><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, cofs, tcnt);
     if (gene_side) k_xt_scan<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, nullptr);
     {
@@ -888,15 +886,15 @@ void pcmf_solver::build_tiles(const int64_t *perm_out) {
     k_xt_perm<XT_TI><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, cofs, cperm);
     if (gene_side) k_xt_perm<XT_TJ><<<grid_for(nT * 32, 128), 128, 0, stream>>>(nT, gofs, gperm);
     tm.mark("tiles: segment ranking");
-    k_xt_scatter_rows<<<grid_for(n * 32, 256), 256, 0, stream>>>(n, rowptr, colidx, map, nJ, tptr, cofs, ccol, postmp);
+    k_xt_scatter_rows<<<(unsigned)std::min<int64_t>(n, (int64_t)sms * 64), 128, 0, stream>>>(n, rowptr, colidx, nJ, tptr, cofs, runofs, ccol);
     tm.mark("tiles: cell-order scatter");
-    k_xt_scatter_cols<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, colptr, rowidx, (const float *)val_csc, postmp, nJ, tptr, gofs, grec, qmap);
+    k_xt_scatter_cols<<<grid_for((int64_t)p * 32, 256), 256, 0, stream>>>(p, n, colptr, rowidx, (const float *)val_csc, perm_out, rowptr, nJ, tptr,
+                                                                           gofs, cofs, runofs, grec, qmap);
     tm.mark("tiles: gene-order scatter");
     CK(cudaMemsetAsync(tq, 0, (size_t)nnz * 8, stream));
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
-    dfree(postmp); dfree(tcnt);
-    if (map != csr2csc) dfree(map);
+    dfree(runofs); dfree(tcnt);
     xt.nI = nI; xt.nJ = nJ; xt.tptr = tptr; xt.grec = grec; xt.gofs = gofs; xt.gperm = gperm; xt.ccol = ccol; xt.q = tq; xt.cofs = cofs; xt.cperm = cperm;
 }
 

@@ -44,8 +44,11 @@ struct TileCellArgs { RowArgs r; XTile x; int32_t p; };
 // ---- builder (once per fit) ---------------------------------------------------------------------------------
 // Runs of equal block index inside a sorted segment (a cell's genes / a gene's cells): the count of every (segment, block)
 // pair goes to slot [tile][local index + 1] of the offset table, which k_xt_scan then turns into offsets.
+// ROWS: also runofs[J * nseg + i] = offset, inside cell i's CSR segment, of its first entry in gene block J (the gene-order
+// scatter turns a CSR entry index into a cell-order position with it).
 template <bool ROWS>
-__global__ void k_xt_count(int64_t nseg, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, int nJ, uint16_t *__restrict__ ofs) {
+__global__ void k_xt_count(int64_t nseg, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, int nJ, uint16_t *__restrict__ ofs,
+                           uint32_t *__restrict__ runofs) {
     constexpr int SH = ROWS ? 8 : 7, L = ROWS ? XT_TI : XT_TJ;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -64,6 +67,7 @@ __global__ void k_xt_count(int64_t nseg, const int64_t *__restrict__ ptr, const 
                 const int64_t t = ROWS ? (sg >> 7) * nJ + B : (int64_t)B * nJ + (sg >> 8);
                 const int loc = ROWS ? (int)(sg & 127) : (int)(sg & 255);
                 ofs[t * (L + 1) + loc + 1] = (uint16_t)total;
+                if (ROWS) runofs[(int64_t)B * nseg + sg] = (uint32_t)(e + 1 - total - e0);      // the run ends at this entry
             }
             const int lastB = __shfl_sync(0xffffffffu, B, 31), lastTot = __shfl_sync(0xffffffffu, total, 31);
             if (lastB == nextB) { carryB = lastB; carryCnt = lastTot; } else { carryB = -1; carryCnt = 0; }
@@ -110,36 +114,23 @@ __global__ void k_xt_perm(int64_t nT, const uint16_t *__restrict__ ofs, uint8_t 
         }
     }
 }
-// cell order: position of every CSR entry inside its tile; the local gene goes to ccol, the position to postmp at the
-// entry's CSC index (the gene-order record carries it, so that the gene pass can leave q where the cell pass reads it)
-__global__ void k_xt_scatter_rows(int64_t n, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-                                  const uint32_t *__restrict__ csr2csc, int nJ, const int64_t *__restrict__ tptr,
-                                  const uint16_t *__restrict__ cofs, uint8_t *__restrict__ ccol, uint16_t *__restrict__ postmp) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < n; i += nw) {
+// cell order: the local gene of every CSR entry at its position inside its tile (tile offset of the cell + rank inside the
+// run of the gene block)
+__global__ void k_xt_scatter_rows(int64_t n, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, int nJ,
+                                  const int64_t *__restrict__ tptr, const uint16_t *__restrict__ cofs, const uint32_t *__restrict__ runofs,
+                                  uint8_t *__restrict__ ccol) {
+    const int64_t total = rowptr[n];
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
         const int64_t e0 = rowptr[i], e1 = rowptr[i + 1];
         const int r = (int)(i & 127);
-        int carryB = -1, carryCnt = 0;
-        for (int64_t eb = e0; eb < e1; eb += 32) {
-            const int64_t e = eb + lane;
-            const bool valid = e < e1;
-            const int j = valid ? colidx[e] : 0;
-            const int B = valid ? (j >> 8) : -2;
-            const unsigned mask = __match_any_sync(0xffffffffu, B);
-            const int nextB = (eb + 32 < e1) ? (colidx[eb + 32] >> 8) : -3;
-            const int before = (B == carryB ? carryCnt : 0);
-            const int rank = __popc(mask & ((1u << lane) - 1u)) + before;
-            if (valid) {
-                const int64_t t = (i >> 7) * nJ + B;
-                const int pos = cofs[t * (XT_TI + 1) + r] + rank;
-                ccol[tptr[t] + pos] = (uint8_t)(j & 255);
-                postmp[csr2csc[e]] = (uint16_t)pos;
-            }
-            const int lastB = __shfl_sync(0xffffffffu, B, 31), lastTot = __shfl_sync(0xffffffffu, __popc(mask) + before, 31);
-            if (lastB == nextB) { carryB = lastB; carryCnt = lastTot; } else { carryB = -1; carryCnt = 0; }
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int j = colidx[e];
+            const int64_t t = (i >> 7) * nJ + (j >> 8);
+            const int pos = cofs[t * (XT_TI + 1) + r] + (int)(e - e0 - runofs[(int64_t)(j >> 8) * n + i]);
+            ccol[tptr[t] + pos] = (uint8_t)(j & 255);
         }
     }
+    (void)total;
 }
 // (eu, eu o ElogU) pairs of every cell: the rows the spike-and-slab gene pass streams (one 16-byte read per factor)
 __global__ void k_eu_pairs(int64_t total, const double *__restrict__ eu, const double *__restrict__ ElogU, double2 *__restrict__ out) {
@@ -148,16 +139,21 @@ __global__ void k_eu_pairs(int64_t total, const double *__restrict__ eu, const d
         out[o] = make_double2(u, u * ElogU[o]);
     }
 }
-// gene order: the record of every CSC entry
-__global__ void k_xt_scatter_cols(int32_t p, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
-                                  const float *__restrict__ val_csc, const uint16_t *__restrict__ postmp, int nJ,
-                                  const int64_t *__restrict__ tptr, const uint16_t *__restrict__ gofs, uint2 *__restrict__ grec,
+// gene order: the record of every CSC entry.  csr_of[f] is the CSR index of CSC entry f (the permutation of the CSC sort), so
+// its cell-order position is the cell's tile offset + its distance from the start of the cell's run in this gene block --
+// no CSR -> CSC map and no second scatter.  The tables are read with locality: a gene walks its cells upwards, and the 256
+// genes of a block walk the same slices of cofs and runofs.
+__global__ void k_xt_scatter_cols(int32_t p, int64_t n, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                  const float *__restrict__ val_csc, const int64_t *__restrict__ csr_of, const int64_t *__restrict__ rowptr,
+                                  int nJ, const int64_t *__restrict__ tptr, const uint16_t *__restrict__ gofs,
+                                  const uint16_t *__restrict__ cofs, const uint32_t *__restrict__ runofs, uint2 *__restrict__ grec,
                                   uint32_t *__restrict__ qmap) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t j = warp; j < p; j += nw) {
         const int64_t e0 = colptr[j], e1 = colptr[j + 1];
         const int c = (int)(j & 255);
+        const int64_t Jn = (j >> 8) * n;
         int carryB = -1, carryCnt = 0;
         for (int64_t eb = e0; eb < e1; eb += 32) {
             const int64_t e = eb + lane;
@@ -171,7 +167,7 @@ __global__ void k_xt_scatter_cols(int32_t p, const int64_t *__restrict__ colptr,
             if (valid) {
                 const int64_t t = (int64_t)B * nJ + (j >> 8);
                 const int64_t tb = tptr[t];
-                const unsigned pc = postmp[e];
+                const unsigned pc = cofs[t * (XT_TI + 1) + (i & 127)] + (unsigned)(csr_of[e] - rowptr[i] - runofs[Jn + i]);
                 if (grec) {       // (null: this factor width keeps the CSC gene pass, only the map is needed)
                     const int pos = gofs[t * (XT_TJ + 1) + c] + rank;
                     grec[tb + pos] = make_uint2((unsigned)(i & 127) | (pc << 8), __float_as_uint(val_csc[e]));
