@@ -3,7 +3,7 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests/test_gpu_fp32.py -m gpu -q ) > gpurun_out/r2h_pytest.log 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -q --durations=8 ) > gpurun_out/r2h_pytest.log 2>&1
 tail -16 gpurun_out/r2h_pytest.log
 timeout 900 python bench.py > gpurun_out/r2h_bench_c4.json 2> gpurun_out/r2h_bench_c4.err || tail -c 800 gpurun_out/r2h_bench_c4.err
 timeout 600 python bench.py --precision fp32 --no-cpu --no-e2e > gpurun_out/r2h_bench_c4_fp32.json 2> gpurun_out/r2h_bench_c4_fp32.err || tail -c 800 gpurun_out/r2h_bench_c4_fp32.err
