@@ -22,6 +22,9 @@ extern "C" {
 #define PCMF_DEV_NO_PSTORE 128      /* never keep it */
 #define PCMF_DEV_ONE_CELL_BLOCK 512 /* gene passes in one cell block */
 #define PCMF_DEV_TINY_CELL_BLOCKS 1024 /* 64-cell blocks */
+#define PCMF_DEV_FORCE_TILES 2048   /* tiled non-zero passes whatever the size */
+#define PCMF_DEV_NO_TILES 4096      /* CSR / CSC non-zero passes whatever the size */
+#define PCMF_DEV_ZI_ALL_DMMA 8192   /* cell-side ZI pass with both products on the FP64 tensor path (no integer tcgen05 product) */
 
 /* per-phase device timings of the last pcmf_iterate/pcmf_optimize call, milliseconds summed over iterations:
  * names[i] points to a static string; returns the number of phases written (<= cap) */

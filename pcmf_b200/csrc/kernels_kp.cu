@@ -1,7 +1,11 @@
 // One instantiation set of the K-templated kernels; compiled once per padded width with -DPCMF_KP=<n>.
 #include <algorithm>
+#include <cstdlib>
 #include "launch.cuh"
 #include "zi_mma.cuh"
+#if PCMF_KP <= 32
+#include "zi_i8.cuh"
+#endif
 #if PCMF_KP >= 16 && PCMF_KP <= 20
 #include "xtile_kernels.cuh"
 #endif
@@ -113,7 +117,58 @@ int launch_zi_genes_mma_t(const ZiBArgs &a, int chunks, cudaStream_t st) {
     k_zi_genes_mma<KP, MT, MMA_TI><<<grid, 128, smem, st>>>(a);
     return 2;
 }
+#if PCMF_KP <= 32
+// pass A with the second product as exact integer arithmetic on tcgen05 (zi_i8.cuh): factor widths up to 32
+template <int NW>
+int launch_zi_cells_i8_t(const ZiAArgs &a_in, cudaStream_t st) {
+    using R = ZiRecI8<KP>;
+    ZiAArgs a = a_in;
+#ifdef PCMF_I8_ABLATE
+    static const int abl = getenv("PCMF_I8_ABL") ? atoi(getenv("PCMF_I8_ABL")) : 0;
+    const int want_ll = a.want_ll & 1;
+    a.want_ll = want_ll | (abl << 8);
+#else
+    const int want_ll = a.want_ll;
+#endif
+    static bool attr_dev[64] = {false};       // function attributes are per device (pcmf_options.ngpus drives several)
+    bool &attr = attr_dev[current_device()];
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_cells_i8<KP, NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::SMEM);
+        cudaFuncSetAttribute(k_zi_cells_i8<KP, NW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::SMEM);
+        cudaFuncSetAttribute(k_zi_cells_i8<KP, NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::SMEM);
+        cudaFuncSetAttribute(k_zi_cells_i8<KP, NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::SMEM);
+        attr = true;
+    }
+    const int64_t groups = (a.p + 7) / 8;
+    double *tail = a.pack + R::off_tail(groups);
+    cudaMemsetAsync(tail, 0, sizeof(double) * I8_TAIL, st);
+    k_i8_colmax<KP><<<pack_grid((int64_t)a.p * KP), 256, 0, st>>>(a.p, a.EVS, reinterpret_cast<unsigned long long *>(tail));
+    k_zi_pack_i8<KP><<<pack_grid(groups * R::NTOT * 8), 256, 0, st>>>(a.p, a.EVS, a.cz, a.flag, a.pack);
+    const int64_t gx = (a.n + 127) / 128;
+    // at least ~8 waves of CTAs (2 resident per SM): split the gene tiles over blockIdx.y when there are few cell blocks
+    const int ntiles = (int)((groups + I8_TJ / 8 - 1) / (I8_TJ / 8));
+    int gy = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles / 16, (148 * 2 * 8 + gx - 1) / gx));
+    if (gx >= 148 * 2 * 8) gy = 1;
+    if (gy > 1) cudaMemsetAsync(a.PV, 0, sizeof(double) * (size_t)a.n * KP, st);
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (want_ll) {
+        if (a.pstore) k_zi_cells_i8<KP, NW, true, true><<<grid, 32 * NW, R::SMEM, st>>>(a);
+        else k_zi_cells_i8<KP, NW, false, true><<<grid, 32 * NW, R::SMEM, st>>>(a);
+    } else {
+        if (a.pstore) k_zi_cells_i8<KP, NW, true, false><<<grid, 32 * NW, R::SMEM, st>>>(a);
+        else k_zi_cells_i8<KP, NW, false, false><<<grid, 32 * NW, R::SMEM, st>>>(a);
+    }
+    return 3;
+}
+int launch_zi_cells_i8(const ZiAArgs &a, cudaStream_t st) {
+    static const int nw = getenv("PCMF_I8_NW") ? atoi(getenv("PCMF_I8_NW")) : 8;
+    return nw == 4 ? launch_zi_cells_i8_t<4>(a, st) : launch_zi_cells_i8_t<8>(a, st);
+}
+#endif
 int launch_zi_cells_mma(const ZiAArgs &a, int variant, cudaStream_t st) {
+#if PCMF_KP <= 32
+    if (!(variant & (8 | 8192))) return launch_zi_cells_i8(a, st);
+#endif
     if ((variant & 8) && MMA_MT == 4) return launch_zi_cells_mma_t<2>(a, st);
     return launch_zi_cells_mma_t<MMA_MT>(a, st);
 }
@@ -145,6 +200,9 @@ void launch_gene_order(bool f32, const OrderArgs &a, int grid, cudaStream_t st) 
 }
 size_t zi_pack_doubles(int64_t rows, int cells_side) {
     const int64_t groups = (rows + 7) / 8;
+#if PCMF_KP <= 32
+    if (!cells_side) return std::max((size_t)groups * ZiRec<KP, true>::REC, ZiRecI8<KP>::pack_doubles(groups));
+#endif
     return (size_t)groups * (cells_side ? ZiRec<KP, false>::REC : ZiRec<KP, true>::REC);
 }
 

@@ -1,0 +1,3 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+bash scripts/gpu_r3_c.sh base:PCMF_I8_ABL=0 nosttm:PCMF_I8_ABL=65 nostg:PCMF_I8_ABL=2 nocs:PCMF_I8_ABL=4 noent:PCMF_I8_ABL=8 nodmma:PCMF_I8_ABL=16 noexpit:PCMF_I8_ABL=32 nommaissue:PCMF_I8_ABL=64 nothing:PCMF_I8_ABL=127
