@@ -154,6 +154,42 @@ __device__ __forceinline__ void i8_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 //   * the warp that counts in LAST owns the tile's tail: flushes the column sums, issues the 20 MMAs and their commit, and
 //     starts the bulk copy of the tile after next into the buffer the MMAs of two tiles ago have released.
 // Two CTAs per SM (tensor memory: 2 x 256 columns; shared memory: 2 x ~92 KB), 16 warps.
+// Select-free expit for the pass without the log-likelihood monitor.  With za = min(|z|, 40), t = e^-za in (4e-18, 1], r = 1 / (1 + t):
+//      P = z >= 0 ? r : t r            1 exactly for z >= 37 and below 2^-57 for z <= -40, where internal::expit (internal.h:151-155)
+//                                      clamps to exactly 1 / 0 from |z| = 30 on: the two differ by at most e^-30 = 9.4e-14
+//      -[P log P + (1 - P) log(1 - P)] = log(1 + t) + za t r     no cancellation, below 40 e^-40 = 1.7e-16 for the clamped entries
+// so the entries X != 0 (z = +-1e300 from the packed record), the whole-gene shortcuts and the rows beyond n need no select of
+// their own, and the running product of (1 + t) <= 2 is read out once per tile.  The clamp is two integer instructions on the
+// high word (the low word rides along: |z| in [40, 40 + 2^-15)).
+// (fast_exp_neg_tab with the table row addressed as one multiply-add on the 32-bit shared-memory address of the lane's copy)
+__device__ __forceinline__ double fast_exp_neg_tab_a(double z, uint32_t tab_addr) {
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+    double t = fma(z, -92.33248261689366, MAGIC);
+    const int m = __double2loint(t);
+    t -= MAGIC;
+    const double r = fma(t, -0.010830424696249145, -z);
+    double p = 4.16666666666666666667e-02;
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double tb;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tb) : "r"((uint32_t)(m & 63) * (uint32_t)(kTabRep * 8) + tab_addr));
+    const double sc = __hiloint2double(__double2hiint(tb) + (int)((unsigned)m << 14), __double2loint(tb));
+    return p * sc;
+}
+__device__ __forceinline__ double expit_sym(double z, uint32_t tab_addr, double &y, double &za_tr) {
+    const int hi = __double2hiint(z);
+    const int ah = min(hi & 0x7fffffff, 0x40440000);
+    const double za = __hiloint2double(ah, __double2loint(z));
+    const double t = fast_exp_neg_tab_a(za, tab_addr);
+    y = 1.0 + t;
+    const double r = fast_rcp2(y);
+    const double tr = t * r;
+    za_tr = za * tr;
+    return hi >= 0 ? r : tr;
+}
+
 template <int KP, int NW, bool STORE_P, bool WITH_LL>
 __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     static_assert(NW == 4 || NW == 8, "one or two warps per 32-cell row block");
@@ -179,6 +215,7 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3, rb = w & 3, gh = w >> 2;
     load_pow2_tab(s_tab);
     const double *tabl = pow2_tab_lane(s_tab);
+    const uint32_t tab_addr = smem_u32(tabl);
     const int ngroups = (a.p + 7) >> 3;
     if (threadIdx.x < KP) s_cf[threadIdx.x] = pack[R::off_tail(ngroups) + 64 + threadIdx.x];
     if (threadIdx.x == 0) {
@@ -338,20 +375,23 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
             for (int mt = 0; mt < MT; ++mt) {
                 const bool nz0 = (bits[mt] >> sh0) & 1u, nz1 = (bits[mt] >> (sh0 + 1)) & 1u;
                 const double z0 = nz0 ? n2.x : c2.x - d[mt][0], z1 = nz1 ? n2.y : c2.y - d[mt][1];
-                double y0, y1, em0, em1; bool big0, big1;
                 double p0, p1;
-                if (!(abl & 32)) { p0 = fast_expit_tab(z0, tabl, y0, big0, em0); p1 = fast_expit_tab(z1, tabl, y1, big1, em1); }
-                else { p0 = z0 * 1e-3; p1 = z1 * 1e-3; y0 = p0; y1 = p1; big0 = big1 = false; em0 = em1 = 1.0; }
                 if (WITH_LL) {
+                    double y0, y1, em0, em1; bool big0, big1;
+                    p0 = fast_expit_tab(z0, tabl, y0, big0, em0); p1 = fast_expit_tab(z1, tabl, y1, big1, em1);
                     ll_prod *= (big0 ? 1.0 : fma(em0, em0, ec2.x)) * (big1 ? 1.0 : fma(em1, em1, ec2.y));
                     ll_lin += (big0 ? 0.0 : z0) + (big1 ? 0.0 : z1);
                     ll_lin -= ((big0 && !nz0 && z0 > 0.0) ? d[mt][0] : 0.0) + ((big1 && !nz1 && z1 > 0.0) ? d[mt][1] : 0.0);
-                }
-                const bool g0 = !big0, g1 = !big1;
-                if (!(abl & 8)) {
+                    // -bernoulli_loglike(prob_D, prob_D) over 0 < P < 1: sum (1-P)(-z) - log(1 + e^-z)
+                    const bool g0 = !big0, g1 = !big1;
                     ent_lin = fma(g0 ? (p0 - 1.0) : 0.0, z0, ent_lin);
                     ent_lin = fma(g1 ? (p1 - 1.0) : 0.0, z1, ent_lin);
                     prod *= (g0 ? y0 : 1.0) * (g1 ? y1 : 1.0);
+                } else {
+                    double y0, y1, h0, h1;
+                    p0 = expit_sym(z0, tab_addr, y0, h0); p1 = expit_sym(z1, tab_addr, y1, h1);
+                    ent_lin -= h0 + h1;
+                    prod *= y0 * y1;
                 }
                 cs0 += p0; cs1 += p1;
                 // rint(P (2^32 - 1)) read off the low mantissa word of 2^52 + P (2^32 - 1)
@@ -371,7 +411,7 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
                 asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};"
                              ::"r"(addr), "r"(pw[2 * h][0]), "r"(pw[2 * h][1]), "r"(pw[2 * h + 1][0]), "r"(pw[2 * h + 1][1]) : "memory");
             }
-            if (prod > 1e100) { ent_log += log(prod); prod = 1.0; }
+            if (WITH_LL && prod > 1e100) { ent_log += log(prod); prod = 1.0; }
             if (WITH_LL && (ll_prod > 1e60 || ll_prod < 1e-60)) { ll_log += log(ll_prod); ll_prod = 1.0; }
             if (!(abl & 4)) {
 #pragma unroll
@@ -382,6 +422,7 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
                 if (g == 0) *reinterpret_cast<double2 *>(cs_buf + rb * TJ + grp * 8 + 2 * q) = make_double2(cs0, cs1);
             }
         }
+        if (!WITH_LL && prod > 1e200) { ent_log += log(prod); prod = 1.0; }     // (1 + t)^(16 GPW) <= 2^64 per tile
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __threadfence_block();
