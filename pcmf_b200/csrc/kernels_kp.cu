@@ -143,7 +143,7 @@ int launch_zi_cells_i8_t(const ZiAArgs &a_in, cudaStream_t st) {
     double *tail = a.pack + R::off_tail(groups);
     cudaMemsetAsync(tail, 0, sizeof(double) * I8_TAIL, st);
     k_i8_colmax<KP><<<pack_grid((int64_t)a.p * KP), 256, 0, st>>>(a.p, a.EVS, reinterpret_cast<unsigned long long *>(tail));
-    k_zi_pack_i8<KP><<<pack_grid(groups * R::NTOT * 8), 256, 0, st>>>(a.p, a.EVS, a.cz, a.flag, a.pack);
+    k_zi_pack_i8<KP, true><<<pack_grid(groups * R::NTOT * 8), 256, 0, st>>>(a.p, a.EVS, a.cz, a.flag, a.pack);
     const int64_t gx = (a.n + 127) / 128;
     // at least ~8 waves of CTAs (2 resident per SM): split the gene tiles over blockIdx.y when there are few cell blocks
     const int ntiles = (int)((groups + I8_TJ / 8 - 1) / (I8_TJ / 8));
@@ -160,6 +160,31 @@ int launch_zi_cells_i8_t(const ZiAArgs &a_in, cudaStream_t st) {
     }
     return 3;
 }
+// pass B on the prob_D the integer cell-side pass stored (k_zi_genes_i8): 384 genes x <= 8192 cells per CTA
+int launch_zi_genes_i8(ZiBArgs a, cudaStream_t st) {
+    using R = ZiRecI8<KP>;
+    using G = ZiGenesI8<KP>;
+    static bool attr_dev[64] = {false};
+    bool &attr = attr_dev[current_device()];
+    if (!attr) {
+        cudaFuncSetAttribute(k_zi_genes_i8<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        attr = true;
+    }
+    const int64_t groups = (a.n + 7) / 8;
+    double *tail = a.pack + R::off_tail(groups, false);
+    cudaMemsetAsync(tail, 0, sizeof(double) * I8_TAIL, st);
+    k_i8_colmax<KP><<<pack_grid(a.n * KP), 256, 0, st>>>(a.n, a.EUn, reinterpret_cast<unsigned long long *>(tail));
+    k_zi_pack_i8<KP, false><<<pack_grid(groups * R::NTOT * 8), 256, 0, st>>>(a.n, a.EUn, nullptr, nullptr, a.pack);
+    // cell chunks of at most 8192 cells (accumulator range), multiples of 32 (one stage = 4 cell groups); the gene blocks of
+    // one chunk are adjacent in the grid, so the digit records they share are read from HBM once
+    int64_t chunks = std::max<int64_t>(1, (a.n + I8B_MAXCELLS - 1) / I8B_MAXCELLS);
+    int64_t rpc = (a.n + chunks - 1) / chunks; rpc = (rpc + 31) / 32 * 32;
+    chunks = (a.n + rpc - 1) / rpc;
+    a.rows_per_chunk = rpc;
+    const int gx = (a.p + I8B_GB * 128 - 1) / (I8B_GB * 128);
+    k_zi_genes_i8<KP><<<dim3((unsigned)gx, (unsigned)chunks), 128, G::SMEM, st>>>(a);
+    return 3;
+}
 int launch_zi_cells_i8(const ZiAArgs &a, cudaStream_t st) {
     static const int nw = getenv("PCMF_I8_NW") ? atoi(getenv("PCMF_I8_NW")) : 8;
     return nw == 4 ? launch_zi_cells_i8_t<4>(a, st) : launch_zi_cells_i8_t<8>(a, st);
@@ -173,6 +198,10 @@ int launch_zi_cells_mma(const ZiAArgs &a, int variant, cudaStream_t st) {
     return launch_zi_cells_mma_t<MMA_MT>(a, st);
 }
 int launch_zi_genes_mma(const ZiBArgs &a, int chunks, int variant, cudaStream_t st) {
+#if PCMF_KP <= 32
+    // the stored prob_D has the tile layout of the cell-side kernel that wrote it: the same switch picks both
+    if (a.pstore && !(variant & (8 | 8192))) return launch_zi_genes_i8(a, st);
+#endif
     if ((variant & 8) && MMA_MT == 4) return launch_zi_genes_mma_t<2>(a, chunks, st);
     return launch_zi_genes_mma_t<MMA_MT>(a, chunks, st);
 }
@@ -202,6 +231,9 @@ size_t zi_pack_doubles(int64_t rows, int cells_side) {
     const int64_t groups = (rows + 7) / 8;
 #if PCMF_KP <= 32
     if (!cells_side) return std::max((size_t)groups * ZiRec<KP, true>::REC, ZiRecI8<KP>::pack_doubles(groups));
+#endif
+#if PCMF_KP <= 32
+    if (cells_side) return std::max((size_t)groups * ZiRec<KP, false>::REC, ZiRecI8<KP>::pack_doubles(groups, false));
 #endif
     return (size_t)groups * (cells_side ? ZiRec<KP, false>::REC : ZiRec<KP, true>::REC);
 }

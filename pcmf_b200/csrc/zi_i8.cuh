@@ -7,10 +7,12 @@
 //     error 1.2e-10 elsewhere), for the copy the gene-side pass streams back (PCMF_PSTORE_SCALE).  The four BYTES of that word are
 //     four base-256 digits b_0..b_3, and a word written to tensor memory is read by tcgen05.mma kind::i8 as four consecutive K
 //     elements: the A operand is the stored word itself,  A[cell][4 j + s] = b_s(Pq[cell][gene j]);  no repacking.
-//   * EVS >= 0 is cut per factor column into five base-256 digits e_0..e_4 (most significant first) of the 40-bit fixed-point
-//     F = rint(EVS 2^(40 - ex_k)), 2^ex_k > max_j EVS_jk.  Pq F = sum_{s,t} b_s e_t 2^(8 (s - t + 4)): the digit products of equal
-//     weight d = s - t share one accumulator,  B_d[k][4 j + s] = e_(s - d)[j][k],  d = 3, 2, 1, 0, -1  ->  5 MMAs (M = 128 cells,
-//     N = 16 | 32 factor columns, K = 32 bytes = 8 genes) per 8-gene group; the dropped weights d <= -2 are < 2^-38 of full scale.
+//   * EVS >= 0 is cut per factor column into ND = 6 base-256 digits e_0..e_5 (most significant first) of the 48-bit fixed-point
+//     F = rint(EVS 2^(48 - ex_k)), 2^ex_k > max_j EVS_jk.  Pq F = sum_{s,t} b_s e_t 2^(8 (s - t + 5)): the digit products of equal
+//     weight d = s - t share one accumulator,  B_d[k][4 j + s] = e_(s - d)[j][k],  d = 3 .. -2, and the six operands are stacked
+//     along N: ONE MMA (M = 128 cells, N = 6 x 24, K = 32 bytes = 8 genes) per 8-gene group.  The dropped weights d <= -3 are
+//     below 2^-46 of full scale (with five digits and weights, as for K > 24, 2^-38: that truncation is a BIAS of every term and
+//     showed as 1.4e-7 on single entries of b2 where P EU is 1e4 below the column maximum).
 //   * u8 x u8 -> s32 in tensor memory is exact: at most 4 digit pairs x 255^2 per gene and accumulator, so the accumulators are
 //     read out (tcgen05.ld), scaled and added to PV in FP64 every 4096 genes, far below 2^31.
 // The kernel is otherwise k_zi_cells_mma: first product lambda = EU_i . EVS_j as DMMA tiles (K = 20 is five m8n8k4 steps, as
@@ -23,7 +25,6 @@
 
 namespace pcmf {
 
-constexpr int I8_ND = 5;               // accumulators: digit weights d = 3, 2, 1, 0, -1
 constexpr int I8_TJ = 32;              // genes per shared-memory tile (one occupancy word per cell and tile)
 constexpr int I8_STAGES = 3;           // tile buffers in shared memory, and P buffers in tensor memory
 constexpr int I8_FLUSH = 128;          // tiles between two read-outs of the integer accumulators (4096 genes)
@@ -32,8 +33,8 @@ constexpr int I8_TAIL = 128;           // doubles after the records: [colmax 64 
 constexpr int I8_STAGES_A = 4;         // tile buffers of the first-product records (released when every warp is through with a tile)
 
 // Packed gene side of the pass, per group of 8 genes:  part A = [ f1: KS x 32 doubles (as ZiRec) | c: 8 | zf: 8 | e^-c: 8 ]  for the
-// FP64 warps, part B = the five digit operands B_3, B_2, B_1, B_0, B_-1 stacked along N ([NTOT rows][32 bytes], K-major canonical; row
-// di NFS + k = digit weight 3 - di, factor k), so that ONE MMA per 8-gene group fills all five accumulators.
+// FP64 warps, part B = the ND digit operands B_3, B_2, .. stacked along N ([NTOT rows][32 bytes], K-major canonical; row
+// di NFS + k = digit weight 3 - di, factor k), so that ONE MMA per 8-gene group fills all ND accumulators.
 // The two parts are separate arrays (all A records, then all B records, then the tail [colmax 64 | cfac 64]) and travel through
 // separate rings of shared-memory buffers: A is needed when a tile starts, B when it ends.
 template <int KP>
@@ -41,15 +42,18 @@ struct ZiRecI8 {
     static_assert(KP <= 32, "the integer second product holds 5 x 32 accumulator columns and 3 x 32 of P in 256 TMEM columns");
     static constexpr int KS = KP / 4;
     static constexpr int NFS = (KP + 7) / 8 * 8;                          // accumulator columns per digit weight
-    static constexpr int NTOT = (I8_ND * NFS + 15) / 16 * 16;             // N of the one MMA per 8-gene group: the five operands stacked
+    static constexpr int ND = (KP <= 24) ? 6 : 5;                         // digits of the streamed factor matrix = digit weights kept: d = 3 .. 4 - ND
+    static constexpr int NTOT = (ND * NFS + 15) / 16 * 16;                // N of the one MMA per 8-gene group: the ND operands stacked
     static constexpr int F1 = KS * 32, CZ = 24, RA = F1 + CZ;             // doubles per group, part A
     static constexpr int B8 = NTOT * 32;                                  // bytes per group, part B: [NTOT rows][32 bytes], K-major canonical
     static constexpr int COL_ACC = 0, COL_A = NTOT, TMEM_COLS = 256;
-    static_assert(COL_A + I8_STAGES * I8_TJ <= TMEM_COLS, "tensor-memory budget");
+    static constexpr int PST = 3;                                         // P buffers in tensor memory (tiles in flight towards the MMAs)
+    static_assert(COL_A + PST * I8_TJ <= TMEM_COLS, "tensor-memory budget");
     static constexpr size_t SMEM = (size_t)(I8_TJ / 8) * (I8_STAGES_A * RA * 8 + I8_STAGES * B8) + sizeof(double) * (I8_STAGES * 4 * I8_TJ + kTabDoubles);
-    static size_t pack_doubles(int64_t groups) { return (size_t)groups * (RA + B8 / 8) + I8_TAIL; }
-    __host__ __device__ static int64_t off_b(int64_t groups) { return groups * RA; }                 // in doubles
-    __host__ __device__ static int64_t off_tail(int64_t groups) { return groups * (RA + B8 / 8); }   // in doubles
+    // (the cell-side packing of EU_new for k_zi_genes_i8 has no part A)
+    static size_t pack_doubles(int64_t groups, bool with_a = true) { return (size_t)groups * ((with_a ? RA : 0) + B8 / 8) + I8_TAIL; }
+    __host__ __device__ static int64_t off_b(int64_t groups, bool with_a = true) { return with_a ? groups * RA : 0; }                 // in doubles
+    __host__ __device__ static int64_t off_tail(int64_t groups, bool with_a = true) { return groups * ((with_a ? RA : 0) + B8 / 8); }   // in doubles
 };
 
 // per-column maximum of a non-negative row-major [rows][KP] matrix (bit patterns of non-negative doubles order as integers)
@@ -72,12 +76,12 @@ __global__ void k_i8_colmax(int64_t rows, const double *__restrict__ M, unsigned
 __host__ __device__ inline int i8_canon(int n, int kb, int N) { return (kb >> 4) * (N / 8) * 128 + (n >> 3) * 128 + (n & 7) * 16 + (kb & 15); }
 
 // Writes both parts of the packed gene side (ZiRecI8) and, in the tail, cfac:  PV_ik = cfac_k sum_d 2^(8 (d + 1)) acc_d[i][k].
-template <int KP>
+template <int KP, bool WITH_A>
 __global__ void k_zi_pack_i8(int64_t rows, const double *__restrict__ EVS, const double *__restrict__ cz, const int32_t *__restrict__ flag,
                              double *__restrict__ out) {
     using R = ZiRecI8<KP>;
     const int64_t ngroups = (rows + 7) >> 3;
-    const unsigned long long *colmax = reinterpret_cast<const unsigned long long *>(out + R::off_tail(ngroups));
+    const unsigned long long *colmax = reinterpret_cast<const unsigned long long *>(out + R::off_tail(ngroups, WITH_A));
     __shared__ double s_mult[KP];
     if (threadIdx.x < KP) {
         const double m = __longlong_as_double((long long)colmax[threadIdx.x]);
@@ -85,15 +89,15 @@ __global__ void k_zi_pack_i8(int64_t rows, const double *__restrict__ EVS, const
         double mult = 0.0, cf = 0.0;
         if (m > 0.0 && m < 1e300) {
             frexp(m, &ex);                                                // m = f 2^ex, f in [0.5, 1)  ->  m < 2^ex
-            mult = ldexp(1.0, 40 - ex);
-            cf = ldexp(1.0 / PCMF_PSTORE_SCALE, ex - 16);
+            mult = ldexp(1.0, 8 * R::ND - ex);
+            cf = ldexp(1.0 / PCMF_PSTORE_SCALE, ex - 8 * R::ND + 24);
         }
         s_mult[threadIdx.x] = mult;
-        if (blockIdx.x == 0) out[R::off_tail(ngroups) + 64 + threadIdx.x] = cf;
+        if (blockIdx.x == 0) out[R::off_tail(ngroups, WITH_A) + 64 + threadIdx.x] = cf;
     }
     __syncthreads();
     // doubles of the record head, one per thread
-    const int64_t head = ngroups * R::RA;
+    const int64_t head = WITH_A ? ngroups * R::RA : 0;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < head; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t grp = idx / R::RA;
         const int o = (int)(idx - grp * R::RA);
@@ -113,22 +117,23 @@ __global__ void k_zi_pack_i8(int64_t rows, const double *__restrict__ EVS, const
         out[idx] = v;
     }
     // digit operands: one thread per (group, operand row, gene in group) writes the row's 4 bytes (s = 0..3) for that gene.
-    // Row r = di NFS + k of the stacked operand: digit weight d = 3 - di, factor k; rows beyond 5 NFS are zero.
+    // Row r = di NFS + k of the stacked operand: digit weight d = 3 - di, factor k; rows beyond ND NFS are zero.
     const int64_t items = ngroups * R::NTOT * 8;
-    unsigned char *b8all = reinterpret_cast<unsigned char *>(out + R::off_b(ngroups));
+    unsigned char *b8all = reinterpret_cast<unsigned char *>(out + R::off_b(ngroups, WITH_A));
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t grp = idx / (R::NTOT * 8);
         const int rem = (int)(idx - grp * (R::NTOT * 8)), r = rem >> 3, jl = rem & 7;
         const int di = r / R::NFS, k = r - di * R::NFS, d = 3 - di;
         const int64_t row = grp * 8 + jl;
         uint32_t w = 0u;
-        if (di < I8_ND && row < rows && k < KP) {
+        if (di < R::ND && row < rows && k < KP) {
             const double x = rint(EVS[row * KP + k] * s_mult[k]);
-            const unsigned long long F = x <= 0.0 ? 0ull : (x >= 1099511627775.0 ? 1099511627775ull : (unsigned long long)x);
+            constexpr unsigned long long FMAX = (1ull << (8 * R::ND)) - 1ull;
+            const unsigned long long F = x <= 0.0 ? 0ull : (x >= (double)FMAX ? FMAX : (unsigned long long)x);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int t = s - d;                                      // digit e_t, t = 0 most significant: bits [8 (4 - t), +8) of F
-                if (t >= 0 && t < 5) w |= (uint32_t)((F >> (8 * (4 - t))) & 255ull) << (8 * s);
+                if (t >= 0 && t < R::ND) w |= (uint32_t)((F >> (8 * (R::ND - 1 - t))) & 255ull) << (8 * s);
             }
         }
         *reinterpret_cast<uint32_t *>(b8all + grp * R::B8 + i8_canon(r, 4 * jl, R::NTOT)) = w;
@@ -190,6 +195,11 @@ __device__ __forceinline__ double expit_sym(double z, uint32_t tab_addr, double 
     return hi >= 0 ? r : tr;
 }
 
+__device__ __forceinline__ void i8_mma_ss(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 template <int KP, int NW, bool STORE_P, bool WITH_LL>
 __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     static_assert(NW == 4 || NW == 8, "one or two warps per 32-cell row block");
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     double *s_tab = s_cs + I8_STAGES * 4 * TJ;                  // kTabDoubles
     __shared__ double sh[32];
     __shared__ double s_cf[KP];
-    __shared__ __align__(8) uint64_t bar_fullA[I8_STAGES_A], bar_fullB[I8_STAGES], bar_mma[I8_STAGES];
+    __shared__ __align__(8) uint64_t bar_fullA[I8_STAGES_A], bar_fullB[I8_STAGES], bar_mma[R::PST];
     __shared__ uint32_t s_bits[NW][I8_STAGES][32];              // per warp: occupancy words of its 32 cells for a tile (cp.async)
     __shared__ int s_cnt[I8_STAGES];
     __shared__ uint32_t tmem_base;
@@ -220,7 +230,9 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     if (threadIdx.x < KP) s_cf[threadIdx.x] = pack[R::off_tail(ngroups) + 64 + threadIdx.x];
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&bar_fullB[s], 1); mbar_init(&bar_mma[s], 1); s_cnt[s] = 0; }
+        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&bar_fullB[s], 1); s_cnt[s] = 0; }
+#pragma unroll
+        for (int s = 0; s < R::PST; ++s) mbar_init(&bar_mma[s], 1);
 #pragma unroll
         for (int s = 0; s < I8_STAGES_A; ++s) mbar_init(&bar_fullA[s], 1);
         mbar_fence_init();
@@ -247,7 +259,8 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     // rows beyond n: lambda starts at 1e305, above every effective logit, so the expit itself clamps them to P = 0 (word 0)
     const unsigned st_ngg = (unsigned)((a.p + 7) >> 3);
     const unsigned st_tile0 = (unsigned)(cell0 >> 3) * st_ngg;
-    uint32_t *const st_lane = STORE_P ? a.pstore + (2 * q) * 8 + g : nullptr;
+    // stored prob_D: tile (cell group, gene group) as two core matrices [cell >> 2][gene][cell & 3] -- the A operand of k_zi_genes_i8
+    uint32_t *const st_lane = STORE_P ? a.pstore + (g >> 2) * 32 + (2 * q) * 4 + (g & 3) : nullptr;
     double ent_lin = 0, ent_log = 0, prod = 1.0;
     double ll_lin = 0, ll_log = 0, ll_prod = 1.0;
 
@@ -290,9 +303,9 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
         // 8-column chunks of the NFS columns per digit weight, dealt to the one or two warps of the row block
 #pragma unroll
         for (int cb = 8 * gh; cb < NFS; cb += 8 * (NW / 4)) {
-            uint32_t v[I8_ND][8];
+            uint32_t v[R::ND][8];
 #pragma unroll
-            for (int di = 0; di < I8_ND; ++di)
+            for (int di = 0; di < R::ND; ++di)
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                              : "=r"(v[di][0]), "=r"(v[di][1]), "=r"(v[di][2]), "=r"(v[di][3]), "=r"(v[di][4]), "=r"(v[di][5]), "=r"(v[di][6]), "=r"(v[di][7])
                              : "r"(lane_addr + (uint32_t)(R::COL_ACC + di * NFS + cb)));
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
                     if (k < KP) {
                         double x = (double)(int32_t)v[0][c];
 #pragma unroll
-                        for (int di = 1; di < I8_ND; ++di) x = fma(x, 256.0, (double)(int32_t)v[di][c]);
+                        for (int di = 1; di < R::ND; ++di) x = fma(x, 256.0, (double)(int32_t)v[di][c]);
                         x *= s_cf[k];
                         // sum_ij prob_D_ij UVt_ij = sum_ik EU_ik PV_ik (zi...cpp:182) is linear in the parts added here
                         sum_pl = fma(__ldg(a.EU + my_cell * KP + k), x, sum_pl);
@@ -332,8 +345,10 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
         const double *buf = s_bufA + sa * BUFA;
         double *cs_buf = s_cs + st * 4 * TJ;
         if (tile + 1 < ntiles) fetch_bits(tile + 1);
-        // the MMAs of three tiles ago are through with the P buffer this tile overwrites
-        if (tile >= I8_STAGES) mbar_wait(&bar_mma[st], ph ^ 1u);
+        // the MMAs of PST tiles ago are through with the P buffer this tile overwrites
+        const int sp = tile % R::PST;
+        const unsigned php = (unsigned)((tile / R::PST) & 1);
+        if (tile >= R::PST) mbar_wait(&bar_mma[sp], php ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         mbar_wait(&bar_fullA[sa], (unsigned)((tile / I8_STAGES_A) & 1));
         if (tile + 1 < ntiles) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -400,14 +415,14 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
                 if (STORE_P && !(abl & 2)) {
                     uint32_t *tp = st_lane + ((size_t)(st_tile + (unsigned)mt * st_ngg) << 6);
                     tp[0] = pw[mt][0];
-                    tp[8] = pw[mt][1];
+                    tp[4] = pw[mt][1];
                 }
             }
             // the words of two row tiles at a time into this tile's P buffer: lanes 32 rb + 16 h + {g, g + 8}, columns 8 grp + {2q, 2q + 1}
             if (!(abl & 1))
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint32_t addr = t0 + ((uint32_t)(rb * 32 + h * 16) << 16) + (uint32_t)(R::COL_A + st * TJ + grp * 8);
+                const uint32_t addr = t0 + ((uint32_t)(rb * 32 + h * 16) << 16) + (uint32_t)(R::COL_A + sp * TJ + grp * 8);
                 asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};"
                              ::"r"(addr), "r"(pw[2 * h][0]), "r"(pw[2 * h][1]), "r"(pw[2 * h + 1][0]), "r"(pw[2 * h + 1][1]) : "memory");
             }
@@ -445,23 +460,23 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
                 if (tile + I8_STAGES_A - 1 < ntiles) issueA(tile + I8_STAGES_A - 1);
                 // part B of the tile after next goes where the MMAs of the tile before this one read theirs
                 if (tile + I8_STAGES - 1 < ntiles) {
-                    if (tile >= 1) mbar_wait(&bar_mma[(tile - 1) % I8_STAGES], (unsigned)((((tile - 1) / I8_STAGES) & 1)));
+                    if (tile >= 1) mbar_wait(&bar_mma[(tile - 1) % R::PST], (unsigned)((((tile - 1) / R::PST) & 1)));
                     issueB(tile + I8_STAGES - 1);
                 }
                 mbar_wait(&bar_fullB[st], ph);
                 const bool fresh = (tile % I8_FLUSH) == 0;           // the accumulators were read out (or never written): overwrite
                 const uint32_t bbase = smem_u32(s_bufB + st * BUFB);
                 for (int grp = 0; grp < ng_valid && !(abl & 64); ++grp)     // one MMA per 8-gene group: M = 128 cells, N = NTOT, K = 32 bytes
-                    i8_mma_ts(t0 + R::COL_ACC, t0 + (uint32_t)(R::COL_A + st * TJ + grp * 8),
+                    i8_mma_ts(t0 + R::COL_ACC, t0 + (uint32_t)(R::COL_A + sp * TJ + grp * 8),
                               i8_desc(bbase + (uint32_t)(grp * R::B8), (NTOT / 8) * 128, 128), idesc, !(fresh && grp == 0));
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma[st])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma[sp])) : "memory");
             }
             __syncwarp();
         }
         if (tile + 1 == ntiles || (tile + 1) % I8_FLUSH == 0) {
             // read the accumulators out before they can overflow (and at the end): every MMA up to this tile must have landed;
             // the MMAs of the next tile are issued only after every warp has counted itself in there, i.e. after its read-out
-            mbar_wait(&bar_mma[st], ph);
+            mbar_wait(&bar_mma[sp], php);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             flush();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -481,6 +496,139 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(R::TMEM_COLS));
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Gene-side pass on the STORED prob_D (pass B, zi_gap_factor_model.cpp:341: tmpMat = prob_D^T EU_new) as the same exact integer
+// product -- and with nothing but the tensor core and the copy engine on the data path:
+//   * the cell-side pass keeps its P words in 8 x 8 tiles laid out as the MMA's shared-memory operand wants them: two core
+//     matrices of [8 genes][4 cells x 4 digit bytes] (word (gene, cell) at (cell >> 2) 32 + gene 4 + (cell & 3)), tile index =
+//     cell group x gene groups + gene group.  The 48 gene groups of a CTA are 12 KB contiguous per cell group: ONE bulk copy
+//     brings them from HBM into the A operand of three M = 128 MMAs (K = 32 bytes = 8 cells; SBO = 256 B, LBO = 128 B);
+//   * EU_new is cut into digits per cell group exactly like EVS per gene group (k_zi_pack_i8 on the n x KP matrix): 4 KB per
+//     8 cells, shared by the three MMAs and, through L2, by the gene blocks of the same cell chunk (adjacent in the grid);
+//   * a CTA owns 384 genes x <= 8192 cells, so its accumulators (3 x NTOT columns of tensor memory) cannot overflow and are read
+//     out once, scaled and added to tmpMat in FP64.
+// One producer thread (bulk copies), one MMA thread, 3 stages of 32 cells; the pass is bound by the HBM stream of P (4 B / entry).
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int I8B_GB = 3;              // 128-gene sub-blocks per CTA (accumulators in tensor memory: GB x NTOT <= 512 columns)
+constexpr int I8B_CG = 4;              // cell groups (of 8) per stage
+constexpr int I8B_STAGES = 3;
+constexpr int I8B_MAXCELLS = 8192;     // cells per CTA: 4 digit pairs x 255^2 x 8192 < 2^31
+
+template <int KP>
+struct ZiGenesI8 {
+    using R = ZiRecI8<KP>;
+    static constexpr int A_CG = I8B_GB * 16 * 256;                         // bytes of P per cell group: 48 gene groups x 256 B
+    static constexpr int B_CG = R::B8;                                     // bytes of EU digits per cell group
+    static constexpr int STAGE = I8B_CG * (A_CG + B_CG);
+    static constexpr size_t SMEM = (size_t)I8B_STAGES * STAGE;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(I8B_GB * R::NTOT <= TMEM_COLS, "tensor-memory budget");
+};
+
+template <int KP>
+__global__ void __launch_bounds__(128, 1) k_zi_genes_i8(ZiBArgs a) {
+    using R = ZiRecI8<KP>;
+    using G = ZiGenesI8<KP>;
+    constexpr int NFS = R::NFS, NTOT = R::NTOT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[I8B_STAGES], bar_empty[I8B_STAGES], bar_done;
+    __shared__ double s_cf[KP];
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, w = tid >> 5;
+    const int64_t ngroups_c = (a.n + 7) >> 3;                           // cell groups: records of the packed EU_new
+    const int ngg = (a.p + 7) >> 3;
+    const int gg0 = (int)blockIdx.x * (I8B_GB * 16), ngg_blk = min(I8B_GB * 16, ngg - gg0);
+    const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_chunk, r1 = min(a.n, r0 + a.rows_per_chunk);     // rows_per_chunk: multiple of 32
+    const int64_t cg0 = r0 >> 3, cg1 = (r1 + 7) >> 3;
+    const int nst = (int)((cg1 - cg0 + I8B_CG - 1) / I8B_CG);
+    if (tid < KP) s_cf[tid] = a.pack[R::off_tail(ngroups_c, false) + 64 + tid];
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < I8B_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_done, 1);
+        mbar_fence_init();
+    }
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(G::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t t0 = tmem_base;
+    const unsigned char *packB = reinterpret_cast<const unsigned char *>(a.pack + R::off_b(ngroups_c, false));
+    if (tid == 0) {
+        // producer: per stage, the P tiles of up to I8B_CG cell groups (one bulk copy each) and their EU digit records (one copy)
+        for (int s = 0; s < nst; ++s) {
+            const int st = s % I8B_STAGES;
+            if (s >= I8B_STAGES) mbar_wait(&bar_empty[st], (unsigned)(((s / I8B_STAGES) - 1) & 1));
+            const int64_t c0 = cg0 + (int64_t)s * I8B_CG;
+            const int nc = (int)min((int64_t)I8B_CG, cg1 - c0);
+            unsigned char *sA = smem_raw + (size_t)st * G::STAGE, *sB = sA + I8B_CG * G::A_CG;
+            mbar_expect_tx(&bar_full[st], (unsigned)(nc * (ngg_blk * 256 + G::B_CG)));
+            for (int c = 0; c < nc; ++c)
+                bulk_g2s(sA + c * G::A_CG, a.pstore + (((c0 + c) * ngg + gg0) << 6), (unsigned)(ngg_blk * 256), &bar_full[st]);
+            bulk_g2s(sB, packB + c0 * G::B_CG, (unsigned)(nc * G::B_CG), &bar_full[st]);
+        }
+    } else if (tid == 32) {
+        // MMA thread: per cell group one MMA per 128-gene sub-block (M = 128 genes, N = NTOT, K = 32 bytes = 8 cells)
+        const uint32_t idesc = i8_idesc(128, NTOT);
+        for (int s = 0; s < nst; ++s) {
+            const int st = s % I8B_STAGES;
+            mbar_wait(&bar_full[st], (unsigned)((s / I8B_STAGES) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t c0 = cg0 + (int64_t)s * I8B_CG;
+            const int nc = (int)min((int64_t)I8B_CG, cg1 - c0);
+            const uint32_t sA = smem_u32(smem_raw + (size_t)st * G::STAGE), sB = sA + I8B_CG * G::A_CG;
+            for (int c = 0; c < nc; ++c)
+#pragma unroll
+                for (int b = 0; b < I8B_GB; ++b)
+                    if (b * 16 < ngg_blk)
+                        i8_mma_ss(t0 + b * NTOT, i8_desc(sA + c * G::A_CG + b * 4096, 128, 256), i8_desc(sB + c * G::B_CG, (NTOT / 8) * 128, 128),
+                                  idesc, (s > 0) || (c > 0));
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[st])) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_done)) : "memory");
+    }
+    __syncwarp();
+    // epilogue: thread = TMEM lane = gene of each sub-block; digit weights recombined in FP64 (exact), scaled, added to tmpMat
+    if (nst > 0) {
+        mbar_wait(&bar_done, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t lane_addr = t0 + ((uint32_t)(w * 32) << 16);
+#pragma unroll
+        for (int b = 0; b < I8B_GB; ++b) {
+            if (b * 16 >= ngg_blk) break;                              // (uniform over the CTA)
+            const int j = gg0 * 8 + b * 128 + tid;
+#pragma unroll
+            for (int cb = 0; cb < NFS; cb += 8) {
+                uint32_t v[R::ND][8];
+#pragma unroll
+                for (int di = 0; di < R::ND; ++di)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(v[di][0]), "=r"(v[di][1]), "=r"(v[di][2]), "=r"(v[di][3]), "=r"(v[di][4]), "=r"(v[di][5]), "=r"(v[di][6]), "=r"(v[di][7])
+                                 : "r"(lane_addr + (uint32_t)(b * NTOT + di * NFS + cb)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (j < a.p) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int k = cb + c;
+                        if (k < a.K) {
+                            double x = (double)(int32_t)v[0][c];
+#pragma unroll
+                            for (int di = 1; di < R::ND; ++di) x = fma(x, 256.0, (double)(int32_t)v[di][c]);
+                            atomicAdd(a.tmpMat + (int64_t)j * KP + k, x * s_cf[k]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(G::TMEM_COLS));
 }
 
 }  // namespace pcmf
