@@ -181,12 +181,14 @@ int launch_zi_genes_i8(ZiBArgs a, cudaStream_t st) {
     int64_t rpc = (a.n + chunks - 1) / chunks; rpc = (rpc + 31) / 32 * 32;
     chunks = (a.n + rpc - 1) / rpc;
     a.rows_per_chunk = rpc;
-    const int gx = (a.p + I8B_GB * 128 - 1) / (I8B_GB * 128);
+    const int gx = (a.p + G::GB * 128 - 1) / (G::GB * 128);
     k_zi_genes_i8<KP><<<dim3((unsigned)gx, (unsigned)chunks), 128, G::SMEM, st>>>(a);
     return 3;
 }
 int launch_zi_cells_i8(const ZiAArgs &a, cudaStream_t st) {
-    static const int nw = getenv("PCMF_I8_NW") ? atoi(getenv("PCMF_I8_NW")) : 8;
+    // (one warp per 32-cell row block: 8 warps per SM with ~190 registers each interleave the eight expit chains of a tile
+    //  group; two warps per row block at 128 registers measured 3.5 ms slower at C4.  PCMF_I8_NW=8 selects the latter.)
+    static const int nw = getenv("PCMF_I8_NW") ? atoi(getenv("PCMF_I8_NW")) : 4;
     return nw == 4 ? launch_zi_cells_i8_t<4>(a, st) : launch_zi_cells_i8_t<8>(a, st);
 }
 #endif

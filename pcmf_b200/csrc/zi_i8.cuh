@@ -39,15 +39,15 @@ constexpr int I8_STAGES_A = 4;         // tile buffers of the first-product reco
 // separate rings of shared-memory buffers: A is needed when a tile starts, B when it ends.
 template <int KP>
 struct ZiRecI8 {
-    static_assert(KP <= 32, "the integer second product holds 5 x 32 accumulator columns and 3 x 32 of P in 256 TMEM columns");
+    static_assert(KP <= 32, "the integer second product holds 6 x 32 accumulator columns and 2 x 32 of P in 256 TMEM columns");
     static constexpr int KS = KP / 4;
     static constexpr int NFS = (KP + 7) / 8 * 8;                          // accumulator columns per digit weight
-    static constexpr int ND = (KP <= 24) ? 6 : 5;                         // digits of the streamed factor matrix = digit weights kept: d = 3 .. 4 - ND
+    static constexpr int ND = 6;                                          // digits of the streamed factor matrix = digit weights kept: d = 3 .. 4 - ND
     static constexpr int NTOT = (ND * NFS + 15) / 16 * 16;                // N of the one MMA per 8-gene group: the ND operands stacked
     static constexpr int F1 = KS * 32, CZ = 24, RA = F1 + CZ;             // doubles per group, part A
     static constexpr int B8 = NTOT * 32;                                  // bytes per group, part B: [NTOT rows][32 bytes], K-major canonical
     static constexpr int COL_ACC = 0, COL_A = NTOT, TMEM_COLS = 256;
-    static constexpr int PST = 3;                                         // P buffers in tensor memory (tiles in flight towards the MMAs)
+    static constexpr int PST = (TMEM_COLS - NTOT) / I8_TJ >= 3 ? 3 : 2;   // P buffers in tensor memory (tiles in flight towards the MMAs)
     static_assert(COL_A + PST * I8_TJ <= TMEM_COLS, "tensor-memory budget");
     static constexpr size_t SMEM = (size_t)(I8_TJ / 8) * (I8_STAGES_A * RA * 8 + I8_STAGES * B8) + sizeof(double) * (I8_STAGES * 4 * I8_TJ + kTabDoubles);
     // (the cell-side packing of EU_new for k_zi_genes_i8 has no part A)
@@ -183,7 +183,7 @@ __device__ __forceinline__ double fast_exp_neg_tab_a(double z, uint32_t tab_addr
     const double sc = __hiloint2double(__double2hiint(tb) + (int)((unsigned)m << 14), __double2loint(tb));
     return p * sc;
 }
-__device__ __forceinline__ double expit_sym(double z, uint32_t tab_addr, double &y, double &za_tr) {
+__device__ __forceinline__ double expit_sym(double z, uint32_t tab_addr, double &y, double &ent) {
     const int hi = __double2hiint(z);
     const int ah = min(hi & 0x7fffffff, 0x40440000);
     const double za = __hiloint2double(ah, __double2loint(z));
@@ -191,7 +191,7 @@ __device__ __forceinline__ double expit_sym(double z, uint32_t tab_addr, double 
     y = 1.0 + t;
     const double r = fast_rcp2(y);
     const double tr = t * r;
-    za_tr = za * tr;
+    ent = fma(-za, tr, ent);          // the caller's running -sum za t r
     return hi >= 0 ? r : tr;
 }
 
@@ -260,8 +260,10 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     const unsigned st_ngg = (unsigned)((a.p + 7) >> 3);
     const unsigned st_tile0 = (unsigned)(cell0 >> 3) * st_ngg;
     // stored prob_D: tile (cell group, gene group) as two core matrices [cell >> 2][gene][cell & 3] -- the A operand of k_zi_genes_i8
-    uint32_t *const st_lane = STORE_P ? a.pstore + (g >> 2) * 32 + (2 * q) * 4 + (g & 3) : nullptr;
-    double ent_lin = 0, ent_log = 0, prod = 1.0;
+    // (lanes g and g ^ 1 swap one word each, so that a lane holds one gene for two adjacent cells: one 8-byte store per row tile,
+    //  a warp's store = the whole 256-byte tile)
+    uint32_t *const st_lane = STORE_P ? a.pstore + (g >> 2) * 32 + (2 * q + (g & 1)) * 4 + (g & 2) : nullptr;
+    double ent_lin = 0, ent_lin2 = 0, ent_log = 0, prod = 1.0;
     double ll_lin = 0, ll_log = 0, ll_prod = 1.0;
 
     const int ntiles_all = (ngroups + NG - 1) / NG;
@@ -403,9 +405,8 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
                     ent_lin = fma(g1 ? (p1 - 1.0) : 0.0, z1, ent_lin);
                     prod *= (g0 ? y0 : 1.0) * (g1 ? y1 : 1.0);
                 } else {
-                    double y0, y1, h0, h1;
-                    p0 = expit_sym(z0, tab_addr, y0, h0); p1 = expit_sym(z1, tab_addr, y1, h1);
-                    ent_lin -= h0 + h1;
+                    double y0, y1;
+                    p0 = expit_sym(z0, tab_addr, y0, ent_lin); p1 = expit_sym(z1, tab_addr, y1, ent_lin2);
                     prod *= y0 * y1;
                 }
                 cs0 += p0; cs1 += p1;
@@ -414,8 +415,9 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
                 pw[mt][1] = (uint32_t)__double2loint(fma(p1, PCMF_PSTORE_SCALE, 4503599627370496.0));
                 if (STORE_P && !(abl & 2)) {
                     uint32_t *tp = st_lane + ((size_t)(st_tile + (unsigned)mt * st_ngg) << 6);
-                    tp[0] = pw[mt][0];
-                    tp[4] = pw[mt][1];
+                    const bool odd = g & 1;
+                    const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? pw[mt][0] : pw[mt][1], 4);
+                    *reinterpret_cast<uint2 *>(tp) = odd ? make_uint2(got, pw[mt][1]) : make_uint2(pw[mt][0], got);
                 }
             }
             // the words of two row tiles at a time into this tile's P buffer: lanes 32 rb + 16 h + {g, g + 8}, columns 8 grp + {2q, 2q + 1}
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
     if (ntiles == 0 && gridDim.y == 1 && gh == 0 && my_cell < a.n)
         for (int k = 0; k < KP; ++k) a.PV[my_cell * KP + k] = 0.0;
     const double sum_log_y = ent_log + log(prod);
-    double ent = ent_lin - sum_log_y;
+    double ent = (ent_lin + ent_lin2) - sum_log_y;
     sum_pl = block_sum(sum_pl, sh); ent = block_sum(ent, sh);
     if (threadIdx.x == 0) { atomicAdd(a.zsc + 0, sum_pl); atomicAdd(a.zsc + 1, ent); }
     if (WITH_LL) {
@@ -511,7 +513,6 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
 //     out once, scaled and added to tmpMat in FP64.
 // One producer thread (bulk copies), one MMA thread, 3 stages of 32 cells; the pass is bound by the HBM stream of P (4 B / entry).
 // ------------------------------------------------------------------------------------------------------------------------------
-constexpr int I8B_GB = 3;              // 128-gene sub-blocks per CTA (accumulators in tensor memory: GB x NTOT <= 512 columns)
 constexpr int I8B_CG = 4;              // cell groups (of 8) per stage
 constexpr int I8B_STAGES = 3;
 constexpr int I8B_MAXCELLS = 8192;     // cells per CTA: 4 digit pairs x 255^2 x 8192 < 2^31
@@ -519,19 +520,20 @@ constexpr int I8B_MAXCELLS = 8192;     // cells per CTA: 4 digit pairs x 255^2 x
 template <int KP>
 struct ZiGenesI8 {
     using R = ZiRecI8<KP>;
-    static constexpr int A_CG = I8B_GB * 16 * 256;                         // bytes of P per cell group: 48 gene groups x 256 B
+    static constexpr int GB = 512 / R::NTOT >= 3 ? 3 : 2;                  // 128-gene sub-blocks per CTA (accumulators: GB x NTOT <= 512 columns)
+    static constexpr int A_CG = GB * 16 * 256;                             // bytes of P per cell group: 16 GB gene groups x 256 B
     static constexpr int B_CG = R::B8;                                     // bytes of EU digits per cell group
     static constexpr int STAGE = I8B_CG * (A_CG + B_CG);
     static constexpr size_t SMEM = (size_t)I8B_STAGES * STAGE;
     static constexpr int TMEM_COLS = 512;
-    static_assert(I8B_GB * R::NTOT <= TMEM_COLS, "tensor-memory budget");
+    static_assert(GB * R::NTOT <= TMEM_COLS, "tensor-memory budget");
 };
 
 template <int KP>
 __global__ void __launch_bounds__(128, 1) k_zi_genes_i8(ZiBArgs a) {
     using R = ZiRecI8<KP>;
     using G = ZiGenesI8<KP>;
-    constexpr int NFS = R::NFS, NTOT = R::NTOT;
+    constexpr int NFS = R::NFS, NTOT = R::NTOT, I8B_GB = G::GB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[I8B_STAGES], bar_empty[I8B_STAGES], bar_done;
     __shared__ double s_cf[KP];
