@@ -15,7 +15,7 @@ def main(path, out, steps):
     names = [r["Kernel Name"] for r in rows]
     t = [float(r["Metric Value"]) for r in rows]
     # the timed region starts after the zero-inflation cell pass of the last warm-up step
-    idx = [i for i, n in enumerate(names) if "k_zi_cells_mma" in n]
+    idx = [i for i, n in enumerate(names) if "k_zi_cells_mma" in n or "k_zi_cells_i8" in n]
     start = idx[-(steps + 1)] + 1
     # and ends before the roofline micro-benchmarks bench.py runs afterwards
     stop = next((i for i in range(start, len(names)) if "k_gather_peak" in names[i] or "k_fill_idx" in names[i]), len(names))
