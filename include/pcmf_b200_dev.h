@@ -24,7 +24,8 @@ extern "C" {
 #define PCMF_DEV_TINY_CELL_BLOCKS 1024 /* 64-cell blocks */
 #define PCMF_DEV_FORCE_TILES 2048   /* tiled non-zero passes whatever the size */
 #define PCMF_DEV_NO_TILES 4096      /* CSR / CSC non-zero passes whatever the size */
-#define PCMF_DEV_ZI_ALL_DMMA 8192   /* cell-side ZI pass with both products on the FP64 tensor path (no integer tcgen05 product) */
+#define PCMF_DEV_ZI_ALL_DMMA 8192   /* dense ZI passes with both products on the FP64 tensor path (no integer tcgen05 product) */
+#define PCMF_DEV_ORDER_EXACT 16384   /* factor ordering with FP64 logarithms in every round (no FP32 pass with error bounds first) */
 
 /* per-phase device timings of the last pcmf_iterate/pcmf_optimize call, milliseconds summed over iterations:
  * names[i] points to a static string; returns the number of phases written (<= cap) */

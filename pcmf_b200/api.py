@@ -494,10 +494,10 @@ class Solver:
         return {"loglikelihood": a.value, "deviance": b.value, "exp_dev": c.value}
 
     def phase_times(self):
-        names = (C.c_char_p * 16)()
-        ms = np.zeros(16)
-        ln = np.zeros(16, np.int64)
-        c = self.L.pcmf_phase_times(self.h, names, ms.ctypes.data_as(_lib.dp), ln.ctypes.data_as(_lib.lp), 16)
+        names = (C.c_char_p * 24)()
+        ms = np.zeros(24)
+        ln = np.zeros(24, np.int64)
+        c = self.L.pcmf_phase_times(self.h, names, ms.ctypes.data_as(_lib.dp), ln.ctypes.data_as(_lib.lp), 24)
         return {names[i].decode(): (float(ms[i]), int(ln[i])) for i in range(c)}
 
     def launch_count(self):

@@ -1241,17 +1241,25 @@ struct OrderArgs {
     const double *EU, *EVS; const int32_t *flag;
     const double *chosen;    // KP doubles: 1 when the factor is already chosen
     double *out;             // KP doubles (atomic)
+    double *bound;           // FAST only: KP doubles (atomic), sum x (|log| + 1) per candidate -> error bound of out
 };
-template <int KP, typename VT>
+// FAST: the K (K + 1) / 2 logarithms per non-zero of the greedy ordering in FP32 (lg2.approx) with a rigorous error bound next
+// to every score: argument rounded three times (<= 1.8e-7 relative, all terms >= 0), __logf <= 2^-21.4 absolute near 1 and
+// 3 ulp elsewhere, so |l_fp32 - l| <= 5.4e-7 (|l| + 1) and |out_k - exact| <= 5.4e-7 bound_k.  The host accepts a round's
+// winner only when its score beats every other candidate's by more than the two bounds (with a factor 2 to spare) and
+// otherwise repeats the round with the FP64 kernel, so the order is the reference's either way.
+template <int KP, typename VT, bool FAST>
 __global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
     __shared__ double sacc[KP];
+    __shared__ double sbnd[KP];
     __shared__ double sch[KP];
     const VT *__restrict__ val = static_cast<const VT *>(a.val);
-    if (threadIdx.x < KP) { sacc[threadIdx.x] = 0.0; sch[threadIdx.x] = threadIdx.x < a.K ? a.chosen[threadIdx.x] : 1.0; }
+    if (threadIdx.x < KP) { sacc[threadIdx.x] = 0.0; sbnd[threadIdx.x] = 0.0; sch[threadIdx.x] = threadIdx.x < a.K ? a.chosen[threadIdx.x] : 1.0; }
     __syncthreads();
     double acc[KP];
+    float accb[FAST ? KP : 1];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+    for (int k = 0; k < KP; ++k) { acc[k] = 0.0; if (FAST) accb[k] = 0.f; }
     for (int j = blockIdx.x; j < a.p; j += gridDim.x) {
         if (a.flag && a.flag[j] == 2) continue;     // rate 0 on the whole gene: clog(0) = 0
         double v[KP];
@@ -1265,9 +1273,29 @@ __global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
             double base = 0.0;
 #pragma unroll
             for (int k = 0; k < KP; ++k) { u[k] *= v[k]; base = fma(u[k], sch[k], base); }
+            if (FAST) {
+                const float bf = (float)base, xf = (float)x;
 #pragma unroll
-            for (int k = 0; k < KP; ++k)
-                if (sch[k] == 0.0) acc[k] = fma(x, custom_log(base + u[k]), acc[k]);
+                for (int k = 0; k < KP; ++k)
+                    if (sch[k] == 0.0) {
+                        const float arg = bf + (float)u[k];
+                        const float l = arg > 0.f ? __logf(arg) : 0.f;
+                        acc[k] = fma(x, (double)l, acc[k]);
+                        accb[k] = fmaf(xf, fabsf(l) + 1.f, accb[k]);
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (sch[k] == 0.0) acc[k] = fma(x, custom_log(base + u[k]), acc[k]);
+            }
+        }
+        if (FAST) {     // the FP32 bound sums are moved to FP64 once per gene (a gene's share of a thread is a few hundred entries)
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const double t = warp_sum((double)accb[k]);
+                if ((threadIdx.x & 31) == 0 && t != 0.0) atomicAdd(&sbnd[k], t);
+                accb[k] = 0.f;
+            }
         }
     }
 #pragma unroll
@@ -1277,6 +1305,7 @@ __global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
     }
     __syncthreads();
     if (threadIdx.x < a.K && sacc[threadIdx.x] != 0.0) atomicAdd(a.out + threadIdx.x, sacc[threadIdx.x]);
+    if (FAST && threadIdx.x < a.K && sbnd[threadIdx.x] != 0.0) atomicAdd(a.bound + threadIdx.x, sbnd[threadIdx.x]);
 }
 
 #ifdef PCMF_COMMON_KERNELS

@@ -226,8 +226,13 @@ void launch_gene_loglam(bool f32, const LamArgs &a, int grid, cudaStream_t st) {
     else k_gene_loglam<KP, double><<<grid, 128, 0, st>>>(a);
 }
 void launch_gene_order(bool f32, const OrderArgs &a, int grid, cudaStream_t st) {
-    if (f32) k_gene_order<KP, float><<<grid, 128, 0, st>>>(a);
-    else k_gene_order<KP, double><<<grid, 128, 0, st>>>(a);
+    if (a.bound) {       // FP32 logarithms with an error bound per score (the host falls back to the exact kernel on a close call)
+        if (f32) k_gene_order<KP, float, true><<<grid, 128, 0, st>>>(a);
+        else k_gene_order<KP, double, true><<<grid, 128, 0, st>>>(a);
+        return;
+    }
+    if (f32) k_gene_order<KP, float, false><<<grid, 128, 0, st>>>(a);
+    else k_gene_order<KP, double, false><<<grid, 128, 0, st>>>(a);
 }
 size_t zi_pack_doubles(int64_t rows, int cells_side) {
     const int64_t groups = (rows + 7) / 8;

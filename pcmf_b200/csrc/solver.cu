@@ -325,6 +325,7 @@ struct pcmf_solver {
 
     // instrumentation
     int64_t launches = 0;
+    int64_t order_exact_rounds = 0;     // rounds of the greedy factor ordering that were repeated with FP64 logarithms
     double ph_ms[PH_COUNT] = {0};
     int64_t ph_launch[PH_COUNT] = {0};
     cudaEvent_t ev_a[PH_COUNT] = {nullptr}, ev_b[PH_COUNT] = {nullptr};
@@ -936,7 +937,7 @@ void pcmf_solver::alloc_state() {
     allmasked = dmalloc<uint8_t>(p); CK(cudaMemsetAsync(allmasked, 0, p, stream));
     unchanged = dmalloc<uint8_t>(p); CK(cudaMemsetAsync(unchanged, 0, p, stream));
     if (opt.world > 1) ar2keep = dmalloc<double>(2 * (size_t)p * KP);
-    mon = dmalloc<double>(8 + 64 + 64); d_order = dmalloc<int32_t>(64);
+    mon = dmalloc<double>(8 + 64 * 3); d_order = dmalloc<int32_t>(64);
     dbg = dmalloc<unsigned long long>(4); CK(cudaMemsetAsync(dbg, 0, 32, stream));
     k_init_guard<<<1, 32, 0, stream>>>(guard[0]); k_init_guard<<<1, 32, 0, stream>>>(guard[1]);
     // kernel_variant bit 64 forces the stored-prob_D path (small test problems), bit 128 disables it
@@ -1521,24 +1522,45 @@ void pcmf_solver::order_factor_now() {
     launches += zi ? 1 : 0;
     std::vector<int> left, chosen;
     for (int k = 0; k < K; ++k) left.push_back(k);
-    std::vector<double> mask(64, 0.0), out(64);
+    std::vector<double> mask(64, 0.0), out(128);
     double base_total = 0;
+    // scratch: mon + 8: scores (64) | mon + 72: error bounds of the FP32 pass (64) | mon + 136: chosen mask (64)
+    const bool try_fast = !(opt.dev_flags & 16384);
     for (int k = 0; k < K; ++k) {
-        CK(cudaMemsetAsync(mon + 8, 0, 64 * sizeof(double), stream));
-        CK(cudaMemcpyAsync(mon + 72, mask.data(), 64 * sizeof(double), cudaMemcpyHostToDevice, stream));
-        OrderArgs oa{p, K, colptr, rowidx, val_csc, EU[cur], EVS, zi ? flag : nullptr, mon + 72, mon + 8};
-        L->gene_order(f32, oa, std::min<int>(p, sms * 32), stream);
-        launches += 1;
-        allreduce(mon + 8, K);
-        CK(cudaMemcpyAsync(out.data(), mon + 8, sizeof(double) * K, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
+        CK(cudaMemcpyAsync(mon + 136, mask.data(), 64 * sizeof(double), cudaMemcpyHostToDevice, stream));
         double val_min = -1; int ind_min = 0; size_t ind_left = 0;
-        for (size_t ind = 0; ind < left.size(); ++ind) {
-            const int c = left[ind];
-            const double r1 = out[c] - (base_total + tk[c]) - lgx_const;
-            const double res = -2.0 * (r1 - ll_XX);
-            if (ind == 0) { val_min = res; ind_min = c; ind_left = ind; }          // model.cpp:161-165
-            if (res < val_min) { val_min = res; ind_min = c; ind_left = ind; }     // model.cpp:168-172
+        // fast = 1: logarithms in FP32 with a rigorous bound; the winner must clear every other candidate by both bounds, or the
+        // round is repeated exactly (fast = 0) -- a single candidate needs no pass at all to be chosen, but keeps the exact path
+        if (left.size() == 1 && try_fast) {       // nothing to compare the last factor with (model.cpp:161-165 picks it whatever its value)
+            ind_min = left[0]; ind_left = 0;
+            chosen.push_back(ind_min);
+            left.erase(left.begin());
+            mask[ind_min] = 1.0; base_total += tk[ind_min];
+            continue;
+        }
+        for (int fast = try_fast ? 1 : 0; fast >= 0; --fast) {
+            CK(cudaMemsetAsync(mon + 8, 0, 128 * sizeof(double), stream));
+            OrderArgs oa{p, K, colptr, rowidx, val_csc, EU[cur], EVS, zi ? flag : nullptr, mon + 136, mon + 8, fast ? mon + 72 : nullptr};
+            L->gene_order(f32, oa, std::min<int>(p, sms * 32), stream);
+            launches += 1;
+            allreduce(mon + 8, 64 + K);
+            CK(cudaMemcpyAsync(out.data(), mon + 8, sizeof(double) * (64 + K), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            std::vector<double> res(left.size());
+            for (size_t ind = 0; ind < left.size(); ++ind) {
+                const int c = left[ind];
+                const double r1 = out[c] - (base_total + tk[c]) - lgx_const;
+                res[ind] = -2.0 * (r1 - ll_XX);
+                if (ind == 0) { val_min = res[ind]; ind_min = c; ind_left = ind; }          // model.cpp:161-165
+                if (res[ind] < val_min) { val_min = res[ind]; ind_min = c; ind_left = ind; }     // model.cpp:168-172
+            }
+            if (!fast) break;
+            // |out_c - exact| <= 5.4e-7 bound_c (k_gene_order<FAST>), res = -2 out + ...: clear margin = 2 x 2 x 5.4e-7 (bound_b + bound_c)
+            bool clear = std::isfinite(val_min);
+            for (size_t ind = 0; ind < left.size() && clear; ++ind)
+                if (ind != ind_left) clear = res[ind] - val_min > 2.2e-6 * (out[64 + left[ind]] + out[64 + ind_min]);
+            if (clear) break;
+            order_exact_rounds += 1;
         }
         chosen.push_back(ind_min);
         left.erase(left.begin() + ind_left);
@@ -2022,6 +2044,13 @@ int pcmf_phase_times(pcmf_solver *s, const char **names, double *ms, int64_t *la
         if (names) names[c] = "stored_prob_D_bytes";
         if (ms) ms[c] = 0.0;
         if (launches) launches[c] = s->pstore ? (int64_t)((s->n + 127) / 128 * 16) * (int64_t)((s->p + 7) / 8) * 256 : 0;
+        ++c;
+    }
+    // rounds of the factor ordering the FP32 pass could not decide (repeated exactly)
+    if (c < cap) {
+        if (names) names[c] = "order_factor_exact_rounds";
+        if (ms) ms[c] = 0.0;
+        if (launches) launches[c] = s->order_exact_rounds;
         ++c;
     }
     // cell blocks the gene passes walk (1: whole genes in one go)

@@ -24,5 +24,5 @@ m = s.monitors()
 torch.cuda.synchronize(); t3 = time.perf_counter()
 print("monitors: %.3f s" % (t3 - t2), m)
 o = s.get_output(want_prob_D=False)
-print("factor order", list(o["factor_order"]))
+print("factor order", list(o["factor_order"]), "exact rounds", s.phase_times().get("order_factor_exact_rounds"))
 s.close(); csr.free()

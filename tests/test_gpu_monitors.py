@@ -287,3 +287,51 @@ def test_loglikelihood_fused_into_the_cell_pass(sparse):
     alone = s.monitors()["loglikelihood"]
     s.close()
     assert abs(alone - res["monitor"]["loglikelihood"][-1]) < 1e-11 * abs(alone)
+
+
+@pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
+@pytest.mark.parametrize("K", [4, 20])
+def test_order_factor_fp32_pass_with_bounds_gives_the_exact_order(zi, sparse, K):
+    """The greedy ordering takes its K (K + 1) / 2 logarithms per non-zero in FP32 with an error bound per score and repeats a
+    round in FP64 only when the winner does not clear every other candidate by the bounds: same order as the all-FP64 ordering
+    (kernel_variant bit 16384) and as the oracle."""
+    X = problem(31 + K, 400, 150, K_true=5)
+    m, s = make_pair(X, K, zi, sparse)
+    _, sx = make_pair(X, K, zi, sparse, kernel_variant=16384)
+    for _ in range(4):
+        m.update_param()
+        m.prepare_next_iterate()
+    s.iterate(4)
+    sx.iterate(4)
+    m.order_factor()
+    s.order_factor()
+    sx.order_factor()
+    o, ox = s.get_output(), sx.get_output()
+    assert list(o["factor_order"]) == list(ox["factor_order"]) == list(m.get("factor_order"))
+    assert sx.phase_times()["order_factor_exact_rounds"][1] == 0          # (not counted when every round is exact anyway)
+    compare_state(m, s, zi, sparse, "after reorder (fp32 pass)")
+    s.close()
+    sx.close()
+
+
+def test_order_factor_tie_falls_back_to_the_exact_round():
+    """Two factors with identical initial values stay identical, so their scores tie exactly: the FP32 pass cannot decide, the
+    round is repeated in FP64 and the first of the two wins as in the reference (model.cpp:161-172)."""
+    X = problem(5, 200, 90, K_true=3)
+    K = 4
+    a1, a2, b1, b2 = datagen.random_init(X, K, seed=9)
+    for A in (a1, a2, b1, b2):
+        A[:, 3] = A[:, 1]
+    from oracle import pyoracle as po
+    m = po.Model(X, K, False, False)
+    m.init_variational_param(a1, a2, b1, b2)
+    s = pcmf_b200.Solver(X, K, False, False, a1=a1, a2=a2, b1=b1, b2=b2)
+    for _ in range(3):
+        m.update_param()
+        m.prepare_next_iterate()
+    s.iterate(3)
+    m.order_factor()
+    s.order_factor()
+    assert list(s.get_output()["factor_order"]) == list(m.get("factor_order"))
+    assert s.phase_times()["order_factor_exact_rounds"][1] >= 1
+    s.close()
