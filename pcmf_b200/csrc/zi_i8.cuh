@@ -442,16 +442,16 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
         if (!WITH_LL && prod > 1e200) { ent_log += log(prod); prod = 1.0; }     // (1 + t)^(16 GPW) <= 2^64 per tile
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __threadfence_block();
+        asm volatile("fence.acq_rel.cta;" ::: "memory");
         __syncwarp();
         // count this warp in; the last one of the CTA owns the tail of the tile
         int last = 0;
         if (lane == 0) last = atomicAdd(&s_cnt[st], 1) == NW - 1;
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
-            __threadfence_block();
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) { atomicExch(&s_cnt[st], 0); __threadfence_block(); }
+            if (lane == 0) { atomicExch(&s_cnt[st], 0); asm volatile("fence.acq_rel.cta;" ::: "memory"); }
             {   // column sums of the tile over the CTA's 128 cells: one atomic per gene
                 const int t = lane;
                 if (t < ng_valid * 8 && j0 + t < a.p)
