@@ -1242,12 +1242,14 @@ struct OrderArgs {
     const double *chosen;    // KP doubles: 1 when the factor is already chosen
     double *out;             // KP doubles (atomic)
     double *bound;           // FAST only: KP doubles (atomic), sum x (|log| + 1) per candidate -> error bound of out
+    const float *EUf, *EVSf; // FAST only: FP32 copies of EU / EVS (half the bytes of the per-round gather of the E[U] rows)
 };
-// FAST: the K (K + 1) / 2 logarithms per non-zero of the greedy ordering in FP32 (lg2.approx) with a rigorous error bound next
-// to every score: argument rounded three times (<= 1.8e-7 relative, all terms >= 0), __logf <= 2^-21.4 absolute near 1 and
-// 3 ulp elsewhere, so |l_fp32 - l| <= 5.4e-7 (|l| + 1) and |out_k - exact| <= 5.4e-7 bound_k.  The host accepts a round's
-// winner only when its score beats every other candidate's by more than the two bounds (with a factor 2 to spare) and
-// otherwise repeats the round with the FP64 kernel, so the order is the reference's either way.
+// FAST: the K (K + 1) / 2 logarithms per non-zero of the greedy ordering in FP32 (lg2.approx) on FP32 copies of EU and EVS, with
+// a rigorous error bound next to every score: a product u_k v_k carries three roundings (1.8e-7 relative), the sum over the
+// chosen factors is taken in FP64 and rounded once (2.4e-7), the argument base + u_k v_k once more (3e-7, all terms >= 0);
+// __logf <= 2^-21.4 absolute near 1 and 3 ulp elsewhere, so |l_fp32 - l| <= 6.6e-7 (|l| + 1) and |out_k - exact| <= 6.6e-7
+// bound_k.  The host accepts a round's winner only when its score beats every other candidate's by more than the two bounds
+// (with a factor 2 to spare) and otherwise repeats the round with the FP64 kernel, so the order is the reference's either way.
 template <int KP, typename VT, bool FAST>
 __global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
     __shared__ double sacc[KP];
@@ -1262,28 +1264,74 @@ __global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
     for (int k = 0; k < KP; ++k) { acc[k] = 0.0; if (FAST) accb[k] = 0.f; }
     for (int j = blockIdx.x; j < a.p; j += gridDim.x) {
         if (a.flag && a.flag[j] == 2) continue;     // rate 0 on the whole gene: clog(0) = 0
-        double v[KP];
-        load_vec<KP>(a.EVS + (int64_t)j * KP, v);
         const int64_t e0 = a.colptr[j], e1 = a.colptr[j + 1];
-        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-            const int64_t i = __ldg(a.rowidx + e);
-            const double x = (double)__ldg(val + e);
-            double u[KP];
-            load_vec<KP>(a.EU + i * KP, u);
-            double base = 0.0;
+        if (FAST) {
+            float vf[KP];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) { u[k] *= v[k]; base = fma(u[k], sch[k], base); }
-            if (FAST) {
+            for (int q4 = 0; q4 < KP / 4; ++q4) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(a.EVSf + (int64_t)j * KP) + q4);
+                vf[4 * q4] = t.x; vf[4 * q4 + 1] = t.y; vf[4 * q4 + 2] = t.z; vf[4 * q4 + 3] = t.w;
+            }
+            // the loop is a dependent chain index -> E[U] row -> arithmetic per entry and the kernel waits on it (ncu: 51 % long
+            // scoreboard at 12 warps per SM): the row of the next entry and the index of the one after are requested first
+            const int64_t step = blockDim.x;
+            int64_t e = e0 + threadIdx.x;
+            float4 ru[KP / 4];
+            double x = 0.0, x_nx = 0.0;
+            int64_t i_nx = 0;
+            if (e < e1) {
+                const int64_t i = __ldg(a.rowidx + e);
+                x = (double)__ldg(val + e);
+#pragma unroll
+                for (int q4 = 0; q4 < KP / 4; ++q4) ru[q4] = __ldg(reinterpret_cast<const float4 *>(a.EUf + i * KP) + q4);
+            }
+            if (e + step < e1) { i_nx = __ldg(a.rowidx + e + step); x_nx = (double)__ldg(val + e + step); }
+            for (; e < e1; e += step) {
+                float4 rn[KP / 4];
+                const bool more = e + step < e1;
+                if (more) {
+#pragma unroll
+                    for (int q4 = 0; q4 < KP / 4; ++q4) rn[q4] = __ldg(reinterpret_cast<const float4 *>(a.EUf + i_nx * KP) + q4);
+                }
+                int64_t i_nx2 = 0; double x_nx2 = 0.0;
+                if (e + 2 * step < e1) { i_nx2 = __ldg(a.rowidx + e + 2 * step); x_nx2 = (double)__ldg(val + e + 2 * step); }
+                float pf[KP];
+#pragma unroll
+                for (int q4 = 0; q4 < KP / 4; ++q4) {
+                    const float4 t = ru[q4];
+                    pf[4 * q4] = t.x * vf[4 * q4]; pf[4 * q4 + 1] = t.y * vf[4 * q4 + 1];
+                    pf[4 * q4 + 2] = t.z * vf[4 * q4 + 2]; pf[4 * q4 + 3] = t.w * vf[4 * q4 + 3];
+                }
+                double base = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (sch[k] != 0.0) base += (double)pf[k];      // (uniform branch; pads have pf = 0)
                 const float bf = (float)base, xf = (float)x;
 #pragma unroll
                 for (int k = 0; k < KP; ++k)
                     if (sch[k] == 0.0) {
-                        const float arg = bf + (float)u[k];
+                        const float arg = bf + pf[k];
                         const float l = arg > 0.f ? __logf(arg) : 0.f;
                         acc[k] = fma(x, (double)l, acc[k]);
                         accb[k] = fmaf(xf, fabsf(l) + 1.f, accb[k]);
                     }
-            } else {
+                if (more) {
+#pragma unroll
+                    for (int q4 = 0; q4 < KP / 4; ++q4) ru[q4] = rn[q4];
+                }
+                x = x_nx; i_nx = i_nx2; x_nx = x_nx2;
+            }
+        } else {
+            double v[KP];
+            load_vec<KP>(a.EVS + (int64_t)j * KP, v);
+            for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+                const int64_t i = __ldg(a.rowidx + e);
+                const double x = (double)__ldg(val + e);
+                double u[KP];
+                load_vec<KP>(a.EU + i * KP, u);
+                double base = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) { u[k] *= v[k]; base = fma(u[k], sch[k], base); }
 #pragma unroll
                 for (int k = 0; k < KP; ++k)
                     if (sch[k] == 0.0) acc[k] = fma(x, custom_log(base + u[k]), acc[k]);
@@ -1309,6 +1357,9 @@ __global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
 }
 
 #ifdef PCMF_COMMON_KERNELS
+__global__ void k_to_float(int64_t total, const double *__restrict__ src, float *__restrict__ dst) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) dst[o] = (float)src[o];
+}
 // likelihood::gamma_loglike(X, p1, p2) summed (likelihood.h:85-88): p1 log p2 + (p1 - 1) log X - p2 X - lgamma(p1)
 __global__ void k_gamma_loglike(int64_t rows, int K, int KP, const double *X, const double *p1, const double *p2, double *out) {
     __shared__ double sh[32];

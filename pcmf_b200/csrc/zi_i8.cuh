@@ -23,8 +23,13 @@
 #include "zi_mma.cuh"
 #include "zi_tc.cuh"
 
+#ifndef PCMF_I8_UNROLL
+#define PCMF_I8_UNROLL 1
+#endif
+
 namespace pcmf {
 
+constexpr int I8_UNROLL = PCMF_I8_UNROLL;   // 8-gene groups of a tile unrolled together in the cell-side pass
 constexpr int I8_TJ = 32;              // genes per shared-memory tile (one occupancy word per cell and tile)
 constexpr int I8_STAGES = 3;           // tile buffers in shared memory, and P buffers in tensor memory
 constexpr int I8_FLUSH = 128;          // tiles between two read-outs of the integer accumulators (4096 genes)
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) bits[mt] = s_bits[w][st][mt * 8 + g];
         const int ng_valid = min(NG, ngroups - tile_id(tile) * NG);
-#pragma unroll 1
+#pragma unroll (I8_UNROLL)
         for (int gi = 0; gi < GPW; ++gi) {
             const int grp = GPW * gh + gi;
             if (grp >= ng_valid) break;
