@@ -1251,10 +1251,11 @@ struct OrderArgs {
 // bound_k.  The host accepts a round's winner only when its score beats every other candidate's by more than the two bounds
 // (with a factor 2 to spare) and otherwise repeats the round with the FP64 kernel, so the order is the reference's either way.
 template <int KP, typename VT, bool FAST>
-__global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
+__global__ void __launch_bounds__(128, (FAST && KP <= 20) ? 3 : 1) k_gene_order(OrderArgs a) {
     __shared__ double sacc[KP];
     __shared__ double sbnd[KP];
     __shared__ double sch[KP];
+    __shared__ __align__(16) float s_vf[KP];
     const VT *__restrict__ val = static_cast<const VT *>(a.val);
     if (threadIdx.x < KP) { sacc[threadIdx.x] = 0.0; sbnd[threadIdx.x] = 0.0; sch[threadIdx.x] = threadIdx.x < a.K ? a.chosen[threadIdx.x] : 1.0; }
     __syncthreads();
@@ -1266,41 +1267,41 @@ __global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
         if (a.flag && a.flag[j] == 2) continue;     // rate 0 on the whole gene: clog(0) = 0
         const int64_t e0 = a.colptr[j], e1 = a.colptr[j + 1];
         if (FAST) {
-            float vf[KP];
-#pragma unroll
-            for (int q4 = 0; q4 < KP / 4; ++q4) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(a.EVSf + (int64_t)j * KP) + q4);
-                vf[4 * q4] = t.x; vf[4 * q4 + 1] = t.y; vf[4 * q4 + 2] = t.z; vf[4 * q4 + 3] = t.w;
-            }
+            // the gene's row in shared memory (registers are what limits the prefetch depth below)
+            __syncthreads();
+            if (threadIdx.x < KP) s_vf[threadIdx.x] = a.EVSf[(int64_t)j * KP + threadIdx.x];
+            __syncthreads();
             // the loop is a dependent chain index -> E[U] row -> arithmetic per entry and the kernel waits on it (ncu: 51 % long
-            // scoreboard at 12 warps per SM): the row of the next entry and the index of the one after are requested first
+            // scoreboard at 12 warps per SM): the rows of the next two entries and the index of the third are in flight
+            // (D rows per thread: 3 up to K = 20, 2 up to 32, 1 beyond -- the rows live in registers)
+            constexpr int D = KP <= 20 ? 3 : (KP <= 32 ? 2 : 1);
             const int64_t step = blockDim.x;
             int64_t e = e0 + threadIdx.x;
-            float4 ru[KP / 4];
-            double x = 0.0, x_nx = 0.0;
-            int64_t i_nx = 0;
-            if (e < e1) {
-                const int64_t i = __ldg(a.rowidx + e);
-                x = (double)__ldg(val + e);
+            float4 r[D][KP / 4];
+            double xs[D + 1];
+            int64_t i_far = 0;
 #pragma unroll
-                for (int q4 = 0; q4 < KP / 4; ++q4) ru[q4] = __ldg(reinterpret_cast<const float4 *>(a.EUf + i * KP) + q4);
-            }
-            if (e + step < e1) { i_nx = __ldg(a.rowidx + e + step); x_nx = (double)__ldg(val + e + step); }
+            for (int d = 0; d <= D; ++d) xs[d] = 0.0;
+            auto fetch_row = [&](int64_t i, float4 (&dst)[KP / 4]) {
+#pragma unroll
+                for (int q4 = 0; q4 < KP / 4; ++q4) dst[q4] = __ldg(reinterpret_cast<const float4 *>(a.EUf + i * KP) + q4);
+            };
+#pragma unroll
+            for (int d = 0; d < D - 1; ++d)
+                if (e + d * step < e1) { xs[d] = (double)__ldg(val + e + d * step); fetch_row(__ldg(a.rowidx + e + d * step), r[d]); }
+            if (e + (D - 1) * step < e1) { xs[D - 1] = (double)__ldg(val + e + (D - 1) * step); i_far = __ldg(a.rowidx + e + (D - 1) * step); }
             for (; e < e1; e += step) {
-                float4 rn[KP / 4];
-                const bool more = e + step < e1;
-                if (more) {
-#pragma unroll
-                    for (int q4 = 0; q4 < KP / 4; ++q4) rn[q4] = __ldg(reinterpret_cast<const float4 *>(a.EUf + i_nx * KP) + q4);
-                }
-                int64_t i_nx2 = 0; double x_nx2 = 0.0;
-                if (e + 2 * step < e1) { i_nx2 = __ldg(a.rowidx + e + 2 * step); x_nx2 = (double)__ldg(val + e + 2 * step); }
+                if (e + (D - 1) * step < e1) fetch_row(i_far, r[D - 1]);
+                if (e + D * step < e1) { i_far = __ldg(a.rowidx + e + D * step); xs[D] = (double)__ldg(val + e + D * step); }
+                float4 (&r0)[KP / 4] = r[0];
+                const double x0 = xs[0];
+                const double x = x0;
                 float pf[KP];
 #pragma unroll
                 for (int q4 = 0; q4 < KP / 4; ++q4) {
-                    const float4 t = ru[q4];
-                    pf[4 * q4] = t.x * vf[4 * q4]; pf[4 * q4 + 1] = t.y * vf[4 * q4 + 1];
-                    pf[4 * q4 + 2] = t.z * vf[4 * q4 + 2]; pf[4 * q4 + 3] = t.w * vf[4 * q4 + 3];
+                    const float4 t = r0[q4];
+                    const float4 vv = *reinterpret_cast<const float4 *>(s_vf + 4 * q4);
+                    pf[4 * q4] = t.x * vv.x; pf[4 * q4 + 1] = t.y * vv.y; pf[4 * q4 + 2] = t.z * vv.z; pf[4 * q4 + 3] = t.w * vv.w;
                 }
                 double base = 0.0;
 #pragma unroll
@@ -1315,11 +1316,12 @@ __global__ void __launch_bounds__(128) k_gene_order(OrderArgs a) {
                         acc[k] = fma(x, (double)l, acc[k]);
                         accb[k] = fmaf(xf, fabsf(l) + 1.f, accb[k]);
                     }
-                if (more) {
 #pragma unroll
-                    for (int q4 = 0; q4 < KP / 4; ++q4) ru[q4] = rn[q4];
-                }
-                x = x_nx; i_nx = i_nx2; x_nx = x_nx2;
+                for (int d = 0; d + 1 < D; ++d)
+#pragma unroll
+                    for (int q4 = 0; q4 < KP / 4; ++q4) r[d][q4] = r[d + 1][q4];
+#pragma unroll
+                for (int d = 0; d < D; ++d) xs[d] = xs[d + 1];
             }
         } else {
             double v[KP];

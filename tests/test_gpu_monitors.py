@@ -290,7 +290,7 @@ def test_loglikelihood_fused_into_the_cell_pass(sparse):
 
 
 @pytest.mark.parametrize("zi,sparse", MODELS, ids=IDS)
-@pytest.mark.parametrize("K", [4, 20])
+@pytest.mark.parametrize("K", [4, 20, 30, 64])
 def test_order_factor_fp32_pass_with_bounds_gives_the_exact_order(zi, sparse, K):
     """The greedy ordering takes its K (K + 1) / 2 logarithms per non-zero in FP32 with an error bound per score and repeats a
     round in FP64 only when the winner does not clear every other candidate by the bounds: same order as the all-FP64 ordering
