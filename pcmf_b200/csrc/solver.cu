@@ -765,10 +765,11 @@ void pcmf_solver::build_csc() {
     k_colptr_from_sorted<<<grid_for(p + 1, 256), 256, 0, stream>>>(nnz, p, keys_out, colptr);
     k_gather_rowidx<<<grid_for(nnz, 256), 256, 0, stream>>>(nnz, perm_out, rowids, rowidx);
     // The non-zero passes run on a 2-D tiled copy of X (xtile.cuh) when the cell pass has enough CTAs to fill the machine
-    // (one per 256 cells) and the factor block fits shared memory twice over; kernel_variant bit 2048 forces the tiles
-    // (small test problems), bit 4096 keeps the CSR / CSC passes.
+    // (one per 256 cells) -- or, with fewer cells, when the matrix is dense enough that a tile's segments are long (C3, 50k x 5k
+    // at 30 %: spike-and-slab pass 3.47 -> 2.05 ms, cell pass 1.71 -> 1.37 ms) -- and the factor block fits shared memory twice
+    // over; kernel_variant bit 2048 forces the tiles (small test problems), bit 4096 keeps the CSR / CSC passes.
     tiled = f32 && KP >= XT_MINKP && KP <= XT_MAXKP && L->tile_cells && nnz > 0 && nnz < 0xffffffffLL && !(opt.dev_flags & 4096) &&
-            (n >= 65536 || (opt.dev_flags & 2048));
+            (n >= 65536 || (n >= 16384 && nnz >= 50000000) || (opt.dev_flags & 2048));
     // ZI / sparse models: the gene passes leave q_ij in CSC order and the cell pass reads it back through this map
     if (!tiled && (zi || sparse) && nnz < 0xffffffffLL && !(opt.dev_flags & 16)) {
         csr2csc = dmalloc<uint32_t>(nnz);

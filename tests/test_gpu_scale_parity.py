@@ -119,6 +119,22 @@ def test_tiled_nonzero_passes_are_the_default_from_65536_cells(zi, sparse, K):
     s.close()
 
 
+def test_tiled_nonzero_passes_are_the_default_for_dense_mid_size_matrices():
+    """BASELINE config 3 is 50k x 5k at ~30 % non-zeros: fewer than 65 536 cells, but 7.5e7 non-zeros, and the tiled passes win
+    there (long tile segments).  The default takes them from 16 384 cells and 5e7 non-zeros on: 17k x 4.5k at ~70 %, zero-inflated
+    + sparse-V, K = 20, against the oracle."""
+    rng = np.random.default_rng(12)
+    n, p = 17_000, 4_500
+    X = rng.poisson(1.2, (n, p)).astype(float)
+    assert (X != 0).sum() >= 50_000_000
+    X[X.sum(1) == 0, 0] = 1
+    X[0, X.sum(0) == 0] = 1
+    m, s = run_pair(X, 20, True, True, prob_S=np.full((p, 20), 0.5), prior_S=np.full(p, 0.5))
+    assert s.phase_times()["tiled_nonzero_passes"][1] == 1
+    check_state(m, s, True, True)
+    s.close()
+
+
 @pytest.mark.parametrize("K", [2, 10, 30, 64])
 def test_c5_shape_latent_dimension_sweep(K):
     """BASELINE config 5 (ZI, K = 2 / 10 / 30 / 64) on a 20k x 3k sub-sample: 6e7 entries, every padded width of the sweep
