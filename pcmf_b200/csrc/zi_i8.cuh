@@ -208,7 +208,10 @@ __device__ __forceinline__ void i8_mma_ss(uint32_t d_tmem, uint64_t da, uint64_t
 // (A fifth warp that owns every tile's tail, so that no compute warp falls behind by the MMA issue, was built and measured: 75.2 ms
 // against 73.0 ms at C4 -- the waits on the P buffers are the skew of equal warps, not the tail.)
 template <int KP, int NW, bool STORE_P, bool WITH_LL>
-__global__ void __launch_bounds__(32 * NW, 2) k_zi_cells_i8(ZiAArgs a) {
+#ifndef PCMF_I8_MINB
+#define PCMF_I8_MINB 2
+#endif
+__global__ void __launch_bounds__(32 * NW, PCMF_I8_MINB) k_zi_cells_i8(ZiAArgs a) {
     static_assert(NW == 4 || NW == 8, "one or two warps per 32-cell row block");
     using R = ZiRecI8<KP>;
     constexpr int MT = 4, KS = R::KS, NFS = R::NFS, NTOT = R::NTOT, TJ = I8_TJ, NG = TJ / 8, BUFA = NG * R::RA, BUFB = NG * R::B8, GPW = NG / (NW / 4);
