@@ -11,8 +11,8 @@
 //     F = rint(EVS 2^(48 - ex_k)), 2^ex_k > max_j EVS_jk.  Pq F = sum_{s,t} b_s e_t 2^(8 (s - t + 5)): the digit products of equal
 //     weight d = s - t share one accumulator,  B_d[k][4 j + s] = e_(s - d)[j][k],  d = 3 .. -2, and the six operands are stacked
 //     along N: ONE MMA (M = 128 cells, N = 6 x 24, K = 32 bytes = 8 genes) per 8-gene group.  The dropped weights d <= -3 are
-//     below 2^-46 of full scale (with five digits and weights, as for K > 24, 2^-38: that truncation is a BIAS of every term and
-//     showed as 1.4e-7 on single entries of b2 where P EU is 1e4 below the column maximum).
+//     below 2^-46 of full scale (with five digits and weights, 2^-38: that truncation is a BIAS of every term and showed as
+//     1.4e-7 on single entries of b2 where P EU is 1e4 below the column maximum).
 //   * u8 x u8 -> s32 in tensor memory is exact: at most 4 digit pairs x 255^2 per gene and accumulator, so the accumulators are
 //     read out (tcgen05.ld), scaled and added to PV in FP64 every 4096 genes, far below 2^31.
 // The kernel is otherwise k_zi_cells_mma: first product lambda = EU_i . EVS_j as DMMA tiles (K = 20 is five m8n8k4 steps, as
@@ -31,7 +31,7 @@ namespace pcmf {
 
 constexpr int I8_UNROLL = PCMF_I8_UNROLL;   // 8-gene groups of a tile unrolled together in the cell-side pass
 constexpr int I8_TJ = 32;              // genes per shared-memory tile (one occupancy word per cell and tile)
-constexpr int I8_STAGES = 3;           // tile buffers in shared memory, and P buffers in tensor memory
+constexpr int I8_STAGES = 3;           // tile buffers of the digit operands in shared memory (and slots of the per-tile counters / column sums)
 constexpr int I8_FLUSH = 128;          // tiles between two read-outs of the integer accumulators (4096 genes)
 constexpr int I8_TAIL = 128;           // doubles after the records: [colmax 64 | cfac 64]
 
@@ -156,14 +156,16 @@ __device__ __forceinline__ void i8_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
                  ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// CTA = 256 threads = 8 warps over 128 cells (the 128 lanes of tensor memory): warp w owns the 32 cells of row block w & 3 as four
-// 8-row tiles, and the 8-gene groups {2 (w >> 2), 2 (w >> 2) + 1} of every 32-gene tile.  No CTA-wide barrier in the main loop:
-//   * a warp waits for the tile's records (bar_full) and for the MMAs that last read the P buffer it is about to overwrite
-//     (bar_mma of three tiles ago), computes, stores its P words to tensor memory and its column sums to shared memory, and
-//     counts itself in (s_cnt);
-//   * the warp that counts in LAST owns the tile's tail: flushes the column sums, issues the 20 MMAs and their commit, and
-//     starts the bulk copy of the tile after next into the buffer the MMAs of two tiles ago have released.
-// Two CTAs per SM (tensor memory: 2 x 256 columns; shared memory: 2 x ~92 KB), 16 warps.
+// CTA = 128 cells (the 128 lanes of tensor memory) = NW warps: NW = 4 (default), warp w owns the 32 cells of row block w as four
+// 8-row tiles and all four 8-gene groups of every 32-gene tile; NW = 8 (PCMF_I8_NW), two warps per row block share its groups.
+// No CTA-wide barrier in the main loop:
+//   * a warp waits for the tile's first-product records (bar_fullA) and for the MMAs that last read the P buffer it is about to
+//     overwrite (bar_mma of PST tiles ago), computes, stores its P words to tensor memory and its column sums to shared memory,
+//     and counts itself in (s_cnt);
+//   * the warp that counts in LAST owns the tile's tail (tile_tail): adds the column sums, starts the bulk copies of later tiles
+//     (part A three tiles ahead, part B two tiles ahead once the MMAs of the tile before have released its buffer), issues the
+//     tile's MMAs -- one per 8-gene group -- and their commit.
+// Two CTAs per SM (tensor memory: 2 x 256 columns; shared memory: 2 x ~96 KB).
 // Select-free expit for the pass without the log-likelihood monitor.  With za = min(|z|, 40), t = e^-za in (4e-18, 1], r = 1 / (1 + t):
 //      P = z >= 0 ? r : t r            1 exactly for z >= 37 and below 2^-57 for z <= -40, where internal::expit (internal.h:151-155)
 //                                      clamps to exactly 1 / 0 from |z| = 30 on: the two differ by at most e^-30 = 9.4e-14
