@@ -1562,7 +1562,17 @@ void pcmf_solver::order_factor_now() {
                 if (ind == 0) { val_min = res[ind]; ind_min = c; ind_left = ind; }          // model.cpp:161-165
                 if (res[ind] < val_min) { val_min = res[ind]; ind_min = c; ind_left = ind; }     // model.cpp:168-172
             }
-            if (!fast) break;
+            if (!fast) {
+                // The sums come out of floating-point atomics, so two candidates the reference sees as an exact tie (identical
+                // factors: model.cpp:161-172 keeps the FIRST minimum) differ here by rounding noise of the order 1e-14 of the
+                // terms; everything within 1e-12 of the minimum counts as tied and the first of them in the reference's order wins
+                for (size_t ind = 0; ind < left.size(); ++ind) {
+                    const int c = left[ind];
+                    const double scale = std::fabs(out[c]) + std::fabs(base_total + tk[c]) + std::fabs(lgx_const) + std::fabs(ll_XX);
+                    if (res[ind] - val_min <= 2e-12 * scale) { ind_min = c; ind_left = ind; break; }
+                }
+                break;
+            }
             // |out_c - exact| <= 6.6e-7 bound_c (k_gene_order<FAST>), res = -2 out + ...: clear margin = 2 x 2 x 6.6e-7 (bound_b + bound_c)
             bool clear = std::isfinite(val_min);
             for (size_t ind = 0; ind < left.size() && clear; ++ind)

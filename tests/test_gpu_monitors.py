@@ -332,6 +332,11 @@ def test_order_factor_tie_falls_back_to_the_exact_round():
     s.iterate(3)
     m.order_factor()
     s.order_factor()
-    assert list(s.get_output()["factor_order"]) == list(m.get("factor_order"))
+    # (the two tied factors are interchangeable: which of them comes first is decided by the summation order of the reductions,
+    #  in the OpenMP oracle as well -- the library itself takes the first, like a sequential run of the reference)
+    same = lambda order: [1 if int(k) == 3 else int(k) for k in order]
+    got = list(s.get_output()["factor_order"])
+    assert same(got) == same(m.get("factor_order"))
+    assert got.index(1) < got.index(3)
     assert s.phase_times()["order_factor_exact_rounds"][1] >= 1
     s.close()
